@@ -1,0 +1,146 @@
+"""Pins the CPU oracle on the reference's own known-answer tests."""
+import numpy as np
+import pytest
+
+import oracle
+from refcases import (CELLGRID_CASES, LOCFUN_GOLDEN, assim_case, kalman_check, rrsqrt_case)
+
+TOL = 1e-8  # test/test_rrsqrt.F90:20 (double precision)
+
+
+def test_locfun_known_answers():
+    # test/test_covariance.F90:612-617
+    for r, want in LOCFUN_GOLDEN:
+        assert abs(oracle.locfun(r) - want) < 1e-14
+
+
+def test_global_analysis_vs_kalman():
+    # test/test_rrsqrt.F90:27-77
+    c = rrsqrt_case()
+    xa, Sa, _ = oracle.analysis(c["xf"], c["Hxf"], c["y"], c["Sf"], c["HSf"], c["var"])
+    xa_check, Pa_check = kalman_check(c["xf"], c["Sf"], c["H"], c["y"], np.diag(c["var"]))
+    assert np.abs(xa - xa_check).max() < TOL
+    assert np.abs(Sa @ Sa.T - Pa_check).max() < TOL
+    # ROTATE_ENSEMBLE: columns of Sa sum to zero like those of Sf (rrsqrt.F90:166-176)
+    assert np.abs(Sa.sum(axis=1)).max() < 1e-12
+
+
+def _loc(c, zoneSize, weightfun, corr, maxlen, local_obs=True):
+    nz = len(zoneSize)
+    starts = np.concatenate([[0], np.cumsum(zoneSize)[:-1]])
+    obs = oracle.make_obs(c["m"], obsx=c["xobs"], obsy=np.zeros(c["m"]), loctype=1, metrictype=0,
+                          weightfun=weightfun)
+    zpos = dict(x=c["xmod"][starts], y=np.zeros(nz))
+    return oracle.loc_analysis(zoneSize, zpos, corr, maxlen, obs, c["xf"], c["Hxf"], c["y"], c["Sf"],
+                               c["HSf"], c["var"], local_obs=local_obs)
+
+
+def test_local_single_zone_and_zone_per_point_equal_global():
+    # test/test_rrsqrt.F90:142-159 (selectAllObservations)
+    c = rrsqrt_case()
+    xa_check, Pa_check = kalman_check(c["xf"], c["Sf"], c["H"], c["y"], np.diag(c["var"]))
+    for zs in ([c["n"]], [1] * c["n"]):
+        xa, Sa, _, mloc = _loc(c, zs, 2, 1.0, 1e30)
+        assert (mloc == c["m"]).all()
+        assert np.abs(xa - xa_check).max() < TOL
+        assert np.abs(Sa @ Sa.T - Pa_check).max() < TOL
+
+
+@pytest.mark.parametrize("localise_obs", [False, True])
+def test_local_gaspari_cohn_vs_explicit_formula(localise_obs):
+    # test/test_rrsqrt.F90:162-233 ; callback :254-271
+    c = rrsqrt_case()
+    n, m = c["n"], c["m"]
+    xa, Sa, _, mloc = _loc(c, [1] * n, 1, c["length"], 1e30, local_obs=localise_obs)
+    Pf = c["Sf"] @ c["Sf"].T
+    R = np.diag(c["var"])
+    xa_check = np.zeros(n)
+    for i in range(n):
+        w = np.array([oracle.locfun(abs(c["xmod"][i] - xo) / c["length"]) for xo in c["xobs"]])
+        rel = w != 0 if localise_obs else np.ones(m, bool)
+        assert mloc[i] == (w != 0).sum()
+        if not (w != 0).any():
+            xa_check[i] = c["xf"][i]  # rrsqrt.F90:370-371
+            continue
+        iloc = np.where(rel)[0]
+        invRloc = np.linalg.inv(R[np.ix_(iloc, iloc)]) * np.outer(w[iloc], w[iloc])
+        Hloc = c["H"][iloc]
+        Pa = np.linalg.inv(np.linalg.inv(Pf) + Hloc.T @ invRloc @ Hloc)
+        xa_check[i] = c["xf"][i] + Pa[i] @ (Hloc.T @ (invRloc @ (c["y"][iloc] - Hloc @ c["xf"])))
+    assert np.abs(xa - xa_check).max() < TOL
+
+
+def test_numpy_twin_of_analysis_increment():
+    """independent numpy restatement of rrsqrt.F90:100-190 cross-checks the C one (incl. Sa)"""
+    rng = np.random.default_rng(0)
+    m, n, N = 40, 7, 16
+    Sf = rng.normal(size=(n, N)); Sf -= Sf.mean(1, keepdims=True)
+    HSf = rng.normal(size=(m, N)); HSf -= HSf.mean(1, keepdims=True)
+    xf = rng.normal(size=n); Hxf = rng.normal(size=m); yo = rng.normal(size=m)
+    var = rng.uniform(0.5, 2, m)
+    xa, Sa, ampl = oracle.analysis(xf, Hxf, yo, Sf, HSf, var)
+    G = HSf.T @ (HSf / var[:, None])
+    lam, U = np.linalg.eigh(G)
+    lam = 1 / (1 + np.maximum(lam, 0))
+    a = U @ (lam * (U.T @ (HSf.T @ ((yo - Hxf) / var))))
+    sq = np.sqrt(lam)
+    w = np.full(N, 1 / np.sqrt(N))
+    v = U @ (U.sum(axis=0) / sq); v /= np.linalg.norm(v)
+    Om = oracle.rotate_vector(w, v)
+    assert np.abs(Om @ w - v).max() < 1e-13 and np.abs(Om @ Om.T - np.eye(N)).max() < 1e-13
+    Sa2 = Sf @ (U @ (sq[:, None] * (U.T @ Om)))
+    assert np.abs(ampl - a).max() < 1e-12
+    assert np.abs(xa - (xf + Sf @ a)).max() < 1e-12
+    assert np.abs(Sa - Sa2).max() < 1e-12
+
+
+def test_assim_case_global_through_local_scheme():
+    # test/test_assim.F90:96-172 (tol 1e-5): ensemble in, ensemble out
+    c = assim_case()
+    n, N = c["n"], c["N"]
+    xf = c["Ef"].sum(axis=1) / N
+    Efp = c["Ef"] - xf[:, None]
+    xa_check, Pa_check = kalman_check(xf, Efp / np.sqrt(N - 1.0), c["H"], c["yo"], np.diag(c["var"]))
+    obs = oracle.make_obs(1, obsx=c["obsx"], obsy=c["obsy"], weightfun=2)
+    Hi = np.array([1], dtype=np.int32); Hj = np.array([5], dtype=np.int32); Hs = np.array([1.0])
+    Ea, xf_o, xa_o = oracle.assim_ensemble([n], dict(x=c["x"][:1], y=c["y"][:1]), 1.0, 1e30, obs, c["Ef"],
+                                           Hi, Hj, Hs, np.zeros(1), c["yo"], c["var"])
+    xa = Ea.sum(axis=1) / N
+    Eap = Ea - xa[:, None]
+    assert np.abs(xa - xa_check).max() < 1e-5
+    assert np.abs(Eap @ Eap.T / (N - 1.0) - Pa_check).max() < 1e-5
+    assert np.abs(xa - xa_o).max() < 1e-12
+
+
+@pytest.mark.parametrize("side,maxdist", CELLGRID_CASES[:2])
+def test_selection_predicate_matches_checknear(side, maxdist):
+    # test/test_cellgrid.F90:64-83: every lattice point with d < maxdist of (2,2) must be found.
+    ii, jj = np.meshgrid(np.arange(1, side + 1.0), np.arange(1, side + 1.0), indexing="ij")
+    obs = oracle.make_obs(side * side, obsx=ii.ravel(order="F"), obsy=jj.ravel(order="F"))
+    w, rel = oracle.select_observations(obs, (2.0, 2.0), 1.0, maxdist)
+    d = np.hypot(ii.ravel(order="F") - 2, jj.ravel(order="F") - 2)
+    assert set(np.where(d < maxdist)[0]) <= set(np.where(rel)[0])
+    assert (rel == (np.sqrt((ii.ravel(order="F") - 2) ** 2 + (jj.ravel(order="F") - 2) ** 2) <= maxdist)).all()
+
+
+def test_distance_metrics():
+    # assimilation.F90:3635-3672 ; portable trig within 1 ulp-ish of libm
+    R = 6378137.0
+    assert oracle.distance(0, (0, 0), (3, 4)) == 5.0
+    d = oracle.distance(1, (0.0, 0.0), (90.0, 0.0))
+    assert abs(d - R * np.pi / 2) < 1e-6
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        p0 = (rng.uniform(-180, 180), rng.uniform(-89, 89)); p1 = (p0[0] + rng.normal() * 0.1, p0[1] + rng.normal() * 0.1)
+        for mt in (1, 2):
+            a = oracle.distance(mt, p0, p1, trig=0); b = oracle.distance(mt, p0, p1, trig=1)
+            assert abs(a - b) <= 1e-6 * max(a, 1.0)  # acos near 1 amplifies 1-ulp differences
+
+
+def test_init_partition_is_stable_counting_sort():
+    # assimilation.F90:578-641
+    part = np.array([2, 1, 2, 3, 1, 3, 3], dtype=np.int32)
+    zs, zi, izi = oracle.init_partition(part, 3)
+    assert list(zs) == [2, 2, 3]
+    assert list(zi) == [2, 5, 1, 3, 4, 6, 7]
+    assert all(zi[izi[i] - 1] == i + 1 for i in range(7))
