@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — local-analysis throughput (grid columns analysed per second) on 1/2/4/8 B200.
+
+Workload (BASELINE.json configs[2], "C3"): synthetic 3-D ocean 1000 x 1000 x 30, N = 64 members,
+1e6 observations with diagonal R, Gaussian localisation corrLen 4 km / cut-off 8 km, Cartesian metric.
+A step = one complete local analysis (locAnalysis, rrsqrt.F90:433) of every water column.
+Multi-GPU: strong scaling — the 1e6 columns are split in contiguous zone ranges (parall.F90:176-177),
+each rank analyses its slab with its observation halo, one NCCL all-gather reassembles the analysed
+anomalies; `value` = all columns / max-over-ranks time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nx .. --ny .. --nz .. --N .. --m ..]
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 20261017
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=1000)
+    ap.add_argument("--ny", type=int, default=1000)
+    ap.add_argument("--nz", type=int, default=30)
+    ap.add_argument("--N", type=int, default=64)
+    ap.add_argument("--m", type=int, default=1000000)
+    ap.add_argument("--corr", type=float, default=4000.0)
+    ap.add_argument("--maxlen", type=float, default=8000.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--eig-kernel", type=int, default=0)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"synthetic 3D ocean {a.nx}x{a.ny}x{a.nz}, N={a.N}, {a.m} obs, diagonal R, local ETKF "
+            f"(gaussian corrLen {a.corr:g} m, cut-off {a.maxlen:g} m, cartesian)")
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampled during the timed region
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic data of one rank, generated on the device
+# --------------------------------------------------------------------------------------------------
+def build_rank_data(a, rank, world, dev):
+    import torch
+    from oak_b200 import synthetic as S
+    from oak_b200.dist import ShardPlan
+    g = S.Grid(a.nx, a.ny, a.nz)
+    obs_np = S.observations(np, g, a.m, SEED)
+    zones = np.arange(g.nzones, dtype=np.int64)
+    zx, zy = g.zone_xy(np, zones)
+    zs = np.full(g.nzones, a.nz, dtype=np.int32)
+    plan = ShardPlan(zs, zx, zy, a.corr, a.maxlen, obs_np["ox"], obs_np["oy"], rank, world)
+    n_loc = plan.r1 - plan.r0
+    Sf = torch.empty((a.N, n_loc), dtype=torch.float64, device=dev)
+    xf = torch.empty(n_loc, dtype=torch.float64, device=dev)
+    step = 1 << 20
+    for s in range(0, n_loc, step):
+        e = min(n_loc, s + step)
+        rows = torch.arange(plan.r0 + s, plan.r0 + e, dtype=torch.int64, device=dev)
+        E = S.ensemble_rows(torch, g, rows, a.N, SEED)
+        mean, anom = S.anomalies(torch, E)
+        xf[s:e] = mean
+        Sf[:, s:e] = anom
+        del E, anom, mean, rows
+    oi = torch.from_numpy(plan.obs_idx).to(dev)
+    obs_t = S.observations(torch, g, a.m, SEED) if dev.type == "cpu" else {
+        k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in obs_np.items()}
+    sub = {k: (v[:, oi] if v.dim() > 1 else v[oi]) for k, v in obs_t.items()}
+    mh = int(oi.numel())
+    HE = torch.empty((a.N, mh), dtype=torch.float64, device=dev)
+    yo = torch.empty(mh, dtype=torch.float64, device=dev)
+    ostep = 1 << 18
+    for s in range(0, mh, ostep):
+        e = min(mh, s + ostep)
+        part = {k: (v[:, s:e] if v.dim() > 1 else v[s:e]) for k, v in sub.items()}
+        he, y = S.obs_space(torch, g, part, a.N, SEED)
+        HE[:, s:e] = he
+        yo[s:e] = y
+    Hxf, HSf = S.anomalies(torch, HE)
+    del HE
+    return dict(grid=g, plan=plan, Sf=Sf, xf=xf, HSf=HSf.contiguous(), Hxf=Hxf.contiguous(), yo=yo,
+                var=sub["var"].contiguous(), ox=obs_np["ox"][plan.obs_idx], oy=obs_np["oy"][plan.obs_idx])
+
+
+def flops_per_zone(N, nz, mloc_mean, cand_mean):
+    """algorithmic work per zone: Gram + eigendecomposition (LAPACK count) + transform +
+    amplitudes + apply + selection"""
+    return (2 * N * N * mloc_mean + 9 * N ** 3 + 2 * N ** 3 + 2 * mloc_mean * N + 4 * N * N +
+            2 * nz * N * N + 2 * nz * N + 25 * cand_mean)
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (port of the reference's CPU path: O(m) scan per zone, dgemm, dsyev) on a sample
+# --------------------------------------------------------------------------------------------------
+def cpu_sample_problem(a, d, nsample):
+    import torch
+    g, plan = d["grid"], d["plan"]
+    rng = np.random.default_rng(1)
+    zl = np.sort(rng.choice(plan.z1 - plan.z0, size=min(nsample, plan.z1 - plan.z0), replace=False))
+    rows = (zl[:, None] * a.nz + np.arange(a.nz)[None, :]).ravel()
+    rt = torch.from_numpy(rows).to(d["Sf"].device)
+    Sf = np.asfortranarray(d["Sf"][:, rt].cpu().numpy().T)
+    xf = d["xf"][rt].cpu().numpy()
+    zx, zy = g.zone_xy(np, (plan.z0 + zl).astype(np.int64))
+    return dict(zl=zl, Sf=Sf, xf=xf, zx=zx, zy=zy, zs=np.full(zl.size, a.nz, np.int32))
+
+
+def run_oracle_sample(a, host, sp, count):
+    import oracle
+    obs = oracle.make_obs(host["m"], obsx=host["ox"], obsy=host["oy"])
+    k = count * a.nz
+    t0 = time.perf_counter()
+    oracle.loc_analysis(sp["zs"][:count], dict(x=sp["zx"][:count], y=sp["zy"][:count]), a.corr, a.maxlen, obs,
+                        sp["xf"][:k], host["Hxf"], host["yo"], sp["Sf"][:k], host["HSf"], host["var"])
+    return time.perf_counter() - t0
+
+
+def host_obs_arrays(d):
+    return dict(m=int(d["yo"].numel()), ox=d["ox"], oy=d["oy"], Hxf=d["Hxf"].cpu().numpy(), yo=d["yo"].cpu().numpy(),
+                var=d["var"].cpu().numpy(), HSf=np.asfortranarray(d["HSf"].cpu().numpy().T))
+
+
+def cpu_baseline(a, d, seconds):
+    import oracle
+    host = host_obs_arrays(d)
+    cores = oracle.max_threads()
+    sp = cpu_sample_problem(a, d, 200000)
+    probe = max(cores * 2, 16)
+    t = run_oracle_sample(a, host, sp, probe)
+    count = int(min(sp["zl"].size, max(probe, probe * seconds / max(t, 1e-6))))
+    t = run_oracle_sample(a, host, sp, count)
+    return {"value": count / t, "unit": "columns/s", "cores": cores, "kind": "port",
+            "sample": f"{count} random columns of the same workload (all {host['m']} observations scanned per "
+                      f"column as assimilation.F90:3745-3757 does, OpenBLAS dgemm/dsyev, OpenMP dynamic over "
+                      f"columns), {t:.1f} s"}, (host, sp)
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.impl == "reference":
+        return reference_arm(a, rank, world)
+
+    import torch.distributed as dist
+    import oak_b200
+    from oak_b200.dist import allgather_slabs
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    d = build_rank_data(a, rank, world, dev)
+    plan, g = d["plan"], d["grid"]
+    n_loc = plan.r1 - plan.r0
+    h = oak_b200.Handle(local, eig_kernel=a.eig_kernel)
+    h.set_zones(plan.zoneSize, zone_x=plan.zx, zone_y=plan.zy, corrLen=plan.corrLen, maxLen=plan.maxLen,
+                loctype=1, metrictype=0, weightfun=0)
+    h.set_observations(obs_x=d["ox"], obs_y=d["oy"])
+    xa = torch.empty(n_loc, dtype=torch.float64, device=dev)
+    Sa = torch.empty_like(d["Sf"])
+    Sa_full = torch.empty((a.N, plan.n), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        st = h.local_analysis_dev(d["xf"], d["Hxf"], d["yo"], d["Sf"], d["HSf"], d["var"], xa, Sa)
+        if world > 1:
+            allgather_slabs(dist, Sa, plan, out=Sa_full)
+        return st
+
+    for _ in range(a.warmup):
+        st = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launches = 0
+    for _ in range(a.steps):
+        st = step()
+        launches += st["launches"]
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    agg = torch.tensor([float(st["obs_relevant_sum"]), float(st["obs_candidate_sum"]), float(st["jacobi_sweeps_sum"]),
+                        float(st["zones_skipped"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    ms = float(tms.item())
+    ms_per_step = ms / a.steps
+    nzones = g.nzones
+    value = nzones / (ms_per_step * 1e-3)
+
+    # ---- per-kernel times (separate profiled pass: batches serialised, CUDA events around each kernel family)
+    h.set_option("profile", 1)
+    stp = h.local_analysis_dev(d["xf"], d["Hxf"], d["yo"], d["Sf"], d["HSf"], d["var"], xa, Sa)
+    h.set_option("profile", 0)
+    peak_dfma = h.fp64_peak(0)
+    peak_dmma = h.fp64_peak(1)
+
+    out = None
+    if rank == 0:
+        analysed = nzones - agg[3].item()
+        mloc_mean = agg[0].item() / max(analysed, 1)
+        cand_mean = agg[1].item() / max(nzones, 1)
+        sweeps_mean = agg[2].item() / max(analysed, 1)
+        nb = max(1, (stp["launches"] - 1) // 3)            # eig launches of this rank in one step
+        z_rank = plan.z1 - plan.z0
+        eig_flops_zone = 9 * a.N ** 3 + 2 * a.N ** 3 + 4 * a.N ** 2
+        eig_ms_launch = stp["ms_eig"] / nb
+        achieved = eig_flops_zone * (z_rank / nb) / (eig_ms_launch * 1e-3) / 1e12
+        fz = flops_per_zone(a.N, a.nz, mloc_mean, cand_mean)
+        roof = {"bound": "fp64", "kernel": "k_eig_fast (batched Cholesky + block-Jacobi + transform)",
+                "achieved": achieved, "peak": peak_dfma, "unit": "TFLOP/s", "frac": achieved / peak_dfma,
+                "traffic": None,
+                "peak_source": "DFMA micro-kernel measured in this run (oakb200_fp64_peak); MEASURED_PEAKS.json has no "
+                               "fp64 figure; DMMA m8n8k4 measured %.1f TFLOP/s" % peak_dmma,
+                "algorithmic_flops_per_zone_kernel": eig_flops_zone, "launches_per_step": nb,
+                "ms_per_launch": eig_ms_launch,
+                "kernel_ms_per_step": {"pack": stp["ms_pack"], "gram": stp["ms_gram"], "eig": stp["ms_eig"],
+                                       "apply": stp["ms_apply"]},
+                "whole_step": {"algorithmic_flops_per_zone": fz, "achieved": value * fz / 1e12 / world,
+                               "frac_of_fp64_peak_per_gpu": value * fz / 1e12 / world / peak_dfma},
+                "hbm_view": {"algorithmic_bytes_per_zone": 2 * a.nz * a.N * 8 + 2 * a.nz * 8 + a.m * a.N * 8 / nzones,
+                             "note": "HBM is not the binding roof (arithmetic intensity >100 flop/B)"}}
+        out = {"metric": "local-analysis grid columns/sec", "value": value, "unit": "columns/s", "n_gpus": world,
+               "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": workload_name(a), "zones": nzones, "parallelism": f"zone-range x{world}",
+                          "l2": "inputs (>= 15 GB state) exceed L2; no explicit flush",
+                          "mean_relevant_obs_per_column": mloc_mean, "mean_candidates_per_column": cand_mean,
+                          "mean_jacobi_sweeps": sweeps_mean, "eig_kernel": a.eig_kernel},
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+
+    # ---- end to end through the host-buffer entry point (pinned host memory, H2D + D2H inside the timed region)
+    e2e = None
+    if not a.no_e2e:
+        try:
+            Sf_h = torch.empty((a.N, n_loc), dtype=torch.float64, pin_memory=True)
+            Sa_h = torch.empty((a.N, n_loc), dtype=torch.float64, pin_memory=True)
+            Sf_h.copy_(d["Sf"])
+            pin = lambda t: t.cpu().pin_memory()
+            xf_h, Hxf_h, yo_h, HSf_h, var_h = pin(d["xf"]), pin(d["Hxf"]), pin(d["yo"]), pin(d["HSf"]), pin(d["var"])
+            xa_h = torch.empty(n_loc, dtype=torch.float64, pin_memory=True)
+            torch.cuda.synchronize()
+            h.local_analysis_pinned(xf_h, Hxf_h, yo_h, Sf_h, HSf_h, var_h, xa_h, Sa_h)  # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(a.e2e_steps):
+                ste = h.local_analysis_pinned(xf_h, Hxf_h, yo_h, Sf_h, HSf_h, var_h, xa_h, Sa_h)
+            torch.cuda.synchronize()
+            te = (time.perf_counter() - t0) / a.e2e_steps
+            tt = torch.tensor([te], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ok = bool(torch.equal(Sa_h[:, :1000].to(dev), Sa[:, :1000]))
+            e2e = {"value": nzones / float(tt.item()), "unit": "columns/s", "h2d_bytes_per_step": ste["h2d_bytes"],
+                   "d2h_bytes_per_step": ste["d2h_bytes"], "steps": a.e2e_steps,
+                   "note": "oakb200_local_analysis on pinned host buffers; state streamed in zone chunks; "
+                           "per-rank slab, no all-gather of host buffers" + ("" if ok else "; MISMATCH vs resident run")}
+            del Sf_h, Sa_h
+        except Exception as ex:  # e.g. not enough pinnable host memory
+            e2e = {"value": None, "unit": "columns/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                   "error": repr(ex)[:300]}
+    if rank == 0:
+        out["e2e"] = e2e
+        if world == 1 and not a.no_cpu:
+            try:
+                out["cpu_baseline"], _ = cpu_baseline(a, d, a.cpu_seconds)
+            except Exception as ex:
+                out["cpu_baseline"] = {"value": None, "unit": "columns/s", "cores": None, "kind": "port",
+                                       "sample": "failed: " + repr(ex)[:200]}
+        print(json.dumps(out))
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_arm(a, rank, world):
+    """The reference's CPU implementation of the path (the oracle port: the Fortran reference cannot be
+    built in this image) on a bounded sample of the same workload, all host threads."""
+    if rank != 0:
+        return
+    import torch
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    d = build_rank_data(a, 0, 1, dev)
+    import oracle
+    host = host_obs_arrays(d)
+    cores = oracle.max_threads()
+    sp = cpu_sample_problem(a, d, 100000)
+    probe = max(cores * 2, 16)
+    t = run_oracle_sample(a, host, sp, probe)
+    count = int(min(sp["zl"].size, max(probe, probe * 4.0 / max(t, 1e-6))))  # ~4 s per step
+    for _ in range(a.warmup):
+        run_oracle_sample(a, host, sp, count)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        run_oracle_sample(a, host, sp, count)
+    tt = (time.perf_counter() - t0) / a.steps
+    v = count / tt
+    sample = (f"{count} random columns per step of the same workload; every column scans all {host['m']} observations "
+              f"(assimilation.F90:3745-3757), dgemm + dsyev per column, OpenMP dynamic over columns")
+    print(json.dumps({"impl": "reference", "metric": "local-analysis grid columns/sec", "value": v,
+                      "unit": "columns/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                      "ms_per_step": tt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                      "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": workload_name(a), "zones": d["grid"].nzones},
+                      "cpu_baseline": {"value": v, "unit": "columns/s", "cores": cores, "kind": "port",
+                                       "sample": sample},
+                      "e2e": {"value": v, "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,147 @@
+/*
+ * oak_b200.h — C ABI of the B200-native local ensemble analysis for OAK.
+ *
+ * This is the drop-in boundary.  The Fortran driver keeps `Assim`
+ * (assimilation.F90:2977) and replaces the body of its LocalScheme branch
+ *     call locanalysis(zoneSize,selectObservations,xf,Hxf,yo,Sf,HSf,R,xa,Sa,locAmplitudes)
+ * (assimilation.F90:3235-3236; signature rrsqrt.F90:433-457) by calls into this library through
+ * ISO_C_BINDING (fortran/oak_b200_shim.F90).
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, <0 on error (oakb200_last_error() has the text);
+ *     the reference prints to unit 0 and `call exit(1)` (ppdef.h:22) — the shim maps !=0 to ERROR_STOP.
+ *   - all arrays are contiguous, column-major, fp64 / int32, owned by the caller; nothing is retained
+ *     after return except what oakb200_set_zones / oakb200_set_observations copy to the device.
+ *   - observation and zone indices in results are 1-based, as the Fortran caller stores them.
+ *   - there is NO CPU fallback: every entry point needs a CUDA device (sm_100a).
+ *   - a handle is not re-entrant; call from one thread (the `!$omp master` thread, between the
+ *     barriers at assimilation.F90:3215 and :3295).
+ */
+#ifndef OAK_B200_H
+#define OAK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define OAKB200_API __attribute__((visibility("default")))
+#else
+#define OAKB200_API
+#endif
+
+typedef struct oakb200_handle oakb200_handle;
+
+/* loctype (assimilation.F90:204-208), metrictype (:108-112) */
+enum { OAKB200_LOC_HORIZONTAL = 1, OAKB200_LOC_DEPTH = 2, OAKB200_LOC_TIME = 3 };
+enum { OAKB200_METRIC_CARTESIAN = 0, OAKB200_METRIC_SPHERICAL = 1, OAKB200_METRIC_SPHERICAL_APPROX = 2 };
+/* weight function of the selectObservations callback:
+ *   GAUSSIAN      relevant = d <= maxLen ; w = exp(-(d/corrLen)^2)       assimilation.F90:3756,:3767
+ *   GASPARI_COHN  w = locfun(d/corrLen) ; relevant = w /= 0               test/test_rrsqrt.F90:254-271, covariance.F90:645-667
+ *   UNIFORM       all observations, w = 1 (selectAllObservations)         test/test_rrsqrt.F90:239-247 */
+enum { OAKB200_WEIGHT_GAUSSIAN = 0, OAKB200_WEIGHT_GASPARI_COHN = 1, OAKB200_WEIGHT_UNIFORM = 2 };
+
+typedef struct {
+  int64_t zones_total;      /* zones visited                                                     */
+  int64_t zones_skipped;    /* zones without relevant observation (rrsqrt.F90:370-371)            */
+  int64_t obs_relevant_sum; /* sum over zones of m_loc                                            */
+  int64_t obs_candidate_sum;/* sum over zones of cell-grid candidates examined                    */
+  int64_t jacobi_sweeps_sum;/* sum over analysed zones of Jacobi sweeps                           */
+  int64_t h2d_bytes, d2h_bytes; /* bytes copied by the host-buffer entry points                   */
+  double ms_total;          /* CUDA-event time of the whole call on the library's streams         */
+  double ms_pack, ms_gram, ms_eig, ms_apply; /* per-kernel-family CUDA-event sums (only filled when
+                                                option "profile" = 1, which serialises the batches) */
+  int64_t launches;         /* kernels launched by this call                                      */
+} oakb200_stats;
+
+OAKB200_API const char *oakb200_last_error(void);
+OAKB200_API int oakb200_version(void);
+
+/* Create / destroy a context on CUDA device `device` (one handle per GPU; one process per GPU
+ * replaces the MPI ranks of parall.F90:53-186). */
+OAKB200_API int oakb200_create(int device, oakb200_handle **h);
+OAKB200_API int oakb200_destroy(oakb200_handle *h);
+
+/* Options (all optional): "eig_kernel" 0 = register-resident block Jacobi (default), 1 = simple
+ * shared-memory Jacobi (cross-check); "zones_per_batch"; "jacobi_tol"; "max_sweeps"; "profile". */
+OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key, double value);
+
+/* Zones = the partition of the (zone-permuted) state vector (assimilation.F90:578-641).
+ * zoneSize[nzones] as passed to locanalysis; zone z owns rows sum(zoneSize[0..z-1]) ... of the state.
+ * zx,zy,zz,zt: coordinate of each zone's FIRST element (rrsqrt.F90:368, assimilation.F90:3713-3740);
+ * zy/zz/zt may be NULL when unused.  corrLen/maxLen: hCorrLengthToObs / hMaxCorrLengthToObs of that
+ * element (assimilation.F90:3756,:3767).  Replaces the module globals the callback reads. */
+OAKB200_API int oakb200_set_zones(oakb200_handle *h, int32_t nzones, const int32_t *zoneSize, const double *zx,
+                      const double *zy, const double *zz, const double *zt, const double *corrLen,
+                      const double *maxLen, int32_t loctype, int32_t metrictype, int32_t weightfun);
+
+/* Observation positions obsGridX/Y/Z/T(m) (assimilation.F90:3155-3160); builds the device cell grid
+ * that replaces the O(m) scan of assimilation.F90:3745-3757 and the cellgrid/near search of
+ * ndgrid.F90:1489-1691.  Arrays not needed by `loctype` may be NULL.  Call after oakb200_set_zones. */
+OAKB200_API int oakb200_set_observations(oakb200_handle *h, int32_t m, const double *obsx, const double *obsy,
+                             const double *obsz, const double *obst);
+
+/* The selectObservations callback for zones [zone_first, zone_first+zone_count) (0-based zone
+ * numbers): CSR output offsets[zone_count+1], idx[] = 1-based observation numbers in increasing
+ * order (the order pack() uses, rrsqrt.F90:395-404), weight[] their weights.  If capacity is too
+ * small returns -5 with offsets[] filled (offsets[zone_count] = required capacity). */
+OAKB200_API int oakb200_select_observations(oakb200_handle *h, int32_t zone_first, int32_t zone_count,
+                                int64_t capacity, int64_t *offsets, int32_t *idx, double *weight);
+
+/* locAnalysis (rrsqrt.F90:433-466) with R = DiagCovar(Rdiag) optionally wrapped by
+ * DCDCovar(d01,.) (assimilation.F90:3086-3092; d01 may be NULL), HOST buffers:
+ *   xf[n], Hxf[m], yo[m], Sf[n x N, ld ldSf], HSf[m x N, ld ldHSf]  ->  xa[n], Sa[n x N, ld ldSa]
+ *   amplitudes[N x nzones] (may be NULL) is zero-filled, as the reference leaves it on the default
+ *   local_obs branch (rrsqrt.F90:324,:386-412).
+ * Sa may alias Sf (in-place update).  The state is streamed through the device in zone chunks, so
+ * n*N may exceed device memory.  Returns -7 if an analysis produced NaN (rrsqrt.F90:145-149). */
+OAKB200_API int oakb200_local_analysis(oakb200_handle *h, int64_t n, int32_t N, int32_t m, const double *xf,
+                           const double *Hxf, const double *yo, const double *Sf, int64_t ldSf,
+                           const double *HSf, int64_t ldHSf, const double *Rdiag, const double *d01,
+                           double *xa, double *Sa, int64_t ldSa, double *amplitudes,
+                           oakb200_stats *stats);
+
+/* Same, all array arguments are DEVICE pointers on the handle's device (state resident in HBM).
+ * The work is ordered after everything already enqueued on `stream` (a cudaStream_t passed as
+ * void*, NULL = the legacy default stream), runs on the library's own streams, and the call returns
+ * only when the results are complete (it synchronises), so they are visible to any stream. */
+OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t n, int32_t N, int32_t m, const double *xf,
+                               const double *Hxf, const double *yo, const double *Sf, int64_t ldSf,
+                               const double *HSf, int64_t ldHSf, const double *Rdiag,
+                               const double *d01, double *xa, double *Sa, int64_t ldSa,
+                               double *amplitudes, void *stream, oakb200_stats *stats);
+
+/* Ensemble branch of Assim around the local scheme (assimilation.F90:3083,:3106-3134 prologue,
+ * :3235 analysis, :3301-3357,:3558-3562 epilogue), HOST buffers:
+ *   E[n x N] ensemble (zone-permuted), H as COO (Hi,Hj 1-based int32, Hs, nnz; matoper.F90:30-39),
+ *   Hshift[m] (may be NULL), yo, Rdiag, d01, anamtype 1 identity / 2 log (anamorphosis.F90:78-120),
+ *   inflation (inflation.mult), maxCorrection[n] (may be NULL)  ->  Ea[n x N]; xf_out/xa_out[n] optional. */
+OAKB200_API int oakb200_assim_ensemble(oakb200_handle *h, int64_t n, int32_t N, int32_t m, const double *E,
+                           int64_t ldE, int64_t nnz, const int32_t *Hi, const int32_t *Hj,
+                           const double *Hs, const double *Hshift, const double *yo,
+                           const double *Rdiag, const double *d01, int32_t anamtype,
+                           double inflation, const double *maxCorrection, double *Ea, int64_t ldEa,
+                           double *xf_out, double *xa_out, oakb200_stats *stats);
+/* Same with DEVICE pointers. */
+OAKB200_API int oakb200_assim_ensemble_dev(oakb200_handle *h, int64_t n, int32_t N, int32_t m, const double *E,
+                               int64_t ldE, int64_t nnz, const int32_t *Hi, const int32_t *Hj,
+                               const double *Hs, const double *Hshift, const double *yo,
+                               const double *Rdiag, const double *d01, int32_t anamtype,
+                               double inflation, const double *maxCorrection, double *Ea,
+                               int64_t ldEa, double *xf_out, double *xa_out, void *stream,
+                               oakb200_stats *stats);
+
+/* Contiguous zone ranges per rank, the formula of parallPartion (parall.F90:166-186) with unit
+ * speeds: rank p of P owns zones [first[p], first[p+1]) ; first has P+1 entries (0-based). */
+OAKB200_API int oakb200_partition_zones(int32_t nzones, int32_t nranks, int32_t *first);
+
+/* Measured fp64 pipe peak on this device, used as the roofline denominator:
+ * mode 0 = DFMA (register-resident FMA chains), 1 = DMMA (mma.sync.m8n8k4.f64). TFLOP/s. */
+OAKB200_API int oakb200_fp64_peak(oakb200_handle *h, int32_t mode, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OAK_B200_H */

@@ -1,0 +1,695 @@
+// api.cu — the C ABI (include/oak_b200.h): handle, zone/observation setup, batching of the zone loop
+// over CUDA streams, host-buffer streaming, statistics.
+//
+// The zone loop of locAnalysisIncrement (rrsqrt.F90:357-418) becomes, per batch of zones,
+//     k_gram (selection + Gram)  ->  k_eig (transform)  ->  k_apply (update of the zone rows)
+// on one of NSLOT streams; consecutive batches go to different streams so that the tail of one
+// batch overlaps the head of the next.  With host buffers the state is cut in chunks of whole
+// zones; chunk c uses slot c % NSLOT: H2D copy, batches, D2H copy, all on the slot's stream, so the
+// copies of one chunk overlap the kernels of the others.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+// from the other translation units
+int oak_build_obsgrid(cudaStream_t st, int m, const double *bx, const double *by, const ObsGrid &g,
+                      uint32_t *key_in, uint32_t *key_out, int32_t *val_in, int32_t *perm,
+                      int32_t *cell_start, double *sx, double *sy, void *tmp, size_t tmp_bytes);
+size_t oak_obsgrid_scratch_bytes(int m, int ncell);
+size_t oak_coo_scratch_bytes(int64_t nnz, int m);
+int oak_coo_to_rows(cudaStream_t st, int64_t nnz, int m, const int32_t *Hi, const int32_t *Hj, uint32_t *key_in,
+                    uint32_t *key_out, int32_t *val_in, int32_t *order, int32_t *rowstart, void *tmp,
+                    size_t tmp_bytes);
+int oak_launch_obsoper_rows(cudaStream_t st, int m, int N, const int32_t *rowstart, const int32_t *order,
+                            const int32_t *Hj, const double *Hs, const double *Hshift, const double *E,
+                            int64_t ldE, double *HE);
+
+static thread_local std::string g_err;
+void oak_set_error(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+extern "C" OAKB200_API const char *oakb200_last_error(void) { return g_err.c_str(); }
+extern "C" OAKB200_API int oakb200_version(void) { return 100; }
+
+namespace {
+
+constexpr int NSLOT = 3;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+      oak_set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+      p = nullptr;
+      return OAK_ERR_NOMEM;
+    }
+    cap = bytes;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Slot {
+  cudaStream_t st = nullptr;
+  DevBuf G, T, c, ampl;        // batch workspace
+  DevBuf S, xf, xa;            // host-streaming chunk buffers
+  cudaEvent_t ev[8] = {};
+};
+
+}  // namespace
+
+struct oakb200_handle {
+  int device = 0;
+  // options
+  int eig_kernel = 0;
+  int zones_per_batch = 0;
+  double tol = 1e-7;
+  int max_sweeps = 30;
+  int profile = 0;
+  double chunk_mb = 256.;
+  int pad_to = 0;
+  // zones
+  bool zones_set = false;
+  int nzones = 0;
+  int64_t nrows = 0;
+  int loctype = 1, metrictype = 0, weightfun = 0;
+  std::vector<int64_t> h_zstart;
+  double rmax = 0.;     // largest finite search radius
+  bool any_unbounded = false;
+  double zlat_absmax = 0.;
+  DevBuf d_zx, d_zy, d_corr, d_maxl, d_zstart, d_mloc;
+  // observations
+  bool obs_set = false;
+  int m = 0;
+  ObsGrid og{};
+  DevBuf d_bx, d_by, d_key_in, d_key_out, d_val_in, d_perm, d_cell_start, d_sx, d_sy, d_tmp;
+  // packed observation rows
+  DevBuf d_rows, d_delta, d_scoef;
+  // host-path staging of observation-space arrays
+  DevBuf d_HSf, d_yo, d_Hxf, d_R, d_d01, d_ampzero;
+  // ensemble path
+  DevBuf d_HE, d_Hi, d_Hj, d_Hs, d_Hshift, d_order, d_rowstart, d_xf, d_xa, d_maxc, d_E;
+  DevBuf d_ctr;
+  Slot slot[NSLOT];
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_user = nullptr;
+
+  ZoneGeom geom() const {
+    ZoneGeom z;
+    z.zx = d_zx.as<double>(); z.zy = d_zy.as<double>();
+    z.corrLen = d_corr.as<double>(); z.maxLen = d_maxl.as<double>();
+    z.zstart = d_zstart.as<int64_t>();
+    z.loctype = loctype; z.metrictype = metrictype; z.weightfun = weightfun;
+    return z;
+  }
+};
+
+namespace {
+
+int padded(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : -1)); }
+int padded(const oakb200_handle *h, int N) {
+  const int np = padded(N);
+  return (np > 0 && h->pad_to > np && h->pad_to <= 128) ? padded(h->pad_to) : np;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int ensure_ws(oakb200_handle *h, Slot &s, int NP, int zb) {
+  int rc;
+  if ((rc = s.G.ensure(sizeof(double) * (size_t)zb * NP * NP))) return rc;
+  if ((rc = s.T.ensure(sizeof(double) * (size_t)zb * NP * NP))) return rc;
+  if ((rc = s.c.ensure(sizeof(double) * (size_t)zb * NP))) return rc;
+  if ((rc = s.ampl.ensure(sizeof(double) * (size_t)zb * NP))) return rc;
+  (void)h;
+  return 0;
+}
+
+int batch_size(const oakb200_handle *h, int NP) {
+  if (h->zones_per_batch > 0) return h->zones_per_batch;
+  const size_t per_zone = sizeof(double) * 2 * (size_t)NP * NP;
+  int zb = (int)((size_t)256 * 1024 * 1024 / per_zone);
+  return std::max(zb, 148);
+}
+
+// Packs the observation-space arrays (device pointers) into sorted rows. Enqueued on `st`.
+int pack_obs(oakb200_handle *h, cudaStream_t st, int N, int NP, const double *HSf, int64_t ldH, const double *yo,
+             const double *Hxf, const double *R, const double *d01) {
+  int rc;
+  const int m = h->m;
+  if ((rc = h->d_rows.ensure(sizeof(double) * (size_t)std::max(m, 1) * NP))) return rc;
+  if ((rc = h->d_delta.ensure(sizeof(double) * (size_t)std::max(m, 1)))) return rc;
+  if ((rc = h->d_scoef.ensure(sizeof(double) * (size_t)std::max(m, 1)))) return rc;
+  return oak_launch_pack_obs(st, m, N, NP, h->og.perm, HSf, ldH, yo, Hxf, R, d01, h->d_rows.as<double>(),
+                             h->d_delta.as<double>(), h->d_scoef.as<double>());
+}
+
+struct ProfAcc { double gram = 0, eig = 0, apply = 0; };
+
+// Runs zones [z0, z1) on slot s. The state buffers hold rows starting at global row `rowbase`.
+int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t rowbase, const double *xf,
+              const double *Sf, int64_t ldS, double *xa, double *Sa, int64_t ldSa, int64_t *launches,
+              ProfAcc *prof) {
+  const int zb = batch_size(h, NP);
+  int rc;
+  if ((rc = ensure_ws(h, s, NP, std::min(zb, z1 - z0)))) return rc;
+  const ZoneGeom zg = h->geom();
+  ObsRows orows{h->d_rows.as<double>(), h->d_delta.as<double>(), h->d_scoef.as<double>()};
+  DevCounters *ctr = h->d_ctr.as<DevCounters>();
+  int32_t *mloc = h->d_mloc.as<int32_t>();
+  for (int b0 = z0; b0 < z1; b0 += zb) {
+    const int nz = std::min(zb, z1 - b0);
+    if (prof) CUDA_TRY(cudaEventRecord(s.ev[0], s.st));
+    if ((rc = oak_launch_gram(s.st, NP, zg, h->og, orows, b0, nz, s.G.as<double>(), s.c.as<double>(), mloc, ctr))) return rc;
+    if (prof) CUDA_TRY(cudaEventRecord(s.ev[1], s.st));
+    if ((rc = oak_launch_eig(s.st, h->eig_kernel, N, NP, b0, nz, mloc, s.G.as<double>(), s.c.as<double>(),
+                             s.T.as<double>(), s.ampl.as<double>(), h->tol, h->max_sweeps, ctr))) return rc;
+    if (prof) CUDA_TRY(cudaEventRecord(s.ev[2], s.st));
+    if ((rc = oak_launch_apply(s.st, N, NP, zg, b0, nz, rowbase, mloc, s.T.as<double>(), s.ampl.as<double>(), xf,
+                               Sf, ldS, xa, Sa, ldSa))) return rc;
+    *launches += 3;
+    if (prof) {
+      CUDA_TRY(cudaEventRecord(s.ev[3], s.st));
+      CUDA_TRY(cudaEventSynchronize(s.ev[3]));
+      float a, b, c;
+      CUDA_TRY(cudaEventElapsedTime(&a, s.ev[0], s.ev[1]));
+      CUDA_TRY(cudaEventElapsedTime(&b, s.ev[1], s.ev[2]));
+      CUDA_TRY(cudaEventElapsedTime(&c, s.ev[2], s.ev[3]));
+      prof->gram += a; prof->eig += b; prof->apply += c;
+    }
+  }
+  return 0;
+}
+
+int check_ready(oakb200_handle *h, int64_t n, int N, int m) {
+  if (!h) { oak_set_error("null handle"); return OAK_ERR_ARG; }
+  if (!h->zones_set) { oak_set_error("oakb200_set_zones has not been called"); return OAK_ERR_STATE; }
+  if (!h->obs_set) { oak_set_error("oakb200_set_observations has not been called"); return OAK_ERR_STATE; }
+  if (n != h->nrows) { oak_set_error("n = %lld does not match sum(zoneSize) = %lld", (long long)n, (long long)h->nrows); return OAK_ERR_ARG; }
+  if (m != h->m) { oak_set_error("m = %d does not match the %d observations set", m, h->m); return OAK_ERR_ARG; }
+  if (N < 2) { oak_set_error("ensemble size N = %d < 2", N); return OAK_ERR_ARG; }
+  if (padded(N) < 0) { oak_set_error("ensemble size N = %d > 128 is not supported", N); return OAK_ERR_UNSUPPORTED; }
+  return 0;
+}
+
+int begin_call(oakb200_handle *h, oakb200_stats *stats) {
+  if (stats) memset(stats, 0, sizeof *stats);
+  CUDA_TRY(cudaMemsetAsync(h->d_ctr.p, 0, sizeof(DevCounters), h->slot[0].st));
+  CUDA_TRY(cudaMemsetAsync(h->d_mloc.p, 0, sizeof(int32_t) * std::max(h->nzones, 1), h->slot[0].st));
+  return 0;
+}
+
+int end_call(oakb200_handle *h, oakb200_stats *stats, int64_t launches, const ProfAcc &prof, float ms_total,
+             float ms_pack) {
+  DevCounters ctr;
+  CUDA_TRY(cudaMemcpy(&ctr, h->d_ctr.p, sizeof ctr, cudaMemcpyDeviceToHost));
+  if (stats) {
+    stats->zones_total = h->nzones;
+    stats->zones_skipped = (int64_t)ctr.skipped;
+    stats->obs_relevant_sum = (int64_t)ctr.relevant;
+    stats->obs_candidate_sum = (int64_t)ctr.candidates;
+    stats->jacobi_sweeps_sum = (int64_t)ctr.sweeps;
+    stats->ms_total = ms_total;
+    stats->ms_pack = ms_pack;
+    stats->ms_gram = prof.gram; stats->ms_eig = prof.eig; stats->ms_apply = prof.apply;
+    stats->launches = launches;
+  }
+  if (ctr.nan_flag) { oak_set_error("NaN in the analysis amplitudes (rrsqrt.F90:145-149)"); return OAK_ERR_NAN; }
+  if (ctr.not_converged) { oak_set_error("Jacobi eigensolve did not converge in %d sweeps for %d zones", h->max_sweeps, ctr.not_converged); return OAK_ERR_NAN; }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" OAKB200_API int oakb200_create(int device, oakb200_handle **out) {
+  if (!out) { oak_set_error("null output pointer"); return OAK_ERR_ARG; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    oak_set_error("no CUDA device available (%s); oak_b200 has no CPU fallback", cudaGetErrorString(e));
+    return OAK_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { oak_set_error("device %d out of range (%d devices)", device, ndev); return OAK_ERR_ARG; }
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    oak_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return OAK_ERR_UNSUPPORTED;
+  }
+  oakb200_handle *h = new oakb200_handle();
+  h->device = device;
+  for (int i = 0; i < NSLOT; i++) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->slot[i].st, cudaStreamNonBlocking));
+    for (auto &ev : h->slot[i].ev) CUDA_TRY(cudaEventCreate(&ev));
+  }
+  CUDA_TRY(cudaEventCreate(&h->ev_a));
+  CUDA_TRY(cudaEventCreate(&h->ev_b));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming));
+  int rc = h->d_ctr.ensure(sizeof(DevCounters));
+  if (rc) { delete h; return rc; }
+  *out = h;
+  return 0;
+}
+
+extern "C" OAKB200_API int oakb200_destroy(oakb200_handle *h) {
+  if (!h) return 0;
+  DeviceGuard guard(h->device);
+  cudaDeviceSynchronize();
+  DevBuf *bufs[] = {&h->d_zx, &h->d_zy, &h->d_corr, &h->d_maxl, &h->d_zstart, &h->d_mloc, &h->d_bx, &h->d_by,
+                    &h->d_key_in, &h->d_key_out, &h->d_val_in, &h->d_perm, &h->d_cell_start, &h->d_sx, &h->d_sy,
+                    &h->d_tmp, &h->d_rows, &h->d_delta, &h->d_scoef, &h->d_HSf, &h->d_yo, &h->d_Hxf, &h->d_R,
+                    &h->d_d01, &h->d_ampzero, &h->d_HE, &h->d_Hi, &h->d_Hj, &h->d_Hs, &h->d_Hshift, &h->d_order,
+                    &h->d_rowstart, &h->d_xf, &h->d_xa, &h->d_maxc, &h->d_E, &h->d_ctr};
+  for (DevBuf *b : bufs) b->release();
+  for (int i = 0; i < NSLOT; i++) {
+    Slot &s = h->slot[i];
+    s.G.release(); s.T.release(); s.c.release(); s.ampl.release(); s.S.release(); s.xf.release(); s.xa.release();
+    for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
+    if (s.st) cudaStreamDestroy(s.st);
+  }
+  if (h->ev_a) cudaEventDestroy(h->ev_a);
+  if (h->ev_b) cudaEventDestroy(h->ev_b);
+  if (h->ev_user) cudaEventDestroy(h->ev_user);
+  delete h;
+  return 0;
+}
+
+extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key, double value) {
+  if (!h || !key) { oak_set_error("null argument"); return OAK_ERR_ARG; }
+  const std::string k(key);
+  if (k == "eig_kernel") h->eig_kernel = (int)value;
+  else if (k == "zones_per_batch") h->zones_per_batch = (int)value;
+  else if (k == "jacobi_tol") h->tol = value;
+  else if (k == "max_sweeps") h->max_sweeps = (int)value;
+  else if (k == "profile") h->profile = (int)value;
+  else if (k == "chunk_mb") h->chunk_mb = value;
+  else if (k == "pad_to") h->pad_to = (int)value;
+  else { oak_set_error("unknown option '%s'", key); return OAK_ERR_ARG; }
+  return 0;
+}
+
+extern "C" OAKB200_API int oakb200_partition_zones(int32_t nzones, int32_t nranks, int32_t *first) {
+  if (nzones < 0 || nranks < 1 || !first) { oak_set_error("bad partition arguments"); return OAK_ERR_ARG; }
+  // startZIndex = nzones*cumulSpeed(p)/total + 1 (1-based), unit speeds   parall.F90:176-177
+  for (int p = 0; p <= nranks; p++) first[p] = (int32_t)(((int64_t)nzones * p) / nranks);
+  return 0;
+}
+
+extern "C" OAKB200_API int oakb200_set_zones(oakb200_handle *h, int32_t nzones, const int32_t *zoneSize, const double *zx,
+                                 const double *zy, const double *zz, const double *zt, const double *corrLen,
+                                 const double *maxLen, int32_t loctype, int32_t metrictype, int32_t weightfun) {
+  if (!h || nzones < 0 || !zoneSize || !corrLen || !maxLen) { oak_set_error("set_zones: null/invalid argument"); return OAK_ERR_ARG; }
+  if (loctype < 1 || loctype > 3) { oak_set_error("set_zones: loctype %d (expected 1,2,3)", loctype); return OAK_ERR_ARG; }
+  if (metrictype < 0 || metrictype > 2) { oak_set_error("Unsupported metric: %d", metrictype); return OAK_ERR_ARG; }
+  if (weightfun < 0 || weightfun > 2) { oak_set_error("set_zones: weightfun %d", weightfun); return OAK_ERR_ARG; }
+  const double *prim = loctype == 1 ? zx : (loctype == 2 ? zz : zt);
+  if (!prim && nzones > 0) { oak_set_error("set_zones: coordinate array needed by loctype %d is NULL", loctype); return OAK_ERR_ARG; }
+  DeviceGuard guard(h->device);
+  h->zones_set = false;
+  h->obs_set = false;  // the cell size depends on the zones' radii
+  h->nzones = nzones;
+  h->loctype = loctype; h->metrictype = metrictype; h->weightfun = weightfun;
+  h->h_zstart.assign((size_t)nzones + 1, 0);
+  for (int z = 0; z < nzones; z++) {
+    if (zoneSize[z] < 0) { oak_set_error("set_zones: negative zone size"); return OAK_ERR_ARG; }
+    h->h_zstart[z + 1] = h->h_zstart[z] + zoneSize[z];
+  }
+  h->nrows = h->h_zstart[nzones];
+  h->rmax = 0.; h->any_unbounded = false; h->zlat_absmax = 0.;
+  std::vector<double> zeros;
+  for (int z = 0; z < nzones; z++) {
+    double R = weightfun == OAKB200_WEIGHT_GAUSSIAN ? maxLen[z] : (weightfun == OAKB200_WEIGHT_GASPARI_COHN ? 2. * corrLen[z] : INFINITY);
+    if (!(R < 1e300)) h->any_unbounded = true;
+    else h->rmax = std::max(h->rmax, R);
+    if (loctype == 1 && zy) h->zlat_absmax = std::max(h->zlat_absmax, std::fabs(zy[z]));
+  }
+  const size_t nb = sizeof(double) * (size_t)std::max(nzones, 1);
+  int rc;
+  if ((rc = h->d_zx.ensure(nb)) || (rc = h->d_zy.ensure(nb)) || (rc = h->d_corr.ensure(nb)) ||
+      (rc = h->d_maxl.ensure(nb)) || (rc = h->d_zstart.ensure(sizeof(int64_t) * ((size_t)nzones + 1))) ||
+      (rc = h->d_mloc.ensure(sizeof(int32_t) * (size_t)std::max(nzones, 1))))
+    return rc;
+  if (nzones > 0) {
+    CUDA_TRY(cudaMemcpy(h->d_zx.p, prim, sizeof(double) * nzones, cudaMemcpyHostToDevice));
+    if (loctype == 1 && zy) CUDA_TRY(cudaMemcpy(h->d_zy.p, zy, sizeof(double) * nzones, cudaMemcpyHostToDevice));
+    else CUDA_TRY(cudaMemset(h->d_zy.p, 0, sizeof(double) * nzones));
+    CUDA_TRY(cudaMemcpy(h->d_corr.p, corrLen, sizeof(double) * nzones, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d_maxl.p, maxLen, sizeof(double) * nzones, cudaMemcpyHostToDevice));
+  }
+  CUDA_TRY(cudaMemcpy(h->d_zstart.p, h->h_zstart.data(), sizeof(int64_t) * ((size_t)nzones + 1), cudaMemcpyHostToDevice));
+  h->zones_set = true;
+  return 0;
+}
+
+extern "C" OAKB200_API int oakb200_set_observations(oakb200_handle *h, int32_t m, const double *obsx, const double *obsy,
+                                        const double *obsz, const double *obst) {
+  if (!h || m < 0) { oak_set_error("set_observations: invalid argument"); return OAK_ERR_ARG; }
+  if (!h->zones_set) { oak_set_error("set_observations: call oakb200_set_zones first"); return OAK_ERR_STATE; }
+  const double *bx = h->loctype == 1 ? obsx : (h->loctype == 2 ? obsz : obst);
+  const double *by = h->loctype == 1 ? obsy : nullptr;
+  if (m > 0 && !bx) { oak_set_error("set_observations: coordinate array needed by loctype %d is NULL", h->loctype); return OAK_ERR_ARG; }
+  DeviceGuard guard(h->device);
+  h->obs_set = false;
+  h->m = m;
+  const bool spherical = h->loctype == 1 && h->metrictype != OAKB200_METRIC_CARTESIAN;
+  ObsGrid g{};
+  g.m = m;
+  g.wrap_x = (h->loctype == 1 && h->metrictype == OAKB200_METRIC_SPHERICAL) ? 1 : 0;
+  // extents of the bucketing coordinates
+  double xmin = 0, xmax = 0, ymin = 0, ymax = 0;
+  bool first = true;
+  for (int l = 0; l < m; l++) {
+    double x = bx[l], y = by ? by[l] : 0.;
+    if (g.wrap_x) x = oak_fold360(x);
+    if (!(x == x) || !(y == y) || std::isinf(x) || std::isinf(y)) continue;
+    if (first) { xmin = xmax = x; ymin = ymax = y; first = false; }
+    else { xmin = std::min(xmin, x); xmax = std::max(xmax, x); ymin = std::min(ymin, y); ymax = std::max(ymax, y); }
+  }
+  if (g.wrap_x) { xmin = 0.; xmax = 360.; }
+  double csx = 0., csy = 0.;
+  const double R = h->rmax;
+  if (R > 0.) {
+    if (spherical) {
+      const double deg = 180. / OAK_PI;
+      csy = 0.5 * (R / OAK_EARTH_RADIUS) * deg;
+      const double cl = std::max(std::cos(std::min(h->zlat_absmax, 89.) / deg), 0.05);
+      csx = csy / cl;
+    } else {
+      csx = csy = 0.5 * R;
+    }
+  }
+  auto ncells = [](double lo, double hi, double cs) -> double {
+    if (!(cs > 0.) || !(hi > lo)) return 1.;
+    return std::floor((hi - lo) / cs) + 1.;
+  };
+  double ncx = ncells(xmin, xmax, csx), ncy = by ? ncells(ymin, ymax, csy) : 1.;
+  const double limit = std::max(4. * m, 4096.);
+  if (ncx * ncy > limit) {  // coarsen: never more than ~4 cells per observation
+    const double f = std::sqrt(ncx * ncy / limit);
+    if (ncy > 1. && ncx > 1.) { csx *= f; csy *= f; }
+    else if (ncx > 1.) csx *= ncx / limit;
+    else csy *= ncy / limit;
+    ncx = ncells(xmin, xmax, csx); ncy = by ? ncells(ymin, ymax, csy) : 1.;
+  }
+  g.ncx = (int)std::min(std::max(ncx, 1.), 65536.);
+  g.ncy = (int)std::min(std::max(ncy, 1.), 65536.);
+  if ((double)g.ncx * g.ncy > 64e6) { g.ncx = 1; g.ncy = 1; }
+  g.x0 = xmin; g.y0 = ymin;
+  g.csx = csx > 0. ? csx : 1.;
+  g.csy = csy > 0. ? csy : 1.;
+  const int ncell = g.ncx * g.ncy;
+  const size_t mb = (size_t)std::max(m, 1);
+  int rc;
+  const size_t tmpb = oak_obsgrid_scratch_bytes(m, ncell);
+  if ((rc = h->d_bx.ensure(8 * mb)) || (rc = h->d_by.ensure(8 * mb)) || (rc = h->d_key_in.ensure(4 * mb)) ||
+      (rc = h->d_key_out.ensure(4 * mb)) || (rc = h->d_val_in.ensure(4 * mb)) || (rc = h->d_perm.ensure(4 * mb)) ||
+      (rc = h->d_cell_start.ensure(4 * ((size_t)ncell + 1))) || (rc = h->d_sx.ensure(8 * mb)) ||
+      (rc = h->d_sy.ensure(8 * mb)) || (rc = h->d_tmp.ensure(tmpb)))
+    return rc;
+  if (m > 0) {
+    CUDA_TRY(cudaMemcpy(h->d_bx.p, bx, 8 * (size_t)m, cudaMemcpyHostToDevice));
+    if (by) CUDA_TRY(cudaMemcpy(h->d_by.p, by, 8 * (size_t)m, cudaMemcpyHostToDevice));
+  }
+  g.cell_start = h->d_cell_start.as<int32_t>();
+  g.perm = h->d_perm.as<int32_t>();
+  g.sx = h->d_sx.as<double>();
+  g.sy = h->d_sy.as<double>();
+  cudaStream_t st = h->slot[0].st;
+  rc = oak_build_obsgrid(st, m, h->d_bx.as<double>(), by ? h->d_by.as<double>() : nullptr, g, h->d_key_in.as<uint32_t>(),
+                         h->d_key_out.as<uint32_t>(), h->d_val_in.as<int32_t>(), h->d_perm.as<int32_t>(),
+                         h->d_cell_start.as<int32_t>(), h->d_sx.as<double>(), h->d_sy.as<double>(), h->d_tmp.p,
+                         h->d_tmp.cap);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  h->og = g;
+  h->obs_set = true;
+  return 0;
+}
+
+extern "C" OAKB200_API int oakb200_select_observations(oakb200_handle *h, int32_t zone_first, int32_t zone_count,
+                                           int64_t capacity, int64_t *offsets, int32_t *idx, double *weight) {
+  if (!h || !offsets) { oak_set_error("select_observations: null argument"); return OAK_ERR_ARG; }
+  if (!h->zones_set || !h->obs_set) { oak_set_error("select_observations: zones/observations not set"); return OAK_ERR_STATE; }
+  if (zone_first < 0 || zone_count < 0 || zone_first + zone_count > h->nzones) { oak_set_error("select_observations: zone range out of bounds"); return OAK_ERR_ARG; }
+  DeviceGuard guard(h->device);
+  cudaStream_t st = h->slot[0].st;
+  const ZoneGeom zg = h->geom();
+  DevBuf d_counts, d_off, d_idx, d_w;
+  int rc = 0;
+  std::vector<int32_t> counts((size_t)zone_count);
+  do {
+    if ((rc = d_counts.ensure(4 * (size_t)std::max(zone_count, 1)))) break;
+    if ((rc = oak_launch_select(st, zg, h->og, zone_first, zone_count, nullptr, d_counts.as<int32_t>(), nullptr, nullptr, false))) break;
+    if (cudaMemcpyAsync(counts.data(), d_counts.p, 4 * (size_t)zone_count, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { oak_set_error("select_observations: copy failed: %s", cudaGetErrorString(cudaGetLastError())); rc = OAK_ERR_CUDA; break; }
+    offsets[0] = 0;
+    for (int z = 0; z < zone_count; z++) offsets[z + 1] = offsets[z] + counts[z];
+    const int64_t total = offsets[zone_count];
+    if (total > capacity || (total > 0 && (!idx || !weight))) { oak_set_error("select_observations: capacity %lld < required %lld", (long long)capacity, (long long)total); rc = OAK_ERR_CAPACITY; break; }
+    if (total == 0) break;
+    if ((rc = d_off.ensure(8 * ((size_t)zone_count + 1))) || (rc = d_idx.ensure(4 * (size_t)total)) || (rc = d_w.ensure(8 * (size_t)total))) break;
+    if (cudaMemcpyAsync(d_off.p, offsets, 8 * ((size_t)zone_count + 1), cudaMemcpyHostToDevice, st) != cudaSuccess) { oak_set_error("select_observations: copy failed"); rc = OAK_ERR_CUDA; break; }
+    if ((rc = oak_launch_select(st, zg, h->og, zone_first, zone_count, d_off.as<int64_t>(), nullptr, d_idx.as<int32_t>(), d_w.as<double>(), true))) break;
+    if (cudaMemcpyAsync(idx, d_idx.p, 4 * (size_t)total, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaMemcpyAsync(weight, d_w.p, 8 * (size_t)total, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { oak_set_error("select_observations: copy failed: %s", cudaGetErrorString(cudaGetLastError())); rc = OAK_ERR_CUDA; break; }
+    // increasing observation number inside each zone, the order pack() produces (rrsqrt.F90:395-404)
+    std::vector<std::pair<int32_t, double>> tmp;
+    for (int z = 0; z < zone_count; z++) {
+      const int64_t a = offsets[z], b = offsets[z + 1];
+      tmp.resize((size_t)(b - a));
+      for (int64_t q = a; q < b; q++) tmp[(size_t)(q - a)] = {idx[q], weight[q]};
+      std::sort(tmp.begin(), tmp.end(), [](const auto &u, const auto &v) { return u.first < v.first; });
+      for (int64_t q = a; q < b; q++) { idx[q] = tmp[(size_t)(q - a)].first; weight[q] = tmp[(size_t)(q - a)].second; }
+    }
+  } while (0);
+  d_counts.release(); d_off.release(); d_idx.release(); d_w.release();
+  return rc;
+}
+
+extern "C" OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t n, int32_t N, int32_t m, const double *xf,
+                                          const double *Hxf, const double *yo, const double *Sf, int64_t ldSf,
+                                          const double *HSf, int64_t ldHSf, const double *Rdiag, const double *d01,
+                                          double *xa, double *Sa, int64_t ldSa, double *amplitudes, void *stream,
+                                          oakb200_stats *stats) {
+  int rc = check_ready(h, n, N, m);
+  if (rc) return rc;
+  if ((n > 0 && (!xf || !Sf || !xa || !Sa)) || (m > 0 && (!Hxf || !yo || !HSf || !Rdiag))) { oak_set_error("local_analysis: null array"); return OAK_ERR_ARG; }
+  if (ldSf < n || ldSa < n || ldHSf < m) { oak_set_error("local_analysis: leading dimension too small"); return OAK_ERR_ARG; }
+  DeviceGuard guard(h->device);
+  const int NP = padded(h, N);
+  cudaStream_t s0 = h->slot[0].st;
+  // order after the caller's stream
+  CUDA_TRY(cudaEventRecord(h->ev_user, (cudaStream_t)stream));
+  for (int i = 0; i < NSLOT; i++) CUDA_TRY(cudaStreamWaitEvent(h->slot[i].st, h->ev_user, 0));
+  if ((rc = begin_call(h, stats))) return rc;
+  CUDA_TRY(cudaEventRecord(h->ev_a, s0));
+  if ((rc = pack_obs(h, s0, N, NP, HSf, ldHSf, yo, Hxf, Rdiag, d01))) return rc;
+  if (amplitudes) CUDA_TRY(cudaMemsetAsync(amplitudes, 0, sizeof(double) * (size_t)N * h->nzones, s0));
+  CUDA_TRY(cudaEventRecord(h->slot[0].ev[4], s0));
+  for (int i = 1; i < NSLOT; i++) CUDA_TRY(cudaStreamWaitEvent(h->slot[i].st, h->slot[0].ev[4], 0));
+  int64_t launches = 1;
+  ProfAcc prof;
+  const int zb = batch_size(h, NP);
+  int bi = 0;
+  for (int z0 = 0; z0 < h->nzones; z0 += zb, bi++) {
+    Slot &s = h->slot[h->profile ? 0 : bi % NSLOT];
+    const int z1 = std::min(h->nzones, z0 + zb);
+    if ((rc = run_zones(h, s, N, NP, z0, z1, 0, xf, Sf, ldSf, xa, Sa, ldSa, &launches, h->profile ? &prof : nullptr))) return rc;
+  }
+  for (int i = 1; i < NSLOT; i++) {
+    CUDA_TRY(cudaEventRecord(h->slot[i].ev[5], h->slot[i].st));
+    CUDA_TRY(cudaStreamWaitEvent(s0, h->slot[i].ev[5], 0));
+  }
+  CUDA_TRY(cudaEventRecord(h->ev_b, s0));
+  CUDA_TRY(cudaEventSynchronize(h->ev_b));
+  float ms = 0.f, msp = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_a, h->ev_b));
+  CUDA_TRY(cudaEventElapsedTime(&msp, h->ev_a, h->slot[0].ev[4]));
+  return end_call(h, stats, launches, prof, ms, msp);
+}
+
+extern "C" OAKB200_API int oakb200_local_analysis(oakb200_handle *h, int64_t n, int32_t N, int32_t m, const double *xf,
+                                      const double *Hxf, const double *yo, const double *Sf, int64_t ldSf,
+                                      const double *HSf, int64_t ldHSf, const double *Rdiag, const double *d01,
+                                      double *xa, double *Sa, int64_t ldSa, double *amplitudes,
+                                      oakb200_stats *stats) {
+  int rc = check_ready(h, n, N, m);
+  if (rc) return rc;
+  if ((n > 0 && (!xf || !Sf || !xa || !Sa)) || (m > 0 && (!Hxf || !yo || !HSf || !Rdiag))) { oak_set_error("local_analysis: null array"); return OAK_ERR_ARG; }
+  if (ldSf < n || ldSa < n || ldHSf < m) { oak_set_error("local_analysis: leading dimension too small"); return OAK_ERR_ARG; }
+  DeviceGuard guard(h->device);
+  const int NP = padded(h, N);
+  cudaStream_t s0 = h->slot[0].st;
+  if ((rc = begin_call(h, stats))) return rc;
+  CUDA_TRY(cudaEventRecord(h->ev_a, s0));
+  int64_t h2d = 0, d2h = 0;
+  // observation-space arrays: whole, once
+  const size_t mb = (size_t)std::max(m, 1);
+  if ((rc = h->d_HSf.ensure(8 * mb * N)) || (rc = h->d_yo.ensure(8 * mb)) || (rc = h->d_Hxf.ensure(8 * mb)) ||
+      (rc = h->d_R.ensure(8 * mb)) || (rc = h->d_d01.ensure(8 * mb)))
+    return rc;
+  if (m > 0) {
+    CUDA_TRY(cudaMemcpy2DAsync(h->d_HSf.p, 8 * (size_t)m, HSf, 8 * (size_t)ldHSf, 8 * (size_t)m, N, cudaMemcpyHostToDevice, s0));
+    CUDA_TRY(cudaMemcpyAsync(h->d_yo.p, yo, 8 * (size_t)m, cudaMemcpyHostToDevice, s0));
+    CUDA_TRY(cudaMemcpyAsync(h->d_Hxf.p, Hxf, 8 * (size_t)m, cudaMemcpyHostToDevice, s0));
+    CUDA_TRY(cudaMemcpyAsync(h->d_R.p, Rdiag, 8 * (size_t)m, cudaMemcpyHostToDevice, s0));
+    if (d01) CUDA_TRY(cudaMemcpyAsync(h->d_d01.p, d01, 8 * (size_t)m, cudaMemcpyHostToDevice, s0));
+    h2d += 8ll * m * (N + 3 + (d01 ? 1 : 0));
+  }
+  if ((rc = pack_obs(h, s0, N, NP, h->d_HSf.as<double>(), m, h->d_yo.as<double>(), h->d_Hxf.as<double>(),
+                     h->d_R.as<double>(), d01 ? h->d_d01.as<double>() : nullptr)))
+    return rc;
+  CUDA_TRY(cudaEventRecord(h->slot[0].ev[4], s0));
+  for (int i = 1; i < NSLOT; i++) CUDA_TRY(cudaStreamWaitEvent(h->slot[i].st, h->slot[0].ev[4], 0));
+  if (amplitudes) memset(amplitudes, 0, sizeof(double) * (size_t)N * h->nzones);  // rrsqrt.F90:324
+  // chunks of whole zones
+  const int64_t rows_target = std::max<int64_t>(1, (int64_t)(h->chunk_mb * 1024. * 1024. / (8. * N)));
+  int64_t launches = 1;
+  ProfAcc prof;
+  int ci = 0;
+  for (int z0 = 0; z0 < h->nzones; ci++) {
+    int z1 = z0;
+    const int64_t r0 = h->h_zstart[z0];
+    while (z1 < h->nzones && (z1 == z0 || h->h_zstart[z1 + 1] - r0 <= rows_target)) z1++;
+    const int64_t rows = h->h_zstart[z1] - r0;
+    Slot &s = h->slot[h->profile ? 0 : ci % NSLOT];
+    if (rows > 0) {
+      if ((rc = s.S.ensure(8 * (size_t)rows * N)) || (rc = s.xf.ensure(8 * (size_t)rows)) || (rc = s.xa.ensure(8 * (size_t)rows))) return rc;
+      CUDA_TRY(cudaMemcpy2DAsync(s.S.p, 8 * (size_t)rows, Sf + r0, 8 * (size_t)ldSf, 8 * (size_t)rows, N, cudaMemcpyHostToDevice, s.st));
+      CUDA_TRY(cudaMemcpyAsync(s.xf.p, xf + r0, 8 * (size_t)rows, cudaMemcpyHostToDevice, s.st));
+      h2d += 8ll * rows * (N + 1);
+    }
+    if ((rc = run_zones(h, s, N, NP, z0, z1, r0, s.xf.as<double>(), s.S.as<double>(), rows, s.xa.as<double>(),
+                        s.S.as<double>(), rows, &launches, h->profile ? &prof : nullptr)))
+      return rc;
+    if (rows > 0) {
+      CUDA_TRY(cudaMemcpy2DAsync(Sa + r0, 8 * (size_t)ldSa, s.S.p, 8 * (size_t)rows, 8 * (size_t)rows, N, cudaMemcpyDeviceToHost, s.st));
+      CUDA_TRY(cudaMemcpyAsync(xa + r0, s.xa.p, 8 * (size_t)rows, cudaMemcpyDeviceToHost, s.st));
+      d2h += 8ll * rows * (N + 1);
+    }
+    z0 = z1;
+  }
+  for (int i = 1; i < NSLOT; i++) {
+    CUDA_TRY(cudaEventRecord(h->slot[i].ev[5], h->slot[i].st));
+    CUDA_TRY(cudaStreamWaitEvent(s0, h->slot[i].ev[5], 0));
+  }
+  CUDA_TRY(cudaEventRecord(h->ev_b, s0));
+  CUDA_TRY(cudaEventSynchronize(h->ev_b));
+  float ms = 0.f, msp = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_a, h->ev_b));
+  CUDA_TRY(cudaEventElapsedTime(&msp, h->ev_a, h->slot[0].ev[4]));
+  rc = end_call(h, stats, launches, prof, ms, msp);
+  if (stats) { stats->h2d_bytes = h2d; stats->d2h_bytes = d2h; }
+  return rc;
+}
+
+extern "C" OAKB200_API int oakb200_assim_ensemble_dev(oakb200_handle *h, int64_t n, int32_t N, int32_t m, const double *E,
+                                          int64_t ldE, int64_t nnz, const int32_t *Hi, const int32_t *Hj,
+                                          const double *Hs, const double *Hshift, const double *yo,
+                                          const double *Rdiag, const double *d01, int32_t anamtype, double inflation,
+                                          const double *maxCorrection, double *Ea, int64_t ldEa, double *xf_out,
+                                          double *xa_out, void *stream, oakb200_stats *stats) {
+  int rc = check_ready(h, n, N, m);
+  if (rc) return rc;
+  if (anamtype != 1 && anamtype != 2) { oak_set_error("assim_ensemble: anamorphosis type %d not supported (1 identity, 2 log)", anamtype); return OAK_ERR_UNSUPPORTED; }
+  if ((n > 0 && (!E || !Ea)) || (nnz > 0 && (!Hi || !Hj || !Hs)) || (m > 0 && (!yo || !Rdiag))) { oak_set_error("assim_ensemble: null array"); return OAK_ERR_ARG; }
+  DeviceGuard guard(h->device);
+  cudaStream_t s0 = h->slot[0].st;
+  CUDA_TRY(cudaEventRecord(h->ev_user, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamWaitEvent(s0, h->ev_user, 0));
+  const size_t mb = (size_t)std::max(m, 1), nzb = (size_t)std::max<int64_t>(nnz, 1);
+  if ((rc = h->d_HE.ensure(8 * mb * N)) || (rc = h->d_Hxf.ensure(8 * mb)) || (rc = h->d_key_in.ensure(4 * std::max(nzb, mb))) ||
+      (rc = h->d_key_out.ensure(4 * std::max(nzb, mb))) || (rc = h->d_val_in.ensure(4 * std::max(nzb, mb))) ||
+      (rc = h->d_order.ensure(4 * nzb)) || (rc = h->d_rowstart.ensure(4 * (mb + 2))) ||
+      (rc = h->d_tmp.ensure(std::max(oak_coo_scratch_bytes(nnz, m), h->d_tmp.cap))) ||
+      (rc = h->d_xf.ensure(8 * (size_t)std::max<int64_t>(n, 1))) || (rc = h->d_xa.ensure(8 * (size_t)std::max<int64_t>(n, 1))))
+    return rc;
+  // NB: d_key_*/d_val_in/d_tmp are shared with the observation grid build, which is complete (synchronous).
+  if ((rc = oak_coo_to_rows(s0, nnz, m, Hi, Hj, h->d_key_in.as<uint32_t>(), h->d_key_out.as<uint32_t>(),
+                            h->d_val_in.as<int32_t>(), h->d_order.as<int32_t>(), h->d_rowstart.as<int32_t>(),
+                            h->d_tmp.p, h->d_tmp.cap)))
+    return rc;
+  // HE = H E + Hshift on the untransformed state (assimilation.F90:3112-3114)
+  if ((rc = oak_launch_obsoper_rows(s0, m, N, h->d_rowstart.as<int32_t>(), h->d_order.as<int32_t>(), Hj, Hs, Hshift, E, ldE, h->d_HE.as<double>()))) return rc;
+  // Hxf, HSf (in place in HE) ; xf, Sf (into Ea)
+  if ((rc = oak_launch_mean_anom(s0, m, N, 1, h->d_HE.as<double>(), m, h->d_Hxf.as<double>(), h->d_HE.as<double>(), m))) return rc;
+  if ((rc = oak_launch_mean_anom(s0, n, N, anamtype, E, ldE, h->d_xf.as<double>(), Ea, ldEa))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(s0));
+  rc = oakb200_local_analysis_dev(h, n, N, m, h->d_xf.as<double>(), h->d_Hxf.as<double>(), yo, Ea, ldEa,
+                                  h->d_HE.as<double>(), m, Rdiag, d01, h->d_xa.as<double>(), Ea, ldEa, nullptr,
+                                  (void *)s0, stats);
+  if (rc) return rc;
+  if ((rc = oak_launch_epilogue(s0, n, N, anamtype, inflation, maxCorrection, h->d_xf.as<double>(), h->d_xa.as<double>(), Ea, ldEa, Ea, ldEa))) return rc;
+  if (xf_out) CUDA_TRY(cudaMemcpyAsync(xf_out, h->d_xf.p, 8 * (size_t)n, cudaMemcpyDeviceToDevice, s0));
+  if (xa_out) CUDA_TRY(cudaMemcpyAsync(xa_out, h->d_xa.p, 8 * (size_t)n, cudaMemcpyDeviceToDevice, s0));
+  CUDA_TRY(cudaStreamSynchronize(s0));
+  if (stats) stats->launches += 6;
+  return 0;
+}
+
+extern "C" OAKB200_API int oakb200_assim_ensemble(oakb200_handle *h, int64_t n, int32_t N, int32_t m, const double *E, int64_t ldE,
+                                      int64_t nnz, const int32_t *Hi, const int32_t *Hj, const double *Hs,
+                                      const double *Hshift, const double *yo, const double *Rdiag, const double *d01,
+                                      int32_t anamtype, double inflation, const double *maxCorrection, double *Ea,
+                                      int64_t ldEa, double *xf_out, double *xa_out, oakb200_stats *stats) {
+  int rc = check_ready(h, n, N, m);
+  if (rc) return rc;
+  if ((n > 0 && (!E || !Ea)) || (nnz > 0 && (!Hi || !Hj || !Hs)) || (m > 0 && (!yo || !Rdiag))) { oak_set_error("assim_ensemble: null array"); return OAK_ERR_ARG; }
+  DeviceGuard guard(h->device);
+  // whole ensemble resident (H E needs arbitrary rows of E): n*N*8 bytes must fit on the device
+  const size_t nb = (size_t)std::max<int64_t>(n, 1), mb = (size_t)std::max(m, 1), nzb = (size_t)std::max<int64_t>(nnz, 1);
+  DevBuf dHi, dHj, dHs, dHshift, dyo, dR, dd01, dmaxc, dxf, dxa;
+  auto cleanup = [&]() { dHi.release(); dHj.release(); dHs.release(); dHshift.release(); dyo.release(); dR.release(); dd01.release(); dmaxc.release(); dxf.release(); dxa.release(); };
+  if ((rc = h->d_E.ensure(8 * nb * N)) || (rc = dHi.ensure(4 * nzb)) || (rc = dHj.ensure(4 * nzb)) || (rc = dHs.ensure(8 * nzb)) ||
+      (rc = dHshift.ensure(8 * mb)) || (rc = dyo.ensure(8 * mb)) || (rc = dR.ensure(8 * mb)) || (rc = dd01.ensure(8 * mb)) ||
+      (rc = dmaxc.ensure(8 * nb)) || (rc = dxf.ensure(8 * nb)) || (rc = dxa.ensure(8 * nb))) { cleanup(); return rc; }
+  cudaError_t e = cudaSuccess;
+  auto up = [&](void *d, const void *s, size_t bytes) { if (e == cudaSuccess && bytes && s) e = cudaMemcpy(d, s, bytes, cudaMemcpyHostToDevice); };
+  if (n > 0) e = cudaMemcpy2D(h->d_E.p, 8 * (size_t)n, E, 8 * (size_t)ldE, 8 * (size_t)n, N, cudaMemcpyHostToDevice);
+  up(dHi.p, Hi, 4 * (size_t)nnz); up(dHj.p, Hj, 4 * (size_t)nnz); up(dHs.p, Hs, 8 * (size_t)nnz);
+  up(dHshift.p, Hshift, 8 * (size_t)m); up(dyo.p, yo, 8 * (size_t)m); up(dR.p, Rdiag, 8 * (size_t)m);
+  up(dd01.p, d01, 8 * (size_t)m); up(dmaxc.p, maxCorrection, 8 * (size_t)n);
+  if (e != cudaSuccess) { oak_set_error("assim_ensemble: H2D copy failed: %s", cudaGetErrorString(e)); cleanup(); return OAK_ERR_CUDA; }
+  rc = oakb200_assim_ensemble_dev(h, n, N, m, h->d_E.as<double>(), n, nnz, dHi.as<int32_t>(), dHj.as<int32_t>(),
+                                  dHs.as<double>(), Hshift ? dHshift.as<double>() : nullptr, dyo.as<double>(),
+                                  dR.as<double>(), d01 ? dd01.as<double>() : nullptr, anamtype, inflation,
+                                  maxCorrection ? dmaxc.as<double>() : nullptr, h->d_E.as<double>(), n,
+                                  dxf.as<double>(), dxa.as<double>(), nullptr, stats);
+  if (rc == 0) {
+    if (n > 0) e = cudaMemcpy2D(Ea, 8 * (size_t)ldEa, h->d_E.p, 8 * (size_t)n, 8 * (size_t)n, N, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && xf_out) e = cudaMemcpy(xf_out, dxf.p, 8 * (size_t)n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && xa_out) e = cudaMemcpy(xa_out, dxa.p, 8 * (size_t)n, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { oak_set_error("assim_ensemble: D2H copy failed: %s", cudaGetErrorString(e)); rc = OAK_ERR_CUDA; }
+    if (stats) { stats->h2d_bytes = 8ll * n * N + 16ll * nnz + 8ll * m * 4; stats->d2h_bytes = 8ll * n * N; }
+  }
+  cleanup();
+  return rc;
+}
+
+extern "C" OAKB200_API int oakb200_fp64_peak(oakb200_handle *h, int32_t mode, double *tflops) {
+  if (!h || !tflops) { oak_set_error("fp64_peak: null argument"); return OAK_ERR_ARG; }
+  DeviceGuard guard(h->device);
+  return oak_fp64_peak(mode, tflops);
+}

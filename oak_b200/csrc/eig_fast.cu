@@ -1,0 +1,477 @@
+// eig_fast.cu — register-resident batched block-Jacobi kernel: the per-zone transform
+// (ampl, T) from (G, c).  Mathematics as in eig_simple.cu (Cholesky of I+G, one-sided Jacobi on
+// the columns of L, matrix functions from Z = L V); this file is the production layout.
+//
+// One CTA per zone.  The NP x NP matrix W lives in registers: the CTA is NP/4 groups of TL lanes,
+// a group owns two blocks of two columns (P = block position 2g, Q = position 2g+1), a lane owns
+// R = NP/TL = 16 rows of each of its 4 columns (64 doubles).  Row pairs are interleaved across the
+// lanes of a group so that the 16-byte shared-memory transfers of neighbouring lanes are contiguous.
+//
+// Ordering: odd-even transposition on the NB = NP/2 block positions.  Even step: a group rotates
+// its own (P,Q).  Odd step: pairs (2g+1, 2g+2): the group lends P through shared memory to its left
+// neighbour, borrows the right neighbour's P, rotates (Q, borrowed) and returns it.  After every
+// block rotation the two blocks swap positions (written as a swapped assignment of the rotation
+// results, no register moves), which is what makes every pair of blocks meet exactly once in NB
+// steps.  Inside a block pair the 4 cross column pairs are rotated in two sub-rounds of two
+// independent rotations; the two columns of a block are rotated against each other once per sweep.
+// Dot products are reduced over the TL lanes of a group with warp shuffles.
+#include "common.cuh"
+#include "eig_common.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+template <int NP, int TL>
+struct Cfg {
+  static constexpr int R = NP / TL;
+  static constexpr int NG = NP / 4;
+  static constexpr int NTH = NG * TL;
+  static constexpr int NB = NP / 2;
+  static constexpr int LDW = NP + 2;  // W / Y leading dimension in shared memory
+  static constexpr int LDX = NP + 4;  // exchange-buffer column stride
+  static_assert(R == 16, "16 rows per lane");
+  static_assert(NTH % 32 == 0, "whole warps");
+};
+
+template <int R>
+__device__ __forceinline__ double dotR(const double (&x)[R], const double (&y)[R]) {
+  double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
+#pragma unroll
+  for (int i = 0; i < R; i += 4) {
+    s0 = fma(x[i], y[i], s0);
+    s1 = fma(x[i + 1], y[i + 1], s1);
+    s2 = fma(x[i + 2], y[i + 2], s2);
+    s3 = fma(x[i + 3], y[i + 3], s3);
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
+template <int TL>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int o = 1; o < TL; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// x' = c x - s y ; y' = s x + c y
+template <int R>
+__device__ __forceinline__ void rot(double (&x)[R], double (&y)[R], double c, double s) {
+#pragma unroll
+  for (int i = 0; i < R; i++) {
+    const double xi = x[i], yi = y[i];
+    x[i] = fma(c, xi, -(s * yi));
+    y[i] = fma(s, xi, c * yi);
+  }
+}
+// same rotation, results stored swapped (x <- y', y <- x')
+template <int R>
+__device__ __forceinline__ void rot_swap(double (&x)[R], double (&y)[R], double c, double s) {
+#pragma unroll
+  for (int i = 0; i < R; i++) {
+    const double xi = x[i], yi = y[i];
+    x[i] = fma(s, xi, c * yi);
+    y[i] = fma(c, xi, -(s * yi));
+  }
+}
+template <int R>
+__device__ __forceinline__ void swap_cols(double (&x)[R], double (&y)[R]) {
+#pragma unroll
+  for (int i = 0; i < R; i++) { const double t = x[i]; x[i] = y[i]; y[i] = t; }
+}
+
+__device__ __forceinline__ float params_t(double a, double b, double g, double &c, double &s, double &tg) {
+  double t;
+  const float k = jacobi_params(a, b, g, c, s, t);
+  tg = t * g;  // |x'|^2 = |x|^2 - t g ,  |y'|^2 = |y|^2 + t g
+  return k;
+}
+
+// Rotates the 4 cross pairs of blocks X={X0,X1}, Y={Y0,Y1} and swaps the blocks.
+// Inactive groups (nothing borrowed) keep X untouched; their Y is scratch.
+template <int R, int TL>
+__device__ __forceinline__ float rotate_block_pair(double (&X0)[R], double (&X1)[R], double (&Y0)[R],
+                                                   double (&Y1)[R], double &nX0, double &nX1,
+                                                   double &nY0, double &nY1, bool active) {
+  float mx = 0.f;
+  {  // sub-round 1: (X0,Y0) (X1,Y1)
+    const double g1 = group_sum<TL>(dotR<R>(X0, Y0)), g2 = group_sum<TL>(dotR<R>(X1, Y1));
+    double c1, s1, c2, s2, tg1, tg2;
+    const float k1 = params_t(nX0, nY0, g1, c1, s1, tg1), k2 = params_t(nX1, nY1, g2, c2, s2, tg2);
+    const bool r1 = active && (k1 > JACOBI_SKIP), r2 = active && (k2 > JACOBI_SKIP);
+    if (!r1) { c1 = 1.; s1 = 0.; tg1 = 0.; }
+    if (!r2) { c2 = 1.; s2 = 0.; tg2 = 0.; }
+    if (active) mx = fmaxf(mx, fmaxf(k1, k2));
+    if (__any_sync(FULL, r1 || r2)) {
+      rot<R>(X0, Y0, c1, s1);
+      rot<R>(X1, Y1, c2, s2);
+    }
+    nX0 -= tg1; nY0 += tg1; nX1 -= tg2; nY1 += tg2;
+  }
+  {  // sub-round 2: (X0,Y1) (X1,Y0), swapped assignment
+    const double g1 = group_sum<TL>(dotR<R>(X0, Y1)), g2 = group_sum<TL>(dotR<R>(X1, Y0));
+    double c1, s1, c2, s2, tg1, tg2;
+    const float k1 = params_t(nX0, nY1, g1, c1, s1, tg1), k2 = params_t(nX1, nY0, g2, c2, s2, tg2);
+    const bool r1 = active && (k1 > JACOBI_SKIP), r2 = active && (k2 > JACOBI_SKIP);
+    if (!r1) { c1 = 1.; s1 = 0.; tg1 = 0.; }
+    if (!r2) { c2 = 1.; s2 = 0.; tg2 = 0.; }
+    if (!active) { c1 = 0.; s1 = 1.; c2 = 0.; s2 = 1.; }  // x stays, scratch y is negated
+    if (active) mx = fmaxf(mx, fmaxf(k1, k2));
+    if (__any_sync(FULL, r1 || r2)) {
+      rot_swap<R>(X0, Y1, c1, s1);
+      rot_swap<R>(X1, Y0, c2, s2);
+    } else if (active) {
+      swap_cols<R>(X0, Y1);
+      swap_cols<R>(X1, Y0);
+    }
+    if (active) {
+      const double a0 = nX0, a1 = nX1;
+      nX0 = nY1 + tg1; nY1 = a0 - tg1;
+      nX1 = nY0 + tg2; nY0 = a1 - tg2;
+    }
+  }
+  return mx;
+}
+
+template <int NP, int TL>
+__global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? 4 : 1))
+    k_eig_fast(int N, const int32_t *__restrict__ mloc, const double *__restrict__ G,
+               const double *__restrict__ cin, double *__restrict__ Tout, double *__restrict__ ampl_out,
+               float tol, int max_sweeps, DevCounters *ctr) {
+  using C = Cfg<NP, TL>;
+  constexpr int R = C::R, NG = C::NG, NTH = C::NTH, NB = C::NB, LDW = C::LDW, LDX = C::LDX;
+  constexpr int NW = NTH / 32;
+  extern __shared__ __align__(16) double sm[];
+  double *sW = sm;                   // NP x LDW : A / L, then exchange buffer, partial sums, Y
+  double *s_vec = sm + NP * LDW;     // 8 vectors of NP
+  double *s_c = s_vec, *s_uv = s_vec + NP, *s_duw = s_vec + 2 * NP, *s_uw = s_vec + 3 * NP;
+  double *s_g1 = s_vec + 4 * NP, *s_g2 = s_vec + 5 * NP, *s_v = s_vec + 6 * NP, *s_xn = s_vec + 7 * NP;
+  __shared__ int s_maxi;
+  __shared__ double s_red[NW];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = tid / TL, r = tid % TL;
+  const int zl = blockIdx.x;
+  if (mloc[zl] == 0) return;
+
+  // ---- load A = I + G ----
+  {
+    const double *Gz = G + (int64_t)zl * NP * NP;
+    for (int idx = tid; idx < NP * NP; idx += NTH) {
+      const int i = idx % NP, j = idx / NP;
+      sW[i + LDW * j] = Gz[idx] + (i == j ? 1. : 0.);
+    }
+    if (tid < NP) s_c[tid] = cin[(int64_t)zl * NP + tid];
+  }
+  __syncthreads();
+  // ---- Cholesky A = L L^T (thread i owns row i), upper triangle zeroed ----
+  for (int j = 0; j < NP; j++) {
+    const double d = sqrt(sW[j + LDW * j]);
+    __syncthreads();
+    if (tid == j) sW[j + LDW * j] = d;
+    if (tid > j && tid < NP) sW[tid + LDW * j] /= d;
+    __syncthreads();
+    if (tid > j && tid < NP) {
+      const double lij = sW[tid + LDW * j];
+      for (int k = j + 1; k <= tid; k++) sW[tid + LDW * k] = fma(-lij, sW[k + LDW * j], sW[tid + LDW * k]);
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < NP * NP; idx += NTH) {
+    const int i = idx % NP, j = idx / NP;
+    if (j > i) sW[i + LDW * j] = 0.;
+  }
+  __syncthreads();
+
+  // ---- registers: group g owns columns 4g..4g+3 ; lane r rows 2*(pi*TL + r) + e ----
+  double P0[R], P1[R], Q0[R], Q1[R];
+  auto ld_col = [&](double(&X)[R], const double *base) {
+#pragma unroll
+    for (int pi = 0; pi < R / 2; pi++) {
+      const double2 v = *reinterpret_cast<const double2 *>(base + 2 * (pi * TL + r));
+      X[2 * pi] = v.x;
+      X[2 * pi + 1] = v.y;
+    }
+  };
+  auto st_col = [&](const double(&X)[R], double *base) {
+#pragma unroll
+    for (int pi = 0; pi < R / 2; pi++)
+      *reinterpret_cast<double2 *>(base + 2 * (pi * TL + r)) = make_double2(X[2 * pi], X[2 * pi + 1]);
+  };
+  ld_col(P0, sW + LDW * (4 * g + 0));
+  ld_col(P1, sW + LDW * (4 * g + 1));
+  ld_col(Q0, sW + LDW * (4 * g + 2));
+  ld_col(Q1, sW + LDW * (4 * g + 3));
+  __syncthreads();  // sW is now free: exchange buffer
+  double *xbuf = sW;
+  double nP0, nP1, nQ0, nQ1;
+
+  auto lend = [&](int region) {
+    st_col(P0, xbuf + LDX * (2 * region));
+    st_col(P1, xbuf + LDX * (2 * region + 1));
+    if (r == 0) { s_xn[2 * region] = nP0; s_xn[2 * region + 1] = nP1; }
+  };
+  auto take = [&](int region) {
+    ld_col(P0, xbuf + LDX * (2 * region));
+    ld_col(P1, xbuf + LDX * (2 * region + 1));
+    nP0 = s_xn[2 * region];
+    nP1 = s_xn[2 * region + 1];
+  };
+
+  int sweeps = 0;
+  for (int sweep = 0; sweep < max_sweeps; sweep++) {
+    if (tid == 0) s_maxi = 0;
+    // fresh norms
+    nP0 = group_sum<TL>(dotR<R>(P0, P0));
+    nP1 = group_sum<TL>(dotR<R>(P1, P1));
+    nQ0 = group_sum<TL>(dotR<R>(Q0, Q0));
+    nQ1 = group_sum<TL>(dotR<R>(Q1, Q1));
+    float mx = 0.f;
+    {  // the two columns of each block against each other
+      const double g1 = group_sum<TL>(dotR<R>(P0, P1)), g2 = group_sum<TL>(dotR<R>(Q0, Q1));
+      double c1, s1, c2, s2, tg1, tg2;
+      const float k1 = params_t(nP0, nP1, g1, c1, s1, tg1), k2 = params_t(nQ0, nQ1, g2, c2, s2, tg2);
+      const bool r1 = k1 > JACOBI_SKIP, r2 = k2 > JACOBI_SKIP;
+      if (!r1) { c1 = 1.; s1 = 0.; tg1 = 0.; }
+      if (!r2) { c2 = 1.; s2 = 0.; tg2 = 0.; }
+      mx = fmaxf(k1, k2);
+      if (__any_sync(FULL, r1 || r2)) {
+        rot<R>(P0, P1, c1, s1);
+        rot<R>(Q0, Q1, c2, s2);
+      }
+      nP0 -= tg1; nP1 += tg1; nQ0 -= tg2; nQ1 += tg2;
+    }
+    for (int step = 0; step < NB; step += 2) {
+      // even step: positions (2g, 2g+1)
+      mx = fmaxf(mx, rotate_block_pair<R, TL>(P0, P1, Q0, Q1, nP0, nP1, nQ0, nQ1, true));
+      // odd step: positions (2g+1, 2g+2)
+      lend(g);
+      __syncthreads();
+      const bool act = g < NG - 1;
+      if (act) take(g + 1);
+      mx = fmaxf(mx, rotate_block_pair<R, TL>(Q0, Q1, P0, P1, nQ0, nQ1, nP0, nP1, act));
+      if (act) lend(g + 1);
+      __syncthreads();
+      take(g);
+    }
+    atomicMax(&s_maxi, __float_as_int(mx));
+    __syncthreads();
+    const float mc = __int_as_float(s_maxi);
+    sweeps = sweep + 1;
+    __syncthreads();
+    if (mc < tol) break;
+    if (sweep == max_sweeps - 1 && tid == 0) atomicAdd(&ctr->not_converged, 1);
+  }
+
+  // ---- epilogue: matrix functions from the orthogonal columns z_j = sigma_j u_j ----
+  // lane-local views of the vectors c and 1_{i<N}
+  double dcol[4], acol[4], bcol[4];
+  {
+    double cr[R], one[R];
+#pragma unroll
+    for (int pi = 0; pi < R / 2; pi++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int row = 2 * (pi * TL + r) + e;
+        cr[2 * pi + e] = s_c[row];
+        one[2 * pi + e] = row < N ? 1. : 0.;
+      }
+    auto stats = [&](const double(&Z)[R], int slot) {
+      const double s2 = group_sum<TL>(dotR<R>(Z, Z));
+      const double zc = group_sum<TL>(dotR<R>(Z, cr));
+      const double z1 = group_sum<TL>(dotR<R>(Z, one));
+      const double s2c = fmax(s2, 1.);  // lambda <- max(lambda,0)   rrsqrt.F90:137
+      const double rs = sqrt(s2c);
+      dcol[slot] = 1. / (s2 * rs);      // (1+lambda)^-1/2 / |z|^2
+      acol[slot] = zc / (s2 * s2c);     // (1+lambda)^-1 (u.c) / |z|
+      bcol[slot] = z1 * rs / s2;        // (1+lambda)^+1/2 (u.1) / |z|
+    };
+    stats(P0, 0); stats(P1, 1); stats(Q0, 2); stats(Q1, 3);
+  }
+  // partial sums over the 4 columns of a group, then over groups through shared memory
+  double *s_part = sW;  // [2][NG][NP]
+  auto scatter2 = [&](const double(&w1)[4], const double(&w2)[4]) {
+#pragma unroll
+    for (int pi = 0; pi < R / 2; pi++) {
+      double2 o1, o2;
+      {
+        const int i = 2 * pi;
+        o1.x = P0[i] * w1[0] + P1[i] * w1[1] + Q0[i] * w1[2] + Q1[i] * w1[3];
+        o2.x = P0[i] * w2[0] + P1[i] * w2[1] + Q0[i] * w2[2] + Q1[i] * w2[3];
+        o1.y = P0[i + 1] * w1[0] + P1[i + 1] * w1[1] + Q0[i + 1] * w1[2] + Q1[i + 1] * w1[3];
+        o2.y = P0[i + 1] * w2[0] + P1[i + 1] * w2[1] + Q0[i + 1] * w2[2] + Q1[i + 1] * w2[3];
+      }
+      const int row = 2 * (pi * TL + r);
+      *reinterpret_cast<double2 *>(s_part + (size_t)g * NP + row) = o1;
+      *reinterpret_cast<double2 *>(s_part + (size_t)(NG + g) * NP + row) = o2;
+    }
+  };
+  __syncthreads();  // everybody is past the last take()
+  scatter2(acol, bcol);
+  __syncthreads();
+  double vi = 0.;
+  if (tid < NP) {
+    double am = 0.;
+    for (int gg = 0; gg < NG; gg++) {
+      am += s_part[(size_t)gg * NP + tid];
+      vi += s_part[(size_t)(NG + gg) * NP + tid];
+    }
+    if (tid >= N) { am = 0.; vi = 0.; }
+    if (am != am) atomicExch(&ctr->nan_flag, 1);  // rrsqrt.F90:145-149
+    ampl_out[(int64_t)zl * NP + tid] = am;
+  }
+  // v = normate(v)  rrsqrt.F90:178
+  {
+    double part = (tid < N) ? vi * vi : 0.;
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+    if (lane == 0) s_red[warp] = part;
+  }
+  __syncthreads();
+  double vnorm2 = 0.;
+#pragma unroll
+  for (int w = 0; w < NW; w++) vnorm2 += s_red[w];
+  const double vnorm = sqrt(vnorm2);
+  if (tid < NP) s_v[tid] = (tid < N) ? vi / vnorm : 0.;
+  __syncthreads();
+  // Omega = H_v diag(1,..,1,sign(v_N) sign(w_N)) H_w ; w = 1/sqrt(N)   (rrsqrt.F90:176-185,:737-744)
+  const double wN = 1. / sqrt((double)N);
+  const double vN = s_v[N - 1];
+  const double sv = copysign(1., vN);
+  const double dNN = sv;  // sign(w_N) = +1
+  const double hv = 1. / (1. + fabs(vN)), hw = 1. / (1. + fabs(wN));
+  if (tid < NP) {
+    double uv = (tid < N) ? s_v[tid] : 0.;
+    double uw = (tid < N) ? wN : 0.;
+    if (tid == N - 1) { uv += sv; uw += 1.; }
+    s_uv[tid] = uv;
+    s_uw[tid] = uw;
+    s_duw[tid] = (tid == N - 1) ? dNN * uw : uw;
+  }
+  __syncthreads();
+  // g1 = M u_v, gm2 = M (D u_w):  t_j = d_j (z_j . x) per column, then sum_j z_j t_j
+  {
+    double xr1[R], xr2[R];
+#pragma unroll
+    for (int pi = 0; pi < R / 2; pi++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int row = 2 * (pi * TL + r) + e;
+        xr1[2 * pi + e] = s_uv[row];
+        xr2[2 * pi + e] = s_duw[row];
+      }
+    double t1[4], t2[4];
+    t1[0] = dcol[0] * group_sum<TL>(dotR<R>(P0, xr1)); t2[0] = dcol[0] * group_sum<TL>(dotR<R>(P0, xr2));
+    t1[1] = dcol[1] * group_sum<TL>(dotR<R>(P1, xr1)); t2[1] = dcol[1] * group_sum<TL>(dotR<R>(P1, xr2));
+    t1[2] = dcol[2] * group_sum<TL>(dotR<R>(Q0, xr1)); t2[2] = dcol[2] * group_sum<TL>(dotR<R>(Q0, xr2));
+    t1[3] = dcol[3] * group_sum<TL>(dotR<R>(Q1, xr1)); t2[3] = dcol[3] * group_sum<TL>(dotR<R>(Q1, xr2));
+    scatter2(t1, t2);
+  }
+  // kappa = hv u_v . (D u_w)
+  {
+    double part = (tid < NP) ? s_uv[tid] * hv * s_duw[tid] : 0.;
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+    if (lane == 0) s_red[warp] = part;  // previous readers of s_red are behind two barriers
+  }
+  __syncthreads();
+  double kappa = 0.;
+#pragma unroll
+  for (int w = 0; w < NW; w++) kappa += s_red[w];
+  if (tid < NP) {
+    double g1 = 0., gm2 = 0.;
+    for (int gg = 0; gg < NG; gg++) {
+      g1 += s_part[(size_t)gg * NP + tid];
+      gm2 += s_part[(size_t)(NG + gg) * NP + tid];
+    }
+    s_g1[tid] = g1;
+    s_g2[tid] = gm2 - kappa * g1;
+  }
+  __syncthreads();
+  // Y = Z diag(sqrt(d)) to shared memory (column j = 4g+slot)
+  double *Ys = sW;
+  {
+    auto put = [&](const double(&Z)[R], int slot) {
+      const double sc = sqrt(dcol[slot]);
+      double *base = Ys + LDW * (4 * g + slot);
+#pragma unroll
+      for (int pi = 0; pi < R / 2; pi++)
+        *reinterpret_cast<double2 *>(base + 2 * (pi * TL + r)) = make_double2(Z[2 * pi] * sc, Z[2 * pi + 1] * sc);
+    };
+    put(P0, 0); put(P1, 1); put(Q0, 2); put(Q1, 3);
+  }
+  __syncthreads();
+  // M = Y Y^T in 8x8 register tiles, then T = (M - g1 (hv u_v)^T) D - g2 (hw u_w)^T, row-major
+  {
+    constexpr int TPR = NP / 8;  // tiles per row
+    const int ti = tid / TPR, tj = tid % TPR;
+    double acc[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+      for (int b = 0; b < 8; b++) acc[a][b] = 0.;
+#pragma unroll 2
+    for (int j = 0; j < NP; j++) {
+      const double *col = Ys + LDW * j;
+      double rv[8], cv[8];
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const double2 v = *reinterpret_cast<const double2 *>(col + 8 * ti + 2 * a);
+        rv[2 * a] = v.x; rv[2 * a + 1] = v.y;
+        const double2 u = *reinterpret_cast<const double2 *>(col + 2 * tj + (NP / 4) * a);
+        cv[2 * a] = u.x; cv[2 * a + 1] = u.y;
+      }
+#pragma unroll
+      for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) acc[a][b] = fma(rv[a], cv[b], acc[a][b]);
+    }
+    double *Tz = Tout + (int64_t)zl * NP * NP;
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int i = 8 * ti + a;
+      const double g1i = s_g1[i] * hv, g2i = s_g2[i] * hw;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int k = 2 * tj + (NP / 4) * b;
+        double t0 = acc[a][2 * b] - g1i * s_uv[k];
+        double t1 = acc[a][2 * b + 1] - g1i * s_uv[k + 1];
+        if (k == N - 1) t0 *= dNN;
+        if (k + 1 == N - 1) t1 *= dNN;
+        t0 -= g2i * s_uw[k];
+        t1 -= g2i * s_uw[k + 1];
+        *reinterpret_cast<double2 *>(Tz + (int64_t)i * NP + k) = make_double2(t0, t1);
+      }
+    }
+  }
+  if (tid == 0) atomicAdd(&ctr->sweeps, (unsigned long long)sweeps);
+}
+
+template <int NP, int TL>
+int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G, const double *c, double *T,
+           double *ampl, double tol, int max_sweeps, DevCounters *ctr) {
+  using C = Cfg<NP, TL>;
+  const size_t smem = sizeof(double) * (NP * C::LDW + 8 * NP);
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(k_eig_fast<NP, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  k_eig_fast<NP, TL><<<nz, C::NTH, smem, st>>>(N, mloc, G, c, T, ampl, (float)tol, max_sweeps, ctr);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int oak_launch_eig_simple(cudaStream_t st, int N, int NP, int nz, const int32_t *mloc, const double *G,
+                          const double *c, double *T, double *ampl, double tol, int max_sweeps,
+                          DevCounters *ctr);
+
+int oak_launch_eig(cudaStream_t st, int kernel, int N, int NP, int zone0, int nz, const int32_t *mloc,
+                   const double *G, const double *c, double *T, double *ampl, double tol, int max_sweeps,
+                   DevCounters *ctr) {
+  if (nz <= 0) return 0;
+  const int32_t *ml = mloc + zone0;
+  if (kernel == 0 && NP == 64) return launch<64, 4>(st, N, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
+  if (kernel == 0 && NP == 128) return launch<128, 8>(st, N, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
+  return oak_launch_eig_simple(st, N, NP, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
+}

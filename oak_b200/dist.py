@@ -1,0 +1,106 @@
+"""Multi-GPU driver: one process per GPU, zones sharded in contiguous ranges, one all-gather.
+
+Replaces the MPI column distribution of parall.F90: rank p owns the zone range of parallPartion
+(parall.F90:176-177, unit speeds), i.e. a contiguous slab of the zone-permuted state, plus the
+observations within one search radius of its zones (the halo).  Observation-space arrays are
+replicated in the reference (rrsqrt.F90:340-352 leaves Hxf/HSf/yo/R global); here each rank keeps only
+its halo subset, in increasing global observation number, so local index sets map back one-to-one.
+The analysed slabs are reassembled with a single NCCL all-gather (no other data-path collective).
+
+The compute step is injected (`analyse`), so the same plumbing runs under gloo on CPUs in the tests
+with the oracle as a stand-in, and under NCCL on B200s with Handle.local_analysis_dev.
+"""
+import numpy as np
+
+from .api import LOC_HORIZONTAL, METRIC_CARTESIAN, WEIGHT_GASPARI_COHN, WEIGHT_GAUSSIAN
+
+EARTH_RADIUS = 6378137.0
+
+
+def partition(nzones, nranks):
+    """first[p] .. first[p+1]: zones of rank p — parall.F90:176-177 with unit speeds (pure host twin of
+    oakb200_partition_zones, so that planning needs no device)."""
+    return np.array([(nzones * p) // nranks for p in range(nranks + 1)], dtype=np.int64)
+
+
+def search_radius(corrLen, maxLen, weightfun):
+    if weightfun == WEIGHT_GAUSSIAN:
+        return np.asarray(maxLen, dtype=np.float64)
+    if weightfun == WEIGHT_GASPARI_COHN:
+        return 2.0 * np.asarray(corrLen, dtype=np.float64)
+    return np.full(np.shape(corrLen), np.inf)
+
+
+def halo_observations(zx, zy, radius, obs_x, obs_y, loctype=LOC_HORIZONTAL, metrictype=METRIC_CARTESIAN):
+    """Global (0-based, increasing) numbers of the observations that can be relevant to any of the given
+    zones: a conservative superset (bounding box of the zones grown by the largest radius, with slack);
+    the exact predicate runs on the device.  Non-Cartesian / non-horizontal set-ups keep everything."""
+    m = len(obs_x)
+    if len(zx) == 0:
+        return np.zeros(0, dtype=np.int64)
+    rmax = float(np.max(radius)) if len(radius) else 0.0
+    if loctype != LOC_HORIZONTAL or metrictype != METRIC_CARTESIAN or not np.isfinite(rmax):
+        return np.arange(m, dtype=np.int64)
+    pad = rmax * (1 + 1e-9) + 1e-9 * (np.abs(zx).max() + np.abs(zy).max() + 1.0)
+    keep = ((obs_x >= zx.min() - pad) & (obs_x <= zx.max() + pad) & (obs_y >= zy.min() - pad) &
+            (obs_y <= zy.max() + pad))
+    return np.nonzero(keep)[0].astype(np.int64)
+
+
+class ShardPlan:
+    """What rank `rank` of `world` owns."""
+
+    def __init__(self, zoneSize, zx, zy, corrLen, maxLen, obs_x, obs_y, rank, world, loctype=LOC_HORIZONTAL,
+                 metrictype=METRIC_CARTESIAN, weightfun=WEIGHT_GAUSSIAN):
+        zoneSize = np.asarray(zoneSize, dtype=np.int64)
+        nz = zoneSize.size
+        first = partition(nz, world)
+        self.rank, self.world = rank, world
+        self.first = first
+        self.z0, self.z1 = int(first[rank]), int(first[rank + 1])
+        start = np.concatenate([[0], np.cumsum(zoneSize)])
+        self.row_first = start[first]                      # per-rank first rows
+        self.r0, self.r1 = int(start[self.z0]), int(start[self.z1])
+        self.n = int(start[-1])
+        cl = np.broadcast_to(np.asarray(corrLen, dtype=np.float64), (nz,))
+        ml = np.broadcast_to(np.asarray(maxLen, dtype=np.float64), (nz,))
+        sl = slice(self.z0, self.z1)
+        self.zoneSize = zoneSize[sl].astype(np.int32)
+        self.zx = np.ascontiguousarray(zx[sl])
+        self.zy = None if zy is None else np.ascontiguousarray(zy[sl])
+        self.corrLen = np.ascontiguousarray(cl[sl])
+        self.maxLen = np.ascontiguousarray(ml[sl])
+        rad = search_radius(self.corrLen, self.maxLen, weightfun)
+        self.obs_idx = halo_observations(self.zx, self.zy if self.zy is not None else np.zeros_like(self.zx), rad,
+                                         np.asarray(obs_x), np.asarray(obs_y) if obs_y is not None else
+                                         np.zeros_like(obs_x), loctype, metrictype)
+        self.equal_slabs = bool(np.all(np.diff(self.row_first) == (self.r1 - self.r0)))
+
+
+def allgather_slabs(dist, Sa_local, plan, out=None):
+    """Reassembles the member-major analysed slabs (N, n_loc) of all ranks into (N, n).
+
+    Equal slabs: one all_gather_into_tensor per member row group, issued asynchronously and waited
+    together (a single grouped collective on NCCL).  Unequal slabs: all_gather on padded buffers."""
+    import torch
+    N = Sa_local.shape[0]
+    if out is None:
+        out = torch.empty((N, plan.n), dtype=Sa_local.dtype, device=Sa_local.device)
+    if plan.world == 1:
+        out.copy_(Sa_local)
+        return out
+    if plan.equal_slabs:
+        works = [dist.all_gather_into_tensor(out[k], Sa_local[k].contiguous(), async_op=True) for k in range(N)]
+        for w in works:
+            w.wait()
+        return out
+    sizes = np.diff(plan.row_first).astype(np.int64)
+    nmax = int(sizes.max())
+    buf = torch.zeros((N, nmax), dtype=Sa_local.dtype, device=Sa_local.device)
+    buf[:, :Sa_local.shape[1]] = Sa_local
+    parts = [torch.empty_like(buf) for _ in range(plan.world)]
+    dist.all_gather(parts, buf)
+    for p in range(plan.world):
+        a, b = int(plan.row_first[p]), int(plan.row_first[p + 1])
+        out[:, a:b] = parts[p][:, :b - a]
+    return out

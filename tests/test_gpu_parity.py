@@ -1,0 +1,329 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and with the reference's own
+known-answer tests.  Tolerances: observation index sets bit-exact; analysed mean / anomalies within
+1e-9 relative (BASELINE.json north_star), written as RTOL below."""
+import numpy as np
+import pytest
+
+import oracle
+from refcases import assim_case, kalman_check, rrsqrt_case
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9  # north star: relative tolerance on the analysed ensemble (fp64)
+TOL_REF = 1e-8  # test/test_rrsqrt.F90:20
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import oak_b200
+    return oak_b200
+
+
+@pytest.fixture(scope="module", params=[0, 1], ids=["eig_fast", "eig_simple"])
+def handle(request, ob):
+    # pad_to=64 sends even the small golden cases through the production register-resident kernel
+    h = ob.Handle(0, eig_kernel=request.param, pad_to=64 if request.param == 0 else 0)
+    yield h
+    h.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# reference known-answer tests (test/test_rrsqrt.F90)
+# ------------------------------------------------------------------------------------------------
+def _sel(ob, c, zoneSize, weightfun, corr, maxlen):
+    starts = np.concatenate([[0], np.cumsum(zoneSize)[:-1]])
+    return ob.Selector(zone_x=c["xmod"][starts], zone_y=np.zeros(len(zoneSize)), corrLen=corr, maxLen=maxlen,
+                       obs_x=c["xobs"], obs_y=np.zeros(c["m"]), loctype=1, metrictype=0, weightfun=weightfun)
+
+
+def test_rrsqrt_single_zone_and_zone_per_point_equal_global(ob, handle):
+    # test/test_rrsqrt.F90:142-159
+    c = rrsqrt_case()
+    xa_check, Pa_check = kalman_check(c["xf"], c["Sf"], c["H"], c["y"], np.diag(c["var"]))
+    for zs in ([c["n"]], [1] * c["n"]):
+        xa, Sa, ampl = ob.locanalysis(zs, _sel(ob, c, zs, 2, 1.0, 1e30), c["xf"], c["Hxf"], c["y"], c["Sf"],
+                                      c["HSf"], ob.DiagCovar(c["var"]), handle=handle)
+        assert np.abs(xa - xa_check).max() < TOL_REF
+        assert np.abs(Sa @ Sa.T - Pa_check).max() < TOL_REF
+        assert np.abs(Sa.sum(axis=1)).max() < 1e-12
+        assert (ampl == 0).all()  # rrsqrt.F90:324
+        xo, So, _ = oracle.analysis(c["xf"], c["Hxf"], c["y"], c["Sf"], c["HSf"], c["var"])
+        assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL
+
+
+def test_rrsqrt_gaspari_cohn(ob, handle):
+    # test/test_rrsqrt.F90:162-233, callback :254-271
+    c = rrsqrt_case()
+    n, m = c["n"], c["m"]
+    zs = [1] * n
+    xa, Sa, _ = ob.locanalysis(zs, _sel(ob, c, zs, 1, c["length"], 1e30), c["xf"], c["Hxf"], c["y"], c["Sf"],
+                               c["HSf"], ob.DiagCovar(c["var"]), handle=handle)
+    Pf = c["Sf"] @ c["Sf"].T
+    R = np.diag(c["var"])
+    xa_check = np.zeros(n)
+    for i in range(n):
+        w = np.array([oracle.locfun(abs(c["xmod"][i] - xo) / c["length"]) for xo in c["xobs"]])
+        iloc = np.where(w != 0)[0]
+        if len(iloc) == 0:
+            xa_check[i] = c["xf"][i]
+            continue
+        invR = np.linalg.inv(R[np.ix_(iloc, iloc)]) * np.outer(w[iloc], w[iloc])
+        Hl = c["H"][iloc]
+        Pa = np.linalg.inv(np.linalg.inv(Pf) + Hl.T @ invR @ Hl)
+        xa_check[i] = c["xf"][i] + Pa[i] @ (Hl.T @ (invR @ (c["y"][iloc] - Hl @ c["xf"])))
+    assert np.abs(xa - xa_check).max() < TOL_REF
+    obs = oracle.make_obs(m, obsx=c["xobs"], obsy=np.zeros(m), weightfun=1)
+    xo, So, _, mloc = oracle.loc_analysis(zs, dict(x=c["xmod"], y=np.zeros(n)), c["length"], 1e30, obs, c["xf"],
+                                          c["Hxf"], c["y"], c["Sf"], c["HSf"], c["var"])
+    assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL
+    # index sets, bit exact
+    off, idx, w = handle.select_observations()
+    assert (np.diff(off) == mloc).all()
+    for i in range(n):
+        wo, ro = oracle.select_observations(obs, (c["xmod"][i], 0.0), c["length"], 1e30)
+        assert list(idx[off[i]:off[i + 1]] - 1) == list(np.nonzero(ro)[0])
+        assert np.abs(w[off[i]:off[i + 1]] - wo[ro]).max() < 1e-15
+
+
+def test_assim_case_ensemble_in_ensemble_out(ob, handle):
+    # test/test_assim.F90:96-172 (tol 1e-5) through the ensemble entry point
+    c = assim_case()
+    n, N = c["n"], c["N"]
+    xf = c["Ef"].sum(axis=1) / N
+    xa_check, Pa_check = kalman_check(xf, (c["Ef"] - xf[:, None]) / np.sqrt(N - 1.0), c["H"], c["yo"],
+                                      np.diag(c["var"]))
+    sel = ob.Selector(zone_x=c["x"][:1], zone_y=c["y"][:1], obs_x=c["obsx"], obs_y=c["obsy"], metrictype=0,
+                      weightfun=2)
+    Ea, xf_o, xa_o = ob.assim_ensemble([n], sel, c["Ef"], [1], [5], [1.0], np.zeros(1), c["yo"],
+                                       ob.DiagCovar(c["var"]), handle=handle)
+    xa = Ea.sum(axis=1) / N
+    Eap = Ea - xa[:, None]
+    assert np.abs(xa - xa_check).max() < 1e-5
+    assert np.abs(Eap @ Eap.T / (N - 1.0) - Pa_check).max() < 1e-5
+    obs = oracle.make_obs(1, obsx=c["obsx"], obsy=c["obsy"], weightfun=2)
+    Eo, xfo, xao = oracle.assim_ensemble([n], dict(x=c["x"][:1], y=c["y"][:1]), 1.0, 1e30, obs, c["Ef"],
+                                         np.array([1], np.int32), np.array([5], np.int32), np.array([1.0]),
+                                         np.zeros(1), c["yo"], c["var"])
+    assert rel(Ea, Eo) < RTOL and rel(xf_o, xfo) < 1e-14 and rel(xa_o, xao) < RTOL
+
+
+# ------------------------------------------------------------------------------------------------
+# observation selection: bit-exact index sets for every metric / loctype / weight function
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric,loctype,weightfun", [(0, 1, 0), (1, 1, 0), (2, 1, 0), (0, 1, 1), (1, 1, 1),
+                                                      (0, 2, 0), (0, 3, 0), (0, 1, 2)])
+def test_selection_index_sets_bit_exact(ob, metric, loctype, weightfun):
+    rng = np.random.default_rng(100 * metric + 10 * loctype + weightfun)
+    nzones, m = 400, 3000
+    if metric == 0:
+        zx, zy = rng.uniform(0, 1e5, nzones), rng.uniform(0, 1e5, nzones)
+        ox, oy = rng.uniform(-1e3, 1.01e5, m), rng.uniform(-1e3, 1.01e5, m)
+        corr, maxl = rng.uniform(2e3, 6e3, nzones), rng.uniform(4e3, 2e4, nzones)
+        # lattice points at exactly the cut-off distance exercise the `<=`
+        zx[:20] = 1000.0 * np.arange(20); zy[:20] = 0.0
+        ox[:20] = 1000.0 * np.arange(20) + 3000.0; oy[:20] = 4000.0
+        maxl[:20] = 5000.0
+    else:
+        zx, zy = rng.uniform(-180, 180, nzones), rng.uniform(-89.5, 89.5, nzones)
+        ox, oy = rng.uniform(-180, 360, m), rng.uniform(-90, 90, m)
+        zx[:5] = [179.9, -179.9, 0.05, 359.9, 10.0]; zy[:5] = [0, 10, -20, 60, 89.9]
+        corr, maxl = rng.uniform(2e5, 6e5, nzones), rng.uniform(3e5, 3e6, nzones)
+        maxl[5:8] = [1.5e7, 2.1e7, 30.0]
+    zz, oz = rng.uniform(0, 100, nzones), rng.uniform(0, 100, m)
+    if loctype != 1:
+        corr, maxl = rng.uniform(2, 6, nzones), rng.uniform(4, 20, nzones)
+    h = ob.Handle(0)
+    h.set_zones(np.ones(nzones, np.int32), zone_x=zx, zone_y=zy, zone_z=zz, zone_t=zz, corrLen=corr, maxLen=maxl,
+                loctype=loctype, metrictype=metric, weightfun=weightfun)
+    h.set_observations(obs_x=ox, obs_y=oy, obs_z=oz, obs_t=oz)
+    off, idx, w = h.select_observations()
+    h.close()
+    obs = oracle.make_obs(m, obsx=ox, obsy=oy, obsz=oz, obst=oz, loctype=loctype, metrictype=metric,
+                          weightfun=weightfun, trig=1)
+    total = 0
+    for z in range(nzones):
+        wo, ro = oracle.select_observations(obs, (zx[z], zy[z], zz[z], zz[z]), corr[z], maxl[z])
+        want = np.nonzero(ro)[0]
+        got = idx[off[z]:off[z + 1]] - 1
+        assert got.size == want.size and (got == want).all(), (z, got.size, want.size)
+        if want.size:
+            assert np.abs(w[off[z]:off[z + 1]] - wo[ro]).max() <= 4e-16 * max(1.0, np.abs(wo[ro]).max())
+        total += want.size
+    assert total > 0
+    if metric == 0 and loctype == 1 and weightfun == 0:
+        for z in range(20):  # the 3-4-5 triangles: d == maxLen exactly must be relevant
+            assert z in (idx[off[z]:off[z + 1]] - 1)
+
+
+def test_selection_matches_cellgrid_contract(ob):
+    # test/test_cellgrid.F90:6-8,:64-83: integer lattices, query (2,2), every point with d < maxdist found
+    for side, maxdist in [(4, 2.0), (20, 3.0), (300, 5.0)]:
+        ii, jj = np.meshgrid(np.arange(1, side + 1.0), np.arange(1, side + 1.0), indexing="ij")
+        ox, oy = ii.ravel(order="F"), jj.ravel(order="F")
+        h = ob.Handle(0)
+        h.set_zones([1], zone_x=[2.0], zone_y=[2.0], corrLen=1.0, maxLen=maxdist, metrictype=0)
+        h.set_observations(obs_x=ox, obs_y=oy)
+        off, idx, _ = h.select_observations()
+        h.close()
+        d = np.sqrt((ox - 2) ** 2 + (oy - 2) ** 2)
+        assert set(np.nonzero(d < maxdist)[0]) <= set(idx - 1)
+        assert list(idx - 1) == list(np.nonzero(d <= maxdist)[0])
+
+
+# ------------------------------------------------------------------------------------------------
+# local analysis on synthetic grids vs the oracle (LAPACK dsyev / BLAS dgemm)
+# ------------------------------------------------------------------------------------------------
+def _oracle_loc(c, zoneSize=None, e01=None, zone_list=None):
+    obs = oracle.make_obs(c["m"], obsx=c["obs"]["ox"], obsy=c["obs"]["oy"])
+    zs = c["zoneSize"] if zoneSize is None else zoneSize
+    return oracle.loc_analysis(zs, dict(x=c["zx"], y=c["zy"]), c["corr"], c["maxlen"], obs, c["xf"], c["Hxf"],
+                               c["yo"], c["Sf"], c["HSf"], c["var"], e01=e01, zone_list=zone_list)
+
+
+def _configure(ob, h, c, zoneSize=None):
+    sel = ob.Selector(zone_x=c["zx"], zone_y=c["zy"], corrLen=c["corr"], maxLen=c["maxlen"], obs_x=c["obs"]["ox"],
+                      obs_y=c["obs"]["oy"], metrictype=0)
+    h.configure(c["zoneSize"] if zoneSize is None else zoneSize, sel)
+
+
+@pytest.mark.parametrize("N,m,nx,ny,nz", [(16, 300, 24, 20, 3), (64, 900, 20, 16, 5), (40, 500, 16, 12, 4),
+                                          (100, 1200, 12, 10, 2), (128, 1500, 10, 8, 3), (20, 5, 30, 30, 1)])
+def test_local_analysis_matches_oracle(ob, handle, N, m, nx, ny, nz):
+    from oak_b200 import synthetic
+    c = synthetic.small_case(nx=nx, ny=ny, nz=nz, N=N, m=m, corr=3000.0, maxlen=6000.0, seed=N + m)
+    _configure(ob, handle, c)
+    xa, Sa, ampl, st = handle.local_analysis(c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], ob.DiagCovar(c["var"]))
+    xo, So, _, mloc = _oracle_loc(c)
+    assert st["obs_relevant_sum"] == mloc.sum()
+    assert st["zones_skipped"] == (mloc == 0).sum()
+    assert rel(xa, xo) < RTOL, rel(xa, xo)
+    assert rel(Sa, So) < RTOL, rel(Sa, So)
+    # columns of Sa keep summing to zero (ensemble input => Omega = I, rrsqrt.F90:166-176)
+    assert np.abs(Sa.sum(axis=1)).max() < 1e-12 * max(1.0, np.abs(Sa).max()) * N
+
+
+def test_edge_cases_empty_zones_all_relevant_excluded_obs_ragged_zones(ob, handle):
+    from oak_b200 import synthetic
+    c = synthetic.small_case(nx=30, ny=10, nz=4, N=24, m=200, corr=2500.0, maxlen=5000.0, seed=3)
+    # observations only in the left third: most zones on the right have none
+    keep = c["obs"]["ox"] < 10000.0
+    for k in ("Hxf", "yo", "var"):
+        c[k] = c[k][keep]
+    c["HSf"] = np.asfortranarray(c["HSf"][keep])
+    c["obs"] = {k: (v[..., keep] if v.ndim > 1 else v[keep]) for k, v in c["obs"].items()}
+    c["m"] = int(keep.sum())
+    nzones = c["grid"].nzones
+    # ragged zones: sizes 1..7, total = n
+    zs = []
+    left = c["Sf"].shape[0]
+    k = 0
+    while left > 0:
+        s = min(left, 1 + (k % 7)); zs.append(s); left -= s; k += 1
+    zs = np.array(zs, np.int32)
+    rng = np.random.default_rng(0)
+    c["zx"] = rng.uniform(0, 30000, zs.size); c["zy"] = rng.uniform(0, 10000, zs.size)
+    maxl = np.full(zs.size, 5000.0); maxl[0] = 1e9      # zone 0 sees every observation
+    c["maxlen"] = maxl
+    c["corr"] = np.full(zs.size, 2500.0)
+    e01 = (rng.uniform(size=c["m"]) > 0.2).astype(np.float64)  # excluded observations (assimilation.F90:3086-3092)
+    _configure(ob, handle, c, zs)
+    R = ob.DCDCovar(e01, ob.DiagCovar(c["var"]))
+    xa, Sa, _, st = handle.local_analysis(c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], R)
+    xo, So, _, mloc = _oracle_loc(c, zs, e01=e01)
+    assert mloc[0] == c["m"] and (mloc == 0).sum() > 5 and st["zones_skipped"] == (mloc == 0).sum()
+    assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL
+    start = np.concatenate([[0], np.cumsum(zs)])
+    for z in np.nonzero(mloc == 0)[0]:  # untouched zones are bit-identical to the forecast
+        assert (Sa[start[z]:start[z + 1]] == c["Sf"][start[z]:start[z + 1]]).all()
+        assert (xa[start[z]:start[z + 1]] == c["xf"][start[z]:start[z + 1]]).all()
+    # m = 0: nothing to do
+    handle.set_observations(obs_x=np.zeros(0), obs_y=np.zeros(0))
+    xa0, Sa0, _, st0 = handle.local_analysis(c["xf"], np.zeros(0), np.zeros(0), c["Sf"], np.zeros((0, 24)),
+                                             ob.DiagCovar(np.zeros(0)))
+    assert (xa0 == c["xf"]).all() and (Sa0 == c["Sf"]).all() and st0["zones_skipped"] == zs.size
+
+
+def test_in_place_chunked_and_device_resident_paths_agree(ob):
+    import torch
+    from oak_b200 import synthetic
+    c = synthetic.small_case(nx=40, ny=30, nz=6, N=64, m=2500, corr=2500.0, maxlen=5000.0, seed=11)
+    h = ob.Handle(0)
+    _configure(ob, h, c)
+    xa1, Sa1, _, st1 = h.local_analysis(c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], ob.DiagCovar(c["var"]))
+    # many small chunks / batches, in place
+    h.set_option("chunk_mb", 0.05)
+    h.set_option("zones_per_batch", 37)
+    S = c["Sf"].copy(order="F")
+    xa2, Sa2, _, st2 = h.local_analysis(c["xf"], c["Hxf"], c["yo"], S, c["HSf"], ob.DiagCovar(c["var"]), out_Sa=S)
+    assert Sa2 is S and (Sa2 == Sa1).all() and (xa2 == xa1).all()
+    assert st2["launches"] > st1["launches"] and st2["h2d_bytes"] == st1["h2d_bytes"]
+    # device-resident entry point on torch tensors (member-major = column-major n x N)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    Sf_d, HSf_d = t(c["Sf"].T), t(c["HSf"].T)
+    xa_d, Sa_d = torch.empty(c["Sf"].shape[0], dtype=torch.float64, device=dev), torch.empty_like(Sf_d)
+    st3 = h.local_analysis_dev(t(c["xf"]), t(c["Hxf"]), t(c["yo"]), Sf_d, HSf_d, t(c["var"]), xa_d, Sa_d)
+    torch.cuda.synchronize()
+    assert (Sa_d.cpu().numpy().T == Sa1).all() and (xa_d.cpu().numpy() == xa1).all()
+    assert st3["h2d_bytes"] == 0 and st3["launches"] >= 4
+    xo, So, _, _ = _oracle_loc(c)
+    assert rel(xa1, xo) < RTOL and rel(Sa1, So) < RTOL
+    h.close()
+
+
+def test_assim_ensemble_with_inflation_anamorphosis_and_saturation(ob, handle):
+    from oak_b200 import synthetic
+    g = synthetic.Grid(18, 14, 3)
+    N, m = 32, 150
+    rows = np.arange(g.n, dtype=np.int64)
+    E = np.exp(0.3 * synthetic.ensemble_rows(np, g, rows, N, 5)).T.copy(order="F")   # strictly positive
+    obs = synthetic.observations(np, g, m, 5)
+    Hi, Hj, Hs = synthetic.coo_operator(g, obs)
+    Hj[:3] = 0; Hs[:3] = 0.0      # out-of-grid rows (assimilation.F90:2597-2611)
+    Hshift = 0.01 * np.arange(m)
+    yo = 1.0 + 0.1 * synthetic.normal(np, np.arange(m, dtype=np.int64), 8, 5)
+    zx, zy = g.zone_xy(np, np.arange(g.nzones, dtype=np.int64))
+    zs = np.full(g.nzones, 3, np.int32)
+    sel = ob.Selector(zone_x=zx, zone_y=zy, corrLen=3000.0, maxLen=6000.0, obs_x=obs["ox"], obs_y=obs["oy"],
+                      metrictype=0)
+    maxc = np.full(g.n, 0.05)
+    Ea, xf, xa = ob.assim_ensemble(zs, sel, E, Hi, Hj, Hs, Hshift, yo, ob.DiagCovar(obs["var"]), anamtype=2,
+                                   inflation=1.05, maxCorrection=maxc, handle=handle)
+    oo = oracle.make_obs(m, obsx=obs["ox"], obsy=obs["oy"])
+    Eo, xfo, xao = oracle.assim_ensemble(zs, dict(x=zx, y=zy), 3000.0, 6000.0, oo, E, Hi, Hj, Hs, Hshift, yo,
+                                         obs["var"], anamtype=2, inflation=1.05, maxCorrection=maxc)
+    assert rel(xf, xfo) < 1e-14 and rel(xa, xao) < RTOL and rel(Ea, Eo) < RTOL
+    assert (np.abs(xa - xf) <= 0.05 * (1 + 1e-12)).all() and (np.abs(xao - xfo) > 0.049).any()
+
+
+def test_error_behaviour(ob):
+    h = ob.Handle(0)
+    with pytest.raises(ob.OakB200Error):      # analysis before configuration
+        h.local_analysis(np.zeros(2), np.zeros(1), np.zeros(1), np.zeros((2, 4)), np.zeros((1, 4)),
+                         ob.DiagCovar(np.ones(1)))
+    h.set_zones([2], zone_x=[0.0], zone_y=[0.0], corrLen=1.0, maxLen=10.0, metrictype=0)
+    h.set_observations(obs_x=[0.0], obs_y=[0.0])
+    with pytest.raises(ob.OakB200Error):      # n mismatch
+        h.local_analysis(np.zeros(3), np.zeros(1), np.zeros(1), np.zeros((3, 4)), np.zeros((1, 4)),
+                         ob.DiagCovar(np.ones(1)))
+    with pytest.raises(ob.OakB200Error):      # N too large
+        h.local_analysis(np.zeros(2), np.zeros(1), np.zeros(1), np.zeros((2, 200)), np.zeros((1, 200)),
+                         ob.DiagCovar(np.ones(1)))
+    with pytest.raises(ob.OakB200Error) as e:  # NaN in the amplitudes is fatal (rrsqrt.F90:145-149)
+        h.local_analysis(np.zeros(2), np.zeros(1), np.array([np.nan]), np.ones((2, 4)), np.ones((1, 4)),
+                         ob.DiagCovar(np.ones(1)))
+    assert e.value.code == -7
+    with pytest.raises(ob.OakB200Error):      # unsupported metric (assimilation.F90:3666-3669)
+        h.set_zones([2], zone_x=[0.0], zone_y=[0.0], corrLen=1.0, maxLen=10.0, metrictype=5)
+    h.close()
+
+
+def test_fp64_peak_microbenchmarks(ob):
+    h = ob.Handle(0)
+    dfma, dmma = h.fp64_peak(0), h.fp64_peak(1)
+    h.close()
+    assert 5.0 < dfma < 100.0 and 1.0 < dmma < 200.0
