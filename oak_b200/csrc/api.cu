@@ -80,7 +80,7 @@ struct oakb200_handle {
   // options
   int eig_kernel = 0;
   int zones_per_batch = 0;
-  double tol = 1e-7;
+  double tol = 2e-11;  // bound on the remaining non-orthogonality (eig_common.cuh: jacobi_converged)
   int max_sweeps = 30;
   int profile = 0;
   double chunk_mb = 256.;

@@ -23,3 +23,12 @@ __device__ __forceinline__ float jacobi_params(double a, double b, double g, dou
   double t;
   return jacobi_params(a, b, g, c, s, t);
 }
+
+// Stopping rule.  After a sweep whose rotated pairs had cosines <= mx and tangents |t| <= mt, the
+// remaining non-orthogonality is bounded by about mx * min(1, mt): for well separated singular values
+// t ~ cos / relative gap is tiny and the convergence is quadratic; inside clusters (rank-deficient G:
+// many sigma = 1) rotations have large angles, re-mix the cosines they touch and the convergence is
+// only linear, so the sweep maximum itself must fall below the tolerance.
+__device__ __forceinline__ bool jacobi_converged(float mx, float mt, float tol) {
+  return mx * fminf(1.f, mt) < tol;
+}

@@ -80,28 +80,37 @@ __device__ __forceinline__ void swap_cols(double (&x)[R], double (&y)[R]) {
   for (int i = 0; i < R; i++) { const double t = x[i]; x[i] = y[i]; y[i] = t; }
 }
 
-__device__ __forceinline__ float params_t(double a, double b, double g, double &c, double &s, double &tg) {
+__device__ __forceinline__ float params_t(double a, double b, double g, double &c, double &s, double &tg,
+                                          float &tabs) {
   double t;
   const float k = jacobi_params(a, b, g, c, s, t);
   tg = t * g;  // |x'|^2 = |x|^2 - t g ,  |y'|^2 = |y|^2 + t g
+  tabs = fabsf((float)t);
   return k;
 }
+
+struct SweepStat {  // maxima over the rotated pairs of a sweep (jacobi_converged)
+  float mx, mt;
+  __device__ __forceinline__ void add(bool rotated, float k, float t) {
+    if (rotated) { mx = fmaxf(mx, k); mt = fmaxf(mt, t); }
+  }
+};
 
 // Rotates the 4 cross pairs of blocks X={X0,X1}, Y={Y0,Y1} and swaps the blocks.
 // Inactive groups (nothing borrowed) keep X untouched; their Y is scratch.
 template <int R, int TL>
-__device__ __forceinline__ float rotate_block_pair(double (&X0)[R], double (&X1)[R], double (&Y0)[R],
-                                                   double (&Y1)[R], double &nX0, double &nX1,
-                                                   double &nY0, double &nY1, bool active) {
-  float mx = 0.f;
+__device__ __forceinline__ void rotate_block_pair(double (&X0)[R], double (&X1)[R], double (&Y0)[R],
+                                                  double (&Y1)[R], double &nX0, double &nX1,
+                                                  double &nY0, double &nY1, bool active, SweepStat &ss) {
   {  // sub-round 1: (X0,Y0) (X1,Y1)
     const double g1 = group_sum<TL>(dotR<R>(X0, Y0)), g2 = group_sum<TL>(dotR<R>(X1, Y1));
     double c1, s1, c2, s2, tg1, tg2;
-    const float k1 = params_t(nX0, nY0, g1, c1, s1, tg1), k2 = params_t(nX1, nY1, g2, c2, s2, tg2);
+    float ta1, ta2;
+    const float k1 = params_t(nX0, nY0, g1, c1, s1, tg1, ta1), k2 = params_t(nX1, nY1, g2, c2, s2, tg2, ta2);
     const bool r1 = active && (k1 > JACOBI_SKIP), r2 = active && (k2 > JACOBI_SKIP);
     if (!r1) { c1 = 1.; s1 = 0.; tg1 = 0.; }
     if (!r2) { c2 = 1.; s2 = 0.; tg2 = 0.; }
-    if (active) mx = fmaxf(mx, fmaxf(k1, k2));
+    ss.add(r1, k1, ta1); ss.add(r2, k2, ta2);
     if (__any_sync(FULL, r1 || r2)) {
       rot<R>(X0, Y0, c1, s1);
       rot<R>(X1, Y1, c2, s2);
@@ -111,12 +120,13 @@ __device__ __forceinline__ float rotate_block_pair(double (&X0)[R], double (&X1)
   {  // sub-round 2: (X0,Y1) (X1,Y0), swapped assignment
     const double g1 = group_sum<TL>(dotR<R>(X0, Y1)), g2 = group_sum<TL>(dotR<R>(X1, Y0));
     double c1, s1, c2, s2, tg1, tg2;
-    const float k1 = params_t(nX0, nY1, g1, c1, s1, tg1), k2 = params_t(nX1, nY0, g2, c2, s2, tg2);
+    float ta1, ta2;
+    const float k1 = params_t(nX0, nY1, g1, c1, s1, tg1, ta1), k2 = params_t(nX1, nY0, g2, c2, s2, tg2, ta2);
     const bool r1 = active && (k1 > JACOBI_SKIP), r2 = active && (k2 > JACOBI_SKIP);
     if (!r1) { c1 = 1.; s1 = 0.; tg1 = 0.; }
     if (!r2) { c2 = 1.; s2 = 0.; tg2 = 0.; }
     if (!active) { c1 = 0.; s1 = 1.; c2 = 0.; s2 = 1.; }  // x stays, scratch y is negated
-    if (active) mx = fmaxf(mx, fmaxf(k1, k2));
+    ss.add(r1, k1, ta1); ss.add(r2, k2, ta2);
     if (__any_sync(FULL, r1 || r2)) {
       rot_swap<R>(X0, Y1, c1, s1);
       rot_swap<R>(X1, Y0, c2, s2);
@@ -130,7 +140,6 @@ __device__ __forceinline__ float rotate_block_pair(double (&X0)[R], double (&X1)
       nX1 = nY0 + tg2; nY0 = a1 - tg2;
     }
   }
-  return mx;
 }
 
 template <int NP, int TL>
@@ -146,7 +155,7 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? 4 : 1))
   double *s_vec = sm + NP * LDW;     // 8 vectors of NP
   double *s_c = s_vec, *s_uv = s_vec + NP, *s_duw = s_vec + 2 * NP, *s_uw = s_vec + 3 * NP;
   double *s_g1 = s_vec + 4 * NP, *s_g2 = s_vec + 5 * NP, *s_v = s_vec + 6 * NP, *s_xn = s_vec + 7 * NP;
-  __shared__ int s_maxi;
+  __shared__ int s_maxi, s_maxt;
   __shared__ double s_red[NW];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -220,21 +229,22 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? 4 : 1))
 
   int sweeps = 0;
   for (int sweep = 0; sweep < max_sweeps; sweep++) {
-    if (tid == 0) s_maxi = 0;
+    if (tid == 0) { s_maxi = 0; s_maxt = 0; }
     // fresh norms
     nP0 = group_sum<TL>(dotR<R>(P0, P0));
     nP1 = group_sum<TL>(dotR<R>(P1, P1));
     nQ0 = group_sum<TL>(dotR<R>(Q0, Q0));
     nQ1 = group_sum<TL>(dotR<R>(Q1, Q1));
-    float mx = 0.f;
+    SweepStat ss{0.f, 0.f};
     {  // the two columns of each block against each other
       const double g1 = group_sum<TL>(dotR<R>(P0, P1)), g2 = group_sum<TL>(dotR<R>(Q0, Q1));
       double c1, s1, c2, s2, tg1, tg2;
-      const float k1 = params_t(nP0, nP1, g1, c1, s1, tg1), k2 = params_t(nQ0, nQ1, g2, c2, s2, tg2);
+      float ta1, ta2;
+      const float k1 = params_t(nP0, nP1, g1, c1, s1, tg1, ta1), k2 = params_t(nQ0, nQ1, g2, c2, s2, tg2, ta2);
       const bool r1 = k1 > JACOBI_SKIP, r2 = k2 > JACOBI_SKIP;
       if (!r1) { c1 = 1.; s1 = 0.; tg1 = 0.; }
       if (!r2) { c2 = 1.; s2 = 0.; tg2 = 0.; }
-      mx = fmaxf(k1, k2);
+      ss.add(r1, k1, ta1); ss.add(r2, k2, ta2);
       if (__any_sync(FULL, r1 || r2)) {
         rot<R>(P0, P1, c1, s1);
         rot<R>(Q0, Q1, c2, s2);
@@ -243,23 +253,24 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? 4 : 1))
     }
     for (int step = 0; step < NB; step += 2) {
       // even step: positions (2g, 2g+1)
-      mx = fmaxf(mx, rotate_block_pair<R, TL>(P0, P1, Q0, Q1, nP0, nP1, nQ0, nQ1, true));
+      rotate_block_pair<R, TL>(P0, P1, Q0, Q1, nP0, nP1, nQ0, nQ1, true, ss);
       // odd step: positions (2g+1, 2g+2)
       lend(g);
       __syncthreads();
       const bool act = g < NG - 1;
       if (act) take(g + 1);
-      mx = fmaxf(mx, rotate_block_pair<R, TL>(Q0, Q1, P0, P1, nQ0, nQ1, nP0, nP1, act));
+      rotate_block_pair<R, TL>(Q0, Q1, P0, P1, nQ0, nQ1, nP0, nP1, act, ss);
       if (act) lend(g + 1);
       __syncthreads();
       take(g);
     }
-    atomicMax(&s_maxi, __float_as_int(mx));
+    atomicMax(&s_maxi, __float_as_int(ss.mx));
+    atomicMax(&s_maxt, __float_as_int(ss.mt));
     __syncthreads();
-    const float mc = __int_as_float(s_maxi);
+    const float mc = __int_as_float(s_maxi), mt = __int_as_float(s_maxt);
     sweeps = sweep + 1;
     __syncthreads();
-    if (mc < tol) break;
+    if (jacobi_converged(mc, mt, tol)) break;
     if (sweep == max_sweeps - 1 && tid == 0) atomicAdd(&ctr->not_converged, 1);
   }
 

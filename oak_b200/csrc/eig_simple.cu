@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(128) k_eig_simple(int N, const int32_t *__rest
   double *s_vec = sm + NP * LD;   // 8 vectors of NP
   double *s_c = s_vec, *s_a = s_vec + NP, *s_b = s_vec + 2 * NP, *s_d = s_vec + 3 * NP;
   double *s_t1 = s_vec + 4 * NP, *s_t2 = s_vec + 5 * NP, *s_g1 = s_vec + 6 * NP, *s_g2 = s_vec + 7 * NP;
-  __shared__ int s_maxcos;
+  __shared__ int s_maxcos, s_maxt;
   __shared__ double s_red[4];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -70,9 +70,9 @@ __global__ void __launch_bounds__(128) k_eig_simple(int N, const int32_t *__rest
   // ---- one-sided Jacobi, round-robin ordering ----
   int sweeps = 0;
   for (int sweep = 0; sweep < max_sweeps; sweep++) {
-    if (tid == 0) s_maxcos = 0;
+    if (tid == 0) { s_maxcos = 0; s_maxt = 0; }
     __syncthreads();
-    float mymax = 0.f;
+    float mymax = 0.f, mymaxt = 0.f;
     for (int r = 0; r < NP - 1; r++) {
       for (int pi = warp; pi < NP / 2; pi += 4) {
         int p, qcol;
@@ -88,10 +88,11 @@ __global__ void __launch_bounds__(128) k_eig_simple(int N, const int32_t *__rest
           b += __shfl_xor_sync(0xffffffffu, b, o);
           g += __shfl_xor_sync(0xffffffffu, g, o);
         }
-        double cs, sn;
-        const float cosang = jacobi_params(a, b, g, cs, sn);
-        mymax = fmaxf(mymax, cosang);
+        double cs, sn, tt;
+        const float cosang = jacobi_params(a, b, g, cs, sn, tt);
         if (cosang > JACOBI_SKIP) {
+          mymax = fmaxf(mymax, cosang);
+          mymaxt = fmaxf(mymaxt, fabsf((float)tt));
           for (int i = lane; i < NP; i += 32) {
             const double x = W[i + LD * p], y = W[i + LD * qcol];
             W[i + LD * p] = cs * x - sn * y;
@@ -102,11 +103,12 @@ __global__ void __launch_bounds__(128) k_eig_simple(int N, const int32_t *__rest
       __syncthreads();
     }
     atomicMax(&s_maxcos, __float_as_int(mymax));
+    atomicMax(&s_maxt, __float_as_int(mymaxt));
     __syncthreads();
     sweeps = sweep + 1;
-    const float mc = __int_as_float(s_maxcos);
+    const float mc = __int_as_float(s_maxcos), mt = __int_as_float(s_maxt);
     __syncthreads();
-    if (mc < (float)tol) break;
+    if (jacobi_converged(mc, mt, (float)tol)) break;
     if (sweep == max_sweeps - 1 && tid == 0) atomicAdd(&ctr->not_converged, 1);
   }
 

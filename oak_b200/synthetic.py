@@ -82,7 +82,12 @@ class Grid:
 
 def ensemble_rows(xp, grid, rows, N, seed=20261017, members=None):
     """E[rows, members] = mu + 0.5 g, returned member-major: shape (len(members), len(rows))."""
-    mem = xp.arange(N) if members is None else members
+    if members is not None:
+        mem = members
+    elif xp is np:
+        mem = np.arange(N, dtype=np.int64)
+    else:
+        mem = xp.arange(N, dtype=rows.dtype, device=rows.device)
     mu = grid.mu_rows(xp, rows)
     idx = rows[None, :] * 4096 + (mem[:, None] if xp is np else mem[:, None].to(rows.dtype))
     return mu[None, :] + 0.5 * normal(xp, idx, 1, seed)
