@@ -54,24 +54,71 @@ __device__ __forceinline__ double group_sum(double v) {
   return v;
 }
 
-// x' = c x - s y ; y' = s x + c y
+// ---------------------------------------------------------------------------------------------
+// Scaled ("fast") rotations.  A column is stored as X with a deferred scale: true column = sg * X.
+// The rotation x' = c (x - t y), y' = c (y + t x) becomes, on the stored columns,
+//     X' = X - (t sg_y/sg_x) Y ,  Y' = Y + (t sg_x/sg_y) X ,  sg' = c sg
+// i.e. two FMAs per row pair instead of four multiply-adds; ig = 1/sg is carried along so that no
+// division is needed, nn = |true column|^2 is updated with the Jacobi identities
+// |x'|^2 = |x|^2 - t g, |y'|^2 = |y|^2 + t g.  Scales are folded back at the start of every sweep.
+// ---------------------------------------------------------------------------------------------
+struct Col {
+  double sg, ig, nn;
+};
+
+#define JACOBI_SKIP2 1e-26f  // (JACOBI_SKIP)^2, on cos^2
+
+struct Rot {
+  double t1, t2, c, ic, tg;
+  float k2, ta;
+  bool on;
+};
+
+// Parameters of the rotation of columns (p,q) from the reduced stored dot product Gam.
+// The angle only steers convergence, so t = tan(theta) is computed in fp32; c = (1+t^2)^-1/2 must make
+// the transformation orthogonal to fp64 accuracy: fp32 seed + two Newton steps in fp64.
+__device__ __forceinline__ Rot rot_params(const Col &p, const Col &q, double Gam, bool active) {
+  Rot r;
+  const double g = (p.sg * q.sg) * Gam;
+  const float gf = (float)g, af = (float)p.nn, bf = (float)q.nn;
+  r.k2 = (gf * gf) * __frcp_rn(af * bf);
+  r.on = active && (r.k2 > JACOBI_SKIP2);
+  const float df = (float)(q.nn - p.nn), g2f = gf + gf;
+  const float h2 = fmaf(df, df, g2f * g2f);
+  const float h = h2 * rsqrtf(h2);
+  const float tf = __fdividef(g2f, df + copysignf(h, df));
+  r.ta = fabsf(tf);
+  const double tt = r.on ? (double)tf : 0.;
+  const double y = fma(tt, tt, 1.);
+  const double hy = 0.5 * y;
+  double c = (double)rsqrtf((float)y);
+  c = c * fma(-hy, c * c, 1.5);
+  c = c * fma(-hy, c * c, 1.5);
+  r.c = c;
+  r.ic = y * c;
+  r.t1 = tt * (q.sg * p.ig);
+  r.t2 = tt * (p.sg * q.ig);
+  r.tg = tt * g;
+  return r;
+}
+
 template <int R>
-__device__ __forceinline__ void rot(double (&x)[R], double (&y)[R], double c, double s) {
+__device__ __forceinline__ void rot_apply(double (&x)[R], double (&y)[R], const Rot &r) {
 #pragma unroll
   for (int i = 0; i < R; i++) {
     const double xi = x[i], yi = y[i];
-    x[i] = fma(c, xi, -(s * yi));
-    y[i] = fma(s, xi, c * yi);
+    x[i] = fma(-r.t1, yi, xi);
+    y[i] = fma(r.t2, xi, yi);
   }
 }
 // same rotation, results stored swapped (x <- y', y <- x')
 template <int R>
-__device__ __forceinline__ void rot_swap(double (&x)[R], double (&y)[R], double c, double s) {
+__device__ __forceinline__ void rot_apply_swap(double (&x)[R], double (&y)[R], const Rot &r) {
 #pragma unroll
   for (int i = 0; i < R; i++) {
     const double xi = x[i], yi = y[i];
-    x[i] = fma(s, xi, c * yi);
-    y[i] = fma(c, xi, -(s * yi));
+    x[i] = fma(r.t2, xi, yi);
+    y[i] = fma(-r.t1, yi, xi);
   }
 }
 template <int R>
@@ -79,20 +126,20 @@ __device__ __forceinline__ void swap_cols(double (&x)[R], double (&y)[R]) {
 #pragma unroll
   for (int i = 0; i < R; i++) { const double t = x[i]; x[i] = y[i]; y[i] = t; }
 }
-
-__device__ __forceinline__ float params_t(double a, double b, double g, double &c, double &s, double &tg,
-                                          float &tabs) {
-  double t;
-  const float k = jacobi_params(a, b, g, c, s, t);
-  tg = t * g;  // |x'|^2 = |x|^2 - t g ,  |y'|^2 = |y|^2 + t g
-  tabs = fabsf((float)t);
-  return k;
+__device__ __forceinline__ void col_update(Col &p, Col &q, const Rot &r) {
+  p.sg *= r.c; p.ig *= r.ic; p.nn -= r.tg;
+  q.sg *= r.c; q.ig *= r.ic; q.nn += r.tg;
+}
+__device__ __forceinline__ void col_update_swap(Col &p, Col &q, const Rot &r) {
+  const Col np = {q.sg * r.c, q.ig * r.ic, q.nn + r.tg};
+  const Col nq = {p.sg * r.c, p.ig * r.ic, p.nn - r.tg};
+  p = np; q = nq;
 }
 
 struct SweepStat {  // maxima over the rotated pairs of a sweep (jacobi_converged)
-  float mx, mt;
-  __device__ __forceinline__ void add(bool rotated, float k, float t) {
-    if (rotated) { mx = fmaxf(mx, k); mt = fmaxf(mt, t); }
+  float mx2, mt;
+  __device__ __forceinline__ void add(const Rot &r) {
+    if (r.on) { mx2 = fmaxf(mx2, r.k2); mt = fmaxf(mt, r.ta); }
   }
 };
 
@@ -100,44 +147,35 @@ struct SweepStat {  // maxima over the rotated pairs of a sweep (jacobi_converge
 // Inactive groups (nothing borrowed) keep X untouched; their Y is scratch.
 template <int R, int TL>
 __device__ __forceinline__ void rotate_block_pair(double (&X0)[R], double (&X1)[R], double (&Y0)[R],
-                                                  double (&Y1)[R], double &nX0, double &nX1,
-                                                  double &nY0, double &nY1, bool active, SweepStat &ss) {
+                                                  double (&Y1)[R], Col &cX0, Col &cX1, Col &cY0, Col &cY1,
+                                                  bool active, SweepStat &ss) {
   {  // sub-round 1: (X0,Y0) (X1,Y1)
     const double g1 = group_sum<TL>(dotR<R>(X0, Y0)), g2 = group_sum<TL>(dotR<R>(X1, Y1));
-    double c1, s1, c2, s2, tg1, tg2;
-    float ta1, ta2;
-    const float k1 = params_t(nX0, nY0, g1, c1, s1, tg1, ta1), k2 = params_t(nX1, nY1, g2, c2, s2, tg2, ta2);
-    const bool r1 = active && (k1 > JACOBI_SKIP), r2 = active && (k2 > JACOBI_SKIP);
-    if (!r1) { c1 = 1.; s1 = 0.; tg1 = 0.; }
-    if (!r2) { c2 = 1.; s2 = 0.; tg2 = 0.; }
-    ss.add(r1, k1, ta1); ss.add(r2, k2, ta2);
-    if (__any_sync(FULL, r1 || r2)) {
-      rot<R>(X0, Y0, c1, s1);
-      rot<R>(X1, Y1, c2, s2);
+    const Rot r1 = rot_params(cX0, cY0, g1, active), r2 = rot_params(cX1, cY1, g2, active);
+    ss.add(r1); ss.add(r2);
+    if (__any_sync(FULL, r1.on || r2.on)) {
+      rot_apply<R>(X0, Y0, r1);
+      rot_apply<R>(X1, Y1, r2);
+      col_update(cX0, cY0, r1);
+      col_update(cX1, cY1, r2);
     }
-    nX0 -= tg1; nY0 += tg1; nX1 -= tg2; nY1 += tg2;
   }
   {  // sub-round 2: (X0,Y1) (X1,Y0), swapped assignment
     const double g1 = group_sum<TL>(dotR<R>(X0, Y1)), g2 = group_sum<TL>(dotR<R>(X1, Y0));
-    double c1, s1, c2, s2, tg1, tg2;
-    float ta1, ta2;
-    const float k1 = params_t(nX0, nY1, g1, c1, s1, tg1, ta1), k2 = params_t(nX1, nY0, g2, c2, s2, tg2, ta2);
-    const bool r1 = active && (k1 > JACOBI_SKIP), r2 = active && (k2 > JACOBI_SKIP);
-    if (!r1) { c1 = 1.; s1 = 0.; tg1 = 0.; }
-    if (!r2) { c2 = 1.; s2 = 0.; tg2 = 0.; }
-    if (!active) { c1 = 0.; s1 = 1.; c2 = 0.; s2 = 1.; }  // x stays, scratch y is negated
-    ss.add(r1, k1, ta1); ss.add(r2, k2, ta2);
-    if (__any_sync(FULL, r1 || r2)) {
-      rot_swap<R>(X0, Y1, c1, s1);
-      rot_swap<R>(X1, Y0, c2, s2);
+    const Rot r1 = rot_params(cX0, cY1, g1, active), r2 = rot_params(cX1, cY0, g2, active);
+    ss.add(r1); ss.add(r2);
+    if (__any_sync(FULL, r1.on || r2.on)) {
+      if (active) {
+        rot_apply_swap<R>(X0, Y1, r1);
+        rot_apply_swap<R>(X1, Y0, r2);
+        col_update_swap(cX0, cY1, r1);
+        col_update_swap(cX1, cY0, r2);
+      }
     } else if (active) {
       swap_cols<R>(X0, Y1);
       swap_cols<R>(X1, Y0);
-    }
-    if (active) {
-      const double a0 = nX0, a1 = nX1;
-      nX0 = nY1 + tg1; nY1 = a0 - tg1;
-      nX1 = nY0 + tg2; nY0 = a1 - tg2;
+      Col t = cX0; cX0 = cY1; cY1 = t;
+      t = cX1; cX1 = cY0; cY0 = t;
     }
   }
 }
@@ -150,45 +188,72 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? 4 : 1))
   using C = Cfg<NP, TL>;
   constexpr int R = C::R, NG = C::NG, NTH = C::NTH, NB = C::NB, LDW = C::LDW, LDX = C::LDX;
   constexpr int NW = NTH / 32;
+  constexpr int TG = NP / 8;  // Cholesky thread grid TG x TG, 8 x 8 elements per thread (cyclic)
+  static_assert(TG * TG == NTH, "Cholesky thread grid");
   extern __shared__ __align__(16) double sm[];
-  double *sW = sm;                   // NP x LDW : A / L, then exchange buffer, partial sums, Y
-  double *s_vec = sm + NP * LDW;     // 8 vectors of NP
+  double *sW = sm;                   // NP x LDW : L, then exchange buffer, partial sums, Y
+  double *s_vec = sm + NP * LDW;     // vectors of NP
   double *s_c = s_vec, *s_uv = s_vec + NP, *s_duw = s_vec + 2 * NP, *s_uw = s_vec + 3 * NP;
-  double *s_g1 = s_vec + 4 * NP, *s_g2 = s_vec + 5 * NP, *s_v = s_vec + 6 * NP, *s_xn = s_vec + 7 * NP;
+  double *s_g1 = s_vec + 4 * NP, *s_g2 = s_vec + 5 * NP, *s_v = s_vec + 6 * NP;
+  double *s_xs = s_vec + 7 * NP;     // [NP/2 columns][3] scalars travelling with lent blocks (3*NP/2 doubles)
   __shared__ int s_maxi, s_maxt;
   __shared__ double s_red[NW];
+  __shared__ double s_piv;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = tid / TL, r = tid % TL;
   const int zl = blockIdx.x;
   if (mloc[zl] == 0) return;
 
-  // ---- load A = I + G ----
+  // ---- Cholesky A = I + G = L L^T, register tiled: thread (ti,tk) owns A(ti+TG*a, tk+TG*b) ----
   {
+    const int ti = tid % TG, tk = tid / TG;
+    double A[8][8];
     const double *Gz = G + (int64_t)zl * NP * NP;
-    for (int idx = tid; idx < NP * NP; idx += NTH) {
-      const int i = idx % NP, j = idx / NP;
-      sW[i + LDW * j] = Gz[idx] + (i == j ? 1. : 0.);
-    }
+#pragma unroll
+    for (int b = 0; b < 8; b++)
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const int i = ti + TG * a, k = tk + TG * b;
+        A[a][b] = Gz[i + NP * k] + (i == k ? 1. : 0.);
+      }
     if (tid < NP) s_c[tid] = cin[(int64_t)zl * NP + tid];
-  }
-  __syncthreads();
-  // ---- Cholesky A = L L^T (thread i owns row i), upper triangle zeroed ----
-  for (int j = 0; j < NP; j++) {
-    const double d = sqrt(sW[j + LDW * j]);
-    __syncthreads();
-    if (tid == j) sW[j + LDW * j] = d;
-    if (tid > j && tid < NP) sW[tid + LDW * j] /= d;
-    __syncthreads();
-    if (tid > j && tid < NP) {
-      const double lij = sW[tid + LDW * j];
-      for (int k = j + 1; k <= tid; k++) sW[tid + LDW * k] = fma(-lij, sW[k + LDW * j], sW[tid + LDW * k]);
+    double *s_col = s_uv;  // column j of L below the diagonal, zeros above (free until the epilogue)
+#pragma unroll
+    for (int ja = 0; ja < 8; ja++) {
+      for (int jt = 0; jt < TG; jt++) {
+        const int j = jt + TG * ja;
+        if (ti == jt && tk == jt) s_piv = A[ja][ja];
+        __syncthreads();
+        if (tk == jt) {  // owners of column j
+          const double piv = s_piv;
+          const double rinv = rsqrt(piv);
+#pragma unroll
+          for (int a = 0; a < 8; a++) {
+            const int i = ti + TG * a;
+            const double l = A[a][ja] * rinv;
+            s_col[i] = (i > j) ? l : 0.;
+            A[a][ja] = (i > j) ? l : (i == j ? piv * rinv : 0.);
+          }
+        }
+        __syncthreads();
+        double lr[8], lc[8];
+#pragma unroll
+        for (int a = 0; a < 8; a++) { lr[a] = s_col[ti + TG * a]; lc[a] = s_col[tk + TG * a]; }
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+          for (int b = 0; b < 8; b++) A[a][b] = fma(-lr[a], lc[b], A[a][b]);
+      }
     }
     __syncthreads();
-  }
-  for (int idx = tid; idx < NP * NP; idx += NTH) {
-    const int i = idx % NP, j = idx / NP;
-    if (j > i) sW[i + LDW * j] = 0.;
+#pragma unroll
+    for (int b = 0; b < 8; b++)
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const int i = ti + TG * a, k = tk + TG * b;
+        sW[i + LDW * k] = (k <= i) ? A[a][b] : 0.;
+      }
   }
   __syncthreads();
 
@@ -213,66 +278,76 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? 4 : 1))
   ld_col(Q1, sW + LDW * (4 * g + 3));
   __syncthreads();  // sW is now free: exchange buffer
   double *xbuf = sW;
-  double nP0, nP1, nQ0, nQ1;
+  Col cP0, cP1, cQ0, cQ1;
 
   auto lend = [&](int region) {
     st_col(P0, xbuf + LDX * (2 * region));
     st_col(P1, xbuf + LDX * (2 * region + 1));
-    if (r == 0) { s_xn[2 * region] = nP0; s_xn[2 * region + 1] = nP1; }
+    if (r == 0) {
+      double *q = s_xs + 6 * region;
+      q[0] = cP0.sg; q[1] = cP0.ig; q[2] = cP0.nn;
+      q[3] = cP1.sg; q[4] = cP1.ig; q[5] = cP1.nn;
+    }
   };
   auto take = [&](int region) {
     ld_col(P0, xbuf + LDX * (2 * region));
     ld_col(P1, xbuf + LDX * (2 * region + 1));
-    nP0 = s_xn[2 * region];
-    nP1 = s_xn[2 * region + 1];
+    const double *q = s_xs + 6 * region;
+    cP0.sg = q[0]; cP0.ig = q[1]; cP0.nn = q[2];
+    cP1.sg = q[3]; cP1.ig = q[4]; cP1.nn = q[5];
+  };
+  // folds the deferred scale into the stored column and refreshes its norm
+  auto renorm = [&](double(&X)[R], Col &cx, bool first) {
+    if (!first) {
+#pragma unroll
+      for (int i = 0; i < R; i++) X[i] *= cx.sg;
+    }
+    cx.sg = 1.; cx.ig = 1.;
+    cx.nn = group_sum<TL>(dotR<R>(X, X));
   };
 
   int sweeps = 0;
   for (int sweep = 0; sweep < max_sweeps; sweep++) {
     if (tid == 0) { s_maxi = 0; s_maxt = 0; }
-    // fresh norms
-    nP0 = group_sum<TL>(dotR<R>(P0, P0));
-    nP1 = group_sum<TL>(dotR<R>(P1, P1));
-    nQ0 = group_sum<TL>(dotR<R>(Q0, Q0));
-    nQ1 = group_sum<TL>(dotR<R>(Q1, Q1));
+    renorm(P0, cP0, sweep == 0); renorm(P1, cP1, sweep == 0);
+    renorm(Q0, cQ0, sweep == 0); renorm(Q1, cQ1, sweep == 0);
     SweepStat ss{0.f, 0.f};
     {  // the two columns of each block against each other
       const double g1 = group_sum<TL>(dotR<R>(P0, P1)), g2 = group_sum<TL>(dotR<R>(Q0, Q1));
-      double c1, s1, c2, s2, tg1, tg2;
-      float ta1, ta2;
-      const float k1 = params_t(nP0, nP1, g1, c1, s1, tg1, ta1), k2 = params_t(nQ0, nQ1, g2, c2, s2, tg2, ta2);
-      const bool r1 = k1 > JACOBI_SKIP, r2 = k2 > JACOBI_SKIP;
-      if (!r1) { c1 = 1.; s1 = 0.; tg1 = 0.; }
-      if (!r2) { c2 = 1.; s2 = 0.; tg2 = 0.; }
-      ss.add(r1, k1, ta1); ss.add(r2, k2, ta2);
-      if (__any_sync(FULL, r1 || r2)) {
-        rot<R>(P0, P1, c1, s1);
-        rot<R>(Q0, Q1, c2, s2);
+      const Rot r1 = rot_params(cP0, cP1, g1, true), r2 = rot_params(cQ0, cQ1, g2, true);
+      ss.add(r1); ss.add(r2);
+      if (__any_sync(FULL, r1.on || r2.on)) {
+        rot_apply<R>(P0, P1, r1);
+        rot_apply<R>(Q0, Q1, r2);
+        col_update(cP0, cP1, r1);
+        col_update(cQ0, cQ1, r2);
       }
-      nP0 -= tg1; nP1 += tg1; nQ0 -= tg2; nQ1 += tg2;
     }
     for (int step = 0; step < NB; step += 2) {
       // even step: positions (2g, 2g+1)
-      rotate_block_pair<R, TL>(P0, P1, Q0, Q1, nP0, nP1, nQ0, nQ1, true, ss);
+      rotate_block_pair<R, TL>(P0, P1, Q0, Q1, cP0, cP1, cQ0, cQ1, true, ss);
       // odd step: positions (2g+1, 2g+2)
       lend(g);
       __syncthreads();
       const bool act = g < NG - 1;
       if (act) take(g + 1);
-      rotate_block_pair<R, TL>(Q0, Q1, P0, P1, nQ0, nQ1, nP0, nP1, act, ss);
+      rotate_block_pair<R, TL>(Q0, Q1, P0, P1, cQ0, cQ1, cP0, cP1, act, ss);
       if (act) lend(g + 1);
       __syncthreads();
       take(g);
     }
-    atomicMax(&s_maxi, __float_as_int(ss.mx));
+    atomicMax(&s_maxi, __float_as_int(ss.mx2));
     atomicMax(&s_maxt, __float_as_int(ss.mt));
     __syncthreads();
-    const float mc = __int_as_float(s_maxi), mt = __int_as_float(s_maxt);
+    const float mc = sqrtf(__int_as_float(s_maxi)), mt = __int_as_float(s_maxt);
     sweeps = sweep + 1;
     __syncthreads();
     if (jacobi_converged(mc, mt, tol)) break;
     if (sweep == max_sweeps - 1 && tid == 0) atomicAdd(&ctr->not_converged, 1);
   }
+  // fold the scales: from here on the stored columns are the true z_j
+#pragma unroll
+  for (int i = 0; i < R; i++) { P0[i] *= cP0.sg; P1[i] *= cP1.sg; Q0[i] *= cQ0.sg; Q1[i] *= cQ1.sg; }
 
   // ---- epilogue: matrix functions from the orthogonal columns z_j = sigma_j u_j ----
   // lane-local views of the vectors c and 1_{i<N}
@@ -460,7 +535,7 @@ template <int NP, int TL>
 int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G, const double *c, double *T,
            double *ampl, double tol, int max_sweeps, DevCounters *ctr) {
   using C = Cfg<NP, TL>;
-  const size_t smem = sizeof(double) * (NP * C::LDW + 8 * NP);
+  const size_t smem = sizeof(double) * (NP * C::LDW + 9 * NP);
   static bool attr_done = false;
   if (!attr_done) {
     CUDA_TRY(cudaFuncSetAttribute(k_eig_fast<NP, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
