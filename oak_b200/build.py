@@ -19,6 +19,9 @@ LIB = os.path.join(HERE, "liboak_b200.so")
 SOURCES = ["api.cu", "obsgrid.cu", "gram.cu", "eig_simple.cu", "eig_fast.cu", "apply.cu", "ensemble.cu",
            "microbench.cu"]
 HEADERS = ["common.cuh", "eig_common.cuh", "../../include/oak_b200.h", "../../include/oak_b200_math.h"]
+# fp32 is only used for rotation angles / convergence tests in eig_fast.cu: flush denormals and use the
+# approximate fp32 division / sqrt there (fp64 arithmetic is unaffected by these switches)
+EXTRA_FLAGS = {"eig_fast.cu": ["-ftz=true", "-prec-div=false", "-prec-sqrt=false"]}
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v"]
 
@@ -35,7 +38,7 @@ def _stamp():
     for f in SOURCES + HEADERS:
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update((" ".join(NVCC_FLAGS) + repr(sorted(EXTRA_FLAGS.items()))).encode())
     return h.hexdigest()
 
 
@@ -49,7 +52,7 @@ def build(force=False, verbose=False):
 
     def one(src):
         obj = os.path.join(BUILD, src.replace(".cu", ".o"))
-        cmd = [cc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [cc] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         p = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(BUILD, src.replace(".cu", ".ptxas.log"))
         with open(log, "w") as fh:

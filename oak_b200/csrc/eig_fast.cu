@@ -7,12 +7,15 @@
 // R = NP/TL = 16 rows of each of its 4 columns (64 doubles).  Row pairs are interleaved across the
 // lanes of a group so that the 16-byte shared-memory transfers of neighbouring lanes are contiguous.
 //
-// Ordering: odd-even transposition on the NB = NP/2 block positions.  Even step: a group rotates
-// its own (P,Q).  Odd step: pairs (2g+1, 2g+2): the group lends P through shared memory to its left
-// neighbour, borrows the right neighbour's P, rotates (Q, borrowed) and returns it.  After every
-// block rotation the two blocks swap positions (written as a swapped assignment of the rotation
-// results, no register moves), which is what makes every pair of blocks meet exactly once in NB
-// steps.  Inside a block pair the 4 cross column pairs are rotated in two sub-rounds of two
+// Ordering: odd-even transposition on the NB = NP/2 block positions; after every block rotation the
+// two blocks swap positions, which is what makes every pair of blocks meet exactly once in NB steps.
+// The swap is never a register move: it is realised by WHICH register block travels.  Even step: a
+// group rotates its own (P,Q) in place; logically position 2g is now in Q, 2g+1 in P.  Odd step, pairs
+// (2g+1, 2g+2): the group lends Q (position 2g) through shared memory to its left neighbour, borrows
+// the right neighbour's Q (position 2g+2) into its Q registers, rotates (P,Q) in place, returns its P
+// registers (the new position 2g+2) and recovers the new position 2g into P.  After the pair of steps
+// P = position 2g and Q = 2g+1 again, so the loop body is register-invariant (no moves, no swapped
+// assignments).  Inside a block pair the 4 cross column pairs are rotated in two sub-rounds of two
 // independent rotations; the two columns of a block are rotated against each other once per sweep.
 // Dot products are reduced over the TL lanes of a group with warp shuffles.
 #include "common.cuh"
@@ -55,12 +58,16 @@ __device__ __forceinline__ double group_sum(double v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Scaled ("fast") rotations.  A column is stored as X with a deferred scale: true column = sg * X.
-// The rotation x' = c (x - t y), y' = c (y + t x) becomes, on the stored columns,
-//     X' = X - (t sg_y/sg_x) Y ,  Y' = Y + (t sg_x/sg_y) X ,  sg' = c sg
-// i.e. two FMAs per row pair instead of four multiply-adds; ig = 1/sg is carried along so that no
-// division is needed, nn = |true column|^2 is updated with the Jacobi identities
-// |x'|^2 = |x|^2 - t g, |y'|^2 = |y|^2 + t g.  Scales are folded back at the start of every sweep.
+// Scaled ("fast") rotations, in place.  A column is stored as X with a deferred scale: true column =
+// sg * X.  The rotation x' = c (x - t y), y' = c (y + t x) is applied to the stored columns as two
+// sequential shears that need no temporaries:
+//     X <- X - t1 Y            t1 = t sg_y / sg_x                  sg_x <- c sg_x
+//     Y <- Y + t2 X(new)       t2 = t c^2 sg_x / sg_y              sg_y <- sg_y / c
+// (y + t x = (1+t^2) (y + t c^2 x'), the factor 1+t^2 = 1/c^2 goes into the scale).  Two FMAs per
+// row pair instead of four multiply-adds, and every result overwrites its own operand, so the loop
+// body keeps every column in the same registers.  ig = 1/sg is carried along so that no division is
+// needed; nn = |true column|^2 follows the Jacobi identities |x'|^2 = |x|^2 - t g, |y'|^2 = |y|^2 + t g.
+// Scales are folded back into the columns at the start of every sweep.
 // ---------------------------------------------------------------------------------------------
 struct Col {
   double sg, ig, nn;
@@ -81,7 +88,7 @@ __device__ __forceinline__ Rot rot_params(const Col &p, const Col &q, double Gam
   Rot r;
   const double g = (p.sg * q.sg) * Gam;
   const float gf = (float)g, af = (float)p.nn, bf = (float)q.nn;
-  r.k2 = (gf * gf) * __frcp_rn(af * bf);
+  r.k2 = __fdividef(gf * gf, af * bf);
   r.on = active && (r.k2 > JACOBI_SKIP2);
   const float df = (float)(q.nn - p.nn), g2f = gf + gf;
   const float h2 = fmaf(df, df, g2f * g2f);
@@ -97,43 +104,22 @@ __device__ __forceinline__ Rot rot_params(const Col &p, const Col &q, double Gam
   r.c = c;
   r.ic = y * c;
   r.t1 = tt * (q.sg * p.ig);
-  r.t2 = tt * (p.sg * q.ig);
+  r.t2 = (tt * (c * c)) * (p.sg * q.ig);
   r.tg = tt * g;
   return r;
 }
 
 template <int R>
 __device__ __forceinline__ void rot_apply(double (&x)[R], double (&y)[R], const Rot &r) {
+  const double m1 = -r.t1;
 #pragma unroll
-  for (int i = 0; i < R; i++) {
-    const double xi = x[i], yi = y[i];
-    x[i] = fma(-r.t1, yi, xi);
-    y[i] = fma(r.t2, xi, yi);
-  }
-}
-// same rotation, results stored swapped (x <- y', y <- x')
-template <int R>
-__device__ __forceinline__ void rot_apply_swap(double (&x)[R], double (&y)[R], const Rot &r) {
+  for (int i = 0; i < R; i++) x[i] = fma(m1, y[i], x[i]);
 #pragma unroll
-  for (int i = 0; i < R; i++) {
-    const double xi = x[i], yi = y[i];
-    x[i] = fma(r.t2, xi, yi);
-    y[i] = fma(-r.t1, yi, xi);
-  }
-}
-template <int R>
-__device__ __forceinline__ void swap_cols(double (&x)[R], double (&y)[R]) {
-#pragma unroll
-  for (int i = 0; i < R; i++) { const double t = x[i]; x[i] = y[i]; y[i] = t; }
+  for (int i = 0; i < R; i++) y[i] = fma(r.t2, x[i], y[i]);
 }
 __device__ __forceinline__ void col_update(Col &p, Col &q, const Rot &r) {
   p.sg *= r.c; p.ig *= r.ic; p.nn -= r.tg;
-  q.sg *= r.c; q.ig *= r.ic; q.nn += r.tg;
-}
-__device__ __forceinline__ void col_update_swap(Col &p, Col &q, const Rot &r) {
-  const Col np = {q.sg * r.c, q.ig * r.ic, q.nn + r.tg};
-  const Col nq = {p.sg * r.c, p.ig * r.ic, p.nn - r.tg};
-  p = np; q = nq;
+  q.sg *= r.ic; q.ig *= r.c; q.nn += r.tg;
 }
 
 struct SweepStat {  // maxima over the rotated pairs of a sweep (jacobi_converged)
@@ -143,8 +129,7 @@ struct SweepStat {  // maxima over the rotated pairs of a sweep (jacobi_converge
   }
 };
 
-// Rotates the 4 cross pairs of blocks X={X0,X1}, Y={Y0,Y1} and swaps the blocks.
-// Inactive groups (nothing borrowed) keep X untouched; their Y is scratch.
+// Rotates the 4 cross pairs of blocks X={X0,X1}, Y={Y0,Y1} in place.
 template <int R, int TL>
 __device__ __forceinline__ void rotate_block_pair(double (&X0)[R], double (&X1)[R], double (&Y0)[R],
                                                   double (&Y1)[R], Col &cX0, Col &cX1, Col &cY0, Col &cY1,
@@ -160,22 +145,15 @@ __device__ __forceinline__ void rotate_block_pair(double (&X0)[R], double (&X1)[
       col_update(cX1, cY1, r2);
     }
   }
-  {  // sub-round 2: (X0,Y1) (X1,Y0), swapped assignment
+  {  // sub-round 2: (X0,Y1) (X1,Y0)
     const double g1 = group_sum<TL>(dotR<R>(X0, Y1)), g2 = group_sum<TL>(dotR<R>(X1, Y0));
     const Rot r1 = rot_params(cX0, cY1, g1, active), r2 = rot_params(cX1, cY0, g2, active);
     ss.add(r1); ss.add(r2);
     if (__any_sync(FULL, r1.on || r2.on)) {
-      if (active) {
-        rot_apply_swap<R>(X0, Y1, r1);
-        rot_apply_swap<R>(X1, Y0, r2);
-        col_update_swap(cX0, cY1, r1);
-        col_update_swap(cX1, cY0, r2);
-      }
-    } else if (active) {
-      swap_cols<R>(X0, Y1);
-      swap_cols<R>(X1, Y0);
-      Col t = cX0; cX0 = cY1; cY1 = t;
-      t = cX1; cX1 = cY0; cY0 = t;
+      rot_apply<R>(X0, Y1, r1);
+      rot_apply<R>(X1, Y0, r2);
+      col_update(cX0, cY1, r1);
+      col_update(cX1, cY0, r2);
     }
   }
 }
@@ -195,7 +173,7 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? 4 : 1))
   double *s_vec = sm + NP * LDW;     // vectors of NP
   double *s_c = s_vec, *s_uv = s_vec + NP, *s_duw = s_vec + 2 * NP, *s_uw = s_vec + 3 * NP;
   double *s_g1 = s_vec + 4 * NP, *s_g2 = s_vec + 5 * NP, *s_v = s_vec + 6 * NP;
-  double *s_xs = s_vec + 7 * NP;     // [NP/2 columns][3] scalars travelling with lent blocks (3*NP/2 doubles)
+  double *s_xs = s_vec + 7 * NP;     // 6 scalars per lent block, NG+1 regions (< 2*NP doubles)
   __shared__ int s_maxi, s_maxt;
   __shared__ double s_red[NW];
   __shared__ double s_piv;
@@ -280,21 +258,21 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? 4 : 1))
   double *xbuf = sW;
   Col cP0, cP1, cQ0, cQ1;
 
-  auto lend = [&](int region) {
-    st_col(P0, xbuf + LDX * (2 * region));
-    st_col(P1, xbuf + LDX * (2 * region + 1));
+  auto lend = [&](int region, const double(&B0)[R], const double(&B1)[R], const Col &c0, const Col &c1) {
+    st_col(B0, xbuf + LDX * (2 * region));
+    st_col(B1, xbuf + LDX * (2 * region + 1));
     if (r == 0) {
       double *q = s_xs + 6 * region;
-      q[0] = cP0.sg; q[1] = cP0.ig; q[2] = cP0.nn;
-      q[3] = cP1.sg; q[4] = cP1.ig; q[5] = cP1.nn;
+      q[0] = c0.sg; q[1] = c0.ig; q[2] = c0.nn;
+      q[3] = c1.sg; q[4] = c1.ig; q[5] = c1.nn;
     }
   };
-  auto take = [&](int region) {
-    ld_col(P0, xbuf + LDX * (2 * region));
-    ld_col(P1, xbuf + LDX * (2 * region + 1));
+  auto take = [&](int region, double(&B0)[R], double(&B1)[R], Col &c0, Col &c1) {
+    ld_col(B0, xbuf + LDX * (2 * region));
+    ld_col(B1, xbuf + LDX * (2 * region + 1));
     const double *q = s_xs + 6 * region;
-    cP0.sg = q[0]; cP0.ig = q[1]; cP0.nn = q[2];
-    cP1.sg = q[3]; cP1.ig = q[4]; cP1.nn = q[5];
+    c0.sg = q[0]; c0.ig = q[1]; c0.nn = q[2];
+    c1.sg = q[3]; c1.ig = q[4]; c1.nn = q[5];
   };
   // folds the deferred scale into the stored column and refreshes its norm
   auto renorm = [&](double(&X)[R], Col &cx, bool first) {
@@ -324,17 +302,21 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? 4 : 1))
       }
     }
     for (int step = 0; step < NB; step += 2) {
-      // even step: positions (2g, 2g+1)
+      // even step: positions (2g, 2g+1); afterwards position 2g lives in Q, 2g+1 in P
       rotate_block_pair<R, TL>(P0, P1, Q0, Q1, cP0, cP1, cQ0, cQ1, true, ss);
       // odd step: positions (2g+1, 2g+2)
-      lend(g);
-      __syncthreads();
       const bool act = g < NG - 1;
-      if (act) take(g + 1);
-      rotate_block_pair<R, TL>(Q0, Q1, P0, P1, cQ0, cQ1, cP0, cP1, act, ss);
-      if (act) lend(g + 1);
+      lend(g, Q0, Q1, cQ0, cQ1);
+      if (!act) lend(NG, P0, P1, cP0, cP1);  // the last group parks its idle block (position NB-1)
       __syncthreads();
-      take(g);
+      if (act) {
+        take(g + 1, Q0, Q1, cQ0, cQ1);
+      }
+      rotate_block_pair<R, TL>(P0, P1, Q0, Q1, cP0, cP1, cQ0, cQ1, act, ss);
+      if (act) lend(g + 1, P0, P1, cP0, cP1);  // the new position 2g+2 goes home
+      __syncthreads();
+      take(g, P0, P1, cP0, cP1);               // the new position 2g
+      if (!act) take(NG, Q0, Q1, cQ0, cQ1);
     }
     atomicMax(&s_maxi, __float_as_int(ss.mx2));
     atomicMax(&s_maxt, __float_as_int(ss.mt));
@@ -536,6 +518,7 @@ int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G,
            double *ampl, double tol, int max_sweeps, DevCounters *ctr) {
   using C = Cfg<NP, TL>;
   const size_t smem = sizeof(double) * (NP * C::LDW + 9 * NP);
+  static_assert((C::NG + 1) * 2 * C::LDX <= NP * C::LDW && 6 * (C::NG + 1) <= 2 * NP, "exchange buffer fits");
   static bool attr_done = false;
   if (!attr_done) {
     CUDA_TRY(cudaFuncSetAttribute(k_eig_fast<NP, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
