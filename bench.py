@@ -226,6 +226,8 @@ def main():
     plan, g = d["plan"], d["grid"]
     n_loc = plan.r1 - plan.r0
     h = oak_b200.Handle(local, eig_kernel=a.eig_kernel)
+    if os.environ.get("OAK_B200_FIXED_SWEEPS"):  # kernel timing experiments only (tools/ab.py)
+        h.set_option("fixed_sweeps", float(os.environ["OAK_B200_FIXED_SWEEPS"]))
     h.set_zones(plan.zoneSize, zone_x=plan.zx, zone_y=plan.zy, corrLen=plan.corrLen, maxLen=plan.maxLen,
                 loctype=1, metrictype=0, weightfun=0)
     h.set_observations(obs_x=d["ox"], obs_y=d["oy"])

@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboak_b200.so")
+# OAK_B200_LIB selects another build of the same library (A/B kernel experiments); default in-tree
+LIB_PATH = os.environ.get("OAK_B200_LIB") or os.path.join(_HERE, "liboak_b200.so")
 _LIB = None
 
 c_dp = C.POINTER(C.c_double)

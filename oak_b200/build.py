@@ -42,6 +42,25 @@ def _stamp():
     return h.hexdigest()
 
 
+def build_variant(out, defines):
+    """A/B experiments: the same sources with -D switches into another .so (not the product build)."""
+    cc = nvcc()
+    vdir = os.path.join(BUILD, "variant_" + os.path.basename(out))
+    os.makedirs(vdir, exist_ok=True)
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(vdir, src.replace(".cu", ".o"))
+        cmd = [cc] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        if p.returncode != 0:
+            raise RuntimeError(p.stderr)
+        if src == "eig_fast.cu":
+            print("\n".join(l for l in p.stderr.splitlines() if "spill" in l or "registers" in l))
+        objs.append(obj)
+    subprocess.check_call([cc, "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return out
+
+
 def build(force=False, verbose=False):
     os.makedirs(BUILD, exist_ok=True)
     stamp_file = os.path.join(BUILD, "stamp")

@@ -302,6 +302,7 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   else if (k == "zones_per_batch") h->zones_per_batch = (int)value;
   else if (k == "jacobi_tol") h->tol = value;
   else if (k == "max_sweeps") h->max_sweeps = (int)value;
+  else if (k == "fixed_sweeps") { h->max_sweeps = (int)value; h->tol = -1.; }  // timing experiments: no convergence test
   else if (k == "profile") h->profile = (int)value;
   else if (k == "chunk_mb") h->chunk_mb = value;
   else if (k == "pad_to") h->pad_to = (int)value;

@@ -21,6 +21,10 @@
 #include "common.cuh"
 #include "eig_common.cuh"
 
+#ifndef EIG_CTAS_PER_SM
+#define EIG_CTAS_PER_SM 4
+#endif
+
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -31,7 +35,7 @@ struct Cfg {
   static constexpr int NG = NP / 4;
   static constexpr int NTH = NG * TL;
   static constexpr int NB = NP / 2;
-  static constexpr int LDW = NP + 2;  // W / Y leading dimension in shared memory
+  static constexpr int LDW = NP;      // W / Y leading dimension in shared memory
   static constexpr int LDX = NP + 4;  // exchange-buffer column stride
   static_assert(R == 16, "16 rows per lane");
   static_assert(NTH % 32 == 0, "whole warps");
@@ -159,7 +163,7 @@ __device__ __forceinline__ void rotate_block_pair(double (&X0)[R], double (&X1)[
 }
 
 template <int NP, int TL>
-__global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? 4 : 1))
+__global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? EIG_CTAS_PER_SM : 1))
     k_eig_fast(int N, const int32_t *__restrict__ mloc, const double *__restrict__ G,
                const double *__restrict__ cin, double *__restrict__ Tout, double *__restrict__ ampl_out,
                float tol, int max_sweeps, DevCounters *ctr) {
@@ -215,13 +219,15 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? 4 : 1))
           }
         }
         __syncthreads();
-        double lr[8], lc[8];
+        double lc[8];
 #pragma unroll
-        for (int a = 0; a < 8; a++) { lr[a] = s_col[ti + TG * a]; lc[a] = s_col[tk + TG * a]; }
+        for (int b = 0; b < 8; b++) lc[b] = s_col[tk + TG * b];
 #pragma unroll
-        for (int a = 0; a < 8; a++)
+        for (int a = 0; a < 8; a++) {
+          const double la = -s_col[ti + TG * a];
 #pragma unroll
-          for (int b = 0; b < 8; b++) A[a][b] = fma(-lr[a], lc[b], A[a][b]);
+          for (int b = 0; b < 8; b++) A[a][b] = fma(la, lc[b], A[a][b]);
+        }
       }
     }
     __syncthreads();
@@ -309,9 +315,7 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? 4 : 1))
       lend(g, Q0, Q1, cQ0, cQ1);
       if (!act) lend(NG, P0, P1, cP0, cP1);  // the last group parks its idle block (position NB-1)
       __syncthreads();
-      if (act) {
-        take(g + 1, Q0, Q1, cQ0, cQ1);
-      }
+      if (act) take(g + 1, Q0, Q1, cQ0, cQ1);
       rotate_block_pair<R, TL>(P0, P1, Q0, Q1, cP0, cP1, cQ0, cQ1, act, ss);
       if (act) lend(g + 1, P0, P1, cP0, cP1);  // the new position 2g+2 goes home
       __syncthreads();
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? 4 : 1))
     sweeps = sweep + 1;
     __syncthreads();
     if (jacobi_converged(mc, mt, tol)) break;
-    if (sweep == max_sweeps - 1 && tid == 0) atomicAdd(&ctr->not_converged, 1);
+    if (sweep == max_sweeps - 1 && tid == 0 && tol >= 0) atomicAdd(&ctr->not_converged, 1);
   }
   // fold the scales: from here on the stored columns are the true z_j
 #pragma unroll
@@ -471,42 +475,48 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? 4 : 1))
   {
     constexpr int TPR = NP / 8;  // tiles per row
     const int ti = tid / TPR, tj = tid % TPR;
-    double acc[8][8];
-#pragma unroll
-    for (int a = 0; a < 8; a++)
-#pragma unroll
-      for (int b = 0; b < 8; b++) acc[a][b] = 0.;
-#pragma unroll 2
-    for (int j = 0; j < NP; j++) {
-      const double *col = Ys + LDW * j;
-      double rv[8], cv[8];
-#pragma unroll
-      for (int a = 0; a < 4; a++) {
-        const double2 v = *reinterpret_cast<const double2 *>(col + 8 * ti + 2 * a);
-        rv[2 * a] = v.x; rv[2 * a + 1] = v.y;
-        const double2 u = *reinterpret_cast<const double2 *>(col + 2 * tj + (NP / 4) * a);
-        cv[2 * a] = u.x; cv[2 * a + 1] = u.y;
-      }
+    double *Tz = Tout + (int64_t)zl * NP * NP;
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {  // two 8 x 4 register tiles: columns 2tj + (NP/4)(2 half + b)
+      double acc[8][4];
 #pragma unroll
       for (int a = 0; a < 8; a++)
 #pragma unroll
-        for (int b = 0; b < 8; b++) acc[a][b] = fma(rv[a], cv[b], acc[a][b]);
-    }
-    double *Tz = Tout + (int64_t)zl * NP * NP;
+        for (int b = 0; b < 4; b++) acc[a][b] = 0.;
+#pragma unroll 2
+      for (int j = 0; j < NP; j++) {
+        const double *col = Ys + LDW * j;
+        double rv[8], cv[4];
 #pragma unroll
-    for (int a = 0; a < 8; a++) {
-      const int i = 8 * ti + a;
-      const double g1i = s_g1[i] * hv, g2i = s_g2[i] * hw;
+        for (int a = 0; a < 4; a++) {
+          const double2 v = *reinterpret_cast<const double2 *>(col + 8 * ti + 2 * a);
+          rv[2 * a] = v.x; rv[2 * a + 1] = v.y;
+        }
 #pragma unroll
-      for (int b = 0; b < 4; b++) {
-        const int k = 2 * tj + (NP / 4) * b;
-        double t0 = acc[a][2 * b] - g1i * s_uv[k];
-        double t1 = acc[a][2 * b + 1] - g1i * s_uv[k + 1];
-        if (k == N - 1) t0 *= dNN;
-        if (k + 1 == N - 1) t1 *= dNN;
-        t0 -= g2i * s_uw[k];
-        t1 -= g2i * s_uw[k + 1];
-        *reinterpret_cast<double2 *>(Tz + (int64_t)i * NP + k) = make_double2(t0, t1);
+        for (int b = 0; b < 2; b++) {
+          const double2 u = *reinterpret_cast<const double2 *>(col + 2 * tj + (NP / 4) * (2 * half + b));
+          cv[2 * b] = u.x; cv[2 * b + 1] = u.y;
+        }
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+          for (int b = 0; b < 4; b++) acc[a][b] = fma(rv[a], cv[b], acc[a][b]);
+      }
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const int i = 8 * ti + a;
+        const double g1i = s_g1[i] * hv, g2i = s_g2[i] * hw;
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+          const int k = 2 * tj + (NP / 4) * (2 * half + b);
+          double t0 = acc[a][2 * b] - g1i * s_uv[k];
+          double t1 = acc[a][2 * b + 1] - g1i * s_uv[k + 1];
+          if (k == N - 1) t0 *= dNN;
+          if (k + 1 == N - 1) t1 *= dNN;
+          t0 -= g2i * s_uw[k];
+          t1 -= g2i * s_uw[k + 1];
+          *reinterpret_cast<double2 *>(Tz + (int64_t)i * NP + k) = make_double2(t0, t1);
+        }
       }
     }
   }

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128) k_eig_simple(int N, const int32_t *__rest
     const float mc = __int_as_float(s_maxcos), mt = __int_as_float(s_maxt);
     __syncthreads();
     if (jacobi_converged(mc, mt, (float)tol)) break;
-    if (sweep == max_sweeps - 1 && tid == 0) atomicAdd(&ctr->not_converged, 1);
+    if (sweep == max_sweeps - 1 && tid == 0 && tol >= 0) atomicAdd(&ctr->not_converged, 1);
   }
 
   // ---- column statistics: s2, z.c, z.1 ----
