@@ -8,7 +8,7 @@ Multi-GPU: strong scaling — the 1e6 columns are split in contiguous zone range
 each rank analyses its slab with its observation halo, one NCCL all-gather reassembles the analysed
 anomalies; `value` = all columns / max-over-ranks time.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nx .. --ny .. --nz .. --N .. --m ..]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nx .. --ny .. --nz .. --N .. --nobs ..]
 """
 import argparse
 import json
@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--ny", type=int, default=1000)
     ap.add_argument("--nz", type=int, default=30)
     ap.add_argument("--N", type=int, default=64)
-    ap.add_argument("--m", type=int, default=1000000)
+    ap.add_argument("--nobs", dest="m", type=int, default=1000000)
     ap.add_argument("--corr", type=float, default=4000.0)
     ap.add_argument("--maxlen", type=float, default=8000.0)
     ap.add_argument("--no-e2e", action="store_true")

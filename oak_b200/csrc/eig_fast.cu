@@ -37,7 +37,7 @@ struct Cfg {
   static constexpr int NB = NP / 2;
   static constexpr int LDW = NP;      // W / Y leading dimension in shared memory
   static constexpr int LDX = NP + 4;  // exchange-buffer column stride
-  static_assert(R == 16, "16 rows per lane");
+  static_assert(R == 16 || R == 8, "8 or 16 rows per lane");
   static_assert(NTH % 32 == 0, "whole warps");
 };
 
@@ -163,7 +163,7 @@ __device__ __forceinline__ void rotate_block_pair(double (&X0)[R], double (&X1)[
 }
 
 template <int NP, int TL>
-__global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? EIG_CTAS_PER_SM : 1))
+__global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? (TL == 4 ? EIG_CTAS_PER_SM : 4) : 1))
     k_eig_fast(int N, const int32_t *__restrict__ mloc, const double *__restrict__ G,
                const double *__restrict__ cin, double *__restrict__ Tout, double *__restrict__ ampl_out,
                float tol, int max_sweeps, DevCounters *ctr) {
@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? EIG_CTAS_PER_SM 
   constexpr int R = C::R, NG = C::NG, NTH = C::NTH, NB = C::NB, LDW = C::LDW, LDX = C::LDX;
   constexpr int NW = NTH / 32;
   constexpr int TG = NP / 8;  // Cholesky thread grid TG x TG, 8 x 8 elements per thread (cyclic)
-  static_assert(TG * TG == NTH, "Cholesky thread grid");
+  static_assert(TG * TG <= NTH, "Cholesky thread grid");
+  const bool chol = threadIdx.x < TG * TG;  // threads beyond the TG x TG grid only take part in the barriers
   extern __shared__ __align__(16) double sm[];
   double *sW = sm;                   // NP x LDW : L, then exchange buffer, partial sums, Y
   double *s_vec = sm + NP * LDW;     // vectors of NP
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? EIG_CTAS_PER_SM 
 
   // ---- Cholesky A = I + G = L L^T, register tiled: thread (ti,tk) owns A(ti+TG*a, tk+TG*b) ----
   {
-    const int ti = tid % TG, tk = tid / TG;
+    const int ti = tid % TG, tk = chol ? tid / TG : 0;
     double A[8][8];
     const double *Gz = G + (int64_t)zl * NP * NP;
 #pragma unroll
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? EIG_CTAS_PER_SM 
 #pragma unroll
       for (int a = 0; a < 8; a++) {
         const int i = ti + TG * a, k = tk + TG * b;
-        A[a][b] = Gz[i + NP * k] + (i == k ? 1. : 0.);
+        A[a][b] = chol ? Gz[i + NP * k] + (i == k ? 1. : 0.) : 0.;
       }
     if (tid < NP) s_c[tid] = cin[(int64_t)zl * NP + tid];
     double *s_col = s_uv;  // column j of L below the diagonal, zeros above (free until the epilogue)
@@ -205,9 +206,9 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? EIG_CTAS_PER_SM 
     for (int ja = 0; ja < 8; ja++) {
       for (int jt = 0; jt < TG; jt++) {
         const int j = jt + TG * ja;
-        if (ti == jt && tk == jt) s_piv = A[ja][ja];
+        if (chol && ti == jt && tk == jt) s_piv = A[ja][ja];
         __syncthreads();
-        if (tk == jt) {  // owners of column j
+        if (chol && tk == jt) {  // owners of column j
           const double piv = s_piv;
           const double rinv = rsqrt(piv);
 #pragma unroll
@@ -219,14 +220,16 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? EIG_CTAS_PER_SM 
           }
         }
         __syncthreads();
-        double lc[8];
+        if (chol) {
+          double lc[8];
 #pragma unroll
-        for (int b = 0; b < 8; b++) lc[b] = s_col[tk + TG * b];
+          for (int b = 0; b < 8; b++) lc[b] = s_col[tk + TG * b];
 #pragma unroll
-        for (int a = 0; a < 8; a++) {
-          const double la = -s_col[ti + TG * a];
+          for (int a = 0; a < 8; a++) {
+            const double la = -s_col[ti + TG * a];
 #pragma unroll
-          for (int b = 0; b < 8; b++) A[a][b] = fma(la, lc[b], A[a][b]);
+            for (int b = 0; b < 8; b++) A[a][b] = fma(la, lc[b], A[a][b]);
+          }
         }
       }
     }
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? EIG_CTAS_PER_SM 
 #pragma unroll
       for (int a = 0; a < 8; a++) {
         const int i = ti + TG * a, k = tk + TG * b;
-        sW[i + LDW * k] = (k <= i) ? A[a][b] : 0.;
+        if (chol) sW[i + LDW * k] = (k <= i) ? A[a][b] : 0.;
       }
   }
   __syncthreads();
@@ -474,10 +477,13 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? EIG_CTAS_PER_SM 
   // M = Y Y^T in 8x8 register tiles, then T = (M - g1 (hv u_v)^T) D - g2 (hw u_w)^T, row-major
   {
     constexpr int TPR = NP / 8;  // tiles per row
-    const int ti = tid / TPR, tj = tid % TPR;
+    constexpr int HPT = 2 * TPR * TPR / NTH;  // 8 x 4 half tiles per thread (2, or 1 with twice the threads)
+    static_assert(HPT == 1 || HPT == 2, "tile mapping");
+    const int tt = tid % (TPR * TPR), h0 = (tid / (TPR * TPR)) * HPT;
+    const int ti = tt / TPR, tj = tt % TPR;
     double *Tz = Tout + (int64_t)zl * NP * NP;
 #pragma unroll 1
-    for (int half = 0; half < 2; half++) {  // two 8 x 4 register tiles: columns 2tj + (NP/4)(2 half + b)
+    for (int half = h0; half < h0 + HPT; half++) {  // 8 x 4 register tiles: columns 2tj + (NP/4)(2 half + b)
       double acc[8][4];
 #pragma unroll
       for (int a = 0; a < 8; a++)
@@ -551,6 +557,7 @@ int oak_launch_eig(cudaStream_t st, int kernel, int N, int NP, int zone0, int nz
   if (nz <= 0) return 0;
   const int32_t *ml = mloc + zone0;
   if (kernel == 0 && NP == 64) return launch<64, 4>(st, N, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
+  if (kernel == 2 && NP == 64) return launch<64, 8>(st, N, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
   if (kernel == 0 && NP == 128) return launch<128, 8>(st, N, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
   return oak_launch_eig_simple(st, N, NP, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
 }

@@ -3,7 +3,7 @@ Timing experiments may produce wrong numerics (max_sweeps is fixed so that the w
 import json, os, subprocess, sys
 for lib in sys.argv[1:]:
     env = dict(os.environ, OAK_B200_LIB=os.path.abspath(lib), OAK_B200_FIXED_SWEEPS="8")
-    p = subprocess.run([sys.executable, "bench.py", "--nx", "300", "--ny", "300", "--m", "90000", "--steps", "2", "--warmup", "1",
+    p = subprocess.run([sys.executable, "bench.py", "--nx", "300", "--ny", "300", "--nobs", "90000", "--steps", "2", "--warmup", "1",
                         "--no-e2e", "--no-cpu"], env=env, capture_output=True, text=True)
     try:
         d = json.loads(p.stdout.strip().splitlines()[-1])

@@ -18,7 +18,7 @@ sanitize)
   timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitize.log 2>&1
   echo "sanitize exit $?"; tail -15 gpurun_out/sanitize.log ;;
 benchsmall)
-  timeout 900 python bench.py --nx 300 --ny 300 --nz 30 --m 90000 --steps 2 --warmup 1 --cpu-seconds 5 > gpurun_out/bench_small.json 2> gpurun_out/bench_small.err
+  timeout 900 python bench.py --nx 300 --ny 300 --nz 30 --nobs 90000 --steps 2 --warmup 1 --cpu-seconds 5 > gpurun_out/bench_small.json 2> gpurun_out/bench_small.err
   echo "benchsmall exit $?"; tail -3 gpurun_out/bench_small.err; cat gpurun_out/bench_small.json ;;
 bench)
   timeout 1500 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
@@ -28,17 +28,17 @@ benchref)
   echo "benchref exit $?"; tail -3 gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json ;;
 ncu)
   timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-     python bench.py --nx 400 --ny 400 --m 160000 --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_bench.log 2>&1
+     python bench.py --nx 400 --ny 400 --nobs 160000 --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_bench.log 2>&1
   echo "ncu exit $?"; tail -3 gpurun_out/ncu_bench.log ;;
 ncufull)
   timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_eig_fast -s 2 -c 2 -f -o gpurun_out/prof_eig \
-     python bench.py --nx 400 --ny 400 --m 160000 --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncufull_eig.log 2>&1
+     python bench.py --nx 400 --ny 400 --nobs 160000 --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncufull_eig.log 2>&1
   echo "ncufull eig exit $?"
   timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_gram -s 2 -c 2 -f -o gpurun_out/prof_gram \
-     python bench.py --nx 400 --ny 400 --m 160000 --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncufull_gram.log 2>&1
+     python bench.py --nx 400 --ny 400 --nobs 160000 --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncufull_gram.log 2>&1
   echo "ncufull gram exit $?"
   timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_apply -s 2 -c 2 -f -o gpurun_out/prof_apply \
-     python bench.py --nx 400 --ny 400 --m 160000 --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncufull_apply.log 2>&1
+     python bench.py --nx 400 --ny 400 --nobs 160000 --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncufull_apply.log 2>&1
   echo "ncufull apply exit $?" ;;
 esac
 done
