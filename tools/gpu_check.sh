@@ -27,7 +27,7 @@ benchref)
   timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
   echo "benchref exit $?"; tail -3 gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json ;;
 ncu)
-  timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+  timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_|DeviceRadixSort|DeviceScan' -c 600 --csv --log-file gpurun_out/launches.csv \
      python bench.py --nx 400 --ny 400 --nobs 160000 --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_bench.log 2>&1
   echo "ncu exit $?"; tail -3 gpurun_out/ncu_bench.log ;;
 ncufull)
