@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--eig-kernel", type=int, default=0)
+    ap.add_argument("--phases", type=int, default=0, help="pipeline phases for N>1 (0: 4 when N>1, else 1)")
     return ap.parse_args()
 
 
@@ -108,16 +109,18 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # synthetic data of one rank, generated on the device
 # --------------------------------------------------------------------------------------------------
-def build_rank_data(a, rank, world, dev):
+def build_rank_data(a, rank, world, dev, first=None, obs_np=None):
+    """Synthetic slab of one rank (in one phase when `first` is given), generated on the device."""
     import torch
     from oak_b200 import synthetic as S
     from oak_b200.dist import ShardPlan
     g = S.Grid(a.nx, a.ny, a.nz)
-    obs_np = S.observations(np, g, a.m, SEED)
+    if obs_np is None:
+        obs_np = S.observations(np, g, a.m, SEED)
     zones = np.arange(g.nzones, dtype=np.int64)
     zx, zy = g.zone_xy(np, zones)
     zs = np.full(g.nzones, a.nz, dtype=np.int32)
-    plan = ShardPlan(zs, zx, zy, a.corr, a.maxlen, obs_np["ox"], obs_np["oy"], rank, world)
+    plan = ShardPlan(zs, zx, zy, a.corr, a.maxlen, obs_np["ox"], obs_np["oy"], rank, world, first=first)
     n_loc = plan.r1 - plan.r0
     Sf = torch.empty((a.N, n_loc), dtype=torch.float64, device=dev)
     xf = torch.empty(n_loc, dtype=torch.float64, device=dev)
@@ -222,17 +225,29 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    d = build_rank_data(a, rank, world, dev)
-    plan, g = d["plan"], d["grid"]
-    n_loc = plan.r1 - plan.r0
-    h = oak_b200.Handle(local, eig_kernel=a.eig_kernel)
-    if os.environ.get("OAK_B200_FIXED_SWEEPS"):  # kernel timing experiments only (tools/ab.py)
-        h.set_option("fixed_sweeps", float(os.environ["OAK_B200_FIXED_SWEEPS"]))
-    h.set_zones(plan.zoneSize, zone_x=plan.zx, zone_y=plan.zy, corrLen=plan.corrLen, maxLen=plan.maxLen,
-                loctype=1, metrictype=0, weightfun=0)
-    h.set_observations(obs_x=d["ox"], obs_y=d["oy"])
-    xa = torch.empty(n_loc, dtype=torch.float64, device=dev)
-    Sa = torch.empty_like(d["Sf"])
+    from oak_b200 import synthetic as S
+    from oak_b200.dist import phase_ranges
+    g = S.Grid(a.nx, a.ny, a.nz)
+    nphase = a.phases if a.phases > 0 else (4 if world > 1 else 1)
+    obs_np = S.observations(np, g, a.m, SEED)
+    # phase j of rank p = a contiguous zone range; the all-gather of phase j overlaps the analysis of j+1
+    phases = []
+    for first in phase_ranges(g.nzones, world, nphase):
+        d = build_rank_data(a, rank, world, dev, first=first, obs_np=obs_np)
+        plan = d["plan"]
+        h = oak_b200.Handle(local, eig_kernel=a.eig_kernel)
+        if os.environ.get("OAK_B200_FIXED_SWEEPS"):  # kernel timing experiments only (tools/ab.py)
+            h.set_option("fixed_sweeps", float(os.environ["OAK_B200_FIXED_SWEEPS"]))
+        h.set_zones(plan.zoneSize, zone_x=plan.zx, zone_y=plan.zy, corrLen=plan.corrLen, maxLen=plan.maxLen,
+                    loctype=1, metrictype=0, weightfun=0)
+        h.set_observations(obs_x=d["ox"], obs_y=d["oy"])
+        d["h"] = h
+        d["xa"] = torch.empty(plan.r1 - plan.r0, dtype=torch.float64, device=dev)
+        d["Sa"] = torch.empty_like(d["Sf"])
+        phases.append(d)
+    d, plan, h = phases[0], phases[0]["plan"], phases[0]["h"]
+    n_loc = sum(p["plan"].r1 - p["plan"].r0 for p in phases)
+    z_rank = sum(p["plan"].z1 - p["plan"].z0 for p in phases)
     Sa_full = torch.empty((a.N, plan.n), dtype=torch.float64, device=dev) if world > 1 else None
 
     def barrier():
@@ -240,11 +255,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def analyse(p, **kw):
+        return p["h"].local_analysis_dev(p["xf"], p["Hxf"], p["yo"], p["Sf"], p["HSf"], p["var"], p["xa"], p["Sa"])
+
+    def add_stats(tot, st):
+        for k, v in st.items():
+            tot[k] = tot.get(k, 0) + v
+        return tot
+
     def step():
-        st = h.local_analysis_dev(d["xf"], d["Hxf"], d["yo"], d["Sf"], d["HSf"], d["var"], xa, Sa)
-        if world > 1:
-            allgather_slabs(dist, Sa, plan, out=Sa_full)
-        return st
+        tot, works = {}, []
+        for p in phases:
+            add_stats(tot, analyse(p))
+            if world > 1:   # asynchronous: overlaps the next phase's kernels
+                works += allgather_slabs(dist, p["Sa"], p["plan"], out=Sa_full, wait=False)
+        for w in works:
+            w.wait()
+        return tot
 
     for _ in range(a.warmup):
         st = step()
@@ -274,9 +301,11 @@ def main():
     value = nzones / (ms_per_step * 1e-3)
 
     # ---- per-kernel times (separate profiled pass: batches serialised, CUDA events around each kernel family)
-    h.set_option("profile", 1)
-    stp = h.local_analysis_dev(d["xf"], d["Hxf"], d["yo"], d["Sf"], d["HSf"], d["var"], xa, Sa)
-    h.set_option("profile", 0)
+    stp = {}
+    for p in phases:
+        p["h"].set_option("profile", 1)
+        add_stats(stp, analyse(p))
+        p["h"].set_option("profile", 0)
     peak_dfma = h.fp64_peak(0)
     peak_dmma = h.fp64_peak(1)
 
@@ -286,8 +315,7 @@ def main():
         mloc_mean = agg[0].item() / max(analysed, 1)
         cand_mean = agg[1].item() / max(nzones, 1)
         sweeps_mean = agg[2].item() / max(analysed, 1)
-        nb = max(1, (stp["launches"] - 1) // 3)            # eig launches of this rank in one step
-        z_rank = plan.z1 - plan.z0
+        nb = max(1, (stp["launches"] - len(phases)) // 3)  # eig launches of this rank in one step
         eig_flops_zone = 9 * a.N ** 3 + 2 * a.N ** 3 + 4 * a.N ** 2
         eig_ms_launch = stp["ms_eig"] / nb
         achieved = eig_flops_zone * (z_rank / nb) / (eig_ms_launch * 1e-3) / 1e12
@@ -308,7 +336,7 @@ def main():
         out = {"metric": "local-analysis grid columns/sec", "value": value, "unit": "columns/s", "n_gpus": world,
                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": workload_name(a), "zones": nzones, "parallelism": f"zone-range x{world}",
+               "config": {"workload": workload_name(a), "zones": nzones, "parallelism": f"zone-range x{world}" + (f", {nphase} pipelined phases (all-gather of phase j overlaps analysis of j+1)" if world > 1 else ""),
                           "l2": "inputs (>= 15 GB state) exceed L2; no explicit flush",
                           "mean_relevant_obs_per_column": mloc_mean, "mean_candidates_per_column": cand_mean,
                           "mean_jacobi_sweeps": sweeps_mean, "eig_kernel": a.eig_kernel},
@@ -318,29 +346,41 @@ def main():
     e2e = None
     if not a.no_e2e:
         try:
-            Sf_h = torch.empty((a.N, n_loc), dtype=torch.float64, pin_memory=True)
-            Sa_h = torch.empty((a.N, n_loc), dtype=torch.float64, pin_memory=True)
-            Sf_h.copy_(d["Sf"])
             pin = lambda t: t.cpu().pin_memory()
-            xf_h, Hxf_h, yo_h, HSf_h, var_h = pin(d["xf"]), pin(d["Hxf"]), pin(d["yo"]), pin(d["HSf"]), pin(d["var"])
-            xa_h = torch.empty(n_loc, dtype=torch.float64, pin_memory=True)
+            hb = []
+            for p in phases:
+                nl = p["plan"].r1 - p["plan"].r0
+                q = dict(Sf=torch.empty((a.N, nl), dtype=torch.float64, pin_memory=True),
+                         Sa=torch.empty((a.N, nl), dtype=torch.float64, pin_memory=True),
+                         xa=torch.empty(nl, dtype=torch.float64, pin_memory=True),
+                         xf=pin(p["xf"]), Hxf=pin(p["Hxf"]), yo=pin(p["yo"]), HSf=pin(p["HSf"]), var=pin(p["var"]))
+                q["Sf"].copy_(p["Sf"])
+                hb.append(q)
             torch.cuda.synchronize()
-            h.local_analysis_pinned(xf_h, Hxf_h, yo_h, Sf_h, HSf_h, var_h, xa_h, Sa_h)  # warm-up
+
+            def e2e_step():
+                tot = {}
+                for p, q in zip(phases, hb):
+                    add_stats(tot, p["h"].local_analysis_pinned(q["xf"], q["Hxf"], q["yo"], q["Sf"], q["HSf"], q["var"],
+                                                                q["xa"], q["Sa"]))
+                return tot
+
+            e2e_step()  # warm-up
             barrier()
             t0 = time.perf_counter()
             for _ in range(a.e2e_steps):
-                ste = h.local_analysis_pinned(xf_h, Hxf_h, yo_h, Sf_h, HSf_h, var_h, xa_h, Sa_h)
+                ste = e2e_step()
             torch.cuda.synchronize()
             te = (time.perf_counter() - t0) / a.e2e_steps
             tt = torch.tensor([te], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ok = bool(torch.equal(Sa_h[:, :1000].to(dev), Sa[:, :1000]))
+            ok = bool(torch.equal(hb[0]["Sa"][:, :1000].to(dev), phases[0]["Sa"][:, :1000]))
             e2e = {"value": nzones / float(tt.item()), "unit": "columns/s", "h2d_bytes_per_step": ste["h2d_bytes"],
                    "d2h_bytes_per_step": ste["d2h_bytes"], "steps": a.e2e_steps,
                    "note": "oakb200_local_analysis on pinned host buffers; state streamed in zone chunks; "
-                           "per-rank slab, no all-gather of host buffers" + ("" if ok else "; MISMATCH vs resident run")}
-            del Sf_h, Sa_h
+                           "bytes are per rank; no all-gather of host buffers" + ("" if ok else "; MISMATCH vs resident run")}
+            del hb
         except Exception as ex:  # e.g. not enough pinnable host memory
             e2e = {"value": None, "unit": "columns/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
                    "error": repr(ex)[:300]}

@@ -47,14 +47,25 @@ def halo_observations(zx, zy, radius, obs_x, obs_y, loctype=LOC_HORIZONTAL, metr
     return np.nonzero(keep)[0].astype(np.int64)
 
 
+def phase_ranges(nzones, world, nphase):
+    """Zone ranges for a pipelined run: the zones are cut in `nphase` consecutive phases, each phase is
+    split over the ranks with the parallPartion formula.  first[j][p] .. first[j][p+1] = zones of rank p
+    in phase j.  With nphase = 1 this is exactly parall.F90:176-177.  More phases let the all-gather of
+    phase j overlap the analysis of phase j+1."""
+    pb = partition(nzones, nphase)
+    return [pb[j] + partition(int(pb[j + 1] - pb[j]), world) for j in range(nphase)]
+
+
 class ShardPlan:
-    """What rank `rank` of `world` owns."""
+    """What rank `rank` of `world` owns (optionally inside one phase: `first` = that phase's boundaries)."""
 
     def __init__(self, zoneSize, zx, zy, corrLen, maxLen, obs_x, obs_y, rank, world, loctype=LOC_HORIZONTAL,
-                 metrictype=METRIC_CARTESIAN, weightfun=WEIGHT_GAUSSIAN):
+                 metrictype=METRIC_CARTESIAN, weightfun=WEIGHT_GAUSSIAN, first=None):
         zoneSize = np.asarray(zoneSize, dtype=np.int64)
         nz = zoneSize.size
-        first = partition(nz, world)
+        if first is None:
+            first = partition(nz, world)
+        first = np.asarray(first, dtype=np.int64)
         self.rank, self.world = rank, world
         self.first = first
         self.z0, self.z1 = int(first[rank]), int(first[rank + 1])
@@ -77,20 +88,24 @@ class ShardPlan:
         self.equal_slabs = bool(np.all(np.diff(self.row_first) == (self.r1 - self.r0)))
 
 
-def allgather_slabs(dist, Sa_local, plan, out=None):
+def allgather_slabs(dist, Sa_local, plan, out=None, wait=True):
     """Reassembles the member-major analysed slabs (N, n_loc) of all ranks into (N, n).
 
-    Equal slabs: one all_gather_into_tensor per member row group, issued asynchronously and waited
-    together (a single grouped collective on NCCL).  Unequal slabs: all_gather on padded buffers."""
+    Equal slabs: one all_gather_into_tensor per member row, issued asynchronously (a grouped collective
+    on NCCL); with wait=False the work handles are returned so that the gather of one phase overlaps the
+    analysis of the next.  Unequal slabs: all_gather on padded buffers (always waited)."""
     import torch
     N = Sa_local.shape[0]
     if out is None:
         out = torch.empty((N, plan.n), dtype=Sa_local.dtype, device=Sa_local.device)
+    a, b = int(plan.row_first[0]), int(plan.row_first[-1])   # rows covered by this plan (a phase or everything)
     if plan.world == 1:
-        out.copy_(Sa_local)
-        return out
+        out[:, a:b].copy_(Sa_local)
+        return out if wait else []
     if plan.equal_slabs:
-        works = [dist.all_gather_into_tensor(out[k], Sa_local[k].contiguous(), async_op=True) for k in range(N)]
+        works = [dist.all_gather_into_tensor(out[k, a:b], Sa_local[k], async_op=True) for k in range(N)]
+        if not wait:
+            return works
         for w in works:
             w.wait()
         return out
@@ -103,4 +118,4 @@ def allgather_slabs(dist, Sa_local, plan, out=None):
     for p in range(plan.world):
         a, b = int(plan.row_first[p]), int(plan.row_first[p + 1])
         out[:, a:b] = parts[p][:, :b - a]
-    return out
+    return out if wait else []

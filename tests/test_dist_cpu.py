@@ -22,44 +22,52 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, uneven, ret):
+def _worker(rank, world, port, uneven, nphase, ret):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import oracle
         from oak_b200 import synthetic
-        from oak_b200.dist import ShardPlan, allgather_slabs
+        from oak_b200.dist import ShardPlan, allgather_slabs, phase_ranges
         c = synthetic.small_case(nx=20, ny=36, nz=3, N=8, m=260, corr=2000.0, maxlen=4000.0)
         zs = c["zoneSize"].copy()
         if uneven:
             zs = (1 + (np.arange(zs.size) % 3)).astype(np.int32)
         n = int(zs.sum())
         Sf, xf = c["Sf"][:n], c["xf"][:n]
-        plan = ShardPlan(zs, c["zx"], c["zy"], c["corr"], c["maxlen"], c["obs"]["ox"], c["obs"]["oy"], rank, world)
-        oi = plan.obs_idx
-        obs = oracle.make_obs(len(oi), obsx=c["obs"]["ox"][oi], obsy=c["obs"]["oy"][oi])
-        xa_l, Sa_l, _, mloc_l = oracle.loc_analysis(plan.zoneSize, dict(x=plan.zx, y=plan.zy), plan.corrLen,
-                                                    plan.maxLen, obs, xf[plan.r0:plan.r1], c["Hxf"][oi],
-                                                    c["yo"][oi], Sf[plan.r0:plan.r1], c["HSf"][oi], c["var"][oi])
-        Sa = allgather_slabs(dist, torch.from_numpy(np.ascontiguousarray(Sa_l.T)), plan)
+        Sa = torch.zeros((c["N"], n), dtype=torch.float64)
+        mloc_parts, halo_max, works = [], 0, []
+        for first in phase_ranges(zs.size, world, nphase):
+            plan = ShardPlan(zs, c["zx"], c["zy"], c["corr"], c["maxlen"], c["obs"]["ox"], c["obs"]["oy"], rank, world,
+                             first=first)
+            oi = plan.obs_idx
+            halo_max = max(halo_max, len(oi))
+            obs = oracle.make_obs(len(oi), obsx=c["obs"]["ox"][oi], obsy=c["obs"]["oy"][oi])
+            xa_l, Sa_l, _, mloc_l = oracle.loc_analysis(plan.zoneSize, dict(x=plan.zx, y=plan.zy), plan.corrLen,
+                                                        plan.maxLen, obs, xf[plan.r0:plan.r1], c["Hxf"][oi],
+                                                        c["yo"][oi], Sf[plan.r0:plan.r1], c["HSf"][oi], c["var"][oi])
+            mloc_parts.append((plan.z0, plan.z1, mloc_l))
+            works += allgather_slabs(dist, torch.from_numpy(np.ascontiguousarray(Sa_l.T)), plan, out=Sa, wait=False)
+        for w in works:
+            w.wait()
         if rank == 0:
             obs_all = oracle.make_obs(c["m"], obsx=c["obs"]["ox"], obsy=c["obs"]["oy"])
             xa_g, Sa_g, _, mloc_g = oracle.loc_analysis(zs, dict(x=c["zx"], y=c["zy"]), c["corr"], c["maxlen"],
                                                         obs_all, xf, c["Hxf"], c["yo"], Sf, c["HSf"], c["var"])
-            ok = np.array_equal(Sa.numpy().T, Sa_g) and np.array_equal(mloc_l, mloc_g[plan.z0:plan.z1])
-            ok = ok and len(oi) < c["m"] and (mloc_g > 0).any()
+            ok = np.array_equal(Sa.numpy().T, Sa_g) and all(np.array_equal(ml, mloc_g[a:b]) for a, b, ml in mloc_parts)
+            ok = ok and halo_max < c["m"] and (mloc_g > 0).any()
             ret.put(bool(ok))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,uneven", [(2, False), (3, True)])
-def test_sharded_pipeline_equals_single_process(world, uneven):
+@pytest.mark.parametrize("world,uneven,nphase", [(2, False, 1), (3, True, 1), (2, False, 3)])
+def test_sharded_pipeline_equals_single_process(world, uneven, nphase):
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, uneven, ret)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, uneven, nphase, ret)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
