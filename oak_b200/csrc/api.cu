@@ -144,11 +144,18 @@ int ensure_ws(oakb200_handle *h, Slot &s, int NP, int zb) {
   return 0;
 }
 
-int batch_size(const oakb200_handle *h, int NP) {
+// Zones per batch: a whole number of waves of the transform kernel (4 CTAs x 148 SMs at NP = 64) so that a
+// batch does not end on a nearly empty wave, small enough that a call has >= ~8 batches per stream slot to
+// overlap the tails, capped by the workspace budget (2 x 128 MB per slot at NP = 64).
+int batch_size(const oakb200_handle *h, int NP, int nzones_call) {
   if (h->zones_per_batch > 0) return h->zones_per_batch;
   const size_t per_zone = sizeof(double) * 2 * (size_t)NP * NP;
-  int zb = (int)((size_t)256 * 1024 * 1024 / per_zone);
-  return std::max(zb, 148);
+  const int cap = (int)((size_t)256 * 1024 * 1024 / per_zone);
+  const int wave = NP <= 64 ? 592 : 148;
+  int zb = nzones_call / (NSLOT * 8);
+  zb = std::max(wave, (zb / wave) * wave);
+  zb = std::min(zb, std::max(wave, (cap / wave) * wave));
+  return zb;
 }
 
 // Packs the observation-space arrays (device pointers) into sorted rows. Enqueued on `st`.
@@ -169,7 +176,7 @@ struct ProfAcc { double gram = 0, eig = 0, apply = 0; };
 int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t rowbase, const double *xf,
               const double *Sf, int64_t ldS, double *xa, double *Sa, int64_t ldSa, int64_t *launches,
               ProfAcc *prof) {
-  const int zb = batch_size(h, NP);
+  const int zb = batch_size(h, NP, h->nzones);
   int rc;
   if ((rc = ensure_ws(h, s, NP, std::min(zb, z1 - z0)))) return rc;
   const ZoneGeom zg = h->geom();
@@ -512,7 +519,7 @@ extern "C" OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t
   for (int i = 1; i < NSLOT; i++) CUDA_TRY(cudaStreamWaitEvent(h->slot[i].st, h->slot[0].ev[4], 0));
   int64_t launches = 1;
   ProfAcc prof;
-  const int zb = batch_size(h, NP);
+  const int zb = batch_size(h, NP, h->nzones);
   int bi = 0;
   for (int z0 = 0; z0 < h->nzones; z0 += zb, bi++) {
     Slot &s = h->slot[h->profile ? 0 : bi % NSLOT];

@@ -51,9 +51,17 @@ def phase_ranges(nzones, world, nphase):
     """Zone ranges for a pipelined run: the zones are cut in `nphase` consecutive phases, each phase is
     split over the ranks with the parallPartion formula.  first[j][p] .. first[j][p+1] = zones of rank p
     in phase j.  With nphase = 1 this is exactly parall.F90:176-177.  More phases let the all-gather of
-    phase j overlap the analysis of phase j+1."""
-    pb = partition(nzones, nphase)
-    return [pb[j] + partition(int(pb[j + 1] - pb[j]), world) for j in range(nphase)]
+    phase j overlap the analysis of phase j+1; the phases shrink towards the end (the gather of the last
+    one is the only exposed communication) and hold a multiple of `world` zones so that slabs are equal."""
+    if nphase <= 1:
+        return [partition(nzones, world)]
+    w = np.array([nphase + 1.0 - 0.5 * j for j in range(nphase)])   # e.g. 4 phases: 5 : 4.5 : 4 : 3.5 ... tapered
+    w[-1] *= 0.5
+    cut = np.concatenate([[0.0], np.cumsum(w)]) / w.sum()
+    pb = [(int(round(c * nzones)) // world) * world for c in cut]
+    pb[0], pb[-1] = 0, nzones
+    pb = sorted(set(pb))
+    return [pb[j] + partition(int(pb[j + 1] - pb[j]), world) for j in range(len(pb) - 1)]
 
 
 class ShardPlan:
@@ -103,7 +111,21 @@ def allgather_slabs(dist, Sa_local, plan, out=None, wait=True):
         out[:, a:b].copy_(Sa_local)
         return out if wait else []
     if plan.equal_slabs:
-        works = [dist.all_gather_into_tensor(out[k, a:b], Sa_local[k], async_op=True) for k in range(N)]
+        # one grouped NCCL operation: the N per-member all-gathers (each lands in the contiguous rows
+        # [a,b) of member k of the column-major n x N result) are coalesced into a single launch
+        outs = [out[k, a:b] for k in range(N)]
+        ins = [Sa_local[k] for k in range(N)]
+        works = None
+        try:
+            from torch.distributed.distributed_c10d import _coalescing_manager
+            with _coalescing_manager(async_ops=True) as cm:
+                for o, i in zip(outs, ins):
+                    dist.all_gather_into_tensor(o, i)
+            works = [cm]
+        except Exception:
+            works = None
+        if works is None:   # backend without coalescing support
+            works = [dist.all_gather_into_tensor(o, i, async_op=True) for o, i in zip(outs, ins)]
         if not wait:
             return works
         for w in works:
