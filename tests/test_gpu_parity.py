@@ -328,3 +328,102 @@ def test_fp64_peak_microbenchmarks(ob):
     dfma, dmma = h.fp64_peak(0), h.fp64_peak(1)
     h.close()
     assert 5.0 < dfma < 100.0 and 1.0 < dmma < 200.0
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs at reduced size (parity-test cases, not bench lines)
+# ------------------------------------------------------------------------------------------------
+def test_config2_shallow_water_2d_three_staggered_variables(ob, handle):
+    """configs[1]: test/shallow_water2d_ens.F90 local ETKF — zeta (nx x ny), ubar ((nx-1) x ny),
+    vbar (nx x (ny-1)) on a C-grid with land points removed, zone = horizontal cell holding its
+    surviving {zeta,ubar,vbar} points (sizes 1..3), N = 20, 5 observations of zeta, rmse 0.05,
+    Cartesian metric, corrLength 10e3, maxLength 40e3 (test/shallow_water2d.init with schemetype = 1)."""
+    nx, ny, N, dx = 30, 24, 20, 5e3
+    rng = np.random.default_rng(42)
+    ii, jj = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    sea = ((ii - nx / 2) ** 2 / (nx / 2) ** 2 + (jj - ny / 2) ** 2 / (ny / 2) ** 2) < 0.92   # basin with closed boundary
+    mask_u = sea[:-1, :] & sea[1:, :]
+    mask_v = sea[:, :-1] & sea[:, 1:]
+    part = (ii + nx * jj)
+    labels = np.concatenate([part[sea], part[:-1, :][mask_u], part[:, :-1][mask_v]])   # Zones.partition of the 3 variables
+    xs = np.concatenate([((ii + 1) * dx)[sea], ((ii[:-1] + 1.5) * dx)[mask_u], ((ii[:, :-1] + 1) * dx)[mask_v]])
+    ys = np.concatenate([((jj + 1) * dx)[sea], ((jj[:-1] + 1) * dx)[mask_u], ((jj[:, :-1] + 1.5) * dx)[mask_v]])
+    # initPartition: gap-free relabel + stable counting sort (assimilation.F90:405-430,:578-641)
+    uniq, relabel = np.unique(labels, return_inverse=True)
+    zs, zoneIndex, _ = oracle.init_partition((relabel + 1).astype(np.int32), uniq.size)
+    perm = zoneIndex - 1
+    n = perm.size
+    starts = np.concatenate([[0], np.cumsum(zs)[:-1]])
+    zx, zy = xs[perm][starts], ys[perm][starts]          # position of each zone's first element
+    assert set(np.unique(zs)) <= {1, 2, 3} and len(set(np.unique(zs))) > 1
+    # ensemble of Gaussian bumps (shallow_water2d_ens.F90:191-209), observations of zeta at 5 sea points
+    gz = rng.normal(size=(3, N))
+    xc, yc, zc = 20e3 + 10e3 * gz[0], 50e3 + 30e3 * gz[1], gz[2]
+    E_full = zc[None, :] * np.exp(-((xs[:, None] - xc) / 30e3) ** 2 - ((ys[:, None] - yc) / 60e3) ** 2)
+    E_full[sea.sum():] = 0.01 * rng.normal(size=(n - sea.sum(), N))   # U, V
+    E = np.asfortranarray(E_full[perm])
+    sea_idx = np.nonzero(sea.ravel(order="F"))[0]
+    obs_pts = rng.choice(sea.sum(), size=5, replace=False)
+    inv = np.empty(n, np.int64); inv[perm] = np.arange(n)
+    Hj = (inv[obs_pts] + 1).astype(np.int32); Hi = np.arange(1, 6, dtype=np.int32); Hs = np.ones(5)
+    ox, oy = xs[obs_pts], ys[obs_pts]
+    yo = 0.3 * rng.normal(size=5)
+    var = np.full(5, 0.05 ** 2)
+    sel = ob.Selector(zone_x=zx, zone_y=zy, corrLen=10e3, maxLen=40e3, obs_x=ox, obs_y=oy, metrictype=0)
+    Ea, xf, xa = ob.assim_ensemble(zs, sel, E, Hi, Hj, Hs, None, yo, ob.DiagCovar(var), handle=handle)
+    oo = oracle.make_obs(5, obsx=ox, obsy=oy)
+    Eo, xfo, xao = oracle.assim_ensemble(zs, dict(x=zx, y=zy), 10e3, 40e3, oo, E, Hi, Hj, Hs, np.zeros(5), yo, var)
+    assert rel(Ea, Eo) < RTOL and rel(xa, xao) < RTOL and rel(xf, xfo) < 1e-14
+    assert np.abs(Ea - E).max() > 1e-3     # the analysis did something
+
+
+def test_config4_dense_observations_large_radius_n128(ob, handle):
+    """configs[3] at reduced size: N = 128, an observation at every surface grid point, large radius."""
+    from oak_b200 import synthetic
+    g = synthetic.Grid(26, 22, 3)
+    N = 128
+    rows = np.arange(g.n, dtype=np.int64)
+    E = synthetic.ensemble_rows(np, g, rows, N, 9)
+    zones = np.arange(g.nzones, dtype=np.int64)
+    zx, zy = g.zone_xy(np, zones)
+    surf = zones * g.nz
+    HE = E[:, surf]                                   # H = identity on the surface level
+    yo = g.mu_rows(np, surf) + 0.05 * synthetic.normal(np, zones, 6, 9)
+    xf, Sf = synthetic.anomalies(np, E)
+    Hxf, HSf = synthetic.anomalies(np, HE)
+    var = np.full(g.nzones, 0.05 ** 2)
+    c = dict(m=g.nzones, obs=dict(ox=zx, oy=zy), zx=zx, zy=zy, corr=5000.0, maxlen=10000.0, xf=xf, Hxf=Hxf, yo=yo,
+             Sf=np.asfortranarray(Sf.T), HSf=np.asfortranarray(HSf.T), var=var,
+             zoneSize=np.full(g.nzones, g.nz, np.int32))
+    _configure(ob, handle, c)
+    xa, Sa, _, st = handle.local_analysis(c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], ob.DiagCovar(var))
+    xo, So, _, mloc = _oracle_loc(c)
+    assert mloc.max() > 250 and st["obs_relevant_sum"] == mloc.sum()
+    assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL
+
+
+def test_config5_time_localisation_inflation_anamorphosis(ob, handle):
+    """configs[4] at reduced size: 4-D state (zone = column over z and t), localisation in time
+    (loctype = 3: |obsT - t|, assimilation.F90:3752-3753), N = 64, inflation.mult = 1.05, log anamorphosis."""
+    from oak_b200 import synthetic
+    nxy, nzt, N, m = 90, 8, 64, 240
+    n = nxy * nzt
+    rng = np.random.default_rng(5)
+    E = np.exp(0.2 * rng.normal(size=(n, N)) + 0.1 * np.sin(np.arange(n))[:, None])
+    zs = np.full(nxy, nzt, np.int32)
+    zt = rng.uniform(0, 10, nxy)                     # time coordinate of each zone's first element
+    ot = rng.uniform(-1, 11, m)
+    rows = rng.integers(0, n, size=(2, m))
+    Hi = np.tile(np.arange(1, m + 1, dtype=np.int32), 2)
+    Hj = (rows.reshape(-1) + 1).astype(np.int32)
+    Hs = np.tile([0.6, 0.4], (m, 1)).T.reshape(-1).copy()
+    yo = 1.0 + 0.1 * rng.normal(size=m)
+    var = rng.uniform(0.01, 0.04, m)
+    sel = ob.Selector(zone_x=np.zeros(nxy), zone_y=np.zeros(nxy), zone_t=zt, corrLen=0.8, maxLen=1.6,
+                      obs_x=np.zeros(m), obs_y=np.zeros(m), obs_t=ot, loctype=3, metrictype=0)
+    Ea, xf, xa = ob.assim_ensemble(zs, sel, E, Hi, Hj, Hs, None, yo, ob.DiagCovar(var), anamtype=2, inflation=1.05,
+                                   handle=handle)
+    oo = oracle.make_obs(m, obst=ot, loctype=3)
+    Eo, xfo, xao = oracle.assim_ensemble(zs, dict(t=zt), 0.8, 1.6, oo, E, Hi, Hj, Hs, np.zeros(m), yo, var,
+                                         anamtype=2, inflation=1.05)
+    assert rel(Ea, Eo) < RTOL and rel(xa, xao) < RTOL
