@@ -13,7 +13,7 @@
 
 namespace {
 
-constexpr int GRAM_CH = 64;    // candidates examined per chunk (warp 0, two per lane)
+constexpr int GRAM_CH = 64;    // candidates examined per chunk (warps 0 and 1, one per lane)
 constexpr int GRAM_MAXR = 64;  // cell ranges per row group
 
 template <int K>
@@ -31,6 +31,22 @@ __device__ __forceinline__ void lds_vec(double *dst, const double *src) {
   }
 }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Software pipeline over chunks of GRAM_CH candidates (per group of cell rows):
+//   E(c)  warps 0,1 evaluate the exact predicate on 32 candidates each and compact the relevant ones
+//         (per-warp segment of the list: position, coef = w^2 d01^2/R, coef*delta)
+//   L(c)  all warps copy the relevant rows (row-major, NP doubles) into a shared row buffer with
+//         16-byte cp.async (LDGSTS), one warp instruction per 512 bytes of a row
+//   F(c)  every thread accumulates its register tile over the staged rows
+// E runs two chunks ahead (3 list buffers), L one chunk ahead (2 row buffers), so the global-memory
+// latency of the rows of chunk c+1 is hidden behind F(c).  Two barriers per chunk.
 template <int NP, int NT>
 __global__ void __launch_bounds__(NT) k_gram(ZoneGeom zg, ObsGrid og, ObsRows orows, int zone0, int nz,
                                              double *__restrict__ G, double *__restrict__ cvec,
@@ -38,12 +54,15 @@ __global__ void __launch_bounds__(NT) k_gram(ZoneGeom zg, ObsGrid og, ObsRows or
   constexpr int TX = NT / 16;
   constexpr int RT = NP / 16;
   constexpr int CT = NP / TX;
+  constexpr int NW = NT / 32;
   static_assert(CT >= 2 && CT % 2 == 0, "column tile must be pairs");
-  extern __shared__ __align__(16) double rowbuf[];  // [GRAM_CH][NP]
-  __shared__ double s_coef[GRAM_CH], s_cd[GRAM_CH];
-  __shared__ int s_pos[GRAM_CH];
+  static_assert(GRAM_CH == 64, "two evaluating warps");
+  extern __shared__ __align__(16) double rowbuf[];  // [2][GRAM_CH][NP]
+  __shared__ double s_coef[3][GRAM_CH], s_cd[3][GRAM_CH];
+  __shared__ int s_pos[3][GRAM_CH];
+  __shared__ int s_cnt[3][2];
   __shared__ int s_rstart[GRAM_MAXR], s_rlen[GRAM_MAXR];
-  __shared__ int s_nrel, s_total;
+  __shared__ int s_total;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int zl = blockIdx.x;
@@ -61,6 +80,70 @@ __global__ void __launch_bounds__(NT) k_gram(ZoneGeom zg, ObsGrid og, ObsRows or
   double cacc = 0.;
   int nrel_total = 0;
   long long ncand_total = 0;
+
+  // E(c): warps 0 and 1, 32 candidates each, into list buffer lb
+  auto eval = [&](int c, int lb, int total) {
+    if (warp < 2) {
+      int qq = c * GRAM_CH + warp * 32 + lane;
+      bool rel = false;
+      double w = 0.;
+      int p = 0;
+      if (qq < total) {
+        int r = 0;
+        while (qq >= s_rlen[r]) { qq -= s_rlen[r]; r++; }
+        p = s_rstart[r] + qq;
+        rel = oak_obs_relevant(q, og.sx[p], og.sy[p], w);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, rel);
+      if (rel) {
+        const int slot = warp * 32 + __popc(bal & ((1u << lane) - 1u));
+        const double coef = (w * w) * orows.scoef[p];
+        s_pos[lb][slot] = p;
+        s_coef[lb][slot] = coef;
+        s_cd[lb][slot] = coef * orows.delta[p];
+      }
+      if (lane == 0) s_cnt[lb][warp] = __popc(bal);
+    }
+  };
+  // L(c): rows of list buffer lb into row buffer rb
+  auto load_rows = [&](int lb, int rb) {
+    double *dstb = rowbuf + (size_t)rb * GRAM_CH * NP;
+#pragma unroll
+    for (int seg = 0; seg < 2; seg++) {
+      const int cnt = s_cnt[lb][seg];
+      for (int r = warp; r < cnt; r += NW) {
+        const int slot = seg * 32 + r;
+        const double *src = orows.rows + (int64_t)s_pos[lb][slot] * NP;
+        for (int cidx = lane * 2; cidx < NP; cidx += 64) cp_async16(dstb + slot * NP + cidx, src + cidx);
+      }
+    }
+  };
+  // F(c)
+  auto fma_rows = [&](int lb, int rb) {
+    const double *srcb = rowbuf + (size_t)rb * GRAM_CH * NP;
+#pragma unroll
+    for (int seg = 0; seg < 2; seg++) {
+      const int cnt = s_cnt[lb][seg];
+      nrel_total += cnt;
+#pragma unroll 2
+      for (int r = 0; r < cnt; r++) {
+        const int slot = seg * 32 + r;
+        const double coef = s_coef[lb][slot];
+        const double *row = srcb + slot * NP;
+        double rv[RT], cv[CT];
+        lds_vec<RT>(rv, row + RT * ty);
+#pragma unroll
+        for (int b = 0; b < CT / 2; b++) lds_vec<2>(cv + 2 * b, row + 2 * tx + 2 * TX * b);
+#pragma unroll
+        for (int a = 0; a < RT; a++) {
+          const double ra = rv[a] * coef;
+#pragma unroll
+          for (int b = 0; b < CT; b++) acc[a][b] = fma(ra, cv[b], acc[a][b]);
+        }
+        if (tid < NP) cacc = fma(s_cd[lb][slot], row[tid], cacc);
+      }
+    }
+  };
 
   for (int cyg = box.cy0; cyg <= box.cy1; cyg += GRAM_MAXR / 2) {
     __syncthreads();
@@ -86,61 +169,28 @@ __global__ void __launch_bounds__(NT) k_gram(ZoneGeom zg, ObsGrid og, ObsRows or
     __syncthreads();
     const int total = s_total;
     ncand_total += total;
+    const int nchunk = (total + GRAM_CH - 1) / GRAM_CH;
+    if (nchunk == 0) continue;
 
-    for (int chunk0 = 0; chunk0 < total; chunk0 += GRAM_CH) {
-      if (warp == 0) {
-        int nrel = 0;
-#pragma unroll
-        for (int h = 0; h < GRAM_CH / 32; h++) {
-          int qq = chunk0 + h * 32 + lane;
-          const bool valid = qq < total;
-          bool rel = false;
-          double w = 0.;
-          int p = 0;
-          if (valid) {
-            int r = 0;
-            while (qq >= s_rlen[r]) { qq -= s_rlen[r]; r++; }
-            p = s_rstart[r] + qq;
-            rel = oak_obs_relevant(q, og.sx[p], og.sy[p], w);
-          }
-          const unsigned bal = __ballot_sync(0xffffffffu, rel);
-          if (rel) {
-            const int slot = nrel + __popc(bal & ((1u << lane) - 1u));
-            const double coef = (w * w) * orows.scoef[p];
-            s_pos[slot] = p;
-            s_coef[slot] = coef;
-            s_cd[slot] = coef * orows.delta[p];
-          }
-          nrel += __popc(bal);
-        }
-        if (lane == 0) s_nrel = nrel;
+    eval(0, 0, total);
+    __syncthreads();
+    load_rows(0, 0);
+    cp_async_commit();
+    if (nchunk > 1) eval(1, 1, total);
+    __syncthreads();
+    for (int c = 0; c < nchunk; c++) {
+      const int lb = c % 3, rb = c & 1;
+      if (c + 1 < nchunk) {
+        load_rows((c + 1) % 3, rb ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
       }
-      __syncthreads();
-      const int nrel = s_nrel;
-      nrel_total += nrel;
-      for (int r = warp; r < nrel; r += NT / 32) {
-        const double *src = orows.rows + (int64_t)s_pos[r] * NP;
-        for (int cidx = lane * 2; cidx < NP; cidx += 64)
-          *reinterpret_cast<double2 *>(&rowbuf[r * NP + cidx]) = *reinterpret_cast<const double2 *>(src + cidx);
-      }
-      __syncthreads();
-#pragma unroll 2
-      for (int r = 0; r < nrel; r++) {
-        const double coef = s_coef[r];
-        const double *row = rowbuf + r * NP;
-        double rv[RT], cv[CT];
-        lds_vec<RT>(rv, row + RT * ty);
-#pragma unroll
-        for (int b = 0; b < CT / 2; b++) lds_vec<2>(cv + 2 * b, row + 2 * tx + 2 * TX * b);
-#pragma unroll
-        for (int a = 0; a < RT; a++) {
-          const double ra = rv[a] * coef;
-#pragma unroll
-          for (int b = 0; b < CT; b++) acc[a][b] = fma(ra, cv[b], acc[a][b]);
-        }
-        if (tid < NP) cacc = fma(s_cd[r], row[tid], cacc);
-      }
-      __syncthreads();
+      __syncthreads();  // rows of chunk c have landed for every thread
+      fma_rows(lb, rb);
+      if (c + 2 < nchunk) eval(c + 2, (c + 2) % 3, total);
+      __syncthreads();  // list c+2 visible; row buffer rb free for chunk c+2
     }
   }
 
@@ -166,7 +216,7 @@ __global__ void __launch_bounds__(NT) k_gram(ZoneGeom zg, ObsGrid og, ObsRows or
 template <int NP, int NT>
 int launch(cudaStream_t st, const ZoneGeom &zg, const ObsGrid &og, const ObsRows &orows, int zone0, int nz,
            double *G, double *c, int32_t *mloc, DevCounters *ctr) {
-  const size_t smem = sizeof(double) * GRAM_CH * NP;
+  const size_t smem = sizeof(double) * 2 * GRAM_CH * NP;
   static bool attr_done = false;
   if (!attr_done) {
     CUDA_TRY(cudaFuncSetAttribute(k_gram<NP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
