@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--eig-kernel", type=int, default=0)
+    ap.add_argument("--jacobi-tol", type=float, default=0.0, help="experiment: override the Jacobi stopping tolerance")
     ap.add_argument("--phases", type=int, default=0, help="pipeline phases for N>1 (0: 4 when N>1, else 1)")
     return ap.parse_args()
 
@@ -239,6 +240,8 @@ def main():
         h = oak_b200.Handle(local, eig_kernel=a.eig_kernel)
         if os.environ.get("OAK_B200_FIXED_SWEEPS"):  # kernel timing experiments only (tools/ab.py)
             h.set_option("fixed_sweeps", float(os.environ["OAK_B200_FIXED_SWEEPS"]))
+        if a.jacobi_tol > 0:
+            h.set_option("jacobi_tol", a.jacobi_tol)
         h.set_zones(plan.zoneSize, zone_x=plan.zx, zone_y=plan.zy, corrLen=plan.corrLen, maxLen=plan.maxLen,
                     loctype=1, metrictype=0, weightfun=0)
         h.set_observations(obs_x=d["ox"], obs_y=d["oy"])
