@@ -29,12 +29,14 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-template <int NP, int TL>
+template <int NP, int TL, int KB>
 struct Cfg {
-  static constexpr int R = NP / TL;
-  static constexpr int NG = NP / 4;
+  static constexpr int R = NP / TL;          // rows of a column per lane
+  static constexpr int NCG = 2 * KB;         // columns per group: two blocks of KB columns
+  static constexpr int NG = NP / NCG;        // groups
   static constexpr int NTH = NG * TL;
-  static constexpr int NB = NP / 2;
+  static constexpr int NB = NP / KB;         // block positions
+  static_assert(KB == 1 || KB == 2, "one or two columns per block");
   static constexpr int LDW = NP;      // W / Y leading dimension in shared memory
   static constexpr int LDX = NP + 4;  // exchange-buffer column stride
   static_assert(R == 16 || R == 8, "8 or 16 rows per lane");
@@ -167,13 +169,13 @@ __device__ __forceinline__ void rotate_block_pair(double (&X0)[R], double (&X1)[
   }
 }
 
-template <int NP, int TL>
-__global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? (TL == 4 ? EIG_CTAS_PER_SM : 4) : 1))
+template <int NP, int TL, int KB>
+__global__ void __launch_bounds__(Cfg<NP, TL, KB>::NTH, (NP == 64 ? (TL == 4 && KB == 2 ? EIG_CTAS_PER_SM : 4) : 1))
     k_eig_fast(int N, const int32_t *__restrict__ mloc, const double *__restrict__ G,
                const double *__restrict__ cin, double *__restrict__ Tout, double *__restrict__ ampl_out,
                float tol, int max_sweeps, DevCounters *ctr) {
-  using C = Cfg<NP, TL>;
-  constexpr int R = C::R, NG = C::NG, NTH = C::NTH, NB = C::NB, LDW = C::LDW, LDX = C::LDX;
+  using C = Cfg<NP, TL, KB>;
+  constexpr int R = C::R, NG = C::NG, NTH = C::NTH, NB = C::NB, LDW = C::LDW, LDX = C::LDX, NCG = C::NCG;
   constexpr int NW = NTH / 32;
   constexpr int TG = NP / 8;  // Cholesky thread grid TG x TG, 8 x 8 elements per thread (cyclic)
   static_assert(TG * TG <= NTH, "Cholesky thread grid");
@@ -264,29 +266,36 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? (TL == 4 ? EIG_C
     for (int pi = 0; pi < R / 2; pi++)
       *reinterpret_cast<double2 *>(base + 2 * (pi * TL + r)) = make_double2(X[2 * pi], X[2 * pi + 1]);
   };
-  ld_col(P0, sW + LDW * (4 * g + 0));
-  ld_col(P1, sW + LDW * (4 * g + 1));
-  ld_col(Q0, sW + LDW * (4 * g + 2));
-  ld_col(Q1, sW + LDW * (4 * g + 3));
+  if constexpr (KB == 2) {
+    ld_col(P0, sW + LDW * (4 * g + 0));
+    ld_col(P1, sW + LDW * (4 * g + 1));
+    ld_col(Q0, sW + LDW * (4 * g + 2));
+    ld_col(Q1, sW + LDW * (4 * g + 3));
+  } else {  // one column per block: P1, Q1 unused
+    ld_col(P0, sW + LDW * (2 * g + 0));
+    ld_col(Q0, sW + LDW * (2 * g + 1));
+#pragma unroll
+    for (int i = 0; i < R; i++) { P1[i] = 0.; Q1[i] = 0.; }
+  }
   __syncthreads();  // sW is now free: exchange buffer
   double *xbuf = sW;
   Col cP0, cP1, cQ0, cQ1;
 
   auto lend = [&](int region, const double(&B0)[R], const double(&B1)[R], const Col &c0, const Col &c1) {
-    st_col(B0, xbuf + LDX * (2 * region));
-    st_col(B1, xbuf + LDX * (2 * region + 1));
+    st_col(B0, xbuf + LDX * (KB * region));
+    if constexpr (KB == 2) st_col(B1, xbuf + LDX * (KB * region + 1));
     if (r == 0) {
-      double *q = s_xs + 6 * region;
+      double *q = s_xs + 3 * KB * region;
       q[0] = c0.sg; q[1] = c0.ig; q[2] = c0.nn;
-      q[3] = c1.sg; q[4] = c1.ig; q[5] = c1.nn;
+      if constexpr (KB == 2) { q[3] = c1.sg; q[4] = c1.ig; q[5] = c1.nn; }
     }
   };
   auto take = [&](int region, double(&B0)[R], double(&B1)[R], Col &c0, Col &c1) {
-    ld_col(B0, xbuf + LDX * (2 * region));
-    ld_col(B1, xbuf + LDX * (2 * region + 1));
-    const double *q = s_xs + 6 * region;
+    ld_col(B0, xbuf + LDX * (KB * region));
+    if constexpr (KB == 2) ld_col(B1, xbuf + LDX * (KB * region + 1));
+    const double *q = s_xs + 3 * KB * region;
     c0.sg = q[0]; c0.ig = q[1]; c0.nn = q[2];
-    c1.sg = q[3]; c1.ig = q[4]; c1.nn = q[5];
+    if constexpr (KB == 2) { c1.sg = q[3]; c1.ig = q[4]; c1.nn = q[5]; }
   };
   // folds the deferred scale into the stored column and refreshes its norm
   auto renorm = [&](double(&X)[R], Col &cx, bool first) {
@@ -301,10 +310,25 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? (TL == 4 ? EIG_C
   int sweeps = 0;
   for (int sweep = 0; sweep < max_sweeps; sweep++) {
     if (tid == 0) { s_maxi = 0; s_maxt = 0; }
-    renorm(P0, cP0, sweep == 0); renorm(P1, cP1, sweep == 0);
-    renorm(Q0, cQ0, sweep == 0); renorm(Q1, cQ1, sweep == 0);
+    renorm(P0, cP0, sweep == 0);
+    renorm(Q0, cQ0, sweep == 0);
+    if constexpr (KB == 2) { renorm(P1, cP1, sweep == 0); renorm(Q1, cQ1, sweep == 0); }
     SweepStat ss{0.f, 0.f};
-    {  // the two columns of each block against each other
+    // one block pair = KB x KB column pairs, rotated in place
+    auto rotate_pair = [&](bool active) {
+      if constexpr (KB == 2) {
+        rotate_block_pair<R, TL>(P0, P1, Q0, Q1, cP0, cP1, cQ0, cQ1, active, ss);
+      } else {
+        const double g1 = group_sum<TL>(dotR<R>(P0, Q0));
+        const Rot r1 = rot_params(cP0, cQ0, g1, active);
+        ss.add(r1);
+        if (__any_sync(FULL, r1.on)) {
+          rot_apply<R>(P0, Q0, r1);
+          col_update(cP0, cQ0, r1);
+        }
+      }
+    };
+    if constexpr (KB == 2) {  // the two columns of each block against each other
       const double g1 = group_sum<TL>(dotR<R>(P0, P1)), g2 = group_sum<TL>(dotR<R>(Q0, Q1));
       const Rot r1 = rot_params(cP0, cP1, g1, true), r2 = rot_params(cQ0, cQ1, g2, true);
       ss.add(r1); ss.add(r2);
@@ -317,14 +341,14 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? (TL == 4 ? EIG_C
     }
     for (int step = 0; step < NB; step += 2) {
       // even step: positions (2g, 2g+1); afterwards position 2g lives in Q, 2g+1 in P
-      rotate_block_pair<R, TL>(P0, P1, Q0, Q1, cP0, cP1, cQ0, cQ1, true, ss);
+      rotate_pair(true);
       // odd step: positions (2g+1, 2g+2)
       const bool act = g < NG - 1;
       lend(g, Q0, Q1, cQ0, cQ1);
       if (!act) lend(NG, P0, P1, cP0, cP1);  // the last group parks its idle block (position NB-1)
       __syncthreads();
       if (act) take(g + 1, Q0, Q1, cQ0, cQ1);
-      rotate_block_pair<R, TL>(P0, P1, Q0, Q1, cP0, cP1, cQ0, cQ1, act, ss);
+      rotate_pair(act);
       if (act) lend(g + 1, P0, P1, cP0, cP1);  // the new position 2g+2 goes home
       __syncthreads();
       take(g, P0, P1, cP0, cP1);               // the new position 2g
@@ -341,7 +365,10 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? (TL == 4 ? EIG_C
   }
   // fold the scales: from here on the stored columns are the true z_j
 #pragma unroll
-  for (int i = 0; i < R; i++) { P0[i] *= cP0.sg; P1[i] *= cP1.sg; Q0[i] *= cQ0.sg; Q1[i] *= cQ1.sg; }
+  for (int i = 0; i < R; i++) {
+    P0[i] *= cP0.sg; Q0[i] *= cQ0.sg;
+    if constexpr (KB == 2) { P1[i] *= cP1.sg; Q1[i] *= cQ1.sg; }
+  }
 
   // ---- epilogue: matrix functions from the orthogonal columns z_j = sigma_j u_j ----
   // lane-local views of the vectors c and 1_{i<N}
@@ -366,7 +393,12 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? (TL == 4 ? EIG_C
       acol[slot] = zc / (s2 * s2c);     // (1+lambda)^-1 (u.c) / |z|
       bcol[slot] = z1 * rs / s2;        // (1+lambda)^+1/2 (u.1) / |z|
     };
-    stats(P0, 0); stats(P1, 1); stats(Q0, 2); stats(Q1, 3);
+    if constexpr (KB == 2) {
+      stats(P0, 0); stats(P1, 1); stats(Q0, 2); stats(Q1, 3);
+    } else {  // slots 0,1 = P0,Q0 ; the unused P1,Q1 registers are zero and get zero weights
+      stats(P0, 0); stats(Q0, 2);
+      dcol[1] = acol[1] = bcol[1] = 0.; dcol[3] = acol[3] = bcol[3] = 0.;
+    }
   }
   // partial sums over the 4 columns of a group, then over groups through shared memory
   double *s_part = sW;  // [2][NG][NP]
@@ -441,9 +473,13 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? (TL == 4 ? EIG_C
       }
     double t1[4], t2[4];
     t1[0] = dcol[0] * group_sum<TL>(dotR<R>(P0, xr1)); t2[0] = dcol[0] * group_sum<TL>(dotR<R>(P0, xr2));
-    t1[1] = dcol[1] * group_sum<TL>(dotR<R>(P1, xr1)); t2[1] = dcol[1] * group_sum<TL>(dotR<R>(P1, xr2));
     t1[2] = dcol[2] * group_sum<TL>(dotR<R>(Q0, xr1)); t2[2] = dcol[2] * group_sum<TL>(dotR<R>(Q0, xr2));
-    t1[3] = dcol[3] * group_sum<TL>(dotR<R>(Q1, xr1)); t2[3] = dcol[3] * group_sum<TL>(dotR<R>(Q1, xr2));
+    if constexpr (KB == 2) {
+      t1[1] = dcol[1] * group_sum<TL>(dotR<R>(P1, xr1)); t2[1] = dcol[1] * group_sum<TL>(dotR<R>(P1, xr2));
+      t1[3] = dcol[3] * group_sum<TL>(dotR<R>(Q1, xr1)); t2[3] = dcol[3] * group_sum<TL>(dotR<R>(Q1, xr2));
+    } else {
+      t1[1] = t2[1] = t1[3] = t2[3] = 0.;
+    }
     scatter2(t1, t2);
   }
   // kappa = hv u_v . (D u_w)
@@ -469,14 +505,15 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? (TL == 4 ? EIG_C
   // Y = Z diag(sqrt(d)) to shared memory (column j = 4g+slot)
   double *Ys = sW;
   {
-    auto put = [&](const double(&Z)[R], int slot) {
+    auto put = [&](const double(&Z)[R], int slot, int colg) {
       const double sc = sqrt(dcol[slot]);
-      double *base = Ys + LDW * (4 * g + slot);
+      double *base = Ys + LDW * (NCG * g + colg);
 #pragma unroll
       for (int pi = 0; pi < R / 2; pi++)
         *reinterpret_cast<double2 *>(base + 2 * (pi * TL + r)) = make_double2(Z[2 * pi] * sc, Z[2 * pi + 1] * sc);
     };
-    put(P0, 0); put(P1, 1); put(Q0, 2); put(Q1, 3);
+    if constexpr (KB == 2) { put(P0, 0, 0); put(P1, 1, 1); put(Q0, 2, 2); put(Q1, 3, 3); }
+    else { put(P0, 0, 0); put(Q0, 2, 1); }
   }
   __syncthreads();
   // M = Y Y^T in 8x8 register tiles, then T = (M - g1 (hv u_v)^T) D - g2 (hw u_w)^T, row-major
@@ -534,18 +571,19 @@ __global__ void __launch_bounds__(Cfg<NP, TL>::NTH, (NP == 64 ? (TL == 4 ? EIG_C
   if (tid == 0) atomicAdd(&ctr->sweeps, (unsigned long long)sweeps);
 }
 
-template <int NP, int TL>
+template <int NP, int TL, int KB>
 int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G, const double *c, double *T,
            double *ampl, double tol, int max_sweeps, DevCounters *ctr) {
-  using C = Cfg<NP, TL>;
+  using C = Cfg<NP, TL, KB>;
   const size_t smem = sizeof(double) * (NP * C::LDW + 9 * NP);
-  static_assert((C::NG + 1) * 2 * C::LDX <= NP * C::LDW && 6 * (C::NG + 1) <= 2 * NP, "exchange buffer fits");
+  static_assert((C::NG + 1) * KB * C::LDX <= NP * C::LDW && 3 * KB * (C::NG + 1) <= 2 * NP, "exchange buffer fits");
+  static_assert(2 * C::NG * NP <= NP * C::LDW, "partial-sum buffer fits");
   static bool attr_done = false;
   if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(k_eig_fast<NP, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_eig_fast<NP, TL, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  k_eig_fast<NP, TL><<<nz, C::NTH, smem, st>>>(N, mloc, G, c, T, ampl, (float)tol, max_sweeps, ctr);
+  k_eig_fast<NP, TL, KB><<<nz, C::NTH, smem, st>>>(N, mloc, G, c, T, ampl, (float)tol, max_sweeps, ctr);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -561,8 +599,11 @@ int oak_launch_eig(cudaStream_t st, int kernel, int N, int NP, int zone0, int nz
                    DevCounters *ctr) {
   if (nz <= 0) return 0;
   const int32_t *ml = mloc + zone0;
-  if (kernel == 0 && NP == 64) return launch<64, 4>(st, N, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
-  if (kernel == 2 && NP == 64) return launch<64, 8>(st, N, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
-  if (kernel == 0 && NP == 128) return launch<128, 8>(st, N, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
+  // 0: production (two columns per block, 4 lanes per group at NP=64 / 8 at NP=128); 2, 3: measured variants
+  if (kernel == 0 && NP == 64) return launch<64, 4, 2>(st, N, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
+  if (kernel == 2 && NP == 64) return launch<64, 8, 2>(st, N, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
+  if (kernel == 3 && NP == 64) return launch<64, 4, 1>(st, N, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
+  if ((kernel == 0 || kernel == 2 || kernel == 3) && NP == 128)
+    return launch<128, 8, 2>(st, N, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
   return oak_launch_eig_simple(st, N, NP, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
 }
