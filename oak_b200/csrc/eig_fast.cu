@@ -84,7 +84,7 @@ struct Col {
 #define JACOBI_SKIP2 1e-26f  // (JACOBI_SKIP)^2, on cos^2
 
 struct Rot {
-  double t1, t2, c, ic, tg;
+  double t1, t2, c, s, ic, tg;
   float k2, ta;
   bool on;
 };
@@ -93,9 +93,9 @@ struct Rot {
 // The angle only steers convergence, so t = tan(theta) is computed in fp32; c = (1+t^2)^-1/2 must make
 // the transformation orthogonal to fp64 accuracy: fp32 rsqrt + one fp32 and one fp64 Newton step
 // (error 1.5 eps32^2 ~ 5e-15 per rotation, unbiased, far below the 1e-9 budget after a few 1e3 rotations).
-__device__ __forceinline__ Rot rot_params(const Col &p, const Col &q, double Gam, bool active) {
+// g is the TRUE dot product of the two columns (stored dot times both scales).
+__device__ __forceinline__ Rot rot_params(const Col &p, const Col &q, double g, bool active) {
   Rot r;
-  const double g = (p.sg * q.sg) * Gam;
   const float gf = (float)g;
   r.k2 = __fdividef(gf * gf, (float)p.nn * (float)q.nn);
   r.on = active && (r.k2 > JACOBI_SKIP2);
@@ -113,6 +113,7 @@ __device__ __forceinline__ Rot rot_params(const Col &p, const Col &q, double Gam
   double c = (double)cf;
   c = c * fma(-0.5 * y, c * c, 1.5);
   r.c = c;
+  r.s = tt * c;
   r.ic = y * c;
   r.t1 = tt * (q.sg * p.ig);
   r.t2 = (tt * (c * c)) * (p.sg * q.ig);
@@ -146,7 +147,8 @@ __device__ __forceinline__ void rotate_block_pair(double (&X0)[R], double (&X1)[
                                                   double (&Y1)[R], Col &cX0, Col &cX1, Col &cY0, Col &cY1,
                                                   bool active, SweepStat &ss) {
   {  // sub-round 1: (X0,Y0) (X1,Y1)
-    const double g1 = group_sum<TL>(dotR<R>(X0, Y0)), g2 = group_sum<TL>(dotR<R>(X1, Y1));
+    const double g1 = (cX0.sg * cY0.sg) * group_sum<TL>(dotR<R>(X0, Y0));
+    const double g2 = (cX1.sg * cY1.sg) * group_sum<TL>(dotR<R>(X1, Y1));
     const Rot r1 = rot_params(cX0, cY0, g1, active), r2 = rot_params(cX1, cY1, g2, active);
     ss.add(r1); ss.add(r2);
     if (__any_sync(FULL, r1.on || r2.on)) {
@@ -157,7 +159,8 @@ __device__ __forceinline__ void rotate_block_pair(double (&X0)[R], double (&X1)[
     }
   }
   {  // sub-round 2: (X0,Y1) (X1,Y0)
-    const double g1 = group_sum<TL>(dotR<R>(X0, Y1)), g2 = group_sum<TL>(dotR<R>(X1, Y0));
+    const double g1 = (cX0.sg * cY1.sg) * group_sum<TL>(dotR<R>(X0, Y1));
+    const double g2 = (cX1.sg * cY0.sg) * group_sum<TL>(dotR<R>(X1, Y0));
     const Rot r1 = rot_params(cX0, cY1, g1, active), r2 = rot_params(cX1, cY0, g2, active);
     ss.add(r1); ss.add(r2);
     if (__any_sync(FULL, r1.on || r2.on)) {
@@ -168,6 +171,58 @@ __device__ __forceinline__ void rotate_block_pair(double (&X0)[R], double (&X1)[
     }
   }
 }
+
+// Same four rotations with ONE reduction phase: the four cross dot products of the block pair are taken
+// up front; the dot products the second sub-round needs, (X0',Y1') and (X1',Y0'), follow from them and
+// from the intra-block dots gX = x0.x1, gY = y0.y1 (carried with the blocks) by the 4x4 Gram algebra of
+// the two first rotations (a'=c1 a - s1 c, c'=s1 a + c1 c, b'=c2 b - s2 d, d'=s2 b + c2 d):
+//   a'.d' = c1 s2 ab + c1 c2 ad - s1 s2 cb - s1 c2 cd      c'.b' = s1 c2 ab - s1 s2 ad + c1 c2 cb - c1 s2 cd
+//   a'.b' = c1 c2 ab - c1 s2 ad - s1 c2 cb + s1 s2 cd      c'.d' = s1 s2 ab + s1 c2 ad + c1 s2 cb + c1 c2 cd
+// and after the second sub-round (a''=c3 a' - s3 d', d''=.., b''=c4 b' - s4 c', c''=..):
+//   gX'' = a''.b'' = c3 c4 a'.b' + s3 s4 c'.d'              gY'' = c''.d'' = s3 s4 a'.b' + c3 c4 c'.d'
+// All scalar work is fp64 on true (unscaled) quantities; the columns are then updated in one pass of
+// 8 in-place FMAs per row.  Halves the number of latency-exposed dot -> shuffle -> parameter chains.
+template <int R, int TL>
+__device__ __forceinline__ void rotate_block_pair_gram(double (&X0)[R], double (&X1)[R], double (&Y0)[R],
+                                                       double (&Y1)[R], Col &cX0, Col &cX1, Col &cY0, Col &cY1,
+                                                       double &gX, double &gY, bool active, SweepStat &ss) {
+  const double d_ac = group_sum<TL>(dotR<R>(X0, Y0)), d_bd = group_sum<TL>(dotR<R>(X1, Y1));
+  const double d_ad = group_sum<TL>(dotR<R>(X0, Y1)), d_cb = group_sum<TL>(dotR<R>(X1, Y0));
+  const double ac = (cX0.sg * cY0.sg) * d_ac, bd = (cX1.sg * cY1.sg) * d_bd;
+  const double ad = (cX0.sg * cY1.sg) * d_ad, cb = (cX1.sg * cY0.sg) * d_cb;
+  const double ab = gX, cd = gY;
+  const Rot r1 = rot_params(cX0, cY0, ac, active), r2 = rot_params(cX1, cY1, bd, active);
+  col_update(cX0, cY0, r1);
+  col_update(cX1, cY1, r2);
+  const double c1c2 = r1.c * r2.c, c1s2 = r1.c * r2.s, s1c2 = r1.s * r2.c, s1s2 = r1.s * r2.s;
+  const double a1d1 = fma(c1s2, ab, fma(c1c2, ad, -fma(s1s2, cb, s1c2 * cd)));
+  const double c1b1 = fma(s1c2, ab, fma(c1c2, cb, -fma(s1s2, ad, c1s2 * cd)));
+  const double a1b1 = fma(c1c2, ab, fma(s1s2, cd, -fma(c1s2, ad, s1c2 * cb)));
+  const double c1d1 = fma(s1s2, ab, fma(s1c2, ad, fma(c1s2, cb, c1c2 * cd)));
+  const Rot r3 = rot_params(cX0, cY1, a1d1, active), r4 = rot_params(cX1, cY0, c1b1, active);
+  col_update(cX0, cY1, r3);
+  col_update(cX1, cY0, r4);
+  const double c3c4 = r3.c * r4.c, s3s4 = r3.s * r4.s;
+  gX = fma(c3c4, a1b1, s3s4 * c1d1);
+  gY = fma(s3s4, a1b1, c3c4 * c1d1);
+  ss.add(r1); ss.add(r2); ss.add(r3); ss.add(r4);
+  if (__any_sync(FULL, r1.on || r2.on || r3.on || r4.on)) {
+    const double m1 = -r1.t1, m2 = -r2.t1, m3 = -r3.t1, m4 = -r4.t1;
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      double x0 = X0[i], x1 = X1[i], y0 = Y0[i], y1 = Y1[i];
+      x0 = fma(m1, y0, x0); x1 = fma(m2, y1, x1);
+      y0 = fma(r1.t2, x0, y0); y1 = fma(r2.t2, x1, y1);
+      x0 = fma(m3, y1, x0); x1 = fma(m4, y0, x1);
+      y1 = fma(r3.t2, x0, y1); y0 = fma(r4.t2, x1, y0);
+      X0[i] = x0; X1[i] = x1; Y0[i] = y0; Y1[i] = y1;
+    }
+  }
+}
+
+#ifndef EIG_GRAM_ALGEBRA
+#define EIG_GRAM_ALGEBRA 1
+#endif
 
 template <int NP, int TL, int KB>
 __global__ void __launch_bounds__(Cfg<NP, TL, KB>::NTH, (NP == 64 ? (TL == 4 && KB == 2 ? EIG_CTAS_PER_SM : 4) : 1))
@@ -281,21 +336,23 @@ __global__ void __launch_bounds__(Cfg<NP, TL, KB>::NTH, (NP == 64 ? (TL == 4 && 
   double *xbuf = sW;
   Col cP0, cP1, cQ0, cQ1;
 
-  auto lend = [&](int region, const double(&B0)[R], const double(&B1)[R], const Col &c0, const Col &c1) {
+  constexpr int SX = (KB == 2) ? 7 : 3;  // scalars travelling with a block: (sg, ig, nn) per column + intra dot
+  double gP = 0., gQ = 0.;               // true dot product of the two columns of block P / Q
+  auto lend = [&](int region, const double(&B0)[R], const double(&B1)[R], const Col &c0, const Col &c1, double gi) {
     st_col(B0, xbuf + LDX * (KB * region));
     if constexpr (KB == 2) st_col(B1, xbuf + LDX * (KB * region + 1));
     if (r == 0) {
-      double *q = s_xs + 3 * KB * region;
+      double *q = s_xs + SX * region;
       q[0] = c0.sg; q[1] = c0.ig; q[2] = c0.nn;
-      if constexpr (KB == 2) { q[3] = c1.sg; q[4] = c1.ig; q[5] = c1.nn; }
+      if constexpr (KB == 2) { q[3] = c1.sg; q[4] = c1.ig; q[5] = c1.nn; q[6] = gi; }
     }
   };
-  auto take = [&](int region, double(&B0)[R], double(&B1)[R], Col &c0, Col &c1) {
+  auto take = [&](int region, double(&B0)[R], double(&B1)[R], Col &c0, Col &c1, double &gi) {
     ld_col(B0, xbuf + LDX * (KB * region));
     if constexpr (KB == 2) ld_col(B1, xbuf + LDX * (KB * region + 1));
-    const double *q = s_xs + 3 * KB * region;
+    const double *q = s_xs + SX * region;
     c0.sg = q[0]; c0.ig = q[1]; c0.nn = q[2];
-    if constexpr (KB == 2) { c1.sg = q[3]; c1.ig = q[4]; c1.nn = q[5]; }
+    if constexpr (KB == 2) { c1.sg = q[3]; c1.ig = q[4]; c1.nn = q[5]; gi = q[6]; }
   };
   // folds the deferred scale into the stored column and refreshes its norm
   auto renorm = [&](double(&X)[R], Col &cx, bool first) {
@@ -316,10 +373,12 @@ __global__ void __launch_bounds__(Cfg<NP, TL, KB>::NTH, (NP == 64 ? (TL == 4 && 
     SweepStat ss{0.f, 0.f};
     // one block pair = KB x KB column pairs, rotated in place
     auto rotate_pair = [&](bool active) {
-      if constexpr (KB == 2) {
+      if constexpr (KB == 2 && EIG_GRAM_ALGEBRA) {
+        rotate_block_pair_gram<R, TL>(P0, P1, Q0, Q1, cP0, cP1, cQ0, cQ1, gP, gQ, active, ss);
+      } else if constexpr (KB == 2) {
         rotate_block_pair<R, TL>(P0, P1, Q0, Q1, cP0, cP1, cQ0, cQ1, active, ss);
       } else {
-        const double g1 = group_sum<TL>(dotR<R>(P0, Q0));
+        const double g1 = (cP0.sg * cQ0.sg) * group_sum<TL>(dotR<R>(P0, Q0));
         const Rot r1 = rot_params(cP0, cQ0, g1, active);
         ss.add(r1);
         if (__any_sync(FULL, r1.on)) {
@@ -329,6 +388,7 @@ __global__ void __launch_bounds__(Cfg<NP, TL, KB>::NTH, (NP == 64 ? (TL == 4 && 
       }
     };
     if constexpr (KB == 2) {  // the two columns of each block against each other
+      // scales are 1 here (just folded): stored dots are true dots
       const double g1 = group_sum<TL>(dotR<R>(P0, P1)), g2 = group_sum<TL>(dotR<R>(Q0, Q1));
       const Rot r1 = rot_params(cP0, cP1, g1, true), r2 = rot_params(cQ0, cQ1, g2, true);
       ss.add(r1); ss.add(r2);
@@ -338,21 +398,23 @@ __global__ void __launch_bounds__(Cfg<NP, TL, KB>::NTH, (NP == 64 ? (TL == 4 && 
         col_update(cP0, cP1, r1);
         col_update(cQ0, cQ1, r2);
       }
+      gP = r1.on ? 0. : g1;  // rotated pairs are orthogonal; skipped ones keep their (negligible) dot
+      gQ = r2.on ? 0. : g2;
     }
     for (int step = 0; step < NB; step += 2) {
       // even step: positions (2g, 2g+1); afterwards position 2g lives in Q, 2g+1 in P
       rotate_pair(true);
       // odd step: positions (2g+1, 2g+2)
       const bool act = g < NG - 1;
-      lend(g, Q0, Q1, cQ0, cQ1);
-      if (!act) lend(NG, P0, P1, cP0, cP1);  // the last group parks its idle block (position NB-1)
+      lend(g, Q0, Q1, cQ0, cQ1, gQ);
+      if (!act) lend(NG, P0, P1, cP0, cP1, gP);  // the last group parks its idle block (position NB-1)
       __syncthreads();
-      if (act) take(g + 1, Q0, Q1, cQ0, cQ1);
+      if (act) take(g + 1, Q0, Q1, cQ0, cQ1, gQ);
       rotate_pair(act);
-      if (act) lend(g + 1, P0, P1, cP0, cP1);  // the new position 2g+2 goes home
+      if (act) lend(g + 1, P0, P1, cP0, cP1, gP);  // the new position 2g+2 goes home
       __syncthreads();
-      take(g, P0, P1, cP0, cP1);               // the new position 2g
-      if (!act) take(NG, Q0, Q1, cQ0, cQ1);
+      take(g, P0, P1, cP0, cP1, gP);               // the new position 2g
+      if (!act) take(NG, Q0, Q1, cQ0, cQ1, gQ);
     }
     atomicMax(&s_maxi, __float_as_int(ss.mx2));
     atomicMax(&s_maxt, __float_as_int(ss.mt));
@@ -576,7 +638,7 @@ int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G,
            double *ampl, double tol, int max_sweeps, DevCounters *ctr) {
   using C = Cfg<NP, TL, KB>;
   const size_t smem = sizeof(double) * (NP * C::LDW + 9 * NP);
-  static_assert((C::NG + 1) * KB * C::LDX <= NP * C::LDW && 3 * KB * (C::NG + 1) <= 2 * NP, "exchange buffer fits");
+  static_assert((C::NG + 1) * KB * C::LDX <= NP * C::LDW && (KB == 2 ? 7 : 3) * (C::NG + 1) <= 2 * NP, "exchange buffer fits");
   static_assert(2 * C::NG * NP <= NP * C::LDW, "partial-sum buffer fits");
   static bool attr_done = false;
   if (!attr_done) {
