@@ -326,7 +326,10 @@ def main():
         fz = flops_per_zone(a.N, a.nz, mloc_mean, cand_mean)
         roof = {"bound": "fp64", "kernel": "k_eig_fast (batched Cholesky + block-Jacobi + transform)",
                 "achieved": achieved, "peak": peak_dfma, "unit": "TFLOP/s", "frac": achieved / peak_dfma,
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of k_eig_fast from the ncu --set full capture in
+                # profiles/r1_ncu_full_eig.txt: 141.3 MB for a 3552-zone launch = 39.8 KB per zone (below the
+                # algorithmic 2 x 32 KB: part of G is still in L2 from k_gram), scaled to this run's launch size
+                "traffic": 39.8e3 * (z_rank / nb) if a.N == 64 else None,
                 "peak_source": "DFMA micro-kernel measured in this run (oakb200_fp64_peak); MEASURED_PEAKS.json has no "
                                "fp64 figure; DMMA m8n8k4 measured %.1f TFLOP/s" % peak_dmma,
                 "algorithmic_flops_per_zone_kernel": eig_flops_zone, "launches_per_step": nb,
