@@ -93,20 +93,38 @@ struct Rot {
 // The angle only steers convergence, so t = tan(theta) is computed in fp32; c = (1+t^2)^-1/2 must make
 // the transformation orthogonal to fp64 accuracy: fp32 rsqrt + one fp32 and one fp64 Newton step
 // (error 1.5 eps32^2 ~ 5e-15 per rotation, unbiased, far below the 1e-9 budget after a few 1e3 rotations).
+// fp32 helpers as single instructions: plain cvt (one F2F; the compiler's -ftz conversion adds a fp64
+// compare and a fix-up multiply per cast), approximate reciprocal / rsqrt with flush-to-zero (one MUFU).
+__device__ __forceinline__ float d2f(double x) {
+  float y;
+  asm("cvt.rn.f32.f64 %0, %1;" : "=f"(y) : "d"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // g is the TRUE dot product of the two columns (stored dot times both scales).
 __device__ __forceinline__ Rot rot_params(const Col &p, const Col &q, double g, bool active) {
   Rot r;
-  const float gf = (float)g;
-  r.k2 = __fdividef(gf * gf, (float)p.nn * (float)q.nn);
+  const float gf = d2f(g);
+  r.k2 = (gf * gf) * rcp_approx(d2f(p.nn) * d2f(q.nn));
   r.on = active && (r.k2 > JACOBI_SKIP2);
-  const float df = (float)(q.nn - p.nn), g2f = gf + gf;
+  const float df = d2f(q.nn - p.nn), g2f = gf + gf;
   const float h2 = fmaf(df, df, g2f * g2f);
-  const float h = h2 * rsqrtf(h2);
-  float tf = __fdividef(g2f, df + copysignf(h, df));
+  const float h = h2 * rsqrt_approx(h2);
+  float tf = g2f * rcp_approx(df + copysignf(h, df));
   r.ta = fabsf(tf);
   tf = r.on ? tf : 0.f;
   const float yf = fmaf(tf, tf, 1.f);
-  float cf = rsqrtf(yf);
+  float cf = rsqrt_approx(yf);
   cf = cf * fmaf(-0.5f * yf, cf * cf, 1.5f);
   const double tt = (double)tf;
   const double y = fma(tt, tt, 1.);
