@@ -79,13 +79,14 @@ struct Col {
   double sg, ig;  // deferred scale of the stored column and its inverse
   double nn;      // |true column|^2.  fp64 on purpose: the difference of two nearly equal norms decides the
                   // angle inside clusters; tracking it in fp32 costs up to 8 extra sweeps there (measured)
+  float sf, nf;   // fp32 shadows of sg and nn for the quantities that only steer the angle / the tests
 };
 
 #define JACOBI_SKIP2 1e-26f  // (JACOBI_SKIP)^2, on cos^2
 
 struct Rot {
-  double t1, t2, c, s, ic, tg;
-  float k2, ta;
+  double t1, t2, c, ic, tg;
+  float cf, sf, tgf, k2, ta;  // fp32 cosine / sine for the Gram algebra, t*g for the fp32 norm shadow
   bool on;
 };
 
@@ -111,11 +112,10 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
   return y;
 }
 
-// g is the TRUE dot product of the two columns (stored dot times both scales).
-__device__ __forceinline__ Rot rot_params(const Col &p, const Col &q, double g, bool active) {
+// gf is the TRUE dot product of the two columns (stored dot times both scales), in fp32.
+__device__ __forceinline__ Rot rot_params(const Col &p, const Col &q, float gf, bool active) {
   Rot r;
-  const float gf = d2f(g);
-  r.k2 = (gf * gf) * rcp_approx(d2f(p.nn) * d2f(q.nn));
+  r.k2 = (gf * gf) * rcp_approx(p.nf * q.nf);
   r.on = active && (r.k2 > JACOBI_SKIP2);
   const float df = d2f(q.nn - p.nn), g2f = gf + gf;
   const float h2 = fmaf(df, df, g2f * g2f);
@@ -126,16 +126,18 @@ __device__ __forceinline__ Rot rot_params(const Col &p, const Col &q, double g, 
   const float yf = fmaf(tf, tf, 1.f);
   float cf = rsqrt_approx(yf);
   cf = cf * fmaf(-0.5f * yf, cf * cf, 1.5f);
+  r.cf = cf;
+  r.sf = tf * cf;
+  r.tgf = tf * gf;
   const double tt = (double)tf;
   const double y = fma(tt, tt, 1.);
   double c = (double)cf;
   c = c * fma(-0.5 * y, c * c, 1.5);
   r.c = c;
-  r.s = tt * c;
   r.ic = y * c;
   r.t1 = tt * (q.sg * p.ig);
-  r.t2 = (tt * (c * c)) * (p.sg * q.ig);
-  r.tg = tt * g;
+  r.t2 = ((tt * c) * c) * (p.sg * q.ig);
+  r.tg = (double)r.tgf;
   return r;
 }
 
@@ -150,6 +152,9 @@ __device__ __forceinline__ void rot_apply(double (&x)[R], double (&y)[R], const 
 __device__ __forceinline__ void col_update(Col &p, Col &q, const Rot &r) {
   p.sg *= r.c; p.ig *= r.ic; p.nn -= r.tg;
   q.sg *= r.ic; q.ig *= r.c; q.nn += r.tg;
+  const float icf = fmaf(r.sf, r.sf * rcp_approx(r.cf), r.cf);  // 1/c = c + s^2/c
+  p.sf *= r.cf; p.nf -= r.tgf;
+  q.sf *= icf; q.nf += r.tgf;
 }
 
 struct SweepStat {  // maxima over the rotated pairs of a sweep (jacobi_converged)
@@ -165,8 +170,8 @@ __device__ __forceinline__ void rotate_block_pair(double (&X0)[R], double (&X1)[
                                                   double (&Y1)[R], Col &cX0, Col &cX1, Col &cY0, Col &cY1,
                                                   bool active, SweepStat &ss) {
   {  // sub-round 1: (X0,Y0) (X1,Y1)
-    const double g1 = (cX0.sg * cY0.sg) * group_sum<TL>(dotR<R>(X0, Y0));
-    const double g2 = (cX1.sg * cY1.sg) * group_sum<TL>(dotR<R>(X1, Y1));
+    const float g1 = (cX0.sf * cY0.sf) * d2f(group_sum<TL>(dotR<R>(X0, Y0)));
+    const float g2 = (cX1.sf * cY1.sf) * d2f(group_sum<TL>(dotR<R>(X1, Y1)));
     const Rot r1 = rot_params(cX0, cY0, g1, active), r2 = rot_params(cX1, cY1, g2, active);
     ss.add(r1); ss.add(r2);
     if (__any_sync(FULL, r1.on || r2.on)) {
@@ -177,8 +182,8 @@ __device__ __forceinline__ void rotate_block_pair(double (&X0)[R], double (&X1)[
     }
   }
   {  // sub-round 2: (X0,Y1) (X1,Y0)
-    const double g1 = (cX0.sg * cY1.sg) * group_sum<TL>(dotR<R>(X0, Y1));
-    const double g2 = (cX1.sg * cY0.sg) * group_sum<TL>(dotR<R>(X1, Y0));
+    const float g1 = (cX0.sf * cY1.sf) * d2f(group_sum<TL>(dotR<R>(X0, Y1)));
+    const float g2 = (cX1.sf * cY0.sf) * d2f(group_sum<TL>(dotR<R>(X1, Y0)));
     const Rot r1 = rot_params(cX0, cY1, g1, active), r2 = rot_params(cX1, cY0, g2, active);
     ss.add(r1); ss.add(r2);
     if (__any_sync(FULL, r1.on || r2.on)) {
@@ -203,26 +208,27 @@ __device__ __forceinline__ void rotate_block_pair(double (&X0)[R], double (&X1)[
 template <int R, int TL>
 __device__ __forceinline__ void rotate_block_pair_gram(double (&X0)[R], double (&X1)[R], double (&Y0)[R],
                                                        double (&Y1)[R], Col &cX0, Col &cX1, Col &cY0, Col &cY1,
-                                                       double &gX, double &gY, bool active, SweepStat &ss) {
+                                                       float &gX, float &gY, bool active, SweepStat &ss) {
   const double d_ac = group_sum<TL>(dotR<R>(X0, Y0)), d_bd = group_sum<TL>(dotR<R>(X1, Y1));
   const double d_ad = group_sum<TL>(dotR<R>(X0, Y1)), d_cb = group_sum<TL>(dotR<R>(X1, Y0));
-  const double ac = (cX0.sg * cY0.sg) * d_ac, bd = (cX1.sg * cY1.sg) * d_bd;
-  const double ad = (cX0.sg * cY1.sg) * d_ad, cb = (cX1.sg * cY0.sg) * d_cb;
-  const double ab = gX, cd = gY;
+  // true dot products; they only steer angles and tests: fp32 from here on
+  const float ac = (cX0.sf * cY0.sf) * d2f(d_ac), bd = (cX1.sf * cY1.sf) * d2f(d_bd);
+  const float ad = (cX0.sf * cY1.sf) * d2f(d_ad), cb = (cX1.sf * cY0.sf) * d2f(d_cb);
+  const float ab = gX, cd = gY;
   const Rot r1 = rot_params(cX0, cY0, ac, active), r2 = rot_params(cX1, cY1, bd, active);
   col_update(cX0, cY0, r1);
   col_update(cX1, cY1, r2);
-  const double c1c2 = r1.c * r2.c, c1s2 = r1.c * r2.s, s1c2 = r1.s * r2.c, s1s2 = r1.s * r2.s;
-  const double a1d1 = fma(c1s2, ab, fma(c1c2, ad, -fma(s1s2, cb, s1c2 * cd)));
-  const double c1b1 = fma(s1c2, ab, fma(c1c2, cb, -fma(s1s2, ad, c1s2 * cd)));
-  const double a1b1 = fma(c1c2, ab, fma(s1s2, cd, -fma(c1s2, ad, s1c2 * cb)));
-  const double c1d1 = fma(s1s2, ab, fma(s1c2, ad, fma(c1s2, cb, c1c2 * cd)));
+  const float c1c2 = r1.cf * r2.cf, c1s2 = r1.cf * r2.sf, s1c2 = r1.sf * r2.cf, s1s2 = r1.sf * r2.sf;
+  const float a1d1 = fmaf(c1s2, ab, fmaf(c1c2, ad, -fmaf(s1s2, cb, s1c2 * cd)));
+  const float c1b1 = fmaf(s1c2, ab, fmaf(c1c2, cb, -fmaf(s1s2, ad, c1s2 * cd)));
+  const float a1b1 = fmaf(c1c2, ab, fmaf(s1s2, cd, -fmaf(c1s2, ad, s1c2 * cb)));
+  const float c1d1 = fmaf(s1s2, ab, fmaf(s1c2, ad, fmaf(c1s2, cb, c1c2 * cd)));
   const Rot r3 = rot_params(cX0, cY1, a1d1, active), r4 = rot_params(cX1, cY0, c1b1, active);
   col_update(cX0, cY1, r3);
   col_update(cX1, cY0, r4);
-  const double c3c4 = r3.c * r4.c, s3s4 = r3.s * r4.s;
-  gX = fma(c3c4, a1b1, s3s4 * c1d1);
-  gY = fma(s3s4, a1b1, c3c4 * c1d1);
+  const float c3c4 = r3.cf * r4.cf, s3s4 = r3.sf * r4.sf;
+  gX = fmaf(c3c4, a1b1, s3s4 * c1d1);
+  gY = fmaf(s3s4, a1b1, c3c4 * c1d1);
   ss.add(r1); ss.add(r2); ss.add(r3); ss.add(r4);
   if (__any_sync(FULL, r1.on || r2.on || r3.on || r4.on)) {
     const double m1 = -r1.t1, m2 = -r2.t1, m3 = -r3.t1, m4 = -r4.t1;
@@ -355,22 +361,26 @@ __global__ void __launch_bounds__(Cfg<NP, TL, KB>::NTH, (NP == 64 ? (TL == 4 && 
   Col cP0, cP1, cQ0, cQ1;
 
   constexpr int SX = (KB == 2) ? 7 : 3;  // scalars travelling with a block: (sg, ig, nn) per column + intra dot
-  double gP = 0., gQ = 0.;               // true dot product of the two columns of block P / Q
-  auto lend = [&](int region, const double(&B0)[R], const double(&B1)[R], const Col &c0, const Col &c1, double gi) {
+  float gP = 0.f, gQ = 0.f;              // true dot product of the two columns of block P / Q (fp32)
+  auto lend = [&](int region, const double(&B0)[R], const double(&B1)[R], const Col &c0, const Col &c1, float gi) {
     st_col(B0, xbuf + LDX * (KB * region));
     if constexpr (KB == 2) st_col(B1, xbuf + LDX * (KB * region + 1));
     if (r == 0) {
       double *q = s_xs + SX * region;
       q[0] = c0.sg; q[1] = c0.ig; q[2] = c0.nn;
-      if constexpr (KB == 2) { q[3] = c1.sg; q[4] = c1.ig; q[5] = c1.nn; q[6] = gi; }
+      if constexpr (KB == 2) { q[3] = c1.sg; q[4] = c1.ig; q[5] = c1.nn; q[6] = (double)gi; }
     }
   };
-  auto take = [&](int region, double(&B0)[R], double(&B1)[R], Col &c0, Col &c1, double &gi) {
+  auto take = [&](int region, double(&B0)[R], double(&B1)[R], Col &c0, Col &c1, float &gi) {
     ld_col(B0, xbuf + LDX * (KB * region));
     if constexpr (KB == 2) ld_col(B1, xbuf + LDX * (KB * region + 1));
     const double *q = s_xs + SX * region;
     c0.sg = q[0]; c0.ig = q[1]; c0.nn = q[2];
-    if constexpr (KB == 2) { c1.sg = q[3]; c1.ig = q[4]; c1.nn = q[5]; gi = q[6]; }
+    c0.sf = d2f(c0.sg); c0.nf = d2f(c0.nn);
+    if constexpr (KB == 2) {
+      c1.sg = q[3]; c1.ig = q[4]; c1.nn = q[5]; gi = d2f(q[6]);
+      c1.sf = d2f(c1.sg); c1.nf = d2f(c1.nn);
+    }
   };
   // folds the deferred scale into the stored column and refreshes its norm
   auto renorm = [&](double(&X)[R], Col &cx, bool first) {
@@ -378,8 +388,9 @@ __global__ void __launch_bounds__(Cfg<NP, TL, KB>::NTH, (NP == 64 ? (TL == 4 && 
 #pragma unroll
       for (int i = 0; i < R; i++) X[i] *= cx.sg;
     }
-    cx.sg = 1.; cx.ig = 1.;
+    cx.sg = 1.; cx.ig = 1.; cx.sf = 1.f;
     cx.nn = group_sum<TL>(dotR<R>(X, X));
+    cx.nf = d2f(cx.nn);
   };
 
   int sweeps = 0;
@@ -396,7 +407,7 @@ __global__ void __launch_bounds__(Cfg<NP, TL, KB>::NTH, (NP == 64 ? (TL == 4 && 
       } else if constexpr (KB == 2) {
         rotate_block_pair<R, TL>(P0, P1, Q0, Q1, cP0, cP1, cQ0, cQ1, active, ss);
       } else {
-        const double g1 = (cP0.sg * cQ0.sg) * group_sum<TL>(dotR<R>(P0, Q0));
+        const float g1 = (cP0.sf * cQ0.sf) * d2f(group_sum<TL>(dotR<R>(P0, Q0)));
         const Rot r1 = rot_params(cP0, cQ0, g1, active);
         ss.add(r1);
         if (__any_sync(FULL, r1.on)) {
@@ -407,7 +418,7 @@ __global__ void __launch_bounds__(Cfg<NP, TL, KB>::NTH, (NP == 64 ? (TL == 4 && 
     };
     if constexpr (KB == 2) {  // the two columns of each block against each other
       // scales are 1 here (just folded): stored dots are true dots
-      const double g1 = group_sum<TL>(dotR<R>(P0, P1)), g2 = group_sum<TL>(dotR<R>(Q0, Q1));
+      const float g1 = d2f(group_sum<TL>(dotR<R>(P0, P1))), g2 = d2f(group_sum<TL>(dotR<R>(Q0, Q1)));
       const Rot r1 = rot_params(cP0, cP1, g1, true), r2 = rot_params(cQ0, cQ1, g2, true);
       ss.add(r1); ss.add(r2);
       if (__any_sync(FULL, r1.on || r2.on)) {
@@ -416,8 +427,8 @@ __global__ void __launch_bounds__(Cfg<NP, TL, KB>::NTH, (NP == 64 ? (TL == 4 && 
         col_update(cP0, cP1, r1);
         col_update(cQ0, cQ1, r2);
       }
-      gP = r1.on ? 0. : g1;  // rotated pairs are orthogonal; skipped ones keep their (negligible) dot
-      gQ = r2.on ? 0. : g2;
+      gP = r1.on ? 0.f : g1;  // rotated pairs are orthogonal; skipped ones keep their (negligible) dot
+      gQ = r2.on ? 0.f : g2;
     }
     for (int step = 0; step < NB; step += 2) {
       // even step: positions (2g, 2g+1); afterwards position 2g lives in Q, 2g+1 in P
