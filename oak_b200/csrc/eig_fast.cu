@@ -45,15 +45,14 @@ struct Cfg {
 
 template <int R>
 __device__ __forceinline__ double dotR(const double (&x)[R], const double (&y)[R]) {
-  double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
+  // two accumulators: the callers interleave two to four independent dot products
+  double s0 = 0., s1 = 0.;
 #pragma unroll
-  for (int i = 0; i < R; i += 4) {
+  for (int i = 0; i < R; i += 2) {
     s0 = fma(x[i], y[i], s0);
     s1 = fma(x[i + 1], y[i + 1], s1);
-    s2 = fma(x[i + 2], y[i + 2], s2);
-    s3 = fma(x[i + 3], y[i + 3], s3);
   }
-  return (s0 + s1) + (s2 + s3);
+  return s0 + s1;
 }
 
 template <int TL>

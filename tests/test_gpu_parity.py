@@ -428,3 +428,18 @@ def test_config5_time_localisation_inflation_anamorphosis(ob, handle):
     Eo, xfo, xao = oracle.assim_ensemble(zs, dict(t=zt), 0.8, 1.6, oo, E, Hi, Hj, Hs, np.zeros(m), yo, var,
                                          anamtype=2, inflation=1.05)
     assert rel(Ea, Eo) < RTOL and rel(xa, xao) < RTOL
+
+
+@pytest.mark.parametrize("scale", [1e-4, 1.0, 40.0])
+def test_dynamic_range_of_the_spectrum(ob, handle, scale):
+    """lambda_max from ~1e-6 to ~1e6: the fp32-steered rotations and the deferred column scales must not
+    lose the 1e-9 parity at either end (dsyev itself is good to ~eps*lambda_max here)."""
+    from oak_b200 import synthetic
+    c = synthetic.small_case(nx=14, ny=12, nz=3, N=64, m=700, corr=3000.0, maxlen=6000.0, seed=77)
+    c["HSf"] = np.asfortranarray(c["HSf"] * scale)
+    c["Hxf"] = c["Hxf"] * scale
+    c["yo"] = c["yo"] * scale
+    _configure(ob, handle, c)
+    xa, Sa, _, st = handle.local_analysis(c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], ob.DiagCovar(c["var"]))
+    xo, So, _, mloc = _oracle_loc(c)
+    assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL, (rel(xa, xo), rel(Sa, So))
