@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--eig-kernel", type=int, default=0)
     ap.add_argument("--jacobi-tol", type=float, default=0.0, help="experiment: override the Jacobi stopping tolerance")
+    ap.add_argument("--sync-phases", action="store_true", help="N>1: blocking library calls instead of the asynchronous pipeline")
     ap.add_argument("--phases", type=int, default=0, help="pipeline phases for N>1 (0: 4 when N>1, else 1)")
     return ap.parse_args()
 
@@ -234,7 +235,9 @@ def main():
     obs_np = S.observations(np, g, a.m, SEED)
     # phase j of rank p = a contiguous zone range; the all-gather of phase j overlaps the analysis of j+1
     phases = []
-    for first in phase_ranges(g.nzones, world, nphase):
+    ranges = phase_ranges(g.nzones, world, nphase)
+    use_async = world > 1 and not a.sync_phases
+    for j, first in enumerate(ranges):
         d = build_rank_data(a, rank, world, dev, first=first, obs_np=obs_np)
         plan = d["plan"]
         h = oak_b200.Handle(local, eig_kernel=a.eig_kernel)
@@ -245,6 +248,12 @@ def main():
         h.set_zones(plan.zoneSize, zone_x=plan.zx, zone_y=plan.zy, corrLen=plan.corrLen, maxLen=plan.maxLen,
                     loctype=1, metrictype=0, weightfun=0)
         h.set_observations(obs_x=d["ox"], obs_y=d["oy"])
+        if use_async:
+            # all phases are enqueued at once; the block scheduler serves the earlier phase first, later phases
+            # fill its tail; the caller's stream waits for each phase, so the all-gathers are stream-ordered
+            h.set_option("stream_priority", -(len(ranges) - 1 - j))
+            h.set_option("order_after_caller", 0)
+            h.set_option("async", 1)
         d["h"] = h
         d["xa"] = torch.empty(plan.r1 - plan.r0, dtype=torch.float64, device=dev)
         d["Sa"] = torch.empty_like(d["Sf"])
@@ -270,11 +279,16 @@ def main():
     def step():
         tot, works = {}, []
         for p in phases:
-            add_stats(tot, analyse(p))
+            st = analyse(p)
+            if not use_async:
+                add_stats(tot, st)
             if world > 1:   # asynchronous: overlaps the next phase's kernels
                 works += allgather_slabs(dist, p["Sa"], p["plan"], out=Sa_full, wait=False)
         for w in works:
             w.wait()
+        if use_async:
+            for p in phases:
+                add_stats(tot, p["h"].synchronize())
         return tot
 
     for _ in range(a.warmup):
@@ -307,6 +321,7 @@ def main():
     # ---- per-kernel times (separate profiled pass: batches serialised, CUDA events around each kernel family)
     stp = {}
     for p in phases:
+        p["h"].set_option("async", 0)
         p["h"].set_option("profile", 1)
         add_stats(stp, analyse(p))
         p["h"].set_option("profile", 0)
@@ -343,7 +358,7 @@ def main():
         out = {"metric": "local-analysis grid columns/sec", "value": value, "unit": "columns/s", "n_gpus": world,
                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": workload_name(a), "zones": nzones, "parallelism": f"zone-range x{world}" + (f", {nphase} pipelined phases (all-gather of phase j overlaps analysis of j+1)" if world > 1 else ""),
+               "config": {"workload": workload_name(a), "zones": nzones, "parallelism": f"zone-range x{world}" + (f", {nphase} pipelined phases (all-gather of phase j overlaps analysis of j+1; " + ("asynchronous, stream priorities" if use_async else "blocking calls") + ")" if world > 1 else ""),
                           "l2": "inputs (>= 15 GB state) exceed L2; no explicit flush",
                           "mean_relevant_obs_per_column": mloc_mean, "mean_candidates_per_column": cand_mean,
                           "mean_jacobi_sweeps": sweeps_mean, "eig_kernel": a.eig_kernel},

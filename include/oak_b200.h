@@ -113,6 +113,13 @@ OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t n, int32_t
                                const double *d01, double *xa, double *Sa, int64_t ldSa,
                                double *amplitudes, void *stream, oakb200_stats *stats);
 
+/* Asynchronous use of oakb200_local_analysis_dev (option "async" = 1): the call returns after enqueueing,
+ * `stream` waits for the result (stream-ordered consumers, e.g. an NCCL all-gather, need no host
+ * synchronisation); status (NaN, convergence) and statistics are collected here.  One outstanding call per
+ * handle.  Related options: "order_after_caller" = 0 (inputs are already complete: do not wait for `stream`
+ * before starting), "stream_priority" (CUDA priority of the library's streams, 0 .. negative = urgent). */
+OAKB200_API int oakb200_synchronize(oakb200_handle *h, oakb200_stats *stats);
+
 /* Ensemble branch of Assim around the local scheme (assimilation.F90:3083,:3106-3134 prologue,
  * :3235 analysis, :3301-3357,:3558-3562 epilogue), HOST buffers:
  *   E[n x N] ensemble (zone-permuted), H as COO (Hi,Hj 1-based int32, Hs, nnz; matoper.F90:30-39),

@@ -32,11 +32,6 @@ def _check(rc):
         raise OakB200Error(rc, _lib.lib().oakb200_last_error().decode(errors="replace"))
 
 
-def _f64(a):
-    return None if a is None else np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel(order="K")) \
-        if np.asarray(a).ndim <= 1 else np.asfortranarray(a, dtype=np.float64)
-
-
 def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
@@ -219,6 +214,12 @@ class Handle:
             C.c_void_p(Rdiag.data_ptr()), None if d01 is None else C.c_void_p(d01.data_ptr()),
             C.c_void_p(xa.data_ptr()), C.c_void_p(Sa.data_ptr()), max(n, 1), None, C.c_void_p(stream),
             C.byref(st)))
+        return st.asdict()
+
+    def synchronize(self):
+        """Completes an asynchronous local_analysis_dev (option async=1): status + stats."""
+        st = _lib.Stats()
+        _check(self._L.oakb200_synchronize(self._h, C.byref(st)))
         return st.asdict()
 
     def local_analysis_pinned(self, xf, Hxf, yo, Sf, HSf, Rdiag, xa, Sa, d01=None):

@@ -85,6 +85,11 @@ struct oakb200_handle {
   int profile = 0;
   double chunk_mb = 256.;
   int pad_to = 0;
+  int async = 0;              // local_analysis_dev returns after enqueueing; oakb200_synchronize collects
+  int order_after_caller = 1; // slot streams wait for the caller's stream before starting
+  int stream_priority = 0;
+  bool pending = false;       // an asynchronous call has not been synchronised yet
+  int64_t pending_launches = 0;
   // zones
   bool zones_set = false;
   int nzones = 0;
@@ -313,6 +318,22 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   else if (k == "profile") h->profile = (int)value;
   else if (k == "chunk_mb") h->chunk_mb = value;
   else if (k == "pad_to") h->pad_to = (int)value;
+  else if (k == "async") h->async = (int)value;
+  else if (k == "order_after_caller") h->order_after_caller = (int)value;
+  else if (k == "stream_priority") {
+    // recreate the slot streams with a CUDA stream priority (0 = default, negative = more urgent): lets a
+    // caller that enqueues several handles at once tell the block scheduler which one goes first
+    DeviceGuard guard(h->device);
+    int lo = 0, hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = least urgent (0), hi = most urgent (negative)
+    const int pr = std::max(hi, std::min(lo, (int)value));
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int i = 0; i < NSLOT; i++) {
+      if (h->slot[i].st) CUDA_TRY(cudaStreamDestroy(h->slot[i].st));
+      CUDA_TRY(cudaStreamCreateWithPriority(&h->slot[i].st, cudaStreamNonBlocking, pr));
+    }
+    h->stream_priority = pr;
+  }
   else { oak_set_error("unknown option '%s'", key); return OAK_ERR_ARG; }
   return 0;
 }
@@ -508,9 +529,12 @@ extern "C" OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t
   DeviceGuard guard(h->device);
   const int NP = padded(h, N);
   cudaStream_t s0 = h->slot[0].st;
+  if (h->pending) { oak_set_error("local_analysis_dev: the previous asynchronous call has not been synchronised (oakb200_synchronize)"); return OAK_ERR_STATE; }
   // order after the caller's stream
-  CUDA_TRY(cudaEventRecord(h->ev_user, (cudaStream_t)stream));
-  for (int i = 0; i < NSLOT; i++) CUDA_TRY(cudaStreamWaitEvent(h->slot[i].st, h->ev_user, 0));
+  if (h->order_after_caller) {
+    CUDA_TRY(cudaEventRecord(h->ev_user, (cudaStream_t)stream));
+    for (int i = 0; i < NSLOT; i++) CUDA_TRY(cudaStreamWaitEvent(h->slot[i].st, h->ev_user, 0));
+  }
   if ((rc = begin_call(h, stats))) return rc;
   CUDA_TRY(cudaEventRecord(h->ev_a, s0));
   if ((rc = pack_obs(h, s0, N, NP, HSf, ldHSf, yo, Hxf, Rdiag, d01))) return rc;
@@ -531,11 +555,36 @@ extern "C" OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t
     CUDA_TRY(cudaStreamWaitEvent(s0, h->slot[i].ev[5], 0));
   }
   CUDA_TRY(cudaEventRecord(h->ev_b, s0));
+  if (h->async && !h->profile) {
+    // the caller's stream waits for the result; statistics and status come from oakb200_synchronize
+    CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_b, 0));
+    h->pending = true;
+    h->pending_launches = launches;
+    if (stats) stats->launches = launches;
+    return 0;
+  }
   CUDA_TRY(cudaEventSynchronize(h->ev_b));
   float ms = 0.f, msp = 0.f;
   CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_a, h->ev_b));
   CUDA_TRY(cudaEventElapsedTime(&msp, h->ev_a, h->slot[0].ev[4]));
   return end_call(h, stats, launches, prof, ms, msp);
+}
+
+extern "C" OAKB200_API int oakb200_synchronize(oakb200_handle *h, oakb200_stats *stats) {
+  if (!h) { oak_set_error("null handle"); return OAK_ERR_ARG; }
+  DeviceGuard guard(h->device);
+  if (!h->pending) {
+    for (int i = 0; i < NSLOT; i++) CUDA_TRY(cudaStreamSynchronize(h->slot[i].st));
+    if (stats) memset(stats, 0, sizeof *stats);
+    return 0;
+  }
+  CUDA_TRY(cudaEventSynchronize(h->ev_b));
+  h->pending = false;
+  float ms = 0.f, msp = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_a, h->ev_b));
+  CUDA_TRY(cudaEventElapsedTime(&msp, h->ev_a, h->slot[0].ev[4]));
+  if (stats) memset(stats, 0, sizeof *stats);
+  return end_call(h, stats, h->pending_launches, ProfAcc(), ms, msp);
 }
 
 extern "C" OAKB200_API int oakb200_local_analysis(oakb200_handle *h, int64_t n, int32_t N, int32_t m, const double *xf,
