@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--eig-kernel", type=int, default=0)
+    ap.add_argument("--eig-kernel", type=int, default=4)
     ap.add_argument("--jacobi-tol", type=float, default=0.0, help="experiment: override the Jacobi stopping tolerance")
     ap.add_argument("--sync-phases", action="store_true", help="N>1: blocking library calls instead of the asynchronous pipeline")
     ap.add_argument("--phases", type=int, default=0, help="pipeline phases for N>1 (0: 4 when N>1, else 1)")

@@ -54,6 +54,7 @@ typedef struct {
   double ms_pack, ms_gram, ms_eig, ms_apply; /* per-kernel-family CUDA-event sums (only filled when
                                                 option "profile" = 1, which serialises the batches) */
   int64_t launches;         /* kernels launched by this call                                      */
+  int64_t zones_fallback;   /* zones the tridiagonal transform route re-did with the Jacobi kernel */
 } oakb200_stats;
 
 OAKB200_API const char *oakb200_last_error(void);
@@ -64,7 +65,8 @@ OAKB200_API int oakb200_version(void);
 OAKB200_API int oakb200_create(int device, oakb200_handle **h);
 OAKB200_API int oakb200_destroy(oakb200_handle *h);
 
-/* Options (all optional): "eig_kernel" 0 = register-resident block Jacobi (default), 1 = simple
+/* Options (all optional): "eig_kernel" 4 = Householder tridiagonalisation + QL + twisted factorisation
+ * (default for N <= 64; flagged zones fall back to 0), 0 = register-resident block Jacobi, 1 = simple
  * shared-memory Jacobi (cross-check); "zones_per_batch"; "jacobi_tol"; "max_sweeps"; "profile". */
 OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key, double value);
 

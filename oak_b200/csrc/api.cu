@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -68,7 +69,7 @@ struct DevBuf {
 
 struct Slot {
   cudaStream_t st = nullptr;
-  DevBuf G, T, c, ampl;        // batch workspace
+  DevBuf G, T, c, ampl, tri;   // batch workspace (tri: d, e, tau, lambda, flags of the tridiagonal route)
   DevBuf S, xf, xa;            // host-streaming chunk buffers
   cudaEvent_t ev[8] = {};
 };
@@ -78,7 +79,7 @@ struct Slot {
 struct oakb200_handle {
   int device = 0;
   // options
-  int eig_kernel = 0;
+  int eig_kernel = 4;
   int zones_per_batch = 0;
   double tol = 2e-11;  // bound on the remaining non-orthogonality (eig_common.cuh: jacobi_converged)
   int max_sweeps = 30;
@@ -145,7 +146,7 @@ int ensure_ws(oakb200_handle *h, Slot &s, int NP, int zb) {
   if ((rc = s.T.ensure(sizeof(double) * (size_t)zb * NP * NP))) return rc;
   if ((rc = s.c.ensure(sizeof(double) * (size_t)zb * NP))) return rc;
   if ((rc = s.ampl.ensure(sizeof(double) * (size_t)zb * NP))) return rc;
-  (void)h;
+  if (h->eig_kernel == 4 && NP <= 64 && (rc = s.tri.ensure(oak_eig_tridiag_ws_bytes(NP, zb)))) return rc;
   return 0;
 }
 
@@ -155,9 +156,12 @@ int ensure_ws(oakb200_handle *h, Slot &s, int NP, int zb) {
 int batch_size(const oakb200_handle *h, int NP, int nzones_call) {
   if (h->zones_per_batch > 0) return h->zones_per_batch;
   const size_t per_zone = sizeof(double) * 2 * (size_t)NP * NP;
-  const int cap = (int)((size_t)256 * 1024 * 1024 / per_zone);
+  // the tridiagonal route has a latency-bound kernel (k_tql: one thread per zone, ~1.6 ms whatever the
+  // batch size up to ~28 k zones), so its batches are larger: 1 GB of workspace instead of 256 MB
+  const bool tri = h->eig_kernel == 4 && NP <= 64;
+  const int cap = (int)((size_t)(tri ? 1024 : 256) * 1024 * 1024 / per_zone);
   const int wave = NP <= 64 ? 592 : 148;
-  int zb = nzones_call / (NSLOT * 8);
+  int zb = nzones_call / (NSLOT * (tri ? 4 : 8));
   zb = std::max(wave, (zb / wave) * wave);
   zb = std::min(zb, std::max(wave, (cap / wave) * wave));
   return zb;
@@ -193,8 +197,18 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
     if (prof) CUDA_TRY(cudaEventRecord(s.ev[0], s.st));
     if ((rc = oak_launch_gram(s.st, NP, zg, h->og, orows, b0, nz, s.G.as<double>(), s.c.as<double>(), mloc, ctr))) return rc;
     if (prof) CUDA_TRY(cudaEventRecord(s.ev[1], s.st));
-    if ((rc = oak_launch_eig(s.st, h->eig_kernel, N, NP, b0, nz, mloc, s.G.as<double>(), s.c.as<double>(),
-                             s.T.as<double>(), s.ampl.as<double>(), h->tol, h->max_sweeps, ctr))) return rc;
+    if (h->eig_kernel == 4 && NP <= 64) {
+      // tridiagonal route; the zones it flags (close eigenvalue groups it could not orthogonalise, ...) are
+      // recomputed by the Jacobi kernel, which skips the zones whose flag is 0
+      int32_t *flags = nullptr;
+      if ((rc = oak_launch_eig_tridiag(s.st, N, NP, nz, mloc + b0, s.G.as<double>(), s.c.as<double>(),
+                                       s.T.as<double>(), s.ampl.as<double>(), s.tri.p, &flags, ctr))) return rc;
+      if ((rc = oak_launch_eig(s.st, 0, N, NP, 0, nz, flags, s.G.as<double>(), s.c.as<double>(),
+                               s.T.as<double>(), s.ampl.as<double>(), h->tol, h->max_sweeps, ctr))) return rc;
+      *launches += 3;
+    } else if ((rc = oak_launch_eig(s.st, h->eig_kernel == 4 ? 0 : h->eig_kernel, N, NP, b0, nz, mloc,
+                                    s.G.as<double>(), s.c.as<double>(), s.T.as<double>(), s.ampl.as<double>(),
+                                    h->tol, h->max_sweeps, ctr))) return rc;
     if (prof) CUDA_TRY(cudaEventRecord(s.ev[2], s.st));
     if ((rc = oak_launch_apply(s.st, N, NP, zg, b0, nz, rowbase, mloc, s.T.as<double>(), s.ampl.as<double>(), xf,
                                Sf, ldS, xa, Sa, ldSa))) return rc;
@@ -244,7 +258,11 @@ int end_call(oakb200_handle *h, oakb200_stats *stats, int64_t launches, const Pr
     stats->ms_pack = ms_pack;
     stats->ms_gram = prof.gram; stats->ms_eig = prof.eig; stats->ms_apply = prof.apply;
     stats->launches = launches;
+    stats->zones_fallback = (int64_t)ctr.fallback;
   }
+  if (getenv("OAKB200_DEBUG"))
+    fprintf(stderr, "[oak_b200] fallback %llu (ql %llu, residual %llu, group %llu, parallel %llu), gram-schmidt projections %llu, sweeps %llu\n",
+            ctr.fallback, ctr.fb_reason[0], ctr.fb_reason[1], ctr.fb_reason[2], ctr.fb_reason[3], ctr.gs_pairs, ctr.sweeps);
   if (ctr.nan_flag) { oak_set_error("NaN in the analysis amplitudes (rrsqrt.F90:145-149)"); return OAK_ERR_NAN; }
   if (ctr.not_converged) { oak_set_error("Jacobi eigensolve did not converge in %d sweeps for %d zones", h->max_sweeps, ctr.not_converged); return OAK_ERR_NAN; }
   return 0;
@@ -296,7 +314,7 @@ extern "C" OAKB200_API int oakb200_destroy(oakb200_handle *h) {
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < NSLOT; i++) {
     Slot &s = h->slot[i];
-    s.G.release(); s.T.release(); s.c.release(); s.ampl.release(); s.S.release(); s.xf.release(); s.xa.release();
+    s.G.release(); s.T.release(); s.c.release(); s.ampl.release(); s.tri.release(); s.S.release(); s.xf.release(); s.xa.release();
     for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
     if (s.st) cudaStreamDestroy(s.st);
   }

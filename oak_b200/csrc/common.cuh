@@ -245,6 +245,9 @@ struct DevCounters {      // device-side statistics / status
   unsigned long long relevant, candidates, sweeps, skipped;
   int nan_flag;
   int not_converged;
+  unsigned long long fallback;  // zones the tridiagonal route handed to the Jacobi kernel
+  unsigned long long fb_reason[4];  // ... because of: QL iterations, residual test, group size, parallel vectors
+  unsigned long long gs_pairs;      // Gram-Schmidt projections done inside close groups
 };
 
 int oak_launch_pack_obs(cudaStream_t st, int m, int N, int NP, const int32_t *perm, const double *HSf,
@@ -257,6 +260,10 @@ int oak_launch_gram(cudaStream_t st, int NP, const ZoneGeom &zg, const ObsGrid &
 int oak_launch_eig(cudaStream_t st, int kernel, int N, int NP, int zone0, int nz, const int32_t *mloc,
                    const double *G, const double *c, double *T, double *ampl, double tol, int max_sweeps,
                    DevCounters *ctr);
+size_t oak_eig_tridiag_ws_bytes(int NP, int nz);
+int oak_launch_eig_tridiag(cudaStream_t st, int N, int NP, int nz, const int32_t *mloc, const double *G,
+                           const double *c, double *T, double *ampl, void *ws, int32_t **flags_out,
+                           DevCounters *ctr);
 int oak_launch_apply(cudaStream_t st, int N, int NP, const ZoneGeom &zg, int zone0, int nz,
                      int64_t rowbase, const int32_t *mloc, const double *T, const double *ampl,
                      const double *xf, const double *Sf, int64_t ldS, double *xa, double *Sa,

@@ -1,0 +1,496 @@
+// eig_tridiag.cu — the per-zone transform (ampl, T) from (G, c) by the tridiagonal route
+// (option "eig_kernel" = 4; NP <= 64).  Replaces dsyev of matoper_inc.F90:991-995 as called by
+// analysisIncrement (rrsqrt.F90:136) with ~7 N^3 flops instead of the ~25 N^3 of the Jacobi kernel:
+//
+//   k_tridiag  G = Q T Q^T, Householder reduction; one CTA per zone, thread t owns row t in registers
+//   k_tql      eigenvalues of T by implicit QL; one THREAD per zone (the iteration is a scalar chain)
+//   k_tvec     eigenvectors of T by the twisted factorisation (thread j owns eigenpair j), Gram-Schmidt
+//              inside groups of close eigenvalues, U = Q W (thread j owns column j in registers), then
+//                  (I+G)^-1/2 = I - Y Y^T ,  Y = U diag((1 - (1+lambda_j)^-1/2)^1/2)
+//                  ampl = c - U diag(lambda/(1+lambda)) U^T c                       rrsqrt.F90:137-142
+//                  v ~ (I+G)^1/2 1 = 1 + U diag((1+lambda)^1/2 - 1) U^T 1           rrsqrt.F90:176-178
+//                  T = (I+G)^-1/2 Omega , Omega = RotateVector(w, v) in closed form  rrsqrt.F90:737-744
+//              (same closed form of Omega as eig_simple.cu).
+//
+// The "I + sum_j (f(lambda_j) - f(0)) u_j u_j^T" form makes eigenvectors of (numerically) zero eigenvalues
+// unnecessary: the null space of rank-deficient G (few observations, padding) is never computed.
+// lambda <- max(lambda, 0) as rrsqrt.F90:137.
+//
+// Robustness: the vectors of T come from independent factorisations, so their orthogonality is
+// residual / gap (residual ~ eps |T|).  Neighbouring pairs whose bound |g| (res_j + res_j-1) / gap exceeds
+// TRI_ORTHTOL are orthogonalised explicitly (harmless for a matrix
+// function: mixing inside a tight group changes f(A) by f' eps |T| only).  Zones where that is not enough
+// (vectors of a group nearly parallel, groups larger than TRI_MAXGROUP, residual test failed, QL not
+// converged) are flagged and recomputed by the Jacobi kernel (eig_fast.cu), which has no such cases.
+#include "common.cuh"
+#include "tridiag_math.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int BW = 16;            // live-range granularity of the unrolled row/column loops
+#define TRI_NULL 1e-13            // |(1+lambda)^-1/2 - 1| below this: eigenpair contributes nothing
+#define TRI_ORTHTOL 1e-11         // accepted loss of orthogonality (times |g|) between neighbouring eigenvectors
+#define TRI_RESTOL 1e-12
+#define TRI_MAXGROUP 6
+#define TRI_MINREM 0.03
+
+// workspace per zone: d[NP] e[NP] tau[NP] lam[NP]
+__device__ __forceinline__ double *ws_zone(double *ws, int NP, int zl) { return ws + (int64_t)zl * 4 * NP; }
+
+template <int NW>
+__device__ __forceinline__ double block_sum(double x, double *sred, int warp, int lane) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+  if (NW == 1) return x;
+  if (lane == 0) sred[warp] = x;
+  __syncthreads();
+  double r = sred[0];
+#pragma unroll
+  for (int w = 1; w < NW; w++) r += sred[w];
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_tridiag
+// ---------------------------------------------------------------------------------------------------
+template <int NP, int OFF>
+struct TriSteps {
+  // Householder steps k = OFF .. min(OFF+BW, N-2)-1; columns < OFF are finished, so every loop over
+  // the row held in registers runs over the static range [OFF, NP)
+  static __device__ __forceinline__ void run(double (&a)[NP], int N, int t, int warp, int lane, double *sx,
+                                             double *sv, double2 *svw, double *sred, double *Vz,
+                                             double *wd, double *we, double *wtau) {
+    constexpr int NW = NP / 32;
+    const int kend = min(OFF + BW, N - 2);
+    for (int k = OFF; k < kend; k++) {
+      const double xk = sx[t], dk = sx[k], alpha = sx[k + 1];
+      const double xt = (t > k + 1) ? xk : 0.;
+      const double sigma2 = block_sum<NW>(xt * xt, sred, warp, lane);
+      double tau = 0., beta = alpha, scale = 0.;
+      if (sigma2 != 0.) {
+        // beta = -sign(alpha) |x| ; tau = (beta - alpha)/beta = 1 + |alpha|/|x| ; 1/(alpha - beta) = sign(alpha)/(|alpha| + |x|)
+        const double n2 = fma(alpha, alpha, sigma2);
+        const double inrm = rsqrt(n2), nrm = n2 * inrm, aa = fabs(alpha);
+        beta = -copysign(nrm, alpha);
+        tau = fma(aa, inrm, 1.);
+        scale = copysign(oak_rcp(aa + nrm), alpha);
+      }
+      const double vt = (t > k + 1) ? xk * scale : (t == k + 1 ? 1. : 0.);
+      sv[t] = vt;
+      Vz[k * NP + t] = vt;
+      if (t == k) { wd[k] = dk; we[k] = beta; wtau[k] = tau; }
+      __syncthreads();
+      if (tau != 0.) {
+        double p = 0.;
+        if (32 * warp + 31 > k) {  // a warp whose rows are all finished only takes part in the barriers
+          double p0 = 0., p1 = 0., p2 = 0., p3 = 0.;
+#pragma unroll
+          for (int j = OFF; j < NP; j += 4) {
+            const double2 v01 = *reinterpret_cast<const double2 *>(sv + j);
+            const double2 v23 = *reinterpret_cast<const double2 *>(sv + j + 2);
+            p0 = fma(a[j], v01.x, p0);
+            p1 = fma(a[j + 1], v01.y, p1);
+            p2 = fma(a[j + 2], v23.x, p2);
+            p3 = fma(a[j + 3], v23.y, p3);
+          }
+          p = (t > k) ? tau * ((p0 + p1) + (p2 + p3)) : 0.;
+        }
+        const double pv = block_sum<NW>(p * vt, sred + 4, warp, lane);
+        const double wt = fma(-0.5 * tau * pv, vt, p);
+        svw[t] = make_double2(vt, wt);
+        __syncthreads();
+        if (32 * warp + 31 > k) {
+#pragma unroll
+          for (int j = OFF; j < NP; j++) {
+            const double2 q = svw[j];
+            a[j] = fma(-vt, q.y, fma(-wt, q.x, a[j]));
+          }
+        }
+      }
+      if (t == k + 1) {
+#pragma unroll
+        for (int j = OFF; j < NP; j += 2) *reinterpret_cast<double2 *>(sx + j) = make_double2(a[j], a[j + 1]);
+      }
+      __syncthreads();
+    }
+    if constexpr (OFF + BW < NP) {
+      if (N - 2 > OFF + BW) TriSteps<NP, OFF + BW>::run(a, N, t, warp, lane, sx, sv, svw, sred, Vz, wd, we, wtau);
+    }
+  }
+};
+
+template <int NP>
+__global__ void __launch_bounds__(NP) k_tridiag(int N, const int32_t *__restrict__ mloc,
+                                                 const double *__restrict__ G, double *__restrict__ V,
+                                                 double *__restrict__ ws) {
+  __shared__ __align__(16) double sx[NP];
+  __shared__ __align__(16) double sv[NP];
+  __shared__ __align__(16) double2 svw[NP];
+  __shared__ double sred[8];
+  const int zl = blockIdx.x;
+  if (mloc[zl] == 0) return;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const double *Gz = G + (int64_t)zl * NP * NP;
+  double *Vz = V + (int64_t)zl * NP * NP;
+  double *wz = ws_zone(ws, NP, zl);
+  double *wd = wz, *we = wz + NP, *wtau = wz + 2 * NP;
+
+  double a[NP];
+#pragma unroll
+  for (int j = 0; j < NP; j++) a[j] = Gz[j * NP + t];  // G is symmetric: row t read as column t (coalesced)
+  if (t == 0) {
+#pragma unroll
+    for (int j = 0; j < NP; j++) sx[j] = a[j];
+  }
+  if (t >= N) { wd[t] = 0.; we[t] = 0.; }
+  wtau[t] = 0.;
+  __syncthreads();
+  TriSteps<NP, 0>::run(a, N, t, warp, lane, sx, sv, svw, sred, Vz, wd, we, wtau);
+  // the published row is row N-2: d_{N-2}, e_{N-2}; then row N-1 gives d_{N-1}
+  if (t == 0) { wd[N - 2] = sx[N - 2]; we[N - 2] = sx[N - 1]; }
+  __syncthreads();
+  if (t == N - 1) {
+#pragma unroll
+    for (int j = 0; j < NP; j++) sx[j] = a[j];
+  }
+  __syncthreads();
+  if (t == 0) { wd[N - 1] = sx[N - 1]; we[N - 1] = 0.; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_tql : one thread per zone; d, e transposed into shared memory with an odd stride
+// ---------------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(32) k_tql(int N, int nz, const int32_t *__restrict__ mloc,
+                                             double *__restrict__ ws, int32_t *__restrict__ flags) {
+  constexpr int S = 33;
+  __shared__ double sd[NP * S], se[NP * S];
+  const int lane = threadIdx.x;
+  const int z0 = blockIdx.x * 32;
+  for (int z = 0; z < 32; z++) {
+    if (z0 + z >= nz) break;
+    const double *wz = ws_zone(ws, NP, z0 + z);
+    for (int i = lane; i < NP; i += 32) {
+      sd[i * S + z] = wz[i];
+      se[i * S + z] = wz[NP + i];
+    }
+  }
+  __syncwarp();
+  const int zl = z0 + lane;
+  const bool active = zl < nz && mloc[zl] != 0;
+  int rot = 0;
+  if (active) {
+    double tn = 0.;
+    for (int i = 0; i < N; i++) tn = fmax(tn, fmax(fabs(sd[i * S + lane]), fabs(se[i * S + lane])));
+    rot = tql_eigenvalues(N, sd + lane, se + lane, S, tn);
+  }
+  if (zl < nz) flags[zl] = (rot < 0) ? 1 : 0;
+  __syncwarp();
+  for (int z = 0; z < 32; z++) {
+    if (z0 + z >= nz) break;
+    double *wz = ws_zone(ws, NP, z0 + z);
+    for (int i = lane; i < NP; i += 32) wz[3 * NP + i] = sd[i * S + z];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_tvec
+// ---------------------------------------------------------------------------------------------------
+template <int NP, int OFF>
+struct BackSteps {
+  // reflectors k = min(OFF+BW, N-2)-1 .. OFF applied to the column u held in registers; rows < OFF of
+  // these reflectors are zero, so the loops run over the static range [OFF, NP)
+  static __device__ __forceinline__ void run(double (&u)[NP], int N, const double *Vs, const double *stau) {
+    if constexpr (OFF + BW < NP) {
+      if (N - 2 > OFF + BW) BackSteps<NP, OFF + BW>::run(u, N, Vs, stau);
+    }
+    for (int k = min(OFF + BW, N - 2) - 1; k >= OFF; k--) {
+      const double tau = stau[k];
+      if (tau == 0.) continue;
+      const double *v = Vs + k * NP;
+      double p0 = 0., p1 = 0., p2 = 0., p3 = 0.;
+#pragma unroll
+      for (int i = OFF; i < NP; i += 4) {
+        const double2 v01 = *reinterpret_cast<const double2 *>(v + i);
+        const double2 v23 = *reinterpret_cast<const double2 *>(v + i + 2);
+        p0 = fma(u[i], v01.x, p0);
+        p1 = fma(u[i + 1], v01.y, p1);
+        p2 = fma(u[i + 2], v23.x, p2);
+        p3 = fma(u[i + 3], v23.y, p3);
+      }
+      const double s = -tau * ((p0 + p1) + (p2 + p3));
+#pragma unroll
+      for (int i = OFF; i < NP; i += 2) {
+        const double2 v01 = *reinterpret_cast<const double2 *>(v + i);
+        u[i] = fma(s, v01.x, u[i]);
+        u[i + 1] = fma(s, v01.y, u[i + 1]);
+      }
+    }
+  }
+};
+
+template <int NP>
+__global__ void __launch_bounds__(NP) k_tvec(int N, const int32_t *__restrict__ mloc,
+                                              const double *__restrict__ ws, const double *__restrict__ cin,
+                                              double *__restrict__ Tout, double *__restrict__ ampl_out,
+                                              int32_t *__restrict__ flags, DevCounters *ctr) {
+  constexpr int LDW = NP + 1;
+  constexpr int NW = NP / 32;
+  constexpr int TR = 8, TC = NP / 8;          // output tile of a thread: TR rows x TC columns
+  constexpr int TJ = NP / TC;                 // thread grid: (NP/TR) x TJ = NP threads
+  extern __shared__ __align__(16) double sm[];
+  double *W = sm;                      // [NP][LDW] : W[i*LDW + j] = element i of vector j ; later V, then Y
+  double *sd = sm + NP * LDW;
+  double *se = sd + NP, *slam = se + NP, *stau = slam + NP, *sc = stau + NP;
+  double *sa = sc + NP, *sb = sa + NP, *suv = sb + NP, *sdw = suv + NP, *suw = sdw + NP;
+  double *sg1 = suw + NP, *sg2 = sg1 + NP, *sgj = sg2 + NP, *sres = sgj + NP;
+  __shared__ double sred[8];
+  __shared__ unsigned sclose[NW];
+  __shared__ int sflag;
+
+  const int zl = blockIdx.x;
+  const int ml = mloc[zl];
+  if (ml == 0) { if (threadIdx.x == 0) flags[zl] = 0; return; }
+  const int j = threadIdx.x, warp = j >> 5, lane = j & 31;
+  const double *wz = ws + (int64_t)zl * 4 * NP;
+  sd[j] = wz[j];
+  se[j] = wz[NP + j];
+  stau[j] = wz[2 * NP + j];
+  slam[j] = wz[3 * NP + j];
+  sc[j] = cin[(int64_t)zl * NP + j];
+  if (j == 0) { sflag = flags[zl]; if (sflag) atomicAdd(&ctr->fb_reason[0], 1ull); }
+  __syncthreads();
+
+  // ---- eigenvector j of T ----
+  double tn = 0.;
+  for (int i = 0; i < N; i++) tn = fmax(tn, fmax(fabs(sd[i]), fabs(se[i])));
+  const double lam = (j < N) ? slam[j] : 0.;
+  const double lamc = fmax(lam, 0.);
+  const double sig = sqrt(1. + lamc);
+  const double gj = (j < N) ? 1. - 1. / sig : 0.;  // = -g_j >= 0
+  const bool live = gj >= TRI_NULL;
+  bool bad = false;
+  double res = 0.;  // |(T - lam) w| of the normalised vector
+  for (int i = N; i < NP; i++) W[i * LDW + j] = 0.;
+  if (live) {
+    const double pivmin = tn * 1e-150;
+    double gam;
+    double zz = twisted_vector(N, sd, se, 1, lam, pivmin, W + j, LDW, &gam);
+    if (!(fabs(gam) <= TRI_RESTOL * tn * sqrt(zz)) || !(zz < 1e300)) {  // one Rayleigh-quotient correction, then give up
+      const double lam2 = lam + gam / zz;
+      zz = twisted_vector(N, sd, se, 1, lam2, pivmin, W + j, LDW, &gam);
+      if (!(fabs(gam) <= TRI_RESTOL * tn * sqrt(zz)) || !(zz < 1e300)) bad = true;
+    }
+    const double sc_ = rsqrt(zz);
+    res = fabs(gam) * sc_;
+    for (int i = 0; i < N; i++) W[i * LDW + j] *= sc_;
+  } else {
+    for (int i = 0; i < N; i++) W[i * LDW + j] = 0.;
+  }
+  sgj[j] = gj;
+  sres[j] = res;
+  __syncthreads();
+  // ---- groups of close eigenvalues ----
+  bool close = false;
+  if (j >= 1 && j < N && live && sgj[j - 1] >= TRI_NULL)
+    close = fmax(gj, sgj[j - 1]) * (res + sres[j - 1] + 4. * OAK_DBL_EPS * tn) > TRI_ORTHTOL * (lam - slam[j - 1]);
+  const unsigned cm = __ballot_sync(FULL, close);
+  if (lane == 0) sclose[warp] = cm;
+  if (bad) { sflag = 1; atomicAdd(&ctr->fb_reason[1], 1ull); }
+  __syncthreads();
+  bool anyclose = false;
+#pragma unroll
+  for (int w = 0; w < NW; w++) anyclose |= (sclose[w] != 0);
+  if (anyclose) {
+    int gstart = 0;
+    for (int k = 1; k < N; k++) {
+      const bool ck = (sclose[k >> 5] >> (k & 31)) & 1;
+      if (!ck) { gstart = k; continue; }
+      if (k - gstart > TRI_MAXGROUP) { if (j == 0) { sflag = 1; atomicAdd(&ctr->fb_reason[2], 1ull); } continue; }
+      if (j == 0) atomicAdd(&ctr->gs_pairs, (unsigned long long)(k - gstart));
+      for (int i = gstart; i < k; i++) {
+        const double prod = (j < N) ? W[j * LDW + i] * W[j * LDW + k] : 0.;
+        __syncthreads();
+        const double dot = block_sum<NW>(prod, sred + 4 * (i & 1), warp, lane);
+        if (j < N) W[j * LDW + k] = fma(-dot, W[j * LDW + i], W[j * LDW + k]);
+      }
+      const double wk = (j < N) ? W[j * LDW + k] : 0.;
+      __syncthreads();
+      const double n2 = block_sum<NW>(wk * wk, sred + 4 * (k & 1), warp, lane);
+      if (!(n2 >= TRI_MINREM * TRI_MINREM)) { if (j == 0) { sflag = 1; atomicAdd(&ctr->fb_reason[3], 1ull); } }
+      else if (j < N) W[j * LDW + k] = wk * rsqrt(n2);
+    }
+    __syncthreads();
+  }
+  if (sflag) {  // recomputed by the Jacobi kernel (launched on flags[] after this kernel)
+    if (j == 0) { flags[zl] = ml; atomicAdd(&ctr->fallback, 1ull); }
+    return;
+  }
+
+  // ---- U = Q W : column j in registers, reflectors from shared memory ----
+  double u[NP];
+#pragma unroll
+  for (int i = 0; i < NP; i++) u[i] = W[i * LDW + j];
+  __syncthreads();
+  {
+    const double2 *Vg = reinterpret_cast<const double2 *>(Tout + (int64_t)zl * NP * NP);
+    double2 *Vs2 = reinterpret_cast<double2 *>(W);
+    const int nv = max(N - 2, 0) * (NP / 2);
+    for (int idx = j; idx < nv; idx += NP) Vs2[idx] = Vg[idx];
+  }
+  __syncthreads();
+  BackSteps<NP, 0>::run(u, N, W, stau);
+
+  // ---- per-eigenpair coefficients ----
+  double q = 0., s1 = 0.;
+#pragma unroll
+  for (int i = 0; i < NP; i++) { q = fma(u[i], sc[i], q); s1 += u[i]; }
+  const double ys = live ? sqrt(gj) : 0.;
+  const double iys = live ? 1. / ys : 0.;
+  __syncthreads();  // every thread is done with the reflectors
+#pragma unroll
+  for (int i = 0; i < NP; i++) W[i * LDW + j] = ys * u[i];
+  sa[j] = -(lamc / (1. + lamc)) * q * iys;
+  sb[j] = (sig - 1.) * s1 * iys;
+  __syncthreads();
+  // ---- ampl, v ----
+  double vi = 0.;
+  {
+    double am = 0.;
+    if (j < N) {
+      am = sc[j]; vi = 1.;
+      for (int k = 0; k < N; k++) {
+        const double y = W[j * LDW + k];
+        am = fma(y, sa[k], am);
+        vi = fma(y, sb[k], vi);
+      }
+    }
+    if (am != am) atomicExch(&ctr->nan_flag, 1);
+    ampl_out[(int64_t)zl * NP + j] = am;
+  }
+  const double vnorm = sqrt(block_sum<NW>(vi * vi, sred, warp, lane));
+  const double wN = 1. / sqrt((double)N);
+  sg1[j] = (j < N) ? vi / vnorm : 0.;  // v
+  __syncthreads();
+  const double vN = sg1[N - 1];
+  const double sv_ = copysign(1., vN);
+  const double dNN = sv_;
+  const double hv = 1. / (1. + fabs(vN)), hw = 1. / (1. + fabs(wN));
+  __syncthreads();
+  {
+    double uv = sg1[j];
+    double uw = (j < N) ? wN : 0.;
+    if (j == N - 1) { uv += sv_; uw += 1.; }
+    suv[j] = uv;                               // u_v
+    sdw[j] = (j == N - 1) ? dNN * uw : uw;     // D u_w
+    suw[j] = uw;                               // u_w
+  }
+  __syncthreads();
+  // g1 = M u_v, gm2 = M (D u_w), M = I - Y Y^T
+  {
+    double p1 = 0., p2 = 0.;
+    for (int i = 0; i < N; i++) {
+      const double y = W[i * LDW + j];
+      p1 = fma(y, suv[i], p1);
+      p2 = fma(y, sdw[i], p2);
+    }
+    sa[j] = p1; sb[j] = p2;
+  }
+  const double kappa = block_sum<NW>(suv[j] * hv * sdw[j], sred + 4, warp, lane);
+  __syncthreads();
+  {
+    double g1 = suv[j], gm2 = sdw[j];
+    for (int k = 0; k < N; k++) {
+      const double y = W[j * LDW + k];
+      g1 = fma(-y, sa[k], g1);
+      gm2 = fma(-y, sb[k], gm2);
+    }
+    sg1[j] = g1;
+    sg2[j] = gm2 - kappa * g1;
+  }
+  __syncthreads();
+  // ---- T[i][k] = (M[i][k] - g1[i] hv u_v[k]) D_k - g2[i] hw u_w[k] , row-major ----
+  {
+    const int ti = j / TJ, tj = j % TJ;
+    double acc[TR][TC];
+#pragma unroll
+    for (int a_ = 0; a_ < TR; a_++)
+#pragma unroll
+      for (int b = 0; b < TC; b++) acc[a_][b] = 0.;
+    int col[TC];
+#pragma unroll
+    for (int b = 0; b < TC; b++) col[b] = 2 * tj + (2 * TJ) * (b >> 1) + (b & 1);
+    for (int k = 0; k < N; k++) {
+      double rv[TR], cv[TC];
+#pragma unroll
+      for (int a_ = 0; a_ < TR; a_++) rv[a_] = W[(TR * ti + a_) * LDW + k];
+#pragma unroll
+      for (int b = 0; b < TC; b++) cv[b] = W[col[b] * LDW + k];
+#pragma unroll
+      for (int a_ = 0; a_ < TR; a_++)
+#pragma unroll
+        for (int b = 0; b < TC; b++) acc[a_][b] = fma(-rv[a_], cv[b], acc[a_][b]);
+    }
+    double *Tz = Tout + (int64_t)zl * NP * NP;
+#pragma unroll
+    for (int a_ = 0; a_ < TR; a_++) {
+      const int i = TR * ti + a_;
+      const double g1i = sg1[i] * hv, g2i = sg2[i] * hw;
+#pragma unroll
+      for (int b = 0; b < TC; b += 2) {
+        const int k = col[b];
+        double t0 = acc[a_][b] + (i == k ? 1. : 0.) - g1i * suv[k];
+        double t1 = acc[a_][b + 1] + (i == k + 1 ? 1. : 0.) - g1i * suv[k + 1];
+        if (k == N - 1) t0 *= dNN;
+        if (k + 1 == N - 1) t1 *= dNN;
+        t0 -= g2i * suw[k];
+        t1 -= g2i * suw[k + 1];
+        *reinterpret_cast<double2 *>(Tz + (int64_t)i * NP + k) = make_double2(t0, t1);
+      }
+    }
+  }
+  if (j == 0) flags[zl] = 0;
+}
+
+template <int NP>
+int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G, const double *c, double *T,
+           double *ampl, double *ws, int32_t *flags, DevCounters *ctr) {
+  constexpr int LDW = NP + 1;
+  const size_t smem = sizeof(double) * (NP * LDW + 14 * NP);
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(k_tvec<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  k_tridiag<NP><<<nz, NP, 0, st>>>(N, mloc, G, T, ws);
+  CUDA_TRY(cudaGetLastError());
+  k_tql<NP><<<(nz + 31) / 32, 32, 0, st>>>(N, nz, mloc, ws, flags);
+  CUDA_TRY(cudaGetLastError());
+  k_tvec<NP><<<nz, NP, smem, st>>>(N, mloc, ws, c, T, ampl, flags, ctr);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// Per-zone workspace of the tridiagonal route: 4 NP doubles (d, e, tau, lambda) + one int32 flag.
+size_t oak_eig_tridiag_ws_bytes(int NP, int nz) {
+  return sizeof(double) * 4 * (size_t)NP * nz + sizeof(int32_t) * (size_t)nz + 64;
+}
+
+// Enqueues k_tridiag, k_tql, k_tvec; on return (stream order) flags[zl] = mloc[zl] for the zones that must be
+// recomputed by the Jacobi kernel and 0 for the others.  V (the reflectors) lives in T until k_tvec replaces it.
+int oak_launch_eig_tridiag(cudaStream_t st, int N, int NP, int nz, const int32_t *mloc, const double *G,
+                           const double *c, double *T, double *ampl, void *ws, int32_t **flags_out,
+                           DevCounters *ctr) {
+  double *wsd = reinterpret_cast<double *>(ws);
+  int32_t *flags = reinterpret_cast<int32_t *>(wsd + 4 * (size_t)NP * nz);
+  *flags_out = flags;
+  switch (NP) {
+    case 32: return launch<32>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr);
+    case 64: return launch<64>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr);
+  }
+  oak_set_error("eig_tridiag: unsupported padded ensemble size %d", NP);
+  return OAK_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,159 @@
+// tridiag_math.cuh — scalar (one thread) routines on a symmetric tridiagonal matrix T = tridiag(e, d, e)
+// used by the tridiagonal route of the per-zone transform (eig_tridiag.cu):
+//   tql_eigenvalues : all eigenvalues by the implicit QL iteration (no vectors), ascending
+//   twisted_vector  : the eigenvector for one eigenvalue by the double (twisted) factorisation of T - lambda I
+// They replace, together with the Householder reduction, LAPACK dsyev of matoper_inc.F90:991-995
+// (rrsqrt.F90:136).  Arrays are strided so that each thread of a warp can own one problem with
+// conflict-free shared-memory accesses.  OAK_HD lets tools/test_tridiag_host.cpp compile the same code with
+// g++ and check it on the CPU (no GPU in the build container).
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define OAK_HD __host__ __device__ __forceinline__
+#else
+#define OAK_HD inline
+#endif
+
+#define OAK_DBL_EPS 2.220446049250313e-16
+
+// 1/x for |x| in the normal range, ~1 ulp: hardware seed + Newton steps (the IEEE division costs ~4x more)
+OAK_HD double oak_rcp(double x) {
+#ifdef __CUDA_ARCH__
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double r = fma(-x, y, 1.);
+  y = fma(y, r, y);
+  r = fma(-x, y, 1.);
+  y = fma(y, r, y);
+  r = fma(-x, y, 1.);
+  return fma(y, r, y);
+#else
+  return 1. / x;
+#endif
+}
+
+OAK_HD double oak_rsqrt(double x) {
+#ifdef __CUDA_ARCH__
+  return rsqrt(x);
+#else
+  return 1. / sqrt(x);
+#endif
+}
+
+// Implicit QL (EISPACK tql1 organisation) on d[0..n-1], e[0..n-2] (strided by s; e[n-1] is scratch).
+// On return d holds the eigenvalues in ascending order.  tn = max(|d|,|e|) sets the absolute deflation
+// threshold (eigenvalues are needed to eps*|T| only: everything downstream is a function of 1 + lambda).
+// Returns the number of rotations, or -1 if an eigenvalue needed more than 60 iterations.
+OAK_HD int tql_eigenvalues(int n, double *d, double *e, int s, double tn) {
+  int rot = 0;
+  const double abstol = 0.5 * OAK_DBL_EPS * tn;
+  if (n > 0) e[(n - 1) * s] = 0.;
+  for (int l = 0; l < n; l++) {
+    int iter = 0;
+    for (;;) {
+      int m = l;
+      for (; m < n - 1; m++) {
+        const double em = fabs(e[m * s]);
+        if (em <= abstol || em <= OAK_DBL_EPS * (fabs(d[m * s]) + fabs(d[(m + 1) * s]))) break;
+      }
+      if (m == l) break;
+      if (++iter > 60) return -1;
+      const double el = e[l * s], dl = d[l * s];
+      double g = (d[(l + 1) * s] - dl) * 0.5 * oak_rcp(el);
+      double r = sqrt(fma(g, g, 1.));
+      g = d[m * s] - dl + el * oak_rcp(g + copysign(r, g));
+      double sn = 1., cs = 1., p = 0.;
+      int i = m - 1;
+      bool under = false;
+      for (; i >= l; i--) {
+        rot++;
+        const double ei = e[i * s];
+        const double f = sn * ei, b = cs * ei;
+        const double h = fma(f, f, g * g);
+        if (h == 0.) {  // recover from underflow (tql1): deflate here and restart
+          d[(i + 1) * s] -= p;
+          e[m * s] = 0.;
+          under = true;
+          break;
+        }
+        const double ir = oak_rsqrt(h);
+        e[(i + 1) * s] = h * ir;
+        sn = f * ir;
+        cs = g * ir;
+        g = d[(i + 1) * s] - p;
+        r = fma(d[i * s] - g, sn, 2. * cs * b);
+        p = sn * r;
+        d[(i + 1) * s] = g + p;
+        g = fma(cs, r, -b);
+      }
+      if (under) continue;
+      d[l * s] -= p;
+      e[l * s] = g;
+      e[m * s] = 0.;
+    }
+  }
+  // ascending order (insertion sort: QL delivers them nearly sorted)
+  for (int i = 1; i < n; i++) {
+    const double v = d[i * s];
+    int j = i - 1;
+    while (j >= 0 && d[j * s] > v) { d[(j + 1) * s] = d[j * s]; j--; }
+    d[(j + 1) * s] = v;
+  }
+  return rot;
+}
+
+// Eigenvector of T for the eigenvalue lam by the twisted factorisation (Fernando; Parlett & Dhillon):
+//   forward pivots  p_0 = d_0 - lam , p_{i+1} = (d_{i+1} - lam) - e_i^2 / p_i
+//   backward pivots q_{n-1} = d_{n-1} - lam , q_i = (d_i - lam) - e_i^2 / q_{i+1}
+//   gamma_i = p_i - e_i^2 / q_{i+1} ; r = argmin |gamma_i| ; z_r = 1 ,
+//   z_{i-1} = -e_{i-1} z_i / p_{i-1} (i <= r) , z_{i+1} = -e_i z_i / q_{i+1} (i >= r)
+// so that (T - lam) z = gamma_r e_r.  d, e are read with stride sd (broadcast arrays: sd = 1); the vector is
+// written to w[i*sw] (unnormalised; also used as the only work array).  Returns |z|^2; gamma_r in *gam.
+OAK_HD double twisted_vector(int n, const double *d, const double *e, int sd, double lam, double pivmin,
+                             double *w, int sw, double *gam) {
+  double p = d[0] - lam;
+  for (int i = 0; i < n - 1; i++) {
+    if (fabs(p) < pivmin) p = -pivmin;
+    w[i * sw] = p;
+    const double ei = e[i * sd];
+    p = fma(-ei * ei, oak_rcp(p), d[(i + 1) * sd] - lam);
+  }
+  if (fabs(p) < pivmin) p = -pivmin;
+  w[(n - 1) * sw] = p;
+  // backward pivots, gamma, position of the twist
+  double q = d[(n - 1) * sd] - lam;
+  double best = fabs(p), gbest = p;
+  int r = n - 1;
+  for (int i = n - 2; i >= 0; i--) {
+    if (fabs(q) < pivmin) q = -pivmin;
+    const double ei = e[i * sd];
+    const double t = ei * ei * oak_rcp(q);
+    const double gm = w[i * sw] - t;
+    q = (d[i * sd] - lam) - t;
+    if (fabs(gm) < best) { best = fabs(gm); gbest = gm; r = i; }
+  }
+  // backward pivots again, kept for i > r (the forward ones are no longer needed there)
+  q = d[(n - 1) * sd] - lam;
+  for (int i = n - 1; i > r; i--) {
+    if (fabs(q) < pivmin) q = -pivmin;
+    w[i * sw] = q;
+    const double ei = e[(i - 1) * sd];
+    q = fma(-ei * ei, oak_rcp(q), d[(i - 1) * sd] - lam);
+  }
+  double zz = 1., z = 1.;
+  for (int i = r; i > 0; i--) {
+    z = -e[(i - 1) * sd] * z * oak_rcp(w[(i - 1) * sw]);
+    w[(i - 1) * sw] = z;
+    zz = fma(z, z, zz);
+  }
+  z = 1.;
+  for (int i = r; i < n - 1; i++) {
+    z = -e[i * sd] * z * oak_rcp(w[(i + 1) * sw]);
+    w[(i + 1) * sw] = z;
+    zz = fma(z, z, zz);
+  }
+  w[r * sw] = 1.;
+  *gam = gbest;
+  return zz;
+}

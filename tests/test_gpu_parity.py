@@ -23,10 +23,11 @@ def ob():
     return oak_b200
 
 
-@pytest.fixture(scope="module", params=[0, 2, 3, 1], ids=["eig_fast", "eig_fast8", "eig_fast_k1", "eig_simple"])
+@pytest.fixture(scope="module", params=[4, 0, 2, 3, 1],
+                ids=["eig_tridiag", "eig_fast", "eig_fast8", "eig_fast_k1", "eig_simple"])
 def handle(request, ob):
     # pad_to=64 sends even the small golden cases through the production register-resident kernels
-    # (0: 4 lanes per column group, 2: 8 lanes per group, 3: one column per block; 1: simple shared-memory
+    # (4: tridiagonal route, the default; 0: 4 lanes per column group, 2: 8 lanes per group, 3: one column per block; 1: simple shared-memory
     # cross-check kernel)
     h = ob.Handle(0, eig_kernel=request.param, pad_to=64 if request.param != 1 else 0)
     yield h

@@ -17,6 +17,9 @@ smoke)
 sanitize)
   timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitize.log 2>&1
   echo "sanitize exit $?"; tail -15 gpurun_out/sanitize.log ;;
+benchsmall0)
+  timeout 900 python bench.py --nx 300 --ny 300 --nz 30 --nobs 90000 --steps 2 --warmup 1 --no-cpu --no-e2e --eig-kernel 0 > gpurun_out/bench_small0.json 2> gpurun_out/bench_small0.err
+  echo "benchsmall0 exit $?"; tail -3 gpurun_out/bench_small0.err; cat gpurun_out/bench_small0.json ;;
 benchsmall)
   timeout 900 python bench.py --nx 300 --ny 300 --nz 30 --nobs 90000 --steps 2 --warmup 1 --cpu-seconds 5 > gpurun_out/bench_small.json 2> gpurun_out/bench_small.err
   echo "benchsmall exit $?"; tail -3 gpurun_out/bench_small.err; cat gpurun_out/bench_small.json ;;
@@ -30,6 +33,12 @@ ncu)
   timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_|DeviceRadixSort|DeviceScan' -c 600 --csv --log-file gpurun_out/launches.csv \
      python bench.py --nx 400 --ny 400 --nobs 160000 --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_bench.log 2>&1
   echo "ncu exit $?"; tail -3 gpurun_out/ncu_bench.log ;;
+ncutri)
+  for kn in k_tridiag k_tvec k_gram k_tql; do
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kn -s 3 -c 1 -f -o gpurun_out/prof_$kn \
+     python bench.py --nx 300 --ny 300 --nobs 90000 --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncufull_$kn.log 2>&1
+  echo "ncufull $kn exit $?"
+  done ;;
 ncufull)
   timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_eig_fast -s 2 -c 2 -f -o gpurun_out/prof_eig \
      python bench.py --nx 400 --ny 400 --nobs 160000 --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncufull_eig.log 2>&1

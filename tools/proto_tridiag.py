@@ -44,13 +44,14 @@ def tql_eigenvalues(d, e):
     d = d.copy(); n = len(d)
     e = np.concatenate([e, [0.0]])
     steps = 0
+    tn = max(np.abs(d).max(), np.abs(e).max()) if n > 1 else abs(d[0])
     for l in range(n):
         it = 0
         while True:
             m = l
             while m < n - 1:
                 dd = abs(d[m]) + abs(d[m + 1])
-                if abs(e[m]) <= EPS * dd:
+                if abs(e[m]) <= EPS * dd or abs(e[m]) <= 0.5 * EPS * tn:
                     break
                 m += 1
             if m == l:
@@ -201,3 +202,48 @@ if __name__ == "__main__":
         worst = max(worst, err)
         print(f"{name:32s} err={err:.2e} steps={info['steps']} gs={info['ngs']} fall={info['nfall']} res={info['maxres']:.1e} orth={info['orth']:.1e}")
     print("worst", worst)
+
+
+def host_check():
+    """the C++ routines of oak_b200/csrc/tridiag_math.cuh compiled for the host, inside the same pipeline"""
+    import ctypes
+    lib = ctypes.CDLL("/tmp/libtridiag_host.so")
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.host_twisted.restype = ctypes.c_double
+    lib.host_twisted.argtypes = [ctypes.c_int, dp, dp, ctypes.c_int, ctypes.c_double, ctypes.c_double, dp, ctypes.c_int, dp]
+    lib.host_tql.argtypes = [ctypes.c_int, dp, dp, ctypes.c_int, ctypes.c_double]
+    global tql_eigenvalues, twisted_vector
+
+    def tql_c(d, e):
+        n = len(d); s = 3
+        db = np.zeros(n * s); eb = np.zeros(n * s)
+        db[::s] = d; eb[:(n - 1) * s:s] = e
+        tn = max(np.abs(d).max(), np.abs(e).max()) if n > 1 else abs(d[0])
+        rot = lib.host_tql(n, db.ctypes.data_as(dp), eb.ctypes.data_as(dp), s, tn)
+        assert rot >= 0
+        return db[::s].copy(), rot
+
+    def tw_c(d, e, lam, pivmin, passes=1):
+        n = len(d); sw = 5
+        w = np.zeros(n * sw); gam = ctypes.c_double()
+        d = np.ascontiguousarray(d); e = np.ascontiguousarray(e)
+        zz = lib.host_twisted(n, d.ctypes.data_as(dp), e.ctypes.data_as(dp), 1, lam, pivmin, w.ctypes.data_as(dp), sw, ctypes.byref(gam))
+        z = w[::sw].copy()
+        return z / np.sqrt(zz), lam, abs(gam.value) / np.sqrt(zz)
+    tql_eigenvalues = tql_c
+    twisted_vector = tw_c
+
+
+if __name__ == "__main__" and "--host" in sys.argv:
+    host_check()
+    worst = 0
+    for N, mloc, ws in [(64, 200, 1), (64, 200, 10), (64, 30, 1), (64, 3, 1), (64, 1000, 3), (128, 1257, 1), (20, 5, 1), (16, 40, 1)]:
+        for s in range(4 if N <= 64 else 2):
+            G = make_G(N, mloc, s + 50, ws); G = 0.5 * (G + G.T)
+            M, lam, info = transform_tridiag(G, passes=1)
+            lr = np.linalg.eigvalsh(G)
+            Mr = ref_M(G)
+            err = np.abs(M - Mr).max() / np.abs(Mr).max()
+            worst = max(worst, err)
+            print(f"host N={N} mloc={mloc} ws={ws} err={err:.2e} lamerr={np.abs(lam-lr).max()/np.abs(lr).max():.1e} rot={info['steps']} res={info['maxres']:.1e}")
+    print("host worst", worst)

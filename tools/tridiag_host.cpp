@@ -1,0 +1,8 @@
+// Host build of oak_b200/csrc/tridiag_math.cuh for CPU checks (tools/proto_tridiag.py --host):
+//   g++ -O2 -shared -fPIC -ffp-contract=off tools/tridiag_host.cpp -o /tmp/libtridiag_host.so
+#include "../oak_b200/csrc/tridiag_math.cuh"
+extern "C" int host_tql(int n, double *d, double *e, int s, double tn) { return tql_eigenvalues(n, d, e, s, tn); }
+extern "C" double host_twisted(int n, const double *d, const double *e, int sd, double lam, double pivmin,
+                               double *w, int sw, double *gam) {
+  return twisted_vector(n, d, e, sd, lam, pivmin, w, sw, gam);
+}
