@@ -334,23 +334,48 @@ def main():
         mloc_mean = agg[0].item() / max(analysed, 1)
         cand_mean = agg[1].item() / max(nzones, 1)
         sweeps_mean = agg[2].item() / max(analysed, 1)
-        nb = max(1, (stp["launches"] - len(phases)) // 3)  # eig launches of this rank in one step
-        eig_flops_zone = 9 * a.N ** 3 + 2 * a.N ** 3 + 4 * a.N ** 2
-        eig_ms_launch = stp["ms_eig"] / nb
-        achieved = eig_flops_zone * (z_rank / nb) / (eig_ms_launch * 1e-3) / 1e12
+        tri = a.eig_kernel == 4 and a.N <= 64
+        per_batch = 6 if tri else 3  # kernels per batch: gram, (tridiag, tql, tvec, fallback | eig), apply
+        nb = max(1, (stp["launches"] - len(phases)) // per_batch)  # batches of this rank in one step
+        N3 = a.N ** 3
         fz = flops_per_zone(a.N, a.nz, mloc_mean, cand_mean)
-        roof = {"bound": "fp64", "kernel": "k_eig_fast (batched Cholesky + block-Jacobi + transform)",
+        # Algorithmic flops per zone credited to each kernel (SURVEY.md §8d split): the LAPACK
+        # count 9 N^3 of dsyev = 4/3 N^3 (dsytrd, reduction to tridiagonal form) + the rest (QL iteration
+        # with vectors + back-transformation), which together with T = U f(L) U^T (2 N^3) and ampl (4 N^2) is
+        # what k_tql + k_tvec replace.
+        stages = {
+            "k_gram": (stp["ms_gram"], 2 * a.N * a.N * mloc_mean + 2 * mloc_mean * a.N + 25 * cand_mean),
+            "k_apply": (stp["ms_apply"], 2 * a.nz * a.N * a.N + 2 * a.nz * a.N),
+        }
+        if tri:
+            stages["k_tridiag"] = (stp["ms_tridiag"], 4.0 / 3.0 * N3)
+            stages["k_tql+k_tvec"] = (stp["ms_tql"] + stp["ms_tvec"], (9 - 4.0 / 3.0) * N3 + 2 * N3 + 4 * a.N * a.N)
+        else:
+            stages["k_eig_fast"] = (stp["ms_eig"], 9 * N3 + 2 * N3 + 4 * a.N * a.N)
+        # dram__bytes_read.sum + dram__bytes_write.sum per zone from the ncu --set full captures under profiles/
+        # (r1_ncu_full_tridiag.txt, r1_ncu_full_tvec.txt, r1_ncu_full_gram2.txt; 7104-zone launches, N = 64)
+        traffic_zone = {"k_gram": 26.0e3, "k_tridiag": 59.5e3, "k_tql+k_tvec": 60.4e3, "k_eig_fast": 39.8e3}
+        stage_out = {}
+        for name, (ms_k, fl) in stages.items():
+            ach = fl * z_rank / (ms_k * 1e-3) / 1e12 if ms_k > 0 else 0.0
+            stage_out[name] = {"ms_per_step": ms_k, "algorithmic_flops_per_zone": fl, "achieved_tflops": ach,
+                               "frac": ach / peak_dfma}
+        dom = max((k for k in stages if k != "k_apply"), key=lambda k: stages[k][0])
+        dom_ms, dom_fl = stages[dom]
+        dom_ms_launch = dom_ms / nb
+        achieved = dom_fl * (z_rank / nb) / (dom_ms_launch * 1e-3) / 1e12
+        roof = {"bound": "fp64", "kernel": dom + " (largest share of the step among: " + ", ".join(stages) + ")",
                 "achieved": achieved, "peak": peak_dfma, "unit": "TFLOP/s", "frac": achieved / peak_dfma,
-                # dram__bytes_read.sum + dram__bytes_write.sum of k_eig_fast from the ncu --set full capture in
-                # profiles/r1_ncu_full_eig.txt: 141.3 MB for a 3552-zone launch = 39.8 KB per zone (below the
-                # algorithmic 2 x 32 KB: part of G is still in L2 from k_gram), scaled to this run's launch size
-                "traffic": 39.8e3 * (z_rank / nb) if a.N == 64 else None,
+                "traffic": traffic_zone.get(dom, 0.0) * (z_rank / nb) if a.N == 64 else None,
                 "peak_source": "DFMA micro-kernel measured in this run (oakb200_fp64_peak); MEASURED_PEAKS.json has no "
                                "fp64 figure; DMMA m8n8k4 measured %.1f TFLOP/s" % peak_dmma,
-                "algorithmic_flops_per_zone_kernel": eig_flops_zone, "launches_per_step": nb,
-                "ms_per_launch": eig_ms_launch,
+                "algorithmic_flops_per_zone_kernel": dom_fl, "launches_per_step": nb,
+                "ms_per_launch": dom_ms_launch, "zones_per_launch": z_rank / nb,
                 "kernel_ms_per_step": {"pack": stp["ms_pack"], "gram": stp["ms_gram"], "eig": stp["ms_eig"],
-                                       "apply": stp["ms_apply"]},
+                                       "apply": stp["ms_apply"], "tridiag": stp.get("ms_tridiag", 0.0),
+                                       "tql": stp.get("ms_tql", 0.0), "tvec": stp.get("ms_tvec", 0.0)},
+                "stages": stage_out,
+                "zones_fallback_to_jacobi": int(stp.get("zones_fallback", 0)),
                 "whole_step": {"algorithmic_flops_per_zone": fz, "achieved": value * fz / 1e12 / world,
                                "frac_of_fp64_peak_per_gpu": value * fz / 1e12 / world / peak_dfma},
                 "hbm_view": {"algorithmic_bytes_per_zone": 2 * a.nz * a.N * 8 + 2 * a.nz * 8 + a.m * a.N * 8 / nzones,

@@ -55,6 +55,8 @@ typedef struct {
                                                 option "profile" = 1, which serialises the batches) */
   int64_t launches;         /* kernels launched by this call                                      */
   int64_t zones_fallback;   /* zones the tridiagonal transform route re-did with the Jacobi kernel */
+  double ms_tridiag, ms_tql, ms_tvec; /* "profile": the three kernels of the tridiagonal route (ms_eig = their
+                                         sum + the fallback launch)                                        */
 } oakb200_stats;
 
 OAKB200_API const char *oakb200_last_error(void);

@@ -17,7 +17,8 @@ class Stats(C.Structure):
                 ("obs_candidate_sum", C.c_int64), ("jacobi_sweeps_sum", C.c_int64), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("ms_total", C.c_double), ("ms_pack", C.c_double),
                 ("ms_gram", C.c_double), ("ms_eig", C.c_double), ("ms_apply", C.c_double),
-                ("launches", C.c_int64), ("zones_fallback", C.c_int64)]
+                ("launches", C.c_int64), ("zones_fallback", C.c_int64),
+                ("ms_tridiag", C.c_double), ("ms_tql", C.c_double), ("ms_tvec", C.c_double)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

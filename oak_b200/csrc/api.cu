@@ -45,7 +45,7 @@ extern "C" OAKB200_API int oakb200_version(void) { return 100; }
 
 namespace {
 
-constexpr int NSLOT = 3;
+constexpr int NSLOT = 4;
 
 struct DevBuf {
   void *p = nullptr;
@@ -71,7 +71,7 @@ struct Slot {
   cudaStream_t st = nullptr;
   DevBuf G, T, c, ampl, tri;   // batch workspace (tri: d, e, tau, lambda, flags of the tridiagonal route)
   DevBuf S, xf, xa;            // host-streaming chunk buffers
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[12] = {};
 };
 
 }  // namespace
@@ -80,6 +80,8 @@ struct oakb200_handle {
   int device = 0;
   // options
   int eig_kernel = 4;
+  double tri_orthtol = 0.;  // tridiagonal route: accepted loss of orthogonality between neighbouring eigenvectors (0: default)
+  int tri_maxgroup = -1;    // ... largest group of close eigenvalues orthogonalised in place (-1: default)
   int zones_per_batch = 0;
   double tol = 2e-11;  // bound on the remaining non-orthogonality (eig_common.cuh: jacobi_converged)
   int max_sweeps = 30;
@@ -179,7 +181,7 @@ int pack_obs(oakb200_handle *h, cudaStream_t st, int N, int NP, const double *HS
                              h->d_delta.as<double>(), h->d_scoef.as<double>());
 }
 
-struct ProfAcc { double gram = 0, eig = 0, apply = 0; };
+struct ProfAcc { double gram = 0, eig = 0, apply = 0, tridiag = 0, tql = 0, tvec = 0; };
 
 // Runs zones [z0, z1) on slot s. The state buffers hold rows starting at global row `rowbase`.
 int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t rowbase, const double *xf,
@@ -202,7 +204,9 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
       // recomputed by the Jacobi kernel, which skips the zones whose flag is 0
       int32_t *flags = nullptr;
       if ((rc = oak_launch_eig_tridiag(s.st, N, NP, nz, mloc + b0, s.G.as<double>(), s.c.as<double>(),
-                                       s.T.as<double>(), s.ampl.as<double>(), s.tri.p, &flags, ctr))) return rc;
+                                       s.T.as<double>(), s.ampl.as<double>(), s.tri.p, &flags, ctr,
+                                       prof ? &s.ev[8] : nullptr, h->tri_orthtol, h->tri_maxgroup))) return rc;
+      if (prof) CUDA_TRY(cudaEventRecord(s.ev[10], s.st));
       if ((rc = oak_launch_eig(s.st, 0, N, NP, 0, nz, flags, s.G.as<double>(), s.c.as<double>(),
                                s.T.as<double>(), s.ampl.as<double>(), h->tol, h->max_sweeps, ctr))) return rc;
       *launches += 3;
@@ -221,6 +225,12 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
       CUDA_TRY(cudaEventElapsedTime(&b, s.ev[1], s.ev[2]));
       CUDA_TRY(cudaEventElapsedTime(&c, s.ev[2], s.ev[3]));
       prof->gram += a; prof->eig += b; prof->apply += c;
+      if (h->eig_kernel == 4 && NP <= 64) {
+        CUDA_TRY(cudaEventElapsedTime(&a, s.ev[1], s.ev[8]));
+        CUDA_TRY(cudaEventElapsedTime(&b, s.ev[8], s.ev[9]));
+        CUDA_TRY(cudaEventElapsedTime(&c, s.ev[9], s.ev[10]));
+        prof->tridiag += a; prof->tql += b; prof->tvec += c;
+      }
     }
   }
   return 0;
@@ -259,6 +269,7 @@ int end_call(oakb200_handle *h, oakb200_stats *stats, int64_t launches, const Pr
     stats->ms_gram = prof.gram; stats->ms_eig = prof.eig; stats->ms_apply = prof.apply;
     stats->launches = launches;
     stats->zones_fallback = (int64_t)ctr.fallback;
+    stats->ms_tridiag = prof.tridiag; stats->ms_tql = prof.tql; stats->ms_tvec = prof.tvec;
   }
   if (getenv("OAKB200_DEBUG"))
     fprintf(stderr, "[oak_b200] fallback %llu (ql %llu, residual %llu, group %llu, parallel %llu), gram-schmidt projections %llu, sweeps %llu\n",
@@ -329,6 +340,8 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   if (!h || !key) { oak_set_error("null argument"); return OAK_ERR_ARG; }
   const std::string k(key);
   if (k == "eig_kernel") h->eig_kernel = (int)value;
+  else if (k == "tri_orthtol") h->tri_orthtol = value;
+  else if (k == "tri_maxgroup") h->tri_maxgroup = (int)value;
   else if (k == "zones_per_batch") h->zones_per_batch = (int)value;
   else if (k == "jacobi_tol") h->tol = value;
   else if (k == "max_sweeps") h->max_sweeps = (int)value;

@@ -263,7 +263,8 @@ int oak_launch_eig(cudaStream_t st, int kernel, int N, int NP, int zone0, int nz
 size_t oak_eig_tridiag_ws_bytes(int NP, int nz);
 int oak_launch_eig_tridiag(cudaStream_t st, int N, int NP, int nz, const int32_t *mloc, const double *G,
                            const double *c, double *T, double *ampl, void *ws, int32_t **flags_out,
-                           DevCounters *ctr);
+                           DevCounters *ctr, cudaEvent_t *ev /* optional: [0] after k_tridiag, [1] after k_tql */,
+                           double orthtol /* <= 0: default */, int maxgroup /* < 0: default */);
 int oak_launch_apply(cudaStream_t st, int N, int NP, const ZoneGeom &zg, int zone0, int nz,
                      int64_t rowbase, const int32_t *mloc, const double *T, const double *ampl,
                      const double *xf, const double *Sf, int64_t ldS, double *xa, double *Sa,

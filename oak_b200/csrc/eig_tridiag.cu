@@ -25,6 +25,16 @@
 #include "common.cuh"
 #include "tridiag_math.cuh"
 
+#ifndef TRI_MINB
+#define TRI_MINB 1   // CTAs per SM requested from the compiler for k_tridiag / k_tvec (register cap)
+#endif
+#ifndef TQL_PWK
+#define TQL_PWK 1    // k_tql: 1 = square-root-free QL (Pal-Walker-Kahan), 0 = plain implicit QL
+#endif
+#ifndef TVEC_MINB
+#define TVEC_MINB 1
+#endif
+
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -52,82 +62,104 @@ __device__ __forceinline__ double block_sum(double x, double *sred, int warp, in
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_tridiag
+// k_tridiag : thread t owns row t of the (symmetric, fully stored) matrix in registers.
+//
+// One Householder step per loop trip, organised so that a step has ONE block reduction and TWO barriers:
+// the matrix-vector product of step k+1 is accumulated inside the rank-2 update loop of step k.
+// State entering step k (column k is being reduced):
+//   x_t = A[t][k] (t > k), y_t = sum_j A[t][j] x_j (the product with the UNSCALED column, so it does not
+//   wait for the norm), row k+1 of A published in shared memory (sx2).
+// With beta = -sign(alpha)|x|, v = (x - beta e_{k+1}) scale, v_{k+1} = 1:
+//   A v = scale (y - beta A[:,k+1]) ,  v^T A v = scale^2 (x^T y - 2 beta y_{k+1} + beta^2 A[k+1][k+1]),
+// so sigma^2 = sum x_t^2 and x^T y are reduced together; p = tau A v, w = p - (tau/2)(p^T v) v follow
+// without another reduction, and the next column x'_t = A[t][k+1] - v_t w_{k+1} - w_t is known BEFORE the
+// update A -= v w^T + w v^T, which therefore accumulates y' = A_new x' on the fly.
 // ---------------------------------------------------------------------------------------------------
 template <int NP, int OFF>
 struct TriSteps {
-  // Householder steps k = OFF .. min(OFF+BW, N-2)-1; columns < OFF are finished, so every loop over
-  // the row held in registers runs over the static range [OFF, NP)
-  static __device__ __forceinline__ void run(double (&a)[NP], int N, int t, int warp, int lane, double *sx,
-                                             double *sv, double2 *svw, double *sred, double *Vz,
-                                             double *wd, double *we, double *wtau) {
+  // steps k = OFF .. min(OFF+BW, N-2)-1; columns < OFF are finished, so every loop over the row held in
+  // registers runs over the static range [OFF, NP)
+  static __device__ __forceinline__ void run(double (&a)[NP], double &x, double &y, int N, int t, int warp,
+                                             int lane, double *sx2, double2 *svw, double *sxn, double *sred,
+                                             double *Vz, double *wd, double *we, double *wtau) {
     constexpr int NW = NP / 32;
     const int kend = min(OFF + BW, N - 2);
     for (int k = OFF; k < kend; k++) {
-      const double xk = sx[t], dk = sx[k], alpha = sx[k + 1];
-      const double xt = (t > k + 1) ? xk : 0.;
-      const double sigma2 = block_sum<NW>(xt * xt, sred, warp, lane);
+      double s1 = (t > k + 1) ? x * x : 0.;
+      double s2 = (t > k) ? x * y : 0.;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(FULL, s1, o);
+        s2 += __shfl_xor_sync(FULL, s2, o);
+      }
+      double *sr = sred + 8 * (k & 1);
+      if (lane == 0) { sr[warp] = s1; sr[2 + warp] = s2; }
+      if (t == k + 1) { sr[6] = x; sr[7] = y; }
+      __syncthreads();
+      if (NW == 2) { s1 = sr[0] + sr[1]; s2 = sr[2] + sr[3]; }
+      const double alpha = sr[6], yk1 = sr[7];
+      const double c1 = sx2[t];       // A[t][k+1]
+      const double akk = sx2[k + 1];  // A[k+1][k+1]
       double tau = 0., beta = alpha, scale = 0.;
-      if (sigma2 != 0.) {
-        // beta = -sign(alpha) |x| ; tau = (beta - alpha)/beta = 1 + |alpha|/|x| ; 1/(alpha - beta) = sign(alpha)/(|alpha| + |x|)
-        const double n2 = fma(alpha, alpha, sigma2);
+      if (s1 != 0.) {
+        // beta = -sign(alpha)|x| ; tau = (beta-alpha)/beta = 1 + |alpha|/|x| ; 1/(alpha-beta) = sign(alpha)/(|alpha|+|x|)
+        const double n2 = fma(alpha, alpha, s1);
         const double inrm = rsqrt(n2), nrm = n2 * inrm, aa = fabs(alpha);
         beta = -copysign(nrm, alpha);
         tau = fma(aa, inrm, 1.);
         scale = copysign(oak_rcp(aa + nrm), alpha);
       }
-      const double vt = (t > k + 1) ? xk * scale : (t == k + 1 ? 1. : 0.);
-      sv[t] = vt;
+      const double ts = tau * scale;
+      const double vAv = scale * scale * fma(beta, fma(beta, akk, -2. * yk1), s2);
+      const double hpv = 0.5 * tau * tau * vAv;  // (tau/2) p^T v
+      const double vt = (t > k + 1) ? x * scale : (t == k + 1 ? 1. : 0.);
+      const double pt = (t > k) ? ts * fma(-beta, c1, y) : 0.;
+      const double wt = fma(-hpv, vt, pt);
+      const double wk1 = fma(ts, fma(-beta, akk, yk1), -hpv);  // w_{k+1}
+      const double xn = (t > k + 1) ? c1 - fma(vt, wk1, wt) : 0.;  // new A[t][k+1]
+      svw[t] = make_double2(vt, wt);
+      sxn[t] = xn;
       Vz[k * NP + t] = vt;
-      if (t == k) { wd[k] = dk; we[k] = beta; wtau[k] = tau; }
+      if (t == k + 1) { we[k] = beta; wtau[k] = tau; wd[k + 1] = fma(-2., wk1, akk); }
       __syncthreads();
-      if (tau != 0.) {
-        double p = 0.;
-        if (32 * warp + 31 > k) {  // a warp whose rows are all finished only takes part in the barriers
-          double p0 = 0., p1 = 0., p2 = 0., p3 = 0.;
+      double y0 = 0., y1 = 0., y2 = 0., y3 = 0.;
+      if (32 * warp + 31 > k + 1) {  // a warp whose rows are all finished only takes part in the barriers
 #pragma unroll
-          for (int j = OFF; j < NP; j += 4) {
-            const double2 v01 = *reinterpret_cast<const double2 *>(sv + j);
-            const double2 v23 = *reinterpret_cast<const double2 *>(sv + j + 2);
-            p0 = fma(a[j], v01.x, p0);
-            p1 = fma(a[j + 1], v01.y, p1);
-            p2 = fma(a[j + 2], v23.x, p2);
-            p3 = fma(a[j + 3], v23.y, p3);
-          }
-          p = (t > k) ? tau * ((p0 + p1) + (p2 + p3)) : 0.;
+        for (int j = OFF; j < NP; j += 4) {
+          const double2 q0 = svw[j], q1 = svw[j + 1], q2 = svw[j + 2], q3 = svw[j + 3];
+          const double2 n01 = *reinterpret_cast<const double2 *>(sxn + j);
+          const double2 n23 = *reinterpret_cast<const double2 *>(sxn + j + 2);
+          a[j] = fma(-vt, q0.y, fma(-wt, q0.x, a[j]));
+          a[j + 1] = fma(-vt, q1.y, fma(-wt, q1.x, a[j + 1]));
+          a[j + 2] = fma(-vt, q2.y, fma(-wt, q2.x, a[j + 2]));
+          a[j + 3] = fma(-vt, q3.y, fma(-wt, q3.x, a[j + 3]));
+          y0 = fma(a[j], n01.x, y0);
+          y1 = fma(a[j + 1], n01.y, y1);
+          y2 = fma(a[j + 2], n23.x, y2);
+          y3 = fma(a[j + 3], n23.y, y3);
         }
-        const double pv = block_sum<NW>(p * vt, sred + 4, warp, lane);
-        const double wt = fma(-0.5 * tau * pv, vt, p);
-        svw[t] = make_double2(vt, wt);
-        __syncthreads();
-        if (32 * warp + 31 > k) {
+        if (t == k + 2) {
 #pragma unroll
-          for (int j = OFF; j < NP; j++) {
-            const double2 q = svw[j];
-            a[j] = fma(-vt, q.y, fma(-wt, q.x, a[j]));
-          }
+          for (int j = OFF; j < NP; j += 2) *reinterpret_cast<double2 *>(sx2 + j) = make_double2(a[j], a[j + 1]);
         }
       }
-      if (t == k + 1) {
-#pragma unroll
-        for (int j = OFF; j < NP; j += 2) *reinterpret_cast<double2 *>(sx + j) = make_double2(a[j], a[j + 1]);
-      }
-      __syncthreads();
+      x = xn;
+      y = (y0 + y1) + (y2 + y3);
     }
     if constexpr (OFF + BW < NP) {
-      if (N - 2 > OFF + BW) TriSteps<NP, OFF + BW>::run(a, N, t, warp, lane, sx, sv, svw, sred, Vz, wd, we, wtau);
+      if (N - 2 > OFF + BW) TriSteps<NP, OFF + BW>::run(a, x, y, N, t, warp, lane, sx2, svw, sxn, sred, Vz, wd, we, wtau);
     }
   }
 };
 
 template <int NP>
-__global__ void __launch_bounds__(NP) k_tridiag(int N, const int32_t *__restrict__ mloc,
+__global__ void __launch_bounds__(NP, TRI_MINB) k_tridiag(int N, const int32_t *__restrict__ mloc,
                                                  const double *__restrict__ G, double *__restrict__ V,
                                                  double *__restrict__ ws) {
-  __shared__ __align__(16) double sx[NP];
-  __shared__ __align__(16) double sv[NP];
+  __shared__ __align__(16) double sx2[NP];
+  __shared__ __align__(16) double sxn[NP];
   __shared__ __align__(16) double2 svw[NP];
-  __shared__ double sred[8];
+  __shared__ double sred[16];
   const int zl = blockIdx.x;
   if (mloc[zl] == 0) return;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -139,23 +171,32 @@ __global__ void __launch_bounds__(NP) k_tridiag(int N, const int32_t *__restrict
   double a[NP];
 #pragma unroll
   for (int j = 0; j < NP; j++) a[j] = Gz[j * NP + t];  // G is symmetric: row t read as column t (coalesced)
-  if (t == 0) {
+  double x = (t >= 1) ? a[0] : 0.;
+  sxn[t] = x;
+  if (t == 1) {
 #pragma unroll
-    for (int j = 0; j < NP; j++) sx[j] = a[j];
+    for (int j = 0; j < NP; j++) sx2[j] = a[j];
   }
+  if (t == 0) wd[0] = a[0];
   if (t >= N) { wd[t] = 0.; we[t] = 0.; }
   wtau[t] = 0.;
   __syncthreads();
-  TriSteps<NP, 0>::run(a, N, t, warp, lane, sx, sv, svw, sred, Vz, wd, we, wtau);
-  // the published row is row N-2: d_{N-2}, e_{N-2}; then row N-1 gives d_{N-1}
-  if (t == 0) { wd[N - 2] = sx[N - 2]; we[N - 2] = sx[N - 1]; }
-  __syncthreads();
-  if (t == N - 1) {
+  double y;
+  {
+    double y0 = 0., y1 = 0., y2 = 0., y3 = 0.;
 #pragma unroll
-    for (int j = 0; j < NP; j++) sx[j] = a[j];
+    for (int j = 0; j < NP; j += 4) {
+      y0 = fma(a[j], sxn[j], y0);
+      y1 = fma(a[j + 1], sxn[j + 1], y1);
+      y2 = fma(a[j + 2], sxn[j + 2], y2);
+      y3 = fma(a[j + 3], sxn[j + 3], y3);
+    }
+    y = (y0 + y1) + (y2 + y3);
   }
+  TriSteps<NP, 0>::run(a, x, y, N, t, warp, lane, sx2, svw, sxn, sred, Vz, wd, we, wtau);
+  // x is now column N-2 (its only entry below the diagonal is e_{N-2}); sx2 holds row N-1
   __syncthreads();
-  if (t == 0) { wd[N - 1] = sx[N - 1]; we[N - 1] = 0.; }
+  if (t == N - 1) { we[N - 2] = x; we[N - 1] = 0.; wd[N - 1] = sx2[N - 1]; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -183,7 +224,14 @@ __global__ void __launch_bounds__(32) k_tql(int N, int nz, const int32_t *__rest
   if (active) {
     double tn = 0.;
     for (int i = 0; i < N; i++) tn = fmax(tn, fmax(fabs(sd[i * S + lane]), fabs(se[i * S + lane])));
+#if TQL_PWK
+    rot = pwk_eigenvalues(N, sd + lane, se + lane, S, tn);
+#else
     rot = tql_eigenvalues(N, sd + lane, se + lane, S, tn);
+#endif
+    // the reciprocals of the iteration are not guarded against denormals: verify instead (NaN-safe)
+    for (int i = 0; i < N; i++)
+      if (!(fabs(sd[i * S + lane]) <= 4. * tn)) rot = -1;
   }
   if (zl < nz) flags[zl] = (rot < 0) ? 1 : 0;
   __syncwarp();
@@ -231,17 +279,19 @@ struct BackSteps {
 };
 
 template <int NP>
-__global__ void __launch_bounds__(NP) k_tvec(int N, const int32_t *__restrict__ mloc,
+__global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__restrict__ mloc,
                                               const double *__restrict__ ws, const double *__restrict__ cin,
                                               double *__restrict__ Tout, double *__restrict__ ampl_out,
-                                              int32_t *__restrict__ flags, DevCounters *ctr) {
+                                              int32_t *__restrict__ flags, DevCounters *ctr, double orthtol,
+                                              int maxgroup) {
   constexpr int LDW = NP + 1;
+  constexpr int LDY = NP + 2;
   constexpr int NW = NP / 32;
   constexpr int TR = 8, TC = NP / 8;          // output tile of a thread: TR rows x TC columns
   constexpr int TJ = NP / TC;                 // thread grid: (NP/TR) x TJ = NP threads
   extern __shared__ __align__(16) double sm[];
   double *W = sm;                      // [NP][LDW] : W[i*LDW + j] = element i of vector j ; later V, then Y
-  double *sd = sm + NP * LDW;
+  double *sd = sm + NP * LDY;
   double *se = sd + NP, *slam = se + NP, *stau = slam + NP, *sc = stau + NP;
   double *sa = sc + NP, *sb = sa + NP, *suv = sb + NP, *sdw = suv + NP, *suw = sdw + NP;
   double *sg1 = suw + NP, *sg2 = sg1 + NP, *sgj = sg2 + NP, *sres = sgj + NP;
@@ -294,7 +344,7 @@ __global__ void __launch_bounds__(NP) k_tvec(int N, const int32_t *__restrict__ 
   // ---- groups of close eigenvalues ----
   bool close = false;
   if (j >= 1 && j < N && live && sgj[j - 1] >= TRI_NULL)
-    close = fmax(gj, sgj[j - 1]) * (res + sres[j - 1] + 4. * OAK_DBL_EPS * tn) > TRI_ORTHTOL * (lam - slam[j - 1]);
+    close = fmax(gj, sgj[j - 1]) * (res + sres[j - 1] + 4. * OAK_DBL_EPS * tn) > orthtol * (lam - slam[j - 1]);
   const unsigned cm = __ballot_sync(FULL, close);
   if (lane == 0) sclose[warp] = cm;
   if (bad) { sflag = 1; atomicAdd(&ctr->fb_reason[1], 1ull); }
@@ -307,7 +357,7 @@ __global__ void __launch_bounds__(NP) k_tvec(int N, const int32_t *__restrict__ 
     for (int k = 1; k < N; k++) {
       const bool ck = (sclose[k >> 5] >> (k & 31)) & 1;
       if (!ck) { gstart = k; continue; }
-      if (k - gstart > TRI_MAXGROUP) { if (j == 0) { sflag = 1; atomicAdd(&ctr->fb_reason[2], 1ull); } continue; }
+      if (k - gstart > maxgroup) { if (j == 0) { sflag = 1; atomicAdd(&ctr->fb_reason[2], 1ull); } continue; }
       if (j == 0) atomicAdd(&ctr->gs_pairs, (unsigned long long)(k - gstart));
       for (int i = gstart; i < k; i++) {
         const double prod = (j < N) ? W[j * LDW + i] * W[j * LDW + k] : 0.;
@@ -349,8 +399,12 @@ __global__ void __launch_bounds__(NP) k_tvec(int N, const int32_t *__restrict__ 
   const double ys = live ? sqrt(gj) : 0.;
   const double iys = live ? 1. / ys : 0.;
   __syncthreads();  // every thread is done with the reflectors
+  // Y = U diag(ys), stored transposed: Yt[k*LDY + i] = Y[i][k] (row k = scaled eigenvector k, contiguous;
+  // LDY = NP+2 keeps the 16-byte stores of neighbouring threads in different banks)
+  double *Yt = W;
 #pragma unroll
-  for (int i = 0; i < NP; i++) W[i * LDW + j] = ys * u[i];
+  for (int i = 0; i < NP; i += 2)
+    *reinterpret_cast<double2 *>(Yt + j * LDY + i) = make_double2(ys * u[i], ys * u[i + 1]);
   sa[j] = -(lamc / (1. + lamc)) * q * iys;
   sb[j] = (sig - 1.) * s1 * iys;
   __syncthreads();
@@ -361,9 +415,9 @@ __global__ void __launch_bounds__(NP) k_tvec(int N, const int32_t *__restrict__ 
     if (j < N) {
       am = sc[j]; vi = 1.;
       for (int k = 0; k < N; k++) {
-        const double y = W[j * LDW + k];
-        am = fma(y, sa[k], am);
-        vi = fma(y, sb[k], vi);
+        const double yv = Yt[k * LDY + j];
+        am = fma(yv, sa[k], am);
+        vi = fma(yv, sb[k], vi);
       }
     }
     if (am != am) atomicExch(&ctr->nan_flag, 1);
@@ -387,24 +441,24 @@ __global__ void __launch_bounds__(NP) k_tvec(int N, const int32_t *__restrict__ 
     suw[j] = uw;                               // u_w
   }
   __syncthreads();
-  // g1 = M u_v, gm2 = M (D u_w), M = I - Y Y^T
+  // g1 = M u_v, gm2 = M (D u_w), M = I - Y Y^T : first Y^T x from the column still held in registers
   {
     double p1 = 0., p2 = 0.;
-    for (int i = 0; i < N; i++) {
-      const double y = W[i * LDW + j];
-      p1 = fma(y, suv[i], p1);
-      p2 = fma(y, sdw[i], p2);
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+      p1 = fma(u[i], suv[i], p1);
+      p2 = fma(u[i], sdw[i], p2);
     }
-    sa[j] = p1; sb[j] = p2;
+    sa[j] = ys * p1; sb[j] = ys * p2;
   }
   const double kappa = block_sum<NW>(suv[j] * hv * sdw[j], sred + 4, warp, lane);
   __syncthreads();
   {
     double g1 = suv[j], gm2 = sdw[j];
     for (int k = 0; k < N; k++) {
-      const double y = W[j * LDW + k];
-      g1 = fma(-y, sa[k], g1);
-      gm2 = fma(-y, sb[k], gm2);
+      const double yv = Yt[k * LDY + j];
+      g1 = fma(-yv, sa[k], g1);
+      gm2 = fma(-yv, sb[k], gm2);
     }
     sg1[j] = g1;
     sg2[j] = gm2 - kappa * g1;
@@ -418,15 +472,20 @@ __global__ void __launch_bounds__(NP) k_tvec(int N, const int32_t *__restrict__ 
     for (int a_ = 0; a_ < TR; a_++)
 #pragma unroll
       for (int b = 0; b < TC; b++) acc[a_][b] = 0.;
-    int col[TC];
-#pragma unroll
-    for (int b = 0; b < TC; b++) col[b] = 2 * tj + (2 * TJ) * (b >> 1) + (b & 1);
+    const double *yr = Yt + TR * ti, *yc = Yt + 2 * tj;
+#pragma unroll 2
     for (int k = 0; k < N; k++) {
       double rv[TR], cv[TC];
 #pragma unroll
-      for (int a_ = 0; a_ < TR; a_++) rv[a_] = W[(TR * ti + a_) * LDW + k];
+      for (int a_ = 0; a_ < TR; a_ += 2) {
+        const double2 r2 = *reinterpret_cast<const double2 *>(yr + k * LDY + a_);
+        rv[a_] = r2.x; rv[a_ + 1] = r2.y;
+      }
 #pragma unroll
-      for (int b = 0; b < TC; b++) cv[b] = W[col[b] * LDW + k];
+      for (int b = 0; b < TC; b += 2) {
+        const double2 c2 = *reinterpret_cast<const double2 *>(yc + k * LDY + (2 * TJ) * (b >> 1));
+        cv[b] = c2.x; cv[b + 1] = c2.y;
+      }
 #pragma unroll
       for (int a_ = 0; a_ < TR; a_++)
 #pragma unroll
@@ -439,7 +498,7 @@ __global__ void __launch_bounds__(NP) k_tvec(int N, const int32_t *__restrict__ 
       const double g1i = sg1[i] * hv, g2i = sg2[i] * hw;
 #pragma unroll
       for (int b = 0; b < TC; b += 2) {
-        const int k = col[b];
+        const int k = 2 * tj + (2 * TJ) * (b >> 1);
         double t0 = acc[a_][b] + (i == k ? 1. : 0.) - g1i * suv[k];
         double t1 = acc[a_][b + 1] + (i == k + 1 ? 1. : 0.) - g1i * suv[k + 1];
         if (k == N - 1) t0 *= dNN;
@@ -455,9 +514,9 @@ __global__ void __launch_bounds__(NP) k_tvec(int N, const int32_t *__restrict__ 
 
 template <int NP>
 int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G, const double *c, double *T,
-           double *ampl, double *ws, int32_t *flags, DevCounters *ctr) {
+           double *ampl, double *ws, int32_t *flags, DevCounters *ctr, cudaEvent_t *ev, double orthtol, int maxgroup) {
   constexpr int LDW = NP + 1;
-  const size_t smem = sizeof(double) * (NP * LDW + 14 * NP);
+  const size_t smem = sizeof(double) * (NP * (NP + 2) + 14 * NP);
   static bool attr_done = false;
   if (!attr_done) {
     CUDA_TRY(cudaFuncSetAttribute(k_tvec<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -465,9 +524,12 @@ int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G,
   }
   k_tridiag<NP><<<nz, NP, 0, st>>>(N, mloc, G, T, ws);
   CUDA_TRY(cudaGetLastError());
+  if (ev) CUDA_TRY(cudaEventRecord(ev[0], st));
   k_tql<NP><<<(nz + 31) / 32, 32, 0, st>>>(N, nz, mloc, ws, flags);
   CUDA_TRY(cudaGetLastError());
-  k_tvec<NP><<<nz, NP, smem, st>>>(N, mloc, ws, c, T, ampl, flags, ctr);
+  if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
+  k_tvec<NP><<<nz, NP, smem, st>>>(N, mloc, ws, c, T, ampl, flags, ctr, orthtol > 0. ? orthtol : TRI_ORTHTOL,
+                                   maxgroup >= 0 ? maxgroup : TRI_MAXGROUP);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -483,13 +545,13 @@ size_t oak_eig_tridiag_ws_bytes(int NP, int nz) {
 // recomputed by the Jacobi kernel and 0 for the others.  V (the reflectors) lives in T until k_tvec replaces it.
 int oak_launch_eig_tridiag(cudaStream_t st, int N, int NP, int nz, const int32_t *mloc, const double *G,
                            const double *c, double *T, double *ampl, void *ws, int32_t **flags_out,
-                           DevCounters *ctr) {
+                           DevCounters *ctr, cudaEvent_t *ev, double orthtol, int maxgroup) {
   double *wsd = reinterpret_cast<double *>(ws);
   int32_t *flags = reinterpret_cast<int32_t *>(wsd + 4 * (size_t)NP * nz);
   *flags_out = flags;
   switch (NP) {
-    case 32: return launch<32>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr);
-    case 64: return launch<64>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr);
+    case 32: return launch<32>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup);
+    case 64: return launch<64>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup);
   }
   oak_set_error("eig_tridiag: unsupported padded ensemble size %d", NP);
   return OAK_ERR_UNSUPPORTED;

@@ -103,6 +103,61 @@ OAK_HD int tql_eigenvalues(int n, double *d, double *e, int s, double tn) {
   return rot;
 }
 
+// The same eigenvalues by the square-root-free QL variant of Pal, Walker and Kahan (the organisation of
+// LAPACK dsterf): works on e_i^2, one reciprocal chain per rotation instead of an inverse square root plus
+// the longer dependent chain of the plain QL step, i.e. about half the latency per rotation, which is
+// what bounds k_tql (one thread per zone).  Same interface as tql_eigenvalues; e is overwritten by squares.
+OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) {
+  int rot = 0;
+  const double eps2 = OAK_DBL_EPS * OAK_DBL_EPS;
+  const double abstol2 = 0.25 * eps2 * tn * tn;
+  for (int i = 0; i < n - 1; i++) { const double ei = e[i * s]; e[i * s] = ei * ei; }
+  if (n > 0) e[(n - 1) * s] = 0.;
+  for (int l = 0; l < n; l++) {
+    int iter = 0;
+    for (;;) {
+      int m = l;
+      for (; m < n - 1; m++) {
+        const double em = e[m * s];
+        if (em <= abstol2 || em <= eps2 * fabs(d[m * s] * d[(m + 1) * s])) break;
+      }
+      if (m == l) break;
+      if (++iter > 60) return -1;
+      const double rte = sqrt(e[l * s]);
+      double p = d[l * s];
+      double sigma = (d[(l + 1) * s] - p) * 0.5 * oak_rcp(rte);
+      const double r0 = sqrt(fma(sigma, sigma, 1.));
+      sigma = p - rte * oak_rcp(sigma + copysign(r0, sigma));
+      double c = 1., sn = 0., gamma = d[m * s] - sigma;
+      p = gamma * gamma;
+      for (int i = m - 1; i >= l; i--) {
+        rot++;
+        const double bb = e[i * s];
+        const double r = p + bb;
+        if (i != m - 1) e[(i + 1) * s] = sn * r;
+        const double oldc = c;
+        const double ir = oak_rcp(r);
+        const double ip = oak_rcp(p);  // independent of ir: the two reciprocals overlap
+        c = p * ir;
+        sn = bb * ir;
+        const double oldgam = gamma, alpha = d[i * s];
+        gamma = fma(c, alpha - sigma, -sn * oldgam);
+        d[(i + 1) * s] = oldgam + (alpha - gamma);
+        p = (c != 0.) ? gamma * gamma * (r * ip) : oldc * bb;
+      }
+      e[l * s] = sn * p;
+      d[l * s] = sigma + gamma;
+    }
+  }
+  for (int i = 1; i < n; i++) {
+    const double v = d[i * s];
+    int j = i - 1;
+    while (j >= 0 && d[j * s] > v) { d[(j + 1) * s] = d[j * s]; j--; }
+    d[(j + 1) * s] = v;
+  }
+  return rot;
+}
+
 // Eigenvector of T for the eigenvalue lam by the twisted factorisation (Fernando; Parlett & Dhillon):
 //   forward pivots  p_0 = d_0 - lam , p_{i+1} = (d_{i+1} - lam) - e_i^2 / p_i
 //   backward pivots q_{n-1} = d_{n-1} - lam , q_i = (d_i - lam) - e_i^2 / q_{i+1}

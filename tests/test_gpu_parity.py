@@ -444,3 +444,32 @@ def test_dynamic_range_of_the_spectrum(ob, handle, scale):
     xa, Sa, _, st = handle.local_analysis(c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], ob.DiagCovar(c["var"]))
     xo, So, _, mloc = _oracle_loc(c)
     assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL, (rel(xa, xo), rel(Sa, So))
+
+
+@pytest.mark.parametrize("N", [24, 64])
+def test_degenerate_spectrum_falls_back_to_jacobi(ob, N):
+    """Repeated non-zero eigenvalues of G (orthogonal observation rows of equal norm, weight and variance):
+    independent factorisations of T - lambda I cannot give an orthonormal basis of the eigenspace, so the
+    tridiagonal route (eig_kernel 4) must hand these zones to the Jacobi kernel; close-but-distinct eigenvalues
+    are orthogonalised in place.  Either way the result matches dsyev within RTOL."""
+    from oak_b200 import synthetic
+    c = synthetic.small_case(nx=6, ny=5, nz=2, N=N, m=6, corr=1e9, maxlen=1e12, seed=5)  # every zone sees all 6 obs
+    rng = np.random.default_rng(3)
+    Q, _ = np.linalg.qr(rng.normal(size=(N, 6)))
+    rows = Q.T.copy()                      # 6 orthonormal rows
+    rows[:3] *= 2.0                        # eigenvalue 4 w^2/r three times
+    rows[3:5] *= 1.0 + np.array([0.0, 3e-7])[:, None]  # two eigenvalues 6e-7 apart (relative)
+    rows[5] *= 0.5
+    c["HSf"] = np.asfortranarray(rows)
+    c["var"] = np.full(6, 0.25)
+    xo, So, _, mloc = _oracle_loc(c)
+    assert (mloc == 6).all()
+    with ob.Handle(0, eig_kernel=4) as h:
+        _configure(ob, h, c)
+        xa, Sa, _, st = h.local_analysis(c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], ob.DiagCovar(c["var"]))
+        assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL, (rel(xa, xo), rel(Sa, So), st["zones_fallback"])
+        # no in-place orthogonalisation allowed: every zone with a close pair goes to the Jacobi kernel
+        h.set_option("tri_maxgroup", 0)
+        xa, Sa, _, st = h.local_analysis(c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], ob.DiagCovar(c["var"]))
+        assert st["zones_fallback"] == len(mloc) and st["jacobi_sweeps_sum"] > 0
+        assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL, (rel(xa, xo), rel(Sa, So))

@@ -6,3 +6,4 @@ extern "C" double host_twisted(int n, const double *d, const double *e, int sd, 
                                double *w, int sw, double *gam) {
   return twisted_vector(n, d, e, sd, lam, pivmin, w, sw, gam);
 }
+extern "C" int host_pwk(int n, double *d, double *e, int s, double tn) { return pwk_eigenvalues(n, d, e, s, tn); }
