@@ -28,6 +28,9 @@
 #ifndef TRI_MINB
 #define TRI_MINB 1   // CTAs per SM requested from the compiler for k_tridiag / k_tvec (register cap)
 #endif
+#ifndef TRI_TILE
+#define TRI_TILE 1   // 1 = k_tridiag_tile (8 x 8 cyclic register tiles), 0 = k_tridiag (row per thread)
+#endif
 #ifndef TQL_PWK
 #define TQL_PWK 1    // k_tql: 1 = square-root-free QL (Pal-Walker-Kahan), 0 = plain implicit QL
 #endif
@@ -122,21 +125,27 @@ struct TriSteps {
       Vz[k * NP + t] = vt;
       if (t == k + 1) { we[k] = beta; wtau[k] = tau; wd[k + 1] = fma(-2., wk1, akk); }
       __syncthreads();
-      double y0 = 0., y1 = 0., y2 = 0., y3 = 0.;
+      double y0 = 0., y1 = 0., y2 = 0., y3 = 0., y4 = 0., y5 = 0., y6 = 0., y7 = 0.;
       if (32 * warp + 31 > k + 1) {  // a warp whose rows are all finished only takes part in the barriers
 #pragma unroll
-        for (int j = OFF; j < NP; j += 4) {
-          const double2 q0 = svw[j], q1 = svw[j + 1], q2 = svw[j + 2], q3 = svw[j + 3];
+        for (int j = OFF; j < NP; j += 8) {
+#pragma unroll
+          for (int jj = 0; jj < 8; jj++) {
+            const double2 q = svw[j + jj];
+            a[j + jj] = fma(-vt, q.y, fma(-wt, q.x, a[j + jj]));
+          }
           const double2 n01 = *reinterpret_cast<const double2 *>(sxn + j);
           const double2 n23 = *reinterpret_cast<const double2 *>(sxn + j + 2);
-          a[j] = fma(-vt, q0.y, fma(-wt, q0.x, a[j]));
-          a[j + 1] = fma(-vt, q1.y, fma(-wt, q1.x, a[j + 1]));
-          a[j + 2] = fma(-vt, q2.y, fma(-wt, q2.x, a[j + 2]));
-          a[j + 3] = fma(-vt, q3.y, fma(-wt, q3.x, a[j + 3]));
+          const double2 n45 = *reinterpret_cast<const double2 *>(sxn + j + 4);
+          const double2 n67 = *reinterpret_cast<const double2 *>(sxn + j + 6);
           y0 = fma(a[j], n01.x, y0);
           y1 = fma(a[j + 1], n01.y, y1);
           y2 = fma(a[j + 2], n23.x, y2);
           y3 = fma(a[j + 3], n23.y, y3);
+          y4 = fma(a[j + 4], n45.x, y4);
+          y5 = fma(a[j + 5], n45.y, y5);
+          y6 = fma(a[j + 6], n67.x, y6);
+          y7 = fma(a[j + 7], n67.y, y7);
         }
         if (t == k + 2) {
 #pragma unroll
@@ -144,7 +153,7 @@ struct TriSteps {
         }
       }
       x = xn;
-      y = (y0 + y1) + (y2 + y3);
+      y = ((y0 + y1) + (y2 + y3)) + ((y4 + y5) + (y6 + y7));
     }
     if constexpr (OFF + BW < NP) {
       if (N - 2 > OFF + BW) TriSteps<NP, OFF + BW>::run(a, x, y, N, t, warp, lane, sx2, svw, sxn, sred, Vz, wd, we, wtau);
@@ -197,6 +206,196 @@ __global__ void __launch_bounds__(NP, TRI_MINB) k_tridiag(int N, const int32_t *
   // x is now column N-2 (its only entry below the diagonal is e_{N-2}); sx2 holds row N-1
   __syncthreads();
   if (t == N - 1) { we[N - 2] = x; we[N - 1] = 0.; wd[N - 1] = sx2[N - 1]; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_tridiag_tile : the same fused Householder step on a 2-D cyclic register tiling.
+//
+// The row-per-thread kernel above is bound by the shared-memory return path, not by the fp64 pipe: every
+// DFMA of the rank-2 update needs its own 8 bytes of (v_j, w_j, x'_j) from shared memory (a broadcast
+// LDS.128 still moves 512 B per warp), i.e. 1 FMA per double loaded against the ~4 the SM can sustain.
+// Here 64 threads form an 8 x 8 grid; thread (rg, cg) holds A[8a + rg][8b + cg], a, b < NP/8 (cyclic in both
+// directions), so a loaded column triple serves NP/8 rows and a loaded row pair NP/8 columns (8 FMA per
+// double at NP = 64).  The cyclic distribution also makes the finished rows AND columns drop out of every
+// thread's static loop ranges every 8 steps (exact triangular work instead of 1.25 x full rows), and the row
+// that has to be published next (k+2) sits in a register slot that is static within such a block.
+// Row sums are combined over the 8 column-group lanes by a transpose-reduction (7 shuffles) that leaves the
+// complete sum of row 8 cg + rg in lane cg: that thread is the row's owner for the scalar part of the step.
+// ---------------------------------------------------------------------------------------------------
+template <int RA>
+__device__ __forceinline__ double transpose_reduce8(double (&yp)[RA], int cg) {
+  // lanes cg = 0..7 (consecutive) each hold RA partial sums; returns in lane cg the total of slot cg (RA = 8)
+  // or of slot cg & 3 (RA = 4: lanes cg and cg ^ 4 both get it)
+  double v4[4];
+  if constexpr (RA == 8) {
+    const bool up = cg & 4;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const double send = up ? yp[i] : yp[i + 4];
+      const double keep = up ? yp[i + 4] : yp[i];
+      v4[i] = keep + __shfl_xor_sync(FULL, send, 4);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) v4[i] = yp[i] + __shfl_xor_sync(FULL, yp[i], 4);
+  }
+  double v2[2];
+  {
+    const bool up = cg & 2;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const double send = up ? v4[i] : v4[i + 2];
+      const double keep = up ? v4[i + 2] : v4[i];
+      v2[i] = keep + __shfl_xor_sync(FULL, send, 2);
+    }
+  }
+  const bool up = cg & 1;
+  const double send = up ? v2[0] : v2[1];
+  const double keep = up ? v2[1] : v2[0];
+  return keep + __shfl_xor_sync(FULL, send, 1);
+}
+
+template <int NP, int KB>
+struct TileSteps {
+  static constexpr int RA = NP / 8;
+  // steps k = 8 KB .. min(8 KB + 8, N-2) - 1 ; row / column slots < KB are finished
+  static __device__ __forceinline__ void run(double (&a)[NP / 8][NP / 8], double &x, double &y, int N, int tid,
+                                             int rg, int cg, int t, bool owner, double *sx2, double2 *svw,
+                                             double *sxn, double *sred, double *Vz, double *wd, double *we,
+                                             double *wtau) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int kend = min(8 * KB + 8, N - 2);
+    for (int k = 8 * KB; k < kend; k++) {
+      double s1 = (owner && t > k + 1) ? x * x : 0.;
+      double s2 = (owner && t > k) ? x * y : 0.;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(FULL, s1, o);
+        s2 += __shfl_xor_sync(FULL, s2, o);
+      }
+      double *sr = sred + 8 * (k & 1);
+      if (lane == 0) { sr[warp] = s1; sr[2 + warp] = s2; }
+      if (owner && t == k + 1) { sr[6] = x; sr[7] = y; }
+      __syncthreads();
+      s1 = sr[0] + sr[1]; s2 = sr[2] + sr[3];
+      const double alpha = sr[6], yk1 = sr[7];
+      const double c1 = sx2[t];       // A[t][k+1]
+      const double akk = sx2[k + 1];  // A[k+1][k+1]
+      double tau = 0., beta = alpha, scale = 0.;
+      if (s1 != 0.) {
+        const double n2 = fma(alpha, alpha, s1);
+        const double inrm = rsqrt(n2), nrm = n2 * inrm, aa = fabs(alpha);
+        beta = -copysign(nrm, alpha);
+        tau = fma(aa, inrm, 1.);
+        scale = copysign(oak_rcp(aa + nrm), alpha);
+      }
+      const double ts = tau * scale;
+      const double vAv = scale * scale * fma(beta, fma(beta, akk, -2. * yk1), s2);
+      const double hpv = 0.5 * tau * tau * vAv;  // (tau/2) p^T v
+      const double vt = (t > k + 1) ? x * scale : (t == k + 1 ? 1. : 0.);
+      const double pt = (t > k) ? ts * fma(-beta, c1, y) : 0.;
+      const double wt = fma(-hpv, vt, pt);
+      const double wk1 = fma(ts, fma(-beta, akk, yk1), -hpv);  // w_{k+1}
+      const double xn = (t > k + 1) ? c1 - fma(vt, wk1, wt) : 0.;  // new A[t][k+1]
+      if (owner) {
+        svw[t] = make_double2(vt, wt);
+        sxn[t] = xn;
+        if (t == k + 1) { we[k] = beta; wtau[k] = tau; wd[k + 1] = fma(-2., wk1, akk); }
+      }
+      __syncthreads();
+      if (tid < NP) Vz[k * NP + tid] = svw[tid].x;  // reflector k, coalesced
+      double yp[RA];
+#pragma unroll
+      for (int i = 0; i < RA; i++) yp[i] = 0.;
+      {
+        double2 cvw[RA];
+        double cxn[RA];
+#pragma unroll
+        for (int b = KB; b < RA; b++) { cvw[b] = svw[8 * b + cg]; cxn[b] = sxn[8 * b + cg]; }
+#pragma unroll
+        for (int i = KB; i < RA; i++) {
+          const double2 r = svw[8 * i + rg];
+#pragma unroll
+          for (int b = KB; b < RA; b++) {
+            a[i][b] = fma(-r.x, cvw[b].y, fma(-r.y, cvw[b].x, a[i][b]));
+            yp[i] = fma(a[i][b], cxn[b], yp[i]);
+          }
+        }
+      }
+      // publish row k+2 (slot (k+2)/8 is KB or KB+1, register index static either way)
+      {
+        const int pr = k + 2;
+        if (rg == (pr & 7)) {
+          if ((pr >> 3) == KB) {
+#pragma unroll
+            for (int b = KB; b < RA; b++) sx2[8 * b + cg] = a[KB][b];
+          } else if constexpr (KB + 1 < RA) {
+#pragma unroll
+            for (int b = KB; b < RA; b++) sx2[8 * b + cg] = a[KB + 1][b];
+          }
+        }
+      }
+      const double ysum = transpose_reduce8<RA>(yp, cg);
+      x = xn;
+      y = ysum;
+    }
+    if constexpr (KB + 1 < NP / 8) {
+      if (N - 2 > 8 * KB + 8) TileSteps<NP, KB + 1>::run(a, x, y, N, tid, rg, cg, t, owner, sx2, svw, sxn, sred, Vz, wd, we, wtau);
+    }
+  }
+};
+
+template <int NP>
+__global__ void __launch_bounds__(64, TRI_MINB) k_tridiag_tile(int N, const int32_t *__restrict__ mloc,
+                                                                const double *__restrict__ G,
+                                                                double *__restrict__ V, double *__restrict__ ws) {
+  constexpr int RA = NP / 8;
+  __shared__ __align__(16) double sx2[NP];
+  __shared__ __align__(16) double sxn[NP];
+  __shared__ __align__(16) double2 svw[NP];
+  __shared__ double sred[16];
+  const int zl = blockIdx.x;
+  if (mloc[zl] == 0) return;
+  const int tid = threadIdx.x, rg = tid >> 3, cg = tid & 7;
+  const bool owner = cg < RA;          // this thread owns row t = 8 cg + rg for the per-row scalars
+  const int t = owner ? 8 * cg + rg : NP - 1;
+  const double *Gz = G + (int64_t)zl * NP * NP;
+  double *Vz = V + (int64_t)zl * NP * NP;
+  double *wz = ws_zone(ws, NP, zl);
+  double *wd = wz, *we = wz + NP, *wtau = wz + 2 * NP;
+
+  double a[RA][RA];
+#pragma unroll
+  for (int i = 0; i < RA; i++)
+#pragma unroll
+    for (int b = 0; b < RA; b++) a[i][b] = Gz[(8 * i + rg) * NP + 8 * b + cg];
+  double x = 0.;
+  if (owner) {
+    x = (t >= 1) ? Gz[t] : 0.;  // column 0 (= row 0: G is symmetric)
+    sxn[t] = x;
+  }
+  if (tid < NP) {
+    sx2[tid] = Gz[NP + tid];    // row 1
+    if (tid >= N) { wd[tid] = 0.; we[tid] = 0.; }
+    wtau[tid] = 0.;
+    if (tid == 0) wd[0] = Gz[0];
+  }
+  __syncthreads();
+  double y;
+  {
+    double yp[RA];
+#pragma unroll
+    for (int i = 0; i < RA; i++) {
+      yp[i] = 0.;
+#pragma unroll
+      for (int b = 0; b < RA; b++) yp[i] = fma(a[i][b], sxn[8 * b + cg], yp[i]);
+    }
+    y = transpose_reduce8<RA>(yp, cg);
+  }
+  TileSteps<NP, 0>::run(a, x, y, N, tid, rg, cg, t, owner, sx2, svw, sxn, sred, Vz, wd, we, wtau);
+  // x of row N-1's owner is now e_{N-2}; sx2 holds row N-1
+  __syncthreads();
+  if (owner && t == N - 1) { we[N - 2] = x; we[N - 1] = 0.; wd[N - 1] = sx2[N - 1]; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -257,17 +456,23 @@ struct BackSteps {
       const double tau = stau[k];
       if (tau == 0.) continue;
       const double *v = Vs + k * NP;
-      double p0 = 0., p1 = 0., p2 = 0., p3 = 0.;
+      double p0 = 0., p1 = 0., p2 = 0., p3 = 0., p4 = 0., p5 = 0., p6 = 0., p7 = 0.;
 #pragma unroll
-      for (int i = OFF; i < NP; i += 4) {
+      for (int i = OFF; i < NP; i += 8) {
         const double2 v01 = *reinterpret_cast<const double2 *>(v + i);
         const double2 v23 = *reinterpret_cast<const double2 *>(v + i + 2);
+        const double2 v45 = *reinterpret_cast<const double2 *>(v + i + 4);
+        const double2 v67 = *reinterpret_cast<const double2 *>(v + i + 6);
         p0 = fma(u[i], v01.x, p0);
         p1 = fma(u[i + 1], v01.y, p1);
         p2 = fma(u[i + 2], v23.x, p2);
         p3 = fma(u[i + 3], v23.y, p3);
+        p4 = fma(u[i + 4], v45.x, p4);
+        p5 = fma(u[i + 5], v45.y, p5);
+        p6 = fma(u[i + 6], v67.x, p6);
+        p7 = fma(u[i + 7], v67.y, p7);
       }
-      const double s = -tau * ((p0 + p1) + (p2 + p3));
+      const double s = -tau * (((p0 + p1) + (p2 + p3)) + ((p4 + p5) + (p6 + p7)));
 #pragma unroll
       for (int i = OFF; i < NP; i += 2) {
         const double2 v01 = *reinterpret_cast<const double2 *>(v + i);
@@ -522,7 +727,11 @@ int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G,
     CUDA_TRY(cudaFuncSetAttribute(k_tvec<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
+#if TRI_TILE
+  k_tridiag_tile<NP><<<nz, 64, 0, st>>>(N, mloc, G, T, ws);
+#else
   k_tridiag<NP><<<nz, NP, 0, st>>>(N, mloc, G, T, ws);
+#endif
   CUDA_TRY(cudaGetLastError());
   if (ev) CUDA_TRY(cudaEventRecord(ev[0], st));
   k_tql<NP><<<(nz + 31) / 32, 32, 0, st>>>(N, nz, mloc, ws, flags);

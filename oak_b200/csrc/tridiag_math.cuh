@@ -17,15 +17,15 @@
 
 #define OAK_DBL_EPS 2.220446049250313e-16
 
-// 1/x for |x| in the normal range, ~1 ulp: hardware seed + Newton steps (the IEEE division costs ~4x more)
+// 1/x for |x| in the normal range, ~1 ulp: hardware seed (~20 bits) + one cubically convergent step
+// y0 (1 + r + r^2), r = 1 - x y0, and one Newton step: 5 dependent FMAs instead of the ~25 instructions of
+// the IEEE division
 OAK_HD double oak_rcp(double x) {
 #ifdef __CUDA_ARCH__
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double r = fma(-x, y, 1.);
-  y = fma(y, r, y);
-  r = fma(-x, y, 1.);
-  y = fma(y, r, y);
+  y = fma(y, fma(r, r, r), y);
   r = fma(-x, y, 1.);
   return fma(y, r, y);
 #else
@@ -113,13 +113,21 @@ OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) {
   const double abstol2 = 0.25 * eps2 * tn * tn;
   for (int i = 0; i < n - 1; i++) { const double ei = e[i * s]; e[i * s] = ei * ei; }
   if (n > 0) e[(n - 1) * s] = 0.;
+  // [l, m] is the current unreduced block: e_m is negligible.  m is found by a scan only when a new block
+  // starts; inside a block the sweep itself notices the off-diagonals it makes negligible (a scan per
+  // iteration, as in dsterf, would cost as much as the sweep here).
+  int m = -1;
   for (int l = 0; l < n; l++) {
     int iter = 0;
     for (;;) {
-      int m = l;
-      for (; m < n - 1; m++) {
-        const double em = e[m * s];
-        if (em <= abstol2 || em <= eps2 * fabs(d[m * s] * d[(m + 1) * s])) break;
+      if (m < l) {
+        for (m = l; m < n - 1; m++) {
+          const double em = e[m * s];
+          if (em <= abstol2 || em <= eps2 * fabs(d[m * s] * d[(m + 1) * s])) break;
+        }
+      } else {
+        const double el = e[l * s];
+        if (el <= abstol2 || el <= eps2 * fabs(d[l * s] * d[(l + 1) * s])) m = l;
       }
       if (m == l) break;
       if (++iter > 60) return -1;
@@ -130,11 +138,13 @@ OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) {
       sigma = p - rte * oak_rcp(sigma + copysign(r0, sigma));
       double c = 1., sn = 0., gamma = d[m * s] - sigma;
       p = gamma * gamma;
+      int msplit = m;          // lowest index whose new off-diagonal is negligible
+      double dnext = 0., enew = 0.;  // d_{i+2} (final) and the new e_{i+1} of the previous trip
       for (int i = m - 1; i >= l; i--) {
         rot++;
         const double bb = e[i * s];
         const double r = p + bb;
-        if (i != m - 1) e[(i + 1) * s] = sn * r;
+        if (i != m - 1) { enew = sn * r; e[(i + 1) * s] = enew; }
         const double oldc = c;
         const double ir = oak_rcp(r);
         const double ip = oak_rcp(p);  // independent of ir: the two reciprocals overlap
@@ -142,11 +152,15 @@ OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) {
         sn = bb * ir;
         const double oldgam = gamma, alpha = d[i * s];
         gamma = fma(c, alpha - sigma, -sn * oldgam);
-        d[(i + 1) * s] = oldgam + (alpha - gamma);
+        const double dn = oldgam + (alpha - gamma);
+        d[(i + 1) * s] = dn;
+        if (i != m - 1 && (enew <= abstol2 || enew <= eps2 * fabs(dn * dnext))) msplit = i + 1;
+        dnext = dn;
         p = (c != 0.) ? gamma * gamma * (r * ip) : oldc * bb;
       }
       e[l * s] = sn * p;
       d[l * s] = sigma + gamma;
+      m = msplit;
     }
   }
   for (int i = 1; i < n; i++) {
