@@ -243,6 +243,8 @@ def main():
         h = oak_b200.Handle(local, eig_kernel=a.eig_kernel)
         if os.environ.get("OAK_B200_FIXED_SWEEPS"):  # kernel timing experiments only (tools/ab.py)
             h.set_option("fixed_sweeps", float(os.environ["OAK_B200_FIXED_SWEEPS"]))
+        if os.environ.get("OAK_B200_ZB"):  # pipeline experiments (tools/ab.py)
+            h.set_option("zones_per_batch", float(os.environ["OAK_B200_ZB"]))
         if a.jacobi_tol > 0:
             h.set_option("jacobi_tol", a.jacobi_tol)
         h.set_zones(plan.zoneSize, zone_x=plan.zx, zone_y=plan.zy, corrLen=plan.corrLen, maxLen=plan.maxLen,

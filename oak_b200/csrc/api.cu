@@ -45,7 +45,10 @@ extern "C" OAKB200_API int oakb200_version(void) { return 100; }
 
 namespace {
 
-constexpr int NSLOT = 4;
+#ifndef OAK_NSLOT
+#define OAK_NSLOT 4
+#endif
+constexpr int NSLOT = OAK_NSLOT;
 
 struct DevBuf {
   void *p = nullptr;
@@ -164,6 +167,9 @@ int batch_size(const oakb200_handle *h, int NP, int nzones_call) {
   const int cap = (int)((size_t)(tri ? 1024 : 256) * 1024 * 1024 / per_zone);
   const int wave = NP <= 64 ? 592 : 148;
   int zb = nzones_call / (NSLOT * (tri ? 4 : 8));
+  // ... and never small when the call is (multi-GPU phases of ~30 k zones): 12 waves per batch, or one batch
+  // per stream slot, measured 56.3 -> 47.4 ms per step on 125 k zones per rank (profiles/r1_notes.md)
+  if (tri) zb = std::max(zb, std::min(7104, (nzones_call + NSLOT - 1) / NSLOT));
   zb = std::max(wave, (zb / wave) * wave);
   zb = std::min(zb, std::max(wave, (cap / wave) * wave));
   return zb;
