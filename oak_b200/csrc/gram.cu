@@ -11,6 +11,10 @@
 // 16-byte shared loads).
 #include "common.cuh"
 
+#ifndef GRAM_SYM
+#define GRAM_SYM 1   // NP = 64: accumulate only the blocks LL, HL, HH of the symmetric G (96 threads)
+#endif
+
 namespace {
 
 constexpr int GRAM_CH = 64;    // candidates examined per chunk (warps 0 and 1, one per lane)
@@ -47,14 +51,18 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //   F(c)  every thread accumulates its register tile over the staged rows
 // E runs two chunks ahead (3 list buffers), L one chunk ahead (2 row buffers), so the global-memory
 // latency of the rows of chunk c+1 is hidden behind F(c).  Two barriers per chunk.
-template <int NP, int NT>
+// SYM (NP = 64, 96 threads): G is symmetric, so only the blocks LL, HL, HH of the 2 x 2 partition into 32 x 32
+// blocks are accumulated (one warp each, 4 x 8 register tiles on an 8 x 4 thread grid) and HL is mirrored
+// into LH when G is written: 25 % fewer DFMA and shared-memory reads than the full product.
+template <int NP, int NT, bool SYM>
 __global__ void __launch_bounds__(NT) k_gram(ZoneGeom zg, ObsGrid og, ObsRows orows, int zone0, int nz,
                                              double *__restrict__ G, double *__restrict__ cvec,
                                              int32_t *__restrict__ mloc, DevCounters *ctr) {
-  constexpr int TX = NT / 16;
-  constexpr int RT = NP / 16;
-  constexpr int CT = NP / TX;
+  constexpr int TX = SYM ? 4 : NT / 16;
+  constexpr int RT = SYM ? 4 : NP / 16;
+  constexpr int CT = SYM ? 8 : NP / TX;
   constexpr int NW = NT / 32;
+  static_assert(!SYM || (NP == 64 && NT == 96), "symmetric variant: N <= 64, three warps");
   static_assert(CT >= 2 && CT % 2 == 0, "column tile must be pairs");
   static_assert(GRAM_CH == 64, "two evaluating warps");
   extern __shared__ __align__(16) double rowbuf[];  // [2][GRAM_CH][NP]
@@ -70,7 +78,10 @@ __global__ void __launch_bounds__(NT) k_gram(ZoneGeom zg, ObsGrid og, ObsRows or
   const int zone = zone0 + zl;
   const ZoneQuery q = oak_zone_query(zg, zone);
   const CellBox box = oak_zone_box(og, q);
-  const int ty = tid / TX, tx = tid % TX;
+  // full product: thread (ty,tx) of a 16 x TX grid; symmetric: warp = block (0: LL, 1: HL, 2: HH), lane = (ty,tx)
+  // of an 8 x 4 grid inside the block
+  const int ty = SYM ? (lane >> 2) : tid / TX, tx = SYM ? (lane & 3) : tid % TX;
+  const int rbase = SYM ? (warp >= 1 ? 32 : 0) : 0, cbase = SYM ? (warp == 2 ? 32 : 0) : 0;
 
   double acc[RT][CT];
 #pragma unroll
@@ -131,9 +142,9 @@ __global__ void __launch_bounds__(NT) k_gram(ZoneGeom zg, ObsGrid og, ObsRows or
         const double coef = s_coef[lb][slot];
         const double *row = srcb + slot * NP;
         double rv[RT], cv[CT];
-        lds_vec<RT>(rv, row + RT * ty);
+        lds_vec<RT>(rv, row + rbase + RT * ty);
 #pragma unroll
-        for (int b = 0; b < CT / 2; b++) lds_vec<2>(cv + 2 * b, row + 2 * tx + 2 * TX * b);
+        for (int b = 0; b < CT / 2; b++) lds_vec<2>(cv + 2 * b, row + cbase + 2 * tx + 2 * TX * b);
 #pragma unroll
         for (int a = 0; a < RT; a++) {
           const double ra = rv[a] * coef;
@@ -199,10 +210,14 @@ __global__ void __launch_bounds__(NT) k_gram(ZoneGeom zg, ObsGrid og, ObsRows or
   for (int a = 0; a < RT; a++)
 #pragma unroll
     for (int b = 0; b < CT / 2; b++) {
-      const int i = RT * ty + a;
-      const int j = 2 * tx + 2 * TX * b;
+      const int i = rbase + RT * ty + a;
+      const int j = cbase + 2 * tx + 2 * TX * b;
       Gz[i + NP * j] = acc[a][2 * b];
       Gz[i + NP * (j + 1)] = acc[a][2 * b + 1];
+      if (SYM && warp == 1) {  // mirror HL into LH
+        Gz[j + NP * i] = acc[a][2 * b];
+        Gz[j + 1 + NP * i] = acc[a][2 * b + 1];
+      }
     }
   if (tid < NP) cvec[(int64_t)zl * NP + tid] = cacc;
   if (tid == 0) {
@@ -213,16 +228,16 @@ __global__ void __launch_bounds__(NT) k_gram(ZoneGeom zg, ObsGrid og, ObsRows or
   }
 }
 
-template <int NP, int NT>
+template <int NP, int NT, bool SYM = false>
 int launch(cudaStream_t st, const ZoneGeom &zg, const ObsGrid &og, const ObsRows &orows, int zone0, int nz,
            double *G, double *c, int32_t *mloc, DevCounters *ctr) {
   const size_t smem = sizeof(double) * 2 * GRAM_CH * NP;
   static bool attr_done = false;
   if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(k_gram<NP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_gram<NP, NT, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  k_gram<NP, NT><<<nz, NT, smem, st>>>(zg, og, orows, zone0, nz, G, c, mloc, ctr);
+  k_gram<NP, NT, SYM><<<nz, NT, smem, st>>>(zg, og, orows, zone0, nz, G, c, mloc, ctr);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -235,7 +250,11 @@ int oak_launch_gram(cudaStream_t st, int NP, const ZoneGeom &zg, const ObsGrid &
   switch (NP) {
     case 16: return launch<16, 128>(st, zg, og, orows, zone0, nz, G, c, mloc, ctr);
     case 32: return launch<32, 128>(st, zg, og, orows, zone0, nz, G, c, mloc, ctr);
+#if GRAM_SYM
+    case 64: return launch<64, 96, true>(st, zg, og, orows, zone0, nz, G, c, mloc, ctr);
+#else
     case 64: return launch<64, 128>(st, zg, og, orows, zone0, nz, G, c, mloc, ctr);
+#endif
     case 128: return launch<128, 256>(st, zg, og, orows, zone0, nz, G, c, mloc, ctr);
   }
   oak_set_error("gram: unsupported padded ensemble size %d", NP);
