@@ -483,6 +483,49 @@ struct BackSteps {
   }
 };
 
+// Back-transformation on 2 x (NP/2) register tiles: thread (cp, rh) = (tid>>1, tid&1) holds columns
+// 2cp, 2cp+1 of U and the rows 4m + 2rh + {0,1}, m < NP/4.  A reflector entry read from shared memory then
+// serves two columns and both the dot product and the update (4 FMA per double instead of 1: the
+// column-per-thread version above is bound by the shared-memory return path); the two partial dot products
+// are completed with the neighbouring lane.
+template <int NP, int OFF>
+struct BackTile {
+  static __device__ __forceinline__ void run(double (&u)[2][NP / 2], int N, int rh, const double *Vs,
+                                             const double *stau) {
+    if constexpr (OFF + BW < NP) {
+      if (N - 2 > OFF + BW) BackTile<NP, OFF + BW>::run(u, N, rh, Vs, stau);
+    }
+    constexpr int M0 = OFF / 4, M1 = NP / 4;
+    for (int k = min(OFF + BW, N - 2) - 1; k >= OFF; k--) {
+      const double tau = stau[k];
+      if (tau == 0.) continue;
+      const double *v = Vs + k * NP + 2 * rh;
+      double2 vv[M1];
+#pragma unroll
+      for (int m = M0; m < M1; m++) vv[m] = *reinterpret_cast<const double2 *>(v + 4 * m);
+      double a0 = 0., a1 = 0., b0 = 0., b1 = 0.;
+#pragma unroll
+      for (int m = M0; m < M1; m++) {
+        a0 = fma(u[0][2 * m], vv[m].x, a0);
+        a1 = fma(u[0][2 * m + 1], vv[m].y, a1);
+        b0 = fma(u[1][2 * m], vv[m].x, b0);
+        b1 = fma(u[1][2 * m + 1], vv[m].y, b1);
+      }
+      double d0 = a0 + a1, d1 = b0 + b1;
+      d0 += __shfl_xor_sync(FULL, d0, 1);
+      d1 += __shfl_xor_sync(FULL, d1, 1);
+      const double s0 = -tau * d0, s1 = -tau * d1;
+#pragma unroll
+      for (int m = M0; m < M1; m++) {
+        u[0][2 * m] = fma(s0, vv[m].x, u[0][2 * m]);
+        u[0][2 * m + 1] = fma(s0, vv[m].y, u[0][2 * m + 1]);
+        u[1][2 * m] = fma(s1, vv[m].x, u[1][2 * m]);
+        u[1][2 * m + 1] = fma(s1, vv[m].y, u[1][2 * m + 1]);
+      }
+    }
+  }
+};
+
 template <int NP>
 __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__restrict__ mloc,
                                               const double *__restrict__ ws, const double *__restrict__ cin,
@@ -583,10 +626,16 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
     return;
   }
 
-  // ---- U = Q W : column j in registers, reflectors from shared memory ----
-  double u[NP];
+  // ---- U = Q W : 2 columns x NP/2 rows per thread in registers, reflectors from shared memory ----
+  const int cp = j >> 1, rh = j & 1;
+  double u[2][NP / 2];
 #pragma unroll
-  for (int i = 0; i < NP; i++) u[i] = W[i * LDW + j];
+  for (int c = 0; c < 2; c++)
+#pragma unroll
+    for (int m = 0; m < NP / 4; m++) {
+      u[c][2 * m] = W[(4 * m + 2 * rh) * LDW + 2 * cp + c];
+      u[c][2 * m + 1] = W[(4 * m + 2 * rh + 1) * LDW + 2 * cp + c];
+    }
   __syncthreads();
   {
     const double2 *Vg = reinterpret_cast<const double2 *>(Tout + (int64_t)zl * NP * NP);
@@ -595,23 +644,42 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
     for (int idx = j; idx < nv; idx += NP) Vs2[idx] = Vg[idx];
   }
   __syncthreads();
-  BackSteps<NP, 0>::run(u, N, W, stau);
+  BackTile<NP, 0>::run(u, N, rh, W, stau);
 
-  // ---- per-eigenpair coefficients ----
-  double q = 0., s1 = 0.;
+  // ---- per-eigenpair coefficients (columns 2cp, 2cp+1; lane rh writes those of column 2cp+rh) ----
+  double ysc[2];
+  {
+    double q[2] = {0., 0.}, s1[2] = {0., 0.};
 #pragma unroll
-  for (int i = 0; i < NP; i++) { q = fma(u[i], sc[i], q); s1 += u[i]; }
-  const double ys = live ? sqrt(gj) : 0.;
-  const double iys = live ? 1. / ys : 0.;
-  __syncthreads();  // every thread is done with the reflectors
+    for (int c = 0; c < 2; c++) {
+#pragma unroll
+      for (int m = 0; m < NP / 4; m++) {
+        q[c] = fma(u[c][2 * m], sc[4 * m + 2 * rh], q[c]);
+        q[c] = fma(u[c][2 * m + 1], sc[4 * m + 2 * rh + 1], q[c]);
+        s1[c] += u[c][2 * m] + u[c][2 * m + 1];
+      }
+      q[c] += __shfl_xor_sync(FULL, q[c], 1);
+      s1[c] += __shfl_xor_sync(FULL, s1[c], 1);
+      const double g = sgj[2 * cp + c];
+      ysc[c] = (g >= TRI_NULL) ? sqrt(g) : 0.;
+    }
+    __syncthreads();  // every thread is done with the reflectors
+    const int jc = 2 * cp + rh;                       // the column this lane writes the coefficients of
+    const double lc = fmax(jc < N ? slam[jc] : 0., 0.);
+    const double sg = sqrt(1. + lc);
+    const double ysj = rh ? ysc[1] : ysc[0], iys = ysj > 0. ? 1. / ysj : 0.;
+    sa[jc] = -(lc / (1. + lc)) * (rh ? q[1] : q[0]) * iys;
+    sb[jc] = (sg - 1.) * (rh ? s1[1] : s1[0]) * iys;
+  }
   // Y = U diag(ys), stored transposed: Yt[k*LDY + i] = Y[i][k] (row k = scaled eigenvector k, contiguous;
-  // LDY = NP+2 keeps the 16-byte stores of neighbouring threads in different banks)
+  // LDY = NP+2 keeps the 16-byte stores of the lanes of a quarter-warp in different banks)
   double *Yt = W;
 #pragma unroll
-  for (int i = 0; i < NP; i += 2)
-    *reinterpret_cast<double2 *>(Yt + j * LDY + i) = make_double2(ys * u[i], ys * u[i + 1]);
-  sa[j] = -(lamc / (1. + lamc)) * q * iys;
-  sb[j] = (sig - 1.) * s1 * iys;
+  for (int c = 0; c < 2; c++)
+#pragma unroll
+    for (int m = 0; m < NP / 4; m++)
+      *reinterpret_cast<double2 *>(Yt + (2 * cp + c) * LDY + 4 * m + 2 * rh) =
+          make_double2(ysc[c] * u[c][2 * m], ysc[c] * u[c][2 * m + 1]);
   __syncthreads();
   // ---- ampl, v ----
   double vi = 0.;
@@ -646,15 +714,24 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
     suw[j] = uw;                               // u_w
   }
   __syncthreads();
-  // g1 = M u_v, gm2 = M (D u_w), M = I - Y Y^T : first Y^T x from the column still held in registers
+  // g1 = M u_v, gm2 = M (D u_w), M = I - Y Y^T : first Y^T x from the columns still held in registers
   {
-    double p1 = 0., p2 = 0.;
+    double p1[2] = {0., 0.}, p2[2] = {0., 0.};
 #pragma unroll
-    for (int i = 0; i < NP; i++) {
-      p1 = fma(u[i], suv[i], p1);
-      p2 = fma(u[i], sdw[i], p2);
+    for (int c = 0; c < 2; c++) {
+#pragma unroll
+      for (int m = 0; m < NP / 4; m++) {
+        const int i0 = 4 * m + 2 * rh;
+        p1[c] = fma(u[c][2 * m], suv[i0], p1[c]);
+        p1[c] = fma(u[c][2 * m + 1], suv[i0 + 1], p1[c]);
+        p2[c] = fma(u[c][2 * m], sdw[i0], p2[c]);
+        p2[c] = fma(u[c][2 * m + 1], sdw[i0 + 1], p2[c]);
+      }
+      p1[c] += __shfl_xor_sync(FULL, p1[c], 1);
+      p2[c] += __shfl_xor_sync(FULL, p2[c], 1);
     }
-    sa[j] = ys * p1; sb[j] = ys * p2;
+    sa[2 * cp + rh] = rh ? ysc[1] * p1[1] : ysc[0] * p1[0];
+    sb[2 * cp + rh] = rh ? ysc[1] * p2[1] : ysc[0] * p2[0];
   }
   const double kappa = block_sum<NW>(suv[j] * hv * sdw[j], sred + 4, warp, lane);
   __syncthreads();
