@@ -48,7 +48,8 @@ def parse():
     ap.add_argument("--eig-kernel", type=int, default=4)
     ap.add_argument("--jacobi-tol", type=float, default=0.0, help="experiment: override the Jacobi stopping tolerance")
     ap.add_argument("--sync-phases", action="store_true", help="N>1: blocking library calls instead of the asynchronous pipeline")
-    ap.add_argument("--phases", type=int, default=0, help="pipeline phases for N>1 (0: 4 when N>1, else 1)")
+    ap.add_argument("--phases", type=int, default=0, help="pipeline phases for N>1 (0: 1 with the fused gather, 4 with --nccl-gather)")
+    ap.add_argument("--nccl-gather", action="store_true", help="N>1: reassemble with NCCL all-gathers instead of the fused peer stores of the apply kernel")
     return ap.parse_args()
 
 
@@ -231,12 +232,13 @@ def main():
     from oak_b200 import synthetic as S
     from oak_b200.dist import phase_ranges
     g = S.Grid(a.nx, a.ny, a.nz)
-    nphase = a.phases if a.phases > 0 else (4 if world > 1 else 1)
+    fused = world > 1 and not a.nccl_gather
+    nphase = a.phases if a.phases > 0 else (4 if (world > 1 and not fused) else 1)
     obs_np = S.observations(np, g, a.m, SEED)
     # phase j of rank p = a contiguous zone range; the all-gather of phase j overlaps the analysis of j+1
     phases = []
     ranges = phase_ranges(g.nzones, world, nphase)
-    use_async = world > 1 and not a.sync_phases
+    use_async = world > 1 and not a.sync_phases and nphase > 1
     for j, first in enumerate(ranges):
         d = build_rank_data(a, rank, world, dev, first=first, obs_np=obs_np)
         plan = d["plan"]
@@ -263,7 +265,22 @@ def main():
     d, plan, h = phases[0], phases[0]["plan"], phases[0]["h"]
     n_loc = sum(p["plan"].r1 - p["plan"].r0 for p in phases)
     z_rank = sum(p["plan"].z1 - p["plan"].z0 for p in phases)
-    Sa_full = torch.empty((a.N, plan.n), dtype=torch.float64, device=dev) if world > 1 else None
+    Sa_full, peer, fused_note = None, None, None
+    if fused:
+        # fused all-gather: every rank's apply kernel stores its rows into the result arrays of all ranks (NVLink)
+        from oak_b200.dist import PeerResult
+        try:
+            peer = PeerResult(dist, h, a.N, plan.n, rank, world, dev)
+            Sp, xp = peer.destinations()
+            for p in phases:
+                p["h"].set_peer_outputs(Sp, xp, plan.n, p["plan"].r0)
+            Sa_full = peer.Sa
+        except Exception as e:   # no peer mapping on this box: the NCCL all-gather path (same kernels otherwise)
+            fused, peer, fused_note = False, None, "peer mapping failed (%s): NCCL all-gather" % (str(e)[:80],)
+            for p in phases:
+                p["h"].set_peer_outputs([], [], 0, 0)
+    if world > 1 and Sa_full is None:
+        Sa_full = torch.empty((a.N, plan.n), dtype=torch.float64, device=dev)
 
     def barrier():
         if world > 1:
@@ -284,14 +301,30 @@ def main():
             st = analyse(p)
             if not use_async:
                 add_stats(tot, st)
-            if world > 1:   # asynchronous: overlaps the next phase's kernels
+            if world > 1 and not fused:   # asynchronous: overlaps the next phase's kernels
                 works += allgather_slabs(dist, p["Sa"], p["plan"], out=Sa_full, wait=False)
         for w in works:
             w.wait()
         if use_async:
             for p in phases:
                 add_stats(tot, p["h"].synchronize())
+        if fused:
+            peer.fence()   # readers after the writers of all ranks
         return tot
+
+    if fused:   # once: the fused result equals the NCCL all-gather of the slabs, bit for bit
+        step()
+        torch.cuda.synchronize()
+        ref = torch.empty_like(Sa_full)
+        for p in phases:
+            allgather_slabs(dist, p["Sa"], p["plan"], out=ref)
+        torch.cuda.synchronize()
+        ok = torch.tensor([1.0 if torch.equal(ref, Sa_full) else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        fused_note = "fused peer stores checked against the NCCL all-gather: " + ("identical" if ok.item() == 1.0 else "MISMATCH")
+        if ok.item() != 1.0:
+            raise SystemExit("fused gather mismatch")
+        del ref
 
     for _ in range(a.warmup):
         st = step()
@@ -385,7 +418,7 @@ def main():
         out = {"metric": "local-analysis grid columns/sec", "value": value, "unit": "columns/s", "n_gpus": world,
                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": workload_name(a), "zones": nzones, "parallelism": f"zone-range x{world}" + (f", {nphase} pipelined phases (all-gather of phase j overlaps analysis of j+1; " + ("asynchronous, stream priorities" if use_async else "blocking calls") + ")" if world > 1 else ""),
+               "config": {"workload": workload_name(a), "zones": nzones, "parallelism": f"zone-range x{world}" + ((", all-gather fused into the apply kernel (stores into every rank's result array over NVLink, CUDA IPC); " + str(fused_note)) if fused else (f", {nphase} pipelined phases (all-gather of phase j overlaps analysis of j+1; " + ("asynchronous, stream priorities" if use_async else "blocking calls") + ")" + (("; " + fused_note) if fused_note else "") if world > 1 else "")),
                           "l2": "inputs (>= 15 GB state) exceed L2; no explicit flush",
                           "mean_relevant_obs_per_column": mloc_mean, "mean_candidates_per_column": cand_mean,
                           "mean_jacobi_sweeps": sweeps_mean, "eig_kernel": a.eig_kernel},
@@ -442,6 +475,11 @@ def main():
                 out["cpu_baseline"] = {"value": None, "unit": "columns/s", "cores": None, "kind": "port",
                                        "sample": "failed: " + repr(ex)[:200]}
         print(json.dumps(out))
+    if peer is not None:
+        Sa_full = None
+        peer.Sa = peer.xa = None
+        torch.cuda.synchronize()
+        peer.close()
     h.close()
     if world > 1:
         dist.destroy_process_group()

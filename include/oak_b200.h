@@ -124,6 +124,23 @@ OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t n, int32_t
  * before starting), "stream_priority" (CUDA priority of the library's streams, 0 .. negative = urgent). */
 OAKB200_API int oakb200_synchronize(oakb200_handle *h, oakb200_stats *stats);
 
+/* Fused all-gather (multi-GPU, one process per GPU; replaces parallGather, parall.F90:507-566): in addition to
+ * Sa / xa, the kernel that applies the transform stores every row of this rank's slab into up to
+ * OAKB200_MAX_PEERS result arrays that live on other GPUs (device pointers valid on this device: CUDA-IPC
+ * mappings of the other ranks' arrays, written over NVLink), so that no separate collective is needed:
+ *     Sa_peer[d][(row0 + i) + ld_peer * k] ,  xa_peer[d][row0 + i]      local row i, member k
+ * npeer = 0 switches it off.  Only the device-pointer entry point uses it.  The caller orders the readers
+ * after the writers of all ranks (e.g. a one-element all-reduce enqueued behind the analysis). */
+#define OAKB200_MAX_PEERS 8
+OAKB200_API int oakb200_set_peer_outputs(oakb200_handle *h, int32_t npeer, double *const *Sa_peer,
+                             double *const *xa_peer, int64_t ld_peer, int64_t row0);
+/* Device memory that other processes of the same node can map (cudaIpc): allocate + export the 64-byte handle,
+ * open a peer's handle (lazy peer access over NVLink), close, free. */
+OAKB200_API int oakb200_ipc_alloc(oakb200_handle *h, int64_t bytes, void **ptr, unsigned char handle[64]);
+OAKB200_API int oakb200_ipc_open(oakb200_handle *h, const unsigned char handle[64], void **ptr);
+OAKB200_API int oakb200_ipc_close(oakb200_handle *h, void *ptr);
+OAKB200_API int oakb200_ipc_free(oakb200_handle *h, void *ptr);
+
 /* Ensemble branch of Assim around the local scheme (assimilation.F90:3083,:3106-3134 prologue,
  * :3235 analysis, :3301-3357,:3558-3562 epilogue), HOST buffers:
  *   E[n x N] ensemble (zone-permuted), H as COO (Hi,Hj 1-based int32, Hs, nnz; matoper.F90:30-39),

@@ -216,6 +216,32 @@ class Handle:
             C.byref(st)))
         return st.asdict()
 
+    def set_peer_outputs(self, Sa_ptrs, xa_ptrs, ld, row0):
+        """Fused all-gather (oakb200_set_peer_outputs): device pointers (ints) of the (N, n) member-major result
+        array and of the mean vector of every destination; rows of this rank start at row0.  [] switches off."""
+        k = len(Sa_ptrs)
+        arr_S = (C.c_void_p * max(k, 1))(*[C.c_void_p(p) for p in Sa_ptrs])
+        arr_x = (C.c_void_p * max(k, 1))(*[C.c_void_p(p) for p in xa_ptrs])
+        _check(self._L.oakb200_set_peer_outputs(self._h, k, arr_S, arr_x, int(ld), int(row0)))
+
+    def ipc_alloc(self, nbytes):
+        """Device buffer other processes can map: returns (pointer, 64-byte handle)."""
+        ptr = C.c_void_p()
+        hd = C.create_string_buffer(64)
+        _check(self._L.oakb200_ipc_alloc(self._h, int(nbytes), C.byref(ptr), hd))
+        return ptr.value, hd.raw
+
+    def ipc_open(self, handle):
+        ptr = C.c_void_p()
+        _check(self._L.oakb200_ipc_open(self._h, handle, C.byref(ptr)))
+        return ptr.value
+
+    def ipc_close(self, ptr):
+        _check(self._L.oakb200_ipc_close(self._h, C.c_void_p(ptr)))
+
+    def ipc_free(self, ptr):
+        _check(self._L.oakb200_ipc_free(self._h, C.c_void_p(ptr)))
+
     def synchronize(self):
         """Completes an asynchronous local_analysis_dev (option async=1): status + stats."""
         st = _lib.Stats()

@@ -84,7 +84,8 @@ struct oakb200_handle {
   // options
   int eig_kernel = 4;
   double tri_orthtol = 0.;  // tridiagonal route: accepted loss of orthogonality between neighbouring eigenvectors (0: default)
-  int tri_maxgroup = -1;    // ... largest group of close eigenvalues orthogonalised in place (-1: default)
+  int tri_maxgroup = -1;
+  PeerOut peers{};            // fused all-gather destinations (oakb200_set_peer_outputs); n = 0: none    // ... largest group of close eigenvalues orthogonalised in place (-1: default)
   int zones_per_batch = 0;
   double tol = 2e-11;  // bound on the remaining non-orthogonality (eig_common.cuh: jacobi_converged)
   int max_sweeps = 30;
@@ -192,7 +193,7 @@ struct ProfAcc { double gram = 0, eig = 0, apply = 0, tridiag = 0, tql = 0, tvec
 // Runs zones [z0, z1) on slot s. The state buffers hold rows starting at global row `rowbase`.
 int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t rowbase, const double *xf,
               const double *Sf, int64_t ldS, double *xa, double *Sa, int64_t ldSa, int64_t *launches,
-              ProfAcc *prof) {
+              ProfAcc *prof, bool use_peers = false) {
   const int zb = batch_size(h, NP, h->nzones);
   int rc;
   if ((rc = ensure_ws(h, s, NP, std::min(zb, z1 - z0)))) return rc;
@@ -220,8 +221,9 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
                                     s.G.as<double>(), s.c.as<double>(), s.T.as<double>(), s.ampl.as<double>(),
                                     h->tol, h->max_sweeps, ctr))) return rc;
     if (prof) CUDA_TRY(cudaEventRecord(s.ev[2], s.st));
+    PeerOut none{};
     if ((rc = oak_launch_apply(s.st, N, NP, zg, b0, nz, rowbase, mloc, s.T.as<double>(), s.ampl.as<double>(), xf,
-                               Sf, ldS, xa, Sa, ldSa))) return rc;
+                               Sf, ldS, xa, Sa, ldSa, use_peers ? h->peers : none))) return rc;
     *launches += 3;
     if (prof) {
       CUDA_TRY(cudaEventRecord(s.ev[3], s.st));
@@ -339,6 +341,67 @@ extern "C" OAKB200_API int oakb200_destroy(oakb200_handle *h) {
   if (h->ev_b) cudaEventDestroy(h->ev_b);
   if (h->ev_user) cudaEventDestroy(h->ev_user);
   delete h;
+  return 0;
+}
+
+extern "C" OAKB200_API int oakb200_set_peer_outputs(oakb200_handle *h, int32_t npeer, double *const *Sa_peer,
+                                                    double *const *xa_peer, int64_t ld_peer, int64_t row0) {
+  if (!h) { oak_set_error("null handle"); return OAK_ERR_ARG; }
+  if (npeer < 0 || npeer > OAKB200_MAX_PEERS || (npeer > 0 && (!Sa_peer || !xa_peer))) {
+    oak_set_error("set_peer_outputs: npeer = %d (0..%d) or null pointer arrays", npeer, OAKB200_MAX_PEERS);
+    return OAK_ERR_ARG;
+  }
+  h->peers = PeerOut{};
+  for (int d = 0; d < npeer; d++) {
+    if (!Sa_peer[d] || !xa_peer[d]) { oak_set_error("set_peer_outputs: null destination %d", d); h->peers = PeerOut{}; return OAK_ERR_ARG; }
+    h->peers.Sa[d] = Sa_peer[d];
+    h->peers.xa[d] = xa_peer[d];
+  }
+  h->peers.n = npeer; h->peers.ld = ld_peer; h->peers.row0 = row0;
+  return 0;
+}
+
+extern "C" OAKB200_API int oakb200_ipc_alloc(oakb200_handle *h, int64_t bytes, void **ptr, unsigned char handle[64]) {
+  if (!h || !ptr || !handle || bytes <= 0) { oak_set_error("ipc_alloc: bad arguments"); return OAK_ERR_ARG; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  DeviceGuard guard(h->device);
+  void *p = nullptr;
+  if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) {
+    cudaGetLastError();
+    oak_set_error("ipc_alloc: cudaMalloc of %lld bytes failed", (long long)bytes);
+    return OAK_ERR_NOMEM;
+  }
+  cudaIpcMemHandle_t hd;
+  cudaError_t e = cudaIpcGetMemHandle(&hd, p);
+  if (e != cudaSuccess) { cudaFree(p); oak_set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); return OAK_ERR_CUDA; }
+  memcpy(handle, &hd, 64);
+  *ptr = p;
+  return 0;
+}
+
+extern "C" OAKB200_API int oakb200_ipc_open(oakb200_handle *h, const unsigned char handle[64], void **ptr) {
+  if (!h || !ptr || !handle) { oak_set_error("ipc_open: bad arguments"); return OAK_ERR_ARG; }
+  DeviceGuard guard(h->device);
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle, 64);
+  void *p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { cudaGetLastError(); oak_set_error("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e)); return OAK_ERR_CUDA; }
+  *ptr = p;
+  return 0;
+}
+
+extern "C" OAKB200_API int oakb200_ipc_close(oakb200_handle *h, void *ptr) {
+  if (!h) return 0;
+  DeviceGuard guard(h->device);
+  if (ptr) CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+
+extern "C" OAKB200_API int oakb200_ipc_free(oakb200_handle *h, void *ptr) {
+  if (!h) return 0;
+  DeviceGuard guard(h->device);
+  if (ptr) CUDA_TRY(cudaFree(ptr));
   return 0;
 }
 
@@ -585,7 +648,8 @@ extern "C" OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t
   for (int z0 = 0; z0 < h->nzones; z0 += zb, bi++) {
     Slot &s = h->slot[h->profile ? 0 : bi % NSLOT];
     const int z1 = std::min(h->nzones, z0 + zb);
-    if ((rc = run_zones(h, s, N, NP, z0, z1, 0, xf, Sf, ldSf, xa, Sa, ldSa, &launches, h->profile ? &prof : nullptr))) return rc;
+    if ((rc = run_zones(h, s, N, NP, z0, z1, 0, xf, Sf, ldSf, xa, Sa, ldSa, &launches, h->profile ? &prof : nullptr,
+                        h->peers.n > 0))) return rc;
   }
   for (int i = 1; i < NSLOT; i++) {
     CUDA_TRY(cudaEventRecord(h->slot[i].ev[5], h->slot[i].st));

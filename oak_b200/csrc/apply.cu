@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
                                                const int32_t *__restrict__ mloc,
                                                const double *__restrict__ T, const double *__restrict__ ampl,
                                                const double *__restrict__ xf, const double *Sf, int64_t ldS,
-                                               double *__restrict__ xa, double *Sa, int64_t ldSa) {
+                                               double *__restrict__ xa, double *Sa, int64_t ldSa,
+                                               const PeerOut P) {
   extern __shared__ __align__(128) double sm[];
   double *sT = sm;                   // [NP][NP] row-major: sT[k*NP + k']
   double *sS = sm + NP * NP;         // [NP][RC+?] member-major chunk: sS[k*LDS + r]
@@ -63,13 +64,22 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
   const int nrow = (int)(zg.zstart[zone + 1] - zg.zstart[zone]);
   const bool analysed = mloc[zone] != 0;
   if (nrow <= 0) return;
+  const int64_t ip = P.row0 + zg.zstart[zone];  // first row of the zone in the peers' (global) arrays
 
   if (!analysed) {
     // zone keeps the forecast
-    for (int r = tid; r < nrow; r += 128) xa[i1 + r] = xf[i1 + r];
-    if (Sa != Sf) {
+    for (int r = tid; r < nrow; r += 128) {
+      const double v = xf[i1 + r];
+      xa[i1 + r] = v;
+      for (int d = 0; d < P.n; d++) P.xa[d][ip + r] = v;
+    }
+    if (Sa != Sf || P.n > 0) {
       for (int k = warp; k < N; k += 4)
-        for (int r = lane; r < nrow; r += 32) Sa[i1 + r + ldSa * k] = Sf[i1 + r + ldS * k];
+        for (int r = lane; r < nrow; r += 32) {
+          const double v = Sf[i1 + r + ldS * k];
+          if (Sa != Sf) Sa[i1 + r + ldSa * k] = v;
+          for (int d = 0; d < P.n; d++) P.Sa[d][ip + r + P.ld * k] = v;
+        }
     }
     return;
   }
@@ -126,7 +136,9 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
     if (tid < rc) {
       double d = 0.;
       for (int k = 0; k < N; k++) d = fma(sS[k * LDS + tid], s_ampl[k], d);
-      xa[i1 + r0 + tid] = xf[i1 + r0 + tid] + d;
+      const double v = xf[i1 + r0 + tid] + d;
+      xa[i1 + r0 + tid] = v;
+      for (int dd = 0; dd < P.n; dd++) P.xa[dd][ip + r0 + tid] = v;
     }
     __syncthreads();  // all reads of sS done: reuse it to transpose the results for coalesced stores
 #pragma unroll
@@ -139,21 +151,26 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
       }
     __syncthreads();
     for (int k = warp; k < N; k += 4)
-      if (lane < rc) Sa[i1 + r0 + lane + ldSa * k] = sS[k * LDS + lane];
+      if (lane < rc) {
+        const double v = sS[k * LDS + lane];
+        Sa[i1 + r0 + lane + ldSa * k] = v;
+        // fused all-gather: the same run of rows into every peer's array (NVLink stores)
+        for (int d = 0; d < P.n; d++) P.Sa[d][ip + r0 + lane + P.ld * k] = v;
+      }
   }
 }
 
 template <int NP>
 int launch(cudaStream_t st, int N, const ZoneGeom &zg, int zone0, int nz, int64_t rowbase, const int32_t *mloc,
            const double *T, const double *ampl, const double *xf, const double *Sf, int64_t ldS, double *xa,
-           double *Sa, int64_t ldSa) {
+           double *Sa, int64_t ldSa, const PeerOut &peers) {
   const size_t smem = sizeof(double) * (NP * NP + NP * (RC + 2) + NP);
   static bool attr_done = false;
   if (!attr_done) {
     CUDA_TRY(cudaFuncSetAttribute(k_apply<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  k_apply<NP><<<nz, 128, smem, st>>>(N, zg, zone0, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa);
+  k_apply<NP><<<nz, 128, smem, st>>>(N, zg, zone0, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -162,12 +179,12 @@ int launch(cudaStream_t st, int N, const ZoneGeom &zg, int zone0, int nz, int64_
 
 int oak_launch_apply(cudaStream_t st, int N, int NP, const ZoneGeom &zg, int zone0, int nz, int64_t rowbase,
                      const int32_t *mloc, const double *T, const double *ampl, const double *xf,
-                     const double *Sf, int64_t ldS, double *xa, double *Sa, int64_t ldSa) {
+                     const double *Sf, int64_t ldS, double *xa, double *Sa, int64_t ldSa, const PeerOut &peers) {
   if (nz <= 0) return 0;
   switch (NP) {
-    case 32: return launch<32>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa);
-    case 64: return launch<64>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa);
-    case 128: return launch<128>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa);
+    case 32: return launch<32>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers);
+    case 64: return launch<64>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers);
+    case 128: return launch<128>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers);
   }
   oak_set_error("apply: unsupported padded ensemble size %d", NP);
   return OAK_ERR_UNSUPPORTED;

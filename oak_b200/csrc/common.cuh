@@ -241,6 +241,14 @@ struct BatchWs {          // per-stream workspace for a batch of zones
   double *ampl;           // [zb][NP]
 };
 
+// destinations of the fused all-gather (oakb200_set_peer_outputs), passed by value to k_apply
+struct PeerOut {
+  double *Sa[OAKB200_MAX_PEERS];
+  double *xa[OAKB200_MAX_PEERS];
+  int64_t ld, row0;
+  int32_t n;
+};
+
 struct DevCounters {      // device-side statistics / status
   unsigned long long relevant, candidates, sweeps, skipped;
   int nan_flag;
@@ -268,7 +276,7 @@ int oak_launch_eig_tridiag(cudaStream_t st, int N, int NP, int nz, const int32_t
 int oak_launch_apply(cudaStream_t st, int N, int NP, const ZoneGeom &zg, int zone0, int nz,
                      int64_t rowbase, const int32_t *mloc, const double *T, const double *ampl,
                      const double *xf, const double *Sf, int64_t ldS, double *xa, double *Sa,
-                     int64_t ldSa);
+                     int64_t ldSa, const PeerOut &peers);
 int oak_fp64_peak(int mode, double *tflops);
 
 // ensemble prologue / epilogue (assimilation.F90:3106-3134, :3301-3357)

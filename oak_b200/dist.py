@@ -141,3 +141,58 @@ def allgather_slabs(dist, Sa_local, plan, out=None, wait=True):
         a, b = int(plan.row_first[p]), int(plan.row_first[p + 1])
         out[:, a:b] = parts[p][:, :b - a]
     return out if wait else []
+
+
+class PeerResult:
+    """The analysed state of the whole domain on every rank, filled by the ranks' own kernels (fused
+    all-gather): each rank allocates Sa (N, n) member-major + xa (n) through the library (cudaMalloc + CUDA IPC
+    handle), the handles are exchanged once with all_gather_object, and every rank maps the arrays of all the
+    others (NVLink peer access).  `destinations(ld, row0)` is what Handle.set_peer_outputs takes: the apply
+    kernel then stores this rank's rows into all `world` arrays, its own included.  Replaces parallGather
+    (parall.F90:507-566) without a data-path collective; readers are ordered after the writers of all ranks by
+    `fence()` (a one-element all-reduce enqueued behind the analysis)."""
+
+    def __init__(self, dist, handle, N, n, rank, world, device):
+        import torch
+        self.dist, self.handle, self.rank, self.world = dist, handle, rank, world
+        self.N, self.n = int(N), int(n)
+        nel = self.N * self.n + self.n
+        self.base, hd = handle.ipc_alloc(8 * nel)
+        handles = [None] * world
+        dist.all_gather_object(handles, hd)
+        self.opened = []
+        self.bases = []
+        for r in range(world):
+            if r == rank:
+                self.bases.append(self.base)
+            else:
+                ptr = handle.ipc_open(handles[r])
+                self.opened.append(ptr)
+                self.bases.append(ptr)
+
+        class _Raw:   # __cuda_array_interface__ view of the library's allocation
+            def __init__(self, ptr, count):
+                self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        flat = torch.as_tensor(_Raw(self.base, nel), device=device)
+        self.Sa = flat[:self.N * self.n].view(self.N, self.n)
+        self.xa = flat[self.N * self.n:]
+        self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+
+    def destinations(self):
+        Sa_ptrs = list(self.bases)
+        xa_ptrs = [b + 8 * self.N * self.n for b in self.bases]
+        return Sa_ptrs, xa_ptrs
+
+    def fence(self):
+        """Stream-ordered barrier over the ranks: returns (on the stream) once every rank's analysis kernels,
+        hence their stores into this rank's arrays, are complete."""
+        self.dist.all_reduce(self._flag)
+
+    def close(self):
+        for ptr in self.opened:
+            self.handle.ipc_close(ptr)
+        self.opened = []
+        if self.base:
+            self.dist.barrier()   # nobody still maps it
+            self.handle.ipc_free(self.base)
+            self.base = None

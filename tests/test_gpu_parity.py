@@ -473,3 +473,43 @@ def test_degenerate_spectrum_falls_back_to_jacobi(ob, N):
         xa, Sa, _, st = h.local_analysis(c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], ob.DiagCovar(c["var"]))
         assert st["zones_fallback"] == len(mloc) and st["jacobi_sweeps_sum"] > 0
         assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL, (rel(xa, xo), rel(Sa, So))
+
+
+def test_fused_gather_peer_outputs_receive_the_slab(ob):
+    """oakb200_set_peer_outputs: the apply kernel stores this rank's rows (analysed and untouched zones) into
+    every destination array at row0 (here two arrays on the same device, allocated through oakb200_ipc_alloc;
+    across GPUs the destinations are CUDA-IPC mappings, exercised by bench.py --gpus N)."""
+    import torch
+    from oak_b200 import synthetic
+    c = synthetic.small_case(nx=24, ny=18, nz=4, N=24, m=150, corr=2500.0, maxlen=5000.0, seed=21)
+    dev = torch.device("cuda", 0)
+    t = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device=dev)
+    N, n = c["Sf"].shape[1], c["Sf"].shape[0]
+    row0, ntot = 7, n + 19                      # the slab sits in the middle of a larger "global" array
+    with ob.Handle(0) as h:
+        _configure(ob, h, c)
+        bufs = [h.ipc_alloc(8 * (N * ntot + ntot)) for _ in range(2)]
+
+        class Raw:
+            def __init__(self, ptr, count):
+                self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        flats = [torch.as_tensor(Raw(ptr, N * ntot + ntot), device=dev) for ptr, _ in bufs]
+        for f in flats:
+            f.fill_(-7.0)
+        h.set_peer_outputs([ptr for ptr, _ in bufs], [ptr + 8 * N * ntot for ptr, _ in bufs], ntot, row0)
+        Sf = t(c["Sf"].T)
+        xa, Sa = torch.empty(n, dtype=torch.float64, device=dev), torch.empty_like(Sf)
+        st = h.local_analysis_dev(t(c["xf"]), t(c["Hxf"]), t(c["yo"]), Sf, t(c["HSf"].T), t(c["var"]), xa, Sa)
+        torch.cuda.synchronize()
+        assert st["zones_skipped"] > 0           # untouched zones are forwarded too
+        for f in flats:
+            S = f[:N * ntot].view(N, ntot)
+            x = f[N * ntot:]
+            assert torch.equal(S[:, row0:row0 + n], Sa) and torch.equal(x[row0:row0 + n], xa)
+            assert (S[:, :row0] == -7.0).all() and (S[:, row0 + n:] == -7.0).all() and (x[:row0] == -7.0).all()
+        h.set_peer_outputs([], [], 0, 0)
+        del flats
+        for ptr, _ in bufs:
+            h.ipc_free(ptr)
+    xo, So, _, _ = _oracle_loc(c)
+    assert rel(xa.cpu().numpy(), xo) < RTOL and rel(Sa.cpu().numpy().T, So) < RTOL
