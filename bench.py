@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--jacobi-tol", type=float, default=0.0, help="experiment: override the Jacobi stopping tolerance")
     ap.add_argument("--sync-phases", action="store_true", help="N>1: blocking library calls instead of the asynchronous pipeline")
     ap.add_argument("--phases", type=int, default=0, help="pipeline phases for N>1 (0: 1 with the fused gather, 4 with --nccl-gather)")
+    ap.add_argument("--peer-mode", type=int, default=1, help="fused gather: 1 = copy engines push each finished batch, 0 = stores of the apply kernel")
     ap.add_argument("--nccl-gather", action="store_true", help="N>1: reassemble with NCCL all-gathers instead of the fused peer stores of the apply kernel")
     return ap.parse_args()
 
@@ -273,6 +274,7 @@ def main():
             peer = PeerResult(dist, h, a.N, plan.n, rank, world, dev)
             Sp, xp = peer.destinations()
             for p in phases:
+                p["h"].set_option("peer_mode", a.peer_mode)
                 p["h"].set_peer_outputs(Sp, xp, plan.n, p["plan"].r0)
             Sa_full = peer.Sa
         except Exception as e:   # no peer mapping on this box: the NCCL all-gather path (same kernels otherwise)
@@ -418,7 +420,7 @@ def main():
         out = {"metric": "local-analysis grid columns/sec", "value": value, "unit": "columns/s", "n_gpus": world,
                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": workload_name(a), "zones": nzones, "parallelism": f"zone-range x{world}" + ((", all-gather fused into the apply kernel (stores into every rank's result array over NVLink, CUDA IPC); " + str(fused_note)) if fused else (f", {nphase} pipelined phases (all-gather of phase j overlaps analysis of j+1; " + ("asynchronous, stream priorities" if use_async else "blocking calls") + ")" + (("; " + fused_note) if fused_note else "") if world > 1 else "")),
+               "config": {"workload": workload_name(a), "zones": nzones, "parallelism": f"zone-range x{world}" + (((", all-gather replaced by peer copies of every finished batch into every rank's result array (copy engines over NVLink, CUDA IPC mappings); " if a.peer_mode == 1 else ", all-gather fused into the apply kernel (stores into every rank's result array over NVLink, CUDA IPC); ") + str(fused_note)) if fused else (f", {nphase} pipelined phases (all-gather of phase j overlaps analysis of j+1; " + ("asynchronous, stream priorities" if use_async else "blocking calls") + ")" + (("; " + fused_note) if fused_note else "") if world > 1 else "")),
                           "l2": "inputs (>= 15 GB state) exceed L2; no explicit flush",
                           "mean_relevant_obs_per_column": mloc_mean, "mean_candidates_per_column": cand_mean,
                           "mean_jacobi_sweeps": sweeps_mean, "eig_kernel": a.eig_kernel},

@@ -72,6 +72,7 @@ struct DevBuf {
 
 struct Slot {
   cudaStream_t st = nullptr;
+  cudaStream_t cst = nullptr;  // copy-engine pushes of finished batches to the peers (peer_mode 1)
   DevBuf G, T, c, ampl, tri;   // batch workspace (tri: d, e, tau, lambda, flags of the tridiagonal route)
   DevBuf S, xf, xa;            // host-streaming chunk buffers
   cudaEvent_t ev[12] = {};
@@ -85,7 +86,8 @@ struct oakb200_handle {
   int eig_kernel = 4;
   double tri_orthtol = 0.;  // tridiagonal route: accepted loss of orthogonality between neighbouring eigenvectors (0: default)
   int tri_maxgroup = -1;
-  PeerOut peers{};            // fused all-gather destinations (oakb200_set_peer_outputs); n = 0: none    // ... largest group of close eigenvalues orthogonalised in place (-1: default)
+  PeerOut peers{};            // fused all-gather destinations (oakb200_set_peer_outputs); n = 0: none
+  int peer_mode = 1;          // 1: copy engines push every finished batch (no SM time); 0: stores of k_apply    // ... largest group of close eigenvalues orthogonalised in place (-1: default)
   int zones_per_batch = 0;
   double tol = 2e-11;  // bound on the remaining non-orthogonality (eig_common.cuh: jacobi_converged)
   int max_sweeps = 30;
@@ -223,7 +225,24 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
     if (prof) CUDA_TRY(cudaEventRecord(s.ev[2], s.st));
     PeerOut none{};
     if ((rc = oak_launch_apply(s.st, N, NP, zg, b0, nz, rowbase, mloc, s.T.as<double>(), s.ampl.as<double>(), xf,
-                               Sf, ldS, xa, Sa, ldSa, use_peers ? h->peers : none))) return rc;
+                               Sf, ldS, xa, Sa, ldSa, (use_peers && h->peer_mode == 0) ? h->peers : none))) return rc;
+    if (use_peers && h->peer_mode == 1) {
+      // fused all-gather, copy-engine flavour: as soon as the batch is applied its rows go to every peer's
+      // array (strided 2-D peer copies over NVLink, no SM involved), overlapping the kernels of the next batches
+      const PeerOut &P = h->peers;
+      const int64_t r0 = h->h_zstart[b0], r1 = h->h_zstart[b0 + nz];
+      if (r1 > r0) {
+        CUDA_TRY(cudaEventRecord(s.ev[11], s.st));
+        CUDA_TRY(cudaStreamWaitEvent(s.cst, s.ev[11], 0));
+        for (int d = 0; d < P.n; d++) {
+          CUDA_TRY(cudaMemcpy2DAsync(P.Sa[d] + P.row0 + r0, sizeof(double) * (size_t)P.ld, Sa + (r0 - rowbase),
+                                     sizeof(double) * (size_t)ldSa, sizeof(double) * (size_t)(r1 - r0), (size_t)N,
+                                     cudaMemcpyDeviceToDevice, s.cst));
+          CUDA_TRY(cudaMemcpyAsync(P.xa[d] + P.row0 + r0, xa + (r0 - rowbase), sizeof(double) * (size_t)(r1 - r0),
+                                   cudaMemcpyDeviceToDevice, s.cst));
+        }
+      }
+    }
     *launches += 3;
     if (prof) {
       CUDA_TRY(cudaEventRecord(s.ev[3], s.st));
@@ -310,6 +329,7 @@ extern "C" OAKB200_API int oakb200_create(int device, oakb200_handle **out) {
   h->device = device;
   for (int i = 0; i < NSLOT; i++) {
     CUDA_TRY(cudaStreamCreateWithFlags(&h->slot[i].st, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->slot[i].cst, cudaStreamNonBlocking));
     for (auto &ev : h->slot[i].ev) CUDA_TRY(cudaEventCreate(&ev));
   }
   CUDA_TRY(cudaEventCreate(&h->ev_a));
@@ -336,6 +356,7 @@ extern "C" OAKB200_API int oakb200_destroy(oakb200_handle *h) {
     s.G.release(); s.T.release(); s.c.release(); s.ampl.release(); s.tri.release(); s.S.release(); s.xf.release(); s.xa.release();
     for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
     if (s.st) cudaStreamDestroy(s.st);
+    if (s.cst) cudaStreamDestroy(s.cst);
   }
   if (h->ev_a) cudaEventDestroy(h->ev_a);
   if (h->ev_b) cudaEventDestroy(h->ev_b);
@@ -411,6 +432,7 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   if (k == "eig_kernel") h->eig_kernel = (int)value;
   else if (k == "tri_orthtol") h->tri_orthtol = value;
   else if (k == "tri_maxgroup") h->tri_maxgroup = (int)value;
+  else if (k == "peer_mode") h->peer_mode = (int)value;
   else if (k == "zones_per_batch") h->zones_per_batch = (int)value;
   else if (k == "jacobi_tol") h->tol = value;
   else if (k == "max_sweeps") h->max_sweeps = (int)value;
@@ -654,6 +676,12 @@ extern "C" OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t
   for (int i = 1; i < NSLOT; i++) {
     CUDA_TRY(cudaEventRecord(h->slot[i].ev[5], h->slot[i].st));
     CUDA_TRY(cudaStreamWaitEvent(s0, h->slot[i].ev[5], 0));
+  }
+  if (h->peers.n > 0 && h->peer_mode == 1) {
+    for (int i = 0; i < NSLOT; i++) {
+      CUDA_TRY(cudaEventRecord(h->slot[i].ev[11], h->slot[i].cst));
+      CUDA_TRY(cudaStreamWaitEvent(s0, h->slot[i].ev[11], 0));
+    }
   }
   CUDA_TRY(cudaEventRecord(h->ev_b, s0));
   if (h->async && !h->profile) {
