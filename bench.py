@@ -314,7 +314,9 @@ def main():
             peer.fence()   # readers after the writers of all ranks
         return tot
 
-    if fused:   # once: the fused result equals the NCCL all-gather of the slabs, bit for bit
+    if fused and a.peer_mode == 2:
+        fused_note = "EXPERIMENT: results not pushed to the peers (compute-only timing, not a valid bench line)"
+    elif fused:   # once: the fused result equals the NCCL all-gather of the slabs, bit for bit
         step()
         torch.cuda.synchronize()
         ref = torch.empty_like(Sa_full)

@@ -87,6 +87,8 @@ struct oakb200_handle {
   double tri_orthtol = 0.;  // tridiagonal route: accepted loss of orthogonality between neighbouring eigenvectors (0: default)
   int tri_maxgroup = -1;
   PeerOut peers{};            // fused all-gather destinations (oakb200_set_peer_outputs); n = 0: none
+  cudaStream_t pstream[OAKB200_MAX_PEERS] = {};  // one copy stream per destination (created on first use)
+  cudaEvent_t pev[OAKB200_MAX_PEERS] = {};
   int peer_mode = 1;          // 1: copy engines push every finished batch (no SM time); 0: stores of k_apply    // ... largest group of close eigenvalues orthogonalised in place (-1: default)
   int zones_per_batch = 0;
   double tol = 2e-11;  // bound on the remaining non-orthogonality (eig_common.cuh: jacobi_converged)
@@ -232,14 +234,16 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
       const PeerOut &P = h->peers;
       const int64_t r0 = h->h_zstart[b0], r1 = h->h_zstart[b0 + nz];
       if (r1 > r0) {
+        // one stream per destination: the copies to different peers run on different copy engines / links
         CUDA_TRY(cudaEventRecord(s.ev[11], s.st));
-        CUDA_TRY(cudaStreamWaitEvent(s.cst, s.ev[11], 0));
         for (int d = 0; d < P.n; d++) {
+          cudaStream_t cs = h->pstream[d];
+          CUDA_TRY(cudaStreamWaitEvent(cs, s.ev[11], 0));
           CUDA_TRY(cudaMemcpy2DAsync(P.Sa[d] + P.row0 + r0, sizeof(double) * (size_t)P.ld, Sa + (r0 - rowbase),
                                      sizeof(double) * (size_t)ldSa, sizeof(double) * (size_t)(r1 - r0), (size_t)N,
-                                     cudaMemcpyDeviceToDevice, s.cst));
+                                     cudaMemcpyDeviceToDevice, cs));
           CUDA_TRY(cudaMemcpyAsync(P.xa[d] + P.row0 + r0, xa + (r0 - rowbase), sizeof(double) * (size_t)(r1 - r0),
-                                   cudaMemcpyDeviceToDevice, s.cst));
+                                   cudaMemcpyDeviceToDevice, cs));
         }
       }
     }
@@ -351,6 +355,10 @@ extern "C" OAKB200_API int oakb200_destroy(oakb200_handle *h) {
                     &h->d_d01, &h->d_ampzero, &h->d_HE, &h->d_Hi, &h->d_Hj, &h->d_Hs, &h->d_Hshift, &h->d_order,
                     &h->d_rowstart, &h->d_xf, &h->d_xa, &h->d_maxc, &h->d_E, &h->d_ctr};
   for (DevBuf *b : bufs) b->release();
+  for (int d = 0; d < OAKB200_MAX_PEERS; d++) {
+    if (h->pstream[d]) cudaStreamDestroy(h->pstream[d]);
+    if (h->pev[d]) cudaEventDestroy(h->pev[d]);
+  }
   for (int i = 0; i < NSLOT; i++) {
     Slot &s = h->slot[i];
     s.G.release(); s.T.release(); s.c.release(); s.ampl.release(); s.tri.release(); s.S.release(); s.xf.release(); s.xa.release();
@@ -379,6 +387,13 @@ extern "C" OAKB200_API int oakb200_set_peer_outputs(oakb200_handle *h, int32_t n
     h->peers.xa[d] = xa_peer[d];
   }
   h->peers.n = npeer; h->peers.ld = ld_peer; h->peers.row0 = row0;
+  DeviceGuard guard(h->device);
+  for (int d = 0; d < npeer; d++) {
+    if (!h->pstream[d]) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&h->pstream[d], cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->pev[d], cudaEventDisableTiming));
+    }
+  }
   return 0;
 }
 
@@ -678,9 +693,9 @@ extern "C" OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t
     CUDA_TRY(cudaStreamWaitEvent(s0, h->slot[i].ev[5], 0));
   }
   if (h->peers.n > 0 && h->peer_mode == 1) {
-    for (int i = 0; i < NSLOT; i++) {
-      CUDA_TRY(cudaEventRecord(h->slot[i].ev[11], h->slot[i].cst));
-      CUDA_TRY(cudaStreamWaitEvent(s0, h->slot[i].ev[11], 0));
+    for (int d = 0; d < h->peers.n; d++) {
+      CUDA_TRY(cudaEventRecord(h->pev[d], h->pstream[d]));
+      CUDA_TRY(cudaStreamWaitEvent(s0, h->pev[d], 0));
     }
   }
   CUDA_TRY(cudaEventRecord(h->ev_b, s0));
