@@ -392,8 +392,8 @@ def main():
         else:
             stages["k_eig_fast"] = (stp["ms_eig"], 9 * N3 + 2 * N3 + 4 * a.N * a.N)
         # dram__bytes_read.sum + dram__bytes_write.sum per zone from the ncu --set full captures under profiles/
-        # (r1_ncu_full_tridiag.txt, r1_ncu_full_tvec.txt, r1_ncu_full_gram2.txt; 7104-zone launches, N = 64)
-        traffic_zone = {"k_gram": 26.0e3, "k_tridiag": 59.5e3, "k_tql+k_tvec": 60.4e3, "k_eig_fast": 39.8e3}
+        # (r1_ncu_full_tridiag.txt, r1_ncu_full_tvec.txt, r1_ncu_full_gram.txt; 7104-zone launches, N = 64)
+        traffic_zone = {"k_gram": 26.1e3, "k_tridiag": 59.5e3, "k_tql+k_tvec": 59.2e3, "k_eig_fast": 39.8e3}
         stage_out = {}
         for name, (ms_k, fl) in stages.items():
             ach = fl * z_rank / (ms_k * 1e-3) / 1e12 if ms_k > 0 else 0.0

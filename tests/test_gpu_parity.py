@@ -481,7 +481,7 @@ def test_fused_gather_peer_outputs_receive_the_slab(ob):
     across GPUs the destinations are CUDA-IPC mappings, exercised by bench.py --gpus N)."""
     import torch
     from oak_b200 import synthetic
-    c = synthetic.small_case(nx=24, ny=18, nz=4, N=24, m=150, corr=2500.0, maxlen=5000.0, seed=21)
+    c = synthetic.small_case(nx=24, ny=18, nz=4, N=24, m=30, corr=1500.0, maxlen=3000.0, seed=21)
     dev = torch.device("cuda", 0)
     t = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device=dev)
     N, n = c["Sf"].shape[1], c["Sf"].shape[0]
