@@ -141,10 +141,16 @@ OAKB200_API int oakb200_ipc_open(oakb200_handle *h, const unsigned char handle[6
 OAKB200_API int oakb200_ipc_close(oakb200_handle *h, void *ptr);
 OAKB200_API int oakb200_ipc_free(oakb200_handle *h, void *ptr);
 
+/* Table of the tabulated anamorphosis (type 3): AnamTrans%anam(v)%transform, K x 2 column-major HOST array,
+ * column 1 = physical values, column 2 = transformed values (assimilation.F90:4539-4567, interp1
+ * anamorphosis.F90:304-339 incl. its clamping rule).  One table for the whole state vector.  K = 0 clears it. */
+OAKB200_API int oakb200_set_anamorphosis_table(oakb200_handle *h, int32_t K, const double *table);
+
 /* Ensemble branch of Assim around the local scheme (assimilation.F90:3083,:3106-3134 prologue,
  * :3235 analysis, :3301-3357,:3558-3562 epilogue), HOST buffers:
  *   E[n x N] ensemble (zone-permuted), H as COO (Hi,Hj 1-based int32, Hs, nnz; matoper.F90:30-39),
- *   Hshift[m] (may be NULL), yo, Rdiag, d01, anamtype 1 identity / 2 log (anamorphosis.F90:78-120),
+ *   Hshift[m] (may be NULL), yo, Rdiag, d01, anamtype 1 identity / 2 log / 3 tabulated (anamorphosis.F90:78-120,
+ *   :304-339; the table comes from oakb200_set_anamorphosis_table),
  *   inflation (inflation.mult), maxCorrection[n] (may be NULL)  ->  Ea[n x N]; xf_out/xa_out[n] optional. */
 OAKB200_API int oakb200_assim_ensemble(oakb200_handle *h, int64_t n, int32_t N, int32_t m, const double *E,
                            int64_t ldE, int64_t nnz, const int32_t *Hi, const int32_t *Hj,

@@ -261,8 +261,22 @@ class Handle:
             C.c_void_p(xa.data_ptr()), C.c_void_p(Sa.data_ptr()), max(n, 1), None, C.byref(st)))
         return st.asdict()
 
-    def assim_ensemble(self, E, Hi, Hj, Hs, Hshift, yo, R, anamtype=1, inflation=1.0, maxCorrection=None):
+    def set_anamorphosis_table(self, table):
+        """AnamTrans%anam(v)%transform of the tabulated anamorphosis (type 3): K x 2, physical values and
+        transformed values (assimilation.F90:4539-4567).  None clears it."""
+        if table is None:
+            _check(self._L.oakb200_set_anamorphosis_table(self._h, 0, None))
+            return
+        t = np.asfortranarray(table, dtype=np.float64)
+        if t.ndim != 2 or t.shape[1] != 2:
+            raise OakB200Error(-2, "anamorphosis table must be K x 2")
+        _check(self._L.oakb200_set_anamorphosis_table(self._h, t.shape[0], _ptr(t)))
+
+    def assim_ensemble(self, E, Hi, Hj, Hs, Hshift, yo, R, anamtype=1, inflation=1.0, maxCorrection=None,
+                       anamtable=None):
         """Ensemble branch of Assim (local scheme) with host arrays. Returns Ea, xf, xa, stats."""
+        if anamtable is not None:
+            self.set_anamorphosis_table(anamtable)
         E = np.asfortranarray(E, dtype=np.float64)
         n, N = E.shape
         yo = np.ascontiguousarray(yo, dtype=np.float64)
@@ -315,13 +329,14 @@ def locanalysis(zoneSize, selectObservations, xf, Hxf, yo, Sf, HSf, R, handle=No
 
 
 def assim_ensemble(zoneSize, selectObservations, E, Hi, Hj, Hs, Hshift, yo, R, anamtype=1, inflation=1.0,
-                   maxCorrection=None, handle=None, device=0):
+                   maxCorrection=None, handle=None, device=0, anamtable=None):
     """Ensemble in, analysed ensemble out (assimilation.F90:3106-3134,:3235-3236,:3301-3357,:3558-3562)."""
     own = handle is None
     h = Handle(device) if own else handle
     try:
         h.configure(zoneSize, selectObservations)
-        Ea, xf, xa, _ = h.assim_ensemble(E, Hi, Hj, Hs, Hshift, yo, R, anamtype, inflation, maxCorrection)
+        Ea, xf, xa, _ = h.assim_ensemble(E, Hi, Hj, Hs, Hshift, yo, R, anamtype, inflation, maxCorrection,
+                                         anamtable=anamtable)
         return Ea, xf, xa
     finally:
         if own:

@@ -86,6 +86,8 @@ struct oakb200_handle {
   int eig_kernel = 4;
   double tri_orthtol = 0.;  // tridiagonal route: accepted loss of orthogonality between neighbouring eigenvectors (0: default)
   int tri_maxgroup = -1;
+  DevBuf d_anam;              // tabulated anamorphosis (K x 2), oakb200_set_anamorphosis_table
+  int anam_K = 0, anam_monotone = 0;
   PeerOut peers{};            // fused all-gather destinations (oakb200_set_peer_outputs); n = 0: none
   cudaStream_t pstream[OAKB200_MAX_PEERS] = {};  // one copy stream per destination (created on first use)
   cudaEvent_t pev[OAKB200_MAX_PEERS] = {};
@@ -353,7 +355,7 @@ extern "C" OAKB200_API int oakb200_destroy(oakb200_handle *h) {
                     &h->d_key_in, &h->d_key_out, &h->d_val_in, &h->d_perm, &h->d_cell_start, &h->d_sx, &h->d_sy,
                     &h->d_tmp, &h->d_rows, &h->d_delta, &h->d_scoef, &h->d_HSf, &h->d_yo, &h->d_Hxf, &h->d_R,
                     &h->d_d01, &h->d_ampzero, &h->d_HE, &h->d_Hi, &h->d_Hj, &h->d_Hs, &h->d_Hshift, &h->d_order,
-                    &h->d_rowstart, &h->d_xf, &h->d_xa, &h->d_maxc, &h->d_E, &h->d_ctr};
+                    &h->d_rowstart, &h->d_xf, &h->d_xa, &h->d_maxc, &h->d_E, &h->d_ctr, &h->d_anam};
   for (DevBuf *b : bufs) b->release();
   for (int d = 0; d < OAKB200_MAX_PEERS; d++) {
     if (h->pstream[d]) cudaStreamDestroy(h->pstream[d]);
@@ -370,6 +372,25 @@ extern "C" OAKB200_API int oakb200_destroy(oakb200_handle *h) {
   if (h->ev_b) cudaEventDestroy(h->ev_b);
   if (h->ev_user) cudaEventDestroy(h->ev_user);
   delete h;
+  return 0;
+}
+
+extern "C" OAKB200_API int oakb200_set_anamorphosis_table(oakb200_handle *h, int32_t K, const double *table) {
+  if (!h) { oak_set_error("null handle"); return OAK_ERR_ARG; }
+  if (K == 0) { h->anam_K = 0; return 0; }
+  if (K < 2 || !table) { oak_set_error("set_anamorphosis_table: K = %d (need >= 2 rows) or null table", K); return OAK_ERR_ARG; }
+  for (int i = 0; i < 2 * K; i++)
+    if (!(table[i] == table[i])) { oak_set_error("set_anamorphosis_table: NaN in the table"); return OAK_ERR_ARG; }
+  int mono = 1;
+  for (int c = 0; c < 2; c++)
+    for (int i = 0; i + 1 < K; i++)
+      if (!(table[c * K + i] < table[c * K + i + 1])) mono = 0;
+  DeviceGuard guard(h->device);
+  int rc = h->d_anam.ensure(sizeof(double) * 2 * (size_t)K);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpy(h->d_anam.p, table, sizeof(double) * 2 * (size_t)K, cudaMemcpyHostToDevice));
+  h->anam_K = K;
+  h->anam_monotone = mono;
   return 0;
 }
 
@@ -814,7 +835,9 @@ extern "C" OAKB200_API int oakb200_assim_ensemble_dev(oakb200_handle *h, int64_t
                                           double *xa_out, void *stream, oakb200_stats *stats) {
   int rc = check_ready(h, n, N, m);
   if (rc) return rc;
-  if (anamtype != 1 && anamtype != 2) { oak_set_error("assim_ensemble: anamorphosis type %d not supported (1 identity, 2 log)", anamtype); return OAK_ERR_UNSUPPORTED; }
+  if (anamtype < 1 || anamtype > 3) { oak_set_error("assim_ensemble: anamorphosis type %d unknown (1 identity, 2 log, 3 tabulated)", anamtype); return OAK_ERR_ARG; }
+  if (anamtype == 3 && h->anam_K < 2) { oak_set_error("assim_ensemble: tabulated anamorphosis without a table (oakb200_set_anamorphosis_table)"); return OAK_ERR_STATE; }
+  const AnamTab at{h->d_anam.as<double>(), h->anam_K, h->anam_monotone};
   if ((n > 0 && (!E || !Ea)) || (nnz > 0 && (!Hi || !Hj || !Hs)) || (m > 0 && (!yo || !Rdiag))) { oak_set_error("assim_ensemble: null array"); return OAK_ERR_ARG; }
   DeviceGuard guard(h->device);
   cudaStream_t s0 = h->slot[0].st;
@@ -835,14 +858,14 @@ extern "C" OAKB200_API int oakb200_assim_ensemble_dev(oakb200_handle *h, int64_t
   // HE = H E + Hshift on the untransformed state (assimilation.F90:3112-3114)
   if ((rc = oak_launch_obsoper_rows(s0, m, N, h->d_rowstart.as<int32_t>(), h->d_order.as<int32_t>(), Hj, Hs, Hshift, E, ldE, h->d_HE.as<double>()))) return rc;
   // Hxf, HSf (in place in HE) ; xf, Sf (into Ea)
-  if ((rc = oak_launch_mean_anom(s0, m, N, 1, h->d_HE.as<double>(), m, h->d_Hxf.as<double>(), h->d_HE.as<double>(), m))) return rc;
-  if ((rc = oak_launch_mean_anom(s0, n, N, anamtype, E, ldE, h->d_xf.as<double>(), Ea, ldEa))) return rc;
+  if ((rc = oak_launch_mean_anom(s0, m, N, 1, AnamTab{nullptr, 0, 0}, h->d_HE.as<double>(), m, h->d_Hxf.as<double>(), h->d_HE.as<double>(), m))) return rc;
+  if ((rc = oak_launch_mean_anom(s0, n, N, anamtype, at, E, ldE, h->d_xf.as<double>(), Ea, ldEa))) return rc;
   CUDA_TRY(cudaStreamSynchronize(s0));
   rc = oakb200_local_analysis_dev(h, n, N, m, h->d_xf.as<double>(), h->d_Hxf.as<double>(), yo, Ea, ldEa,
                                   h->d_HE.as<double>(), m, Rdiag, d01, h->d_xa.as<double>(), Ea, ldEa, nullptr,
                                   (void *)s0, stats);
   if (rc) return rc;
-  if ((rc = oak_launch_epilogue(s0, n, N, anamtype, inflation, maxCorrection, h->d_xf.as<double>(), h->d_xa.as<double>(), Ea, ldEa, Ea, ldEa))) return rc;
+  if ((rc = oak_launch_epilogue(s0, n, N, anamtype, at, inflation, maxCorrection, h->d_xf.as<double>(), h->d_xa.as<double>(), Ea, ldEa, Ea, ldEa))) return rc;
   if (xf_out) CUDA_TRY(cudaMemcpyAsync(xf_out, h->d_xf.p, 8 * (size_t)n, cudaMemcpyDeviceToDevice, s0));
   if (xa_out) CUDA_TRY(cudaMemcpyAsync(xa_out, h->d_xa.p, 8 * (size_t)n, cudaMemcpyDeviceToDevice, s0));
   CUDA_TRY(cudaStreamSynchronize(s0));

@@ -241,6 +241,13 @@ struct BatchWs {          // per-stream workspace for a batch of zones
   double *ampl;           // [zb][NP]
 };
 
+// tabulated anamorphosis (AnamTrans%anam(v)%transform, K x 2 column-major on the device; oakb200_set_anamorphosis_table)
+struct AnamTab {
+  const double *tab;   // [0..K) physical values, [K..2K) transformed values
+  int32_t K;
+  int32_t monotone;    // both columns strictly increasing: the bracket search may bisect
+};
+
 // destinations of the fused all-gather (oakb200_set_peer_outputs), passed by value to k_apply
 struct PeerOut {
   double *Sa[OAKB200_MAX_PEERS];
@@ -282,8 +289,8 @@ int oak_fp64_peak(int mode, double *tflops);
 // ensemble prologue / epilogue (assimilation.F90:3106-3134, :3301-3357)
 int oak_launch_obsoper(cudaStream_t st, int m, int N, int64_t nnz, const int32_t *Hi, const int32_t *Hj,
                        const double *Hs, const double *Hshift, const double *E, int64_t ldE, double *HE);
-int oak_launch_mean_anom(cudaStream_t st, int64_t rows, int N, int anamtype, const double *E, int64_t ldE,
+int oak_launch_mean_anom(cudaStream_t st, int64_t rows, int N, int anamtype, AnamTab at, const double *E, int64_t ldE,
                          double *mean, double *S, int64_t ldS);
-int oak_launch_epilogue(cudaStream_t st, int64_t rows, int N, int anamtype, double inflation,
+int oak_launch_epilogue(cudaStream_t st, int64_t rows, int N, int anamtype, AnamTab at, double inflation,
                         const double *maxCorr, const double *xf, double *xa, const double *Sa,
                         int64_t ldSa, double *Ea, int64_t ldEa);

@@ -11,8 +11,47 @@
 
 namespace {
 
-__device__ __forceinline__ double anam_fwd(int type, double x) { return type == 2 ? log(x) : x; }
-__device__ __forceinline__ double anam_inv(int type, double x) { return type == 2 ? exp(x) : x; }
+// interp1 (anamorphosis.F90:304-339): first bracket x_k <= xi < x_k+1, (1-alpha) y_k + alpha y_k+1; without a
+// bracket y_1 (xi < x_1) or y_K, and `out`.  A strictly increasing x has at most one bracket, found by bisection;
+// otherwise the reference's linear scan.  Explicitly rounded operations (no FMA contraction): same bits as the
+// Fortran expression evaluated in IEEE arithmetic.
+__device__ __forceinline__ double oak_interp1(int K, const double *x, const double *y, bool monotone, double xi, bool &out) {
+  int k = -1;
+  if (monotone) {
+    if (xi >= x[0] && xi < x[K - 1]) {
+      int lo = 0, hi = K - 1;  // x[lo] <= xi < x[hi]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (x[mid] <= xi) lo = mid; else hi = mid;
+      }
+      k = lo;
+    }
+  } else {
+    for (int kp = 0; kp < K - 1; kp++)
+      if (x[kp] <= xi && xi < x[kp + 1]) { k = kp; break; }
+  }
+  out = (k == -1);
+  if (k != -1) {
+    const double alpha = __ddiv_rn(__dsub_rn(xi, x[k]), __dsub_rn(x[k + 1], x[k]));
+    return __dadd_rn(__dmul_rn(__dsub_rn(1., alpha), y[k]), __dmul_rn(alpha, y[k + 1]));
+  }
+  return (xi < x[0]) ? y[0] : y[K - 1];
+}
+
+// anamtransform for one element (assimilation.F90:4516-4576): 1 identity, 2 log/exp, 3 tabulated.  An
+// extrapolated tabulated value is replaced by the first / last entry of the table's INPUT-side column,
+// chosen by comparing the already interpolated value with transform(1,ti) (:4560-4567, reproduced as is).
+__device__ __forceinline__ double oak_anam(int type, bool forward, const AnamTab &at, double x) {
+  if (type == 2) return forward ? log(x) : exp(x);
+  if (type == 3) {
+    const double *ti = forward ? at.tab : at.tab + at.K, *tj = forward ? at.tab + at.K : at.tab;
+    bool out;
+    double v = oak_interp1(at.K, ti, tj, at.monotone != 0, x, out);
+    if (out) v = (v < ti[0]) ? ti[0] : ti[at.K - 1];
+    return v;
+  }
+  return x;
+}
 
 // ---- COO -> row-sorted (stable: the entries of a row keep the caller's order, so the sum is
 // accumulated in the same order as the sequential loop of matoper_inc.F90:238-240) ----
@@ -44,7 +83,7 @@ __global__ void k_obsoper(int m, const int32_t *rowstart, const int32_t *order, 
 }
 
 // ---- mean + scaled anomalies, one pass: a tile of 64 rows x N members staged in shared memory ----
-__global__ void __launch_bounds__(256) k_mean_anom(int64_t rows, int N, int anamtype, const double *E,
+__global__ void __launch_bounds__(256) k_mean_anom(int64_t rows, int N, int anamtype, AnamTab at, const double *E,
                                                    int64_t ldE, double *mean, double *S, int64_t ldS,
                                                    double scaling) {
   extern __shared__ double tile[];  // [N][64]
@@ -52,7 +91,7 @@ __global__ void __launch_bounds__(256) k_mean_anom(int64_t rows, int N, int anam
   const int64_t r0 = (int64_t)blockIdx.x * 64;
   const int tid = threadIdx.x, lr = tid & 63, kq = tid >> 6;  // 4 members in flight
   const int64_t row = r0 + lr;
-  for (int k = kq; k < N; k += 4) tile[k * 64 + lr] = row < rows ? anam_fwd(anamtype, E[row + ldE * k]) : 0.;
+  for (int k = kq; k < N; k += 4) tile[k * 64 + lr] = row < rows ? oak_anam(anamtype, true, at, E[row + ldE * k]) : 0.;
   __syncthreads();
   if (tid < 64) {
     double s = 0.;
@@ -68,7 +107,7 @@ __global__ void __launch_bounds__(256) k_mean_anom(int64_t rows, int N, int anam
   }
 }
 
-__global__ void k_epilogue(int64_t rows, int N, int anamtype, double inflation, double scaling,
+__global__ void k_epilogue(int64_t rows, int N, int anamtype, AnamTab at, double inflation, double scaling,
                            const double *maxCorr, const double *xf, double *xa, const double *Sa,
                            int64_t ldSa, double *Ea, int64_t ldEa) {
   const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -84,7 +123,7 @@ __global__ void k_epilogue(int64_t rows, int N, int anamtype, double inflation, 
   for (int k = blockIdx.y; k < N; k += gridDim.y) {
     double s = Sa[row + ldSa * k];
     if (inflation != 1.) s = __dmul_rn(s, inflation);               // :3301-3304
-    Ea[row + ldEa * k] = anam_inv(anamtype, __dadd_rn(x, __dmul_rn(s, scaling)));  // :3318-3326
+    Ea[row + ldEa * k] = oak_anam(anamtype, false, at, __dadd_rn(x, __dmul_rn(s, scaling)));  // :3318-3326
   }
   if (blockIdx.y == 0) xa[row] = x;
 }
@@ -126,7 +165,7 @@ int oak_launch_obsoper_rows(cudaStream_t st, int m, int N, const int32_t *rowsta
   return 0;
 }
 
-int oak_launch_mean_anom(cudaStream_t st, int64_t rows, int N, int anamtype, const double *E, int64_t ldE,
+int oak_launch_mean_anom(cudaStream_t st, int64_t rows, int N, int anamtype, AnamTab at, const double *E, int64_t ldE,
                          double *mean, double *S, int64_t ldS) {
   if (rows == 0) return 0;
   const size_t smem = sizeof(double) * 64 * N;
@@ -136,18 +175,18 @@ int oak_launch_mean_anom(cudaStream_t st, int64_t rows, int N, int anamtype, con
     attr_done = true;
   }
   const double scaling = sqrt((double)N - 1.);
-  k_mean_anom<<<(unsigned)((rows + 63) / 64), 256, smem, st>>>(rows, N, anamtype, E, ldE, mean, S, ldS, scaling);
+  k_mean_anom<<<(unsigned)((rows + 63) / 64), 256, smem, st>>>(rows, N, anamtype, at, E, ldE, mean, S, ldS, scaling);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
-int oak_launch_epilogue(cudaStream_t st, int64_t rows, int N, int anamtype, double inflation,
+int oak_launch_epilogue(cudaStream_t st, int64_t rows, int N, int anamtype, AnamTab at, double inflation,
                         const double *maxCorr, const double *xf, double *xa, const double *Sa,
                         int64_t ldSa, double *Ea, int64_t ldEa) {
   if (rows == 0) return 0;
   const double scaling = sqrt((double)N - 1.);
   dim3 grid((unsigned)((rows + 255) / 256), 1);
-  k_epilogue<<<grid, 256, 0, st>>>(rows, N, anamtype, inflation, scaling, maxCorr, xf, xa, Sa, ldSa, Ea, ldEa);
+  k_epilogue<<<grid, 256, 0, st>>>(rows, N, anamtype, at, inflation, scaling, maxCorr, xf, xa, Sa, ldSa, Ea, ldEa);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -156,9 +156,32 @@ def loc_analysis(zoneSize, zone_pos, corrLen, maxLen, obs, xf, Hxf, yo, Sf, HSf,
     return xa, Sa, ampl, mloc
 
 
+def interp1(x, y, xi):
+    """anamorphosis.F90:304-339 — returns (yi, out)"""
+    x = _f(x); y = _f(y)
+    out = C.c_int(0)
+    f = lib().oracle_interp1
+    f.restype = C.c_double
+    yi = f(C.c_int(x.size), _dp(x), _dp(y), C.c_double(xi), C.byref(out))
+    return yi, bool(out.value)
+
+
+def anamtransform(forward, anamtype, x, table=None):
+    """assimilation.F90:4516-4576 on a vector (one variable): type 1 identity, 2 log/exp, 3 tabulated
+    (table = K x 2: physical values, transformed values)"""
+    f = lib().oracle_anam
+    f.restype = C.c_double
+    tab = _f(np.asfortranarray(table)) if table is not None else None
+    K = 0 if tab is None else tab.shape[0]
+    return np.array([f(C.c_int(anamtype), C.c_int(1 if forward else 0), C.c_int(K), _dp(tab), C.c_double(v))
+                     for v in np.asarray(x, dtype=np.float64).ravel()])
+
+
 def assim_ensemble(zoneSize, zone_pos, corrLen, maxLen, obs, E, Hi, Hj, Hs, Hshift, yo, var,
-                   e01=None, anamtype=1, inflation=1.0, maxCorrection=None):
+                   e01=None, anamtype=1, inflation=1.0, maxCorrection=None, anamtable=None):
     """ensemble branch of Assim with the local scheme — assimilation.F90:3106-3134, :3235, :3301-3357"""
+    tab = _f(np.asfortranarray(anamtable)) if anamtable is not None else None
+    lib().oracle_set_anam_table(C.c_int(0 if tab is None else tab.shape[0]), _dp(tab))
     E = _f(E)
     n, N = E.shape
     zs = np.ascontiguousarray(zoneSize, dtype=np.int32)

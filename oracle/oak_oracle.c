@@ -437,10 +437,43 @@ void oracle_obsoper(int m, int64_t nnz, const int32_t *Hi, const int32_t *Hj, co
     for (int i = 0; i < m; i++) Hx[i] += Hshift[i];
 }
 
-/* anamorphosis forward/inverse for the types exercised here:
- * 1 identity, 2 log/exp (anamorphosis.F90:78-120; assimilation.F90:4516-4576) */
-static inline double anam_fwd(int type, double x) { return type == 2 ? log(x) : x; }
-static inline double anam_inv(int type, double x) { return type == 2 ? exp(x) : x; }
+/* interp1 — anamorphosis.F90:304-339: first bracket x(kp) <= xi < x(kp+1), linear blend
+ * (1-alpha) y(k) + alpha y(k+1); outside every bracket: y(1) if xi < x(1), else y(end); *out = no bracket. */
+double oracle_interp1(int K, const double *x, const double *y, double xi, int *out) {
+  int k = -1;
+  for (int kp = 0; kp < K - 1; kp++)
+    if (x[kp] <= xi && xi < x[kp + 1]) { k = kp; break; }
+  double yi;
+  if (k != -1) {
+    const double alpha = (xi - x[k]) / (x[k + 1] - x[k]);
+    yi = (1 - alpha) * y[k] + alpha * y[k + 1];
+  } else {
+    yi = (xi < x[0]) ? y[0] : y[K - 1];
+  }
+  if (out) *out = (k == -1);
+  return yi;
+}
+
+/* anamtransform, one element — assimilation.F90:4516-4576.  Types: 1 identity, 2 log/exp, 3 tabulated
+ * (transform(:,1) physical values, transform(:,2) transformed values; tab = K x 2 column-major).  For type 3 an
+ * extrapolated value is overwritten by the end of the table's INPUT-side column (:4560-4567): the already
+ * interpolated (output-side) value is compared with transform(1,ti) — reproduced as is. */
+double oracle_anam(int type, int forward, int K, const double *tab, double x) {
+  if (type == 2) return forward ? log(x) : exp(x);
+  if (type == 3) {
+    const double *ti = forward ? tab : tab + K, *tj = forward ? tab + K : tab;
+    int out;
+    double v = oracle_interp1(K, ti, tj, x, &out);
+    if (out) v = (v < ti[0]) ? ti[0] : ti[K - 1];
+    return v;
+  }
+  return x;
+}
+static const double *g_anamtab = 0;  /* table of the tabulated anamorphosis (set by oracle_set_anam_table) */
+static int g_anamK = 0;
+void oracle_set_anam_table(int K, const double *tab) { g_anamtab = tab; g_anamK = K; }
+static inline double anam_fwd(int type, double x) { return oracle_anam(type, 1, g_anamK, g_anamtab, x); }
+static inline double anam_inv(int type, double x) { return oracle_anam(type, 0, g_anamK, g_anamtab, x); }
 
 /* ---------------------------------------------------------------------------
  * Ensemble branch of Assim with the local scheme:

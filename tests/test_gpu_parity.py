@@ -513,3 +513,36 @@ def test_fused_gather_peer_outputs_receive_the_slab(ob):
             h.ipc_free(ptr)
     xo, So, _, _ = _oracle_loc(c)
     assert rel(xa.cpu().numpy(), xo) < RTOL and rel(Sa.cpu().numpy().T, So) < RTOL
+
+
+@pytest.mark.parametrize("monotone", [True, False])
+def test_assim_ensemble_tabulated_anamorphosis(ob, monotone):
+    """Anamorphosis type 3 (assimilation.F90:4539-4567, interp1 anamorphosis.F90:304-339): piecewise-linear table,
+    values outside the table (forward AND inverse direction) take the reference's clamping rule; a non-monotone
+    table goes through the linear first-bracket scan."""
+    from oak_b200 import synthetic
+    g = synthetic.Grid(16, 12, 3)
+    N, m = 24, 120
+    rows = np.arange(g.n, dtype=np.int64)
+    E = np.exp(0.5 * synthetic.ensemble_rows(np, g, rows, N, 9)).T.copy(order="F")   # ~0.2 .. 5
+    xs = np.array([0.5, 0.7, 1.0, 1.3, 1.7, 2.0])          # ~2 % of the values fall outside on either side
+    tab = np.column_stack([xs, np.log(xs) * 2.0])
+    if not monotone:
+        tab = tab[[0, 1, 3, 2, 4, 5]]
+    obs = synthetic.observations(np, g, m, 9)
+    Hi, Hj, Hs = synthetic.coo_operator(g, obs)
+    yo = 1.2 + 0.2 * synthetic.normal(np, np.arange(m, dtype=np.int64), 8, 9)
+    zx, zy = g.zone_xy(np, np.arange(g.nzones, dtype=np.int64))
+    zs = np.full(g.nzones, 3, np.int32)
+    sel = ob.Selector(zone_x=zx, zone_y=zy, corrLen=3000.0, maxLen=6000.0, obs_x=obs["ox"], obs_y=obs["oy"],
+                      metrictype=0)
+    with ob.Handle(0) as h:
+        with pytest.raises(ob.OakB200Error):       # type 3 without a table
+            ob.assim_ensemble(zs, sel, E, Hi, Hj, Hs, None, yo, ob.DiagCovar(obs["var"]), anamtype=3, handle=h)
+        Ea, xf, xa = ob.assim_ensemble(zs, sel, E, Hi, Hj, Hs, None, yo, ob.DiagCovar(obs["var"]), anamtype=3,
+                                       inflation=1.02, handle=h, anamtable=tab)
+    oo = oracle.make_obs(m, obsx=obs["ox"], obsy=obs["oy"])
+    Eo, xfo, xao = oracle.assim_ensemble(zs, dict(x=zx, y=zy), 3000.0, 6000.0, oo, E, Hi, Hj, Hs, np.zeros(m), yo,
+                                         obs["var"], anamtype=3, inflation=1.02, anamtable=tab)
+    assert ((E < xs[0]).any() and (E > xs[-1]).any())      # the clamping rule is exercised
+    assert rel(xf, xfo) < 1e-14 and rel(xa, xao) < RTOL and rel(Ea, Eo) < RTOL

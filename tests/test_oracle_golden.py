@@ -144,3 +144,56 @@ def test_init_partition_is_stable_counting_sort():
     assert list(zs) == [2, 2, 3]
     assert list(zi) == [2, 5, 1, 3, 4, 6, 7]
     assert all(zi[izi[i] - 1] == i + 1 for i in range(7))
+
+
+def _interp1_fortran(x, y, xi):
+    """anamorphosis.F90:304-339, statement by statement (1-based loop turned 0-based)"""
+    yi, k = xi, -1
+    for kp in range(len(x) - 1):
+        if x[kp] <= xi and xi < x[kp + 1]:
+            k = kp
+            break
+    if k != -1:
+        alpha = (xi - x[k]) / (x[k + 1] - x[k])
+        yi = (1 - alpha) * y[k] + alpha * y[k + 1]
+    else:
+        yi = y[0] if xi < x[0] else y[-1]
+    return yi, k == -1
+
+
+def _anamtransform_fortran(forward, table, x):
+    """assimilation.F90:4539-4567 (type 3) on one value, including the overwrite of an extrapolated value by
+    the end of the INPUT-side column, selected by comparing the interpolated value with transform(1,ti)"""
+    ti, tj = (0, 1) if forward else (1, 0)
+    v, out = _interp1_fortran(table[:, ti], table[:, tj], x)
+    if out:
+        v = table[0, ti] if v < table[0, ti] else table[-1, ti]
+    return v
+
+
+def test_tabulated_anamorphosis_interp1_and_clamping_rule():
+    # a monotone table (empirical-CDF-like) and a non-monotone one (the linear scan takes the FIRST bracket)
+    xs = np.array([0.0, 0.1, 0.5, 2.0, 10.0])
+    tab = np.column_stack([xs, np.log1p(xs) * 3.0 - 1.0])
+    tab_nm = np.column_stack([np.array([0.0, 2.0, 1.0, 3.0]), np.array([5.0, 6.0, 7.0, 9.0])])
+    xi = np.concatenate([np.linspace(-1.0, 12.0, 53), xs, [np.nextafter(10.0, 0.0), 1.5, 2.5]])
+    for t in (tab, tab_nm):
+        for v in xi:
+            yi, out = oracle.interp1(t[:, 0], t[:, 1], v)
+            yr, outr = _interp1_fortran(t[:, 0], t[:, 1], v)
+            assert yi == yr and out == outr
+        for fwd in (True, False):
+            got = oracle.anamtransform(fwd, 3, xi, t)
+            ref = np.array([_anamtransform_fortran(fwd, t, v) for v in xi])
+            assert (got == ref).all()
+    # inside the table the transform is inverted by the inverse transform
+    inside = np.linspace(0.0, 9.99, 41)
+    back = oracle.anamtransform(False, 3, oracle.anamtransform(True, 3, inside, tab), tab)
+    assert np.abs(back - inside).max() < 1e-12
+    # known answers: interior blend, the two extrapolation sides and the clamping quirk
+    assert oracle.interp1(xs, tab[:, 1], 0.3)[0] == 0.5 * tab[1, 1] + 0.5 * tab[2, 1]
+    assert oracle.interp1(xs, tab[:, 1], -3.0) == (tab[0, 1], True)
+    assert oracle.interp1(xs, tab[:, 1], 10.0) == (tab[-1, 1], True)       # xi = x(end) is outside: x(k) <= xi < x(k+1)
+    assert oracle.anamtransform(True, 3, [-3.0], tab)[0] == tab[0, 0]         # y(1) = -1 < x(1) = 0  -> x(1)
+    assert oracle.anamtransform(True, 3, [50.0], tab)[0] == tab[-1, 0]        # y(end) = 6.19 >= x(1) -> x(end)
+    assert (oracle.anamtransform(True, 2, [1.0, np.e], None) == np.log([1.0, np.e])).all()
