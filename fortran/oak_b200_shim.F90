@@ -39,6 +39,8 @@ module oak_b200
    integer(c_int64_t) :: h2d_bytes, d2h_bytes
    real(c_double)     :: ms_total, ms_pack, ms_gram, ms_eig, ms_apply
    integer(c_int64_t) :: launches
+   integer(c_int64_t) :: zones_fallback
+   real(c_double)     :: ms_tridiag, ms_tql, ms_tvec
  end type
 
  interface
@@ -65,6 +67,14 @@ module oak_b200
      type(c_ptr), value :: h
      integer(c_int32_t), value :: m
      real(c_double) :: obsx(*), obsy(*), obsz(*), obst(*)
+     integer(c_int) :: rc
+   end function
+   ! table of the tabulated anamorphosis (AnamTrans%anam(v)%transform, K x 2), used by oakb200_assim_ensemble
+   function oakb200_set_anamorphosis_table(h, K, table) bind(C, name='oakb200_set_anamorphosis_table') result(rc)
+     import
+     type(c_ptr), value :: h
+     integer(c_int32_t), value :: K
+     real(c_double) :: table(K,*)
      integer(c_int) :: rc
    end function
    function oakb200_local_analysis(h, n, N, m, xf, Hxf, yo, Sf, ldSf, HSf, ldHSf, Rdiag, d01, xa, Sa, ldSa, &
