@@ -268,19 +268,33 @@ def main():
     z_rank = sum(p["plan"].z1 - p["plan"].z0 for p in phases)
     Sa_full, peer, fused_note = None, None, None
     if fused:
-        # fused all-gather: every rank's apply kernel stores its rows into the result arrays of all ranks (NVLink)
+        # fused all-gather: every finished batch of this rank goes straight into the result arrays of all ranks
+        # (CUDA-IPC mappings over NVLink).  The set-up is collective: if ANY rank cannot map its peers, all ranks
+        # fall back together to the NCCL all-gather (same kernels otherwise), so nobody waits in a collective alone.
         from oak_b200.dist import PeerResult
+        err = None
         try:
             peer = PeerResult(dist, h, a.N, plan.n, rank, world, dev)
+            err = peer.failed
+        except Exception as e:
+            err, peer = str(e)[:80], None
+        okf = torch.tensor([0.0 if err else 1.0], device=dev)
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        if okf.item() == 1.0:
             Sp, xp = peer.destinations()
             for p in phases:
                 p["h"].set_option("peer_mode", a.peer_mode)
                 p["h"].set_peer_outputs(Sp, xp, plan.n, p["plan"].r0)
             Sa_full = peer.Sa
-        except Exception as e:   # no peer mapping on this box: the NCCL all-gather path (same kernels otherwise)
-            fused, peer, fused_note = False, None, "peer mapping failed (%s): NCCL all-gather" % (str(e)[:80],)
-            for p in phases:
-                p["h"].set_peer_outputs([], [], 0, 0)
+        else:
+            fused, fused_note = False, "peer mapping failed on some rank (%s): NCCL all-gather, single phase" % (err or "another rank",)
+            if peer is not None:
+                peer.Sa = peer.xa = None
+                peer.close_mappings()
+            dist.barrier()
+            if peer is not None:
+                peer.free()
+                peer = None
     if world > 1 and Sa_full is None:
         Sa_full = torch.empty((a.N, plan.n), dtype=torch.float64, device=dev)
 

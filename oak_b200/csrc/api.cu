@@ -200,7 +200,13 @@ struct ProfAcc { double gram = 0, eig = 0, apply = 0, tridiag = 0, tql = 0, tvec
 int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t rowbase, const double *xf,
               const double *Sf, int64_t ldS, double *xa, double *Sa, int64_t ldSa, int64_t *launches,
               ProfAcc *prof, bool use_peers = false) {
-  const int zb = batch_size(h, NP, h->nzones);
+  int zb = batch_size(h, NP, h->nzones);
+  if (h->zones_per_batch <= 0 && z1 - z0 > zb) {
+    // a chunk of the host path holds a little more than one batch: split it evenly instead of one full batch
+    // plus a tiny one (the tiny one would still pay the fixed latency of k_tql)
+    const int nb = (z1 - z0 + zb - 1) / zb;
+    zb = std::min(zb, (z1 - z0 + nb - 1) / nb);
+  }
   int rc;
   if ((rc = ensure_ws(h, s, NP, std::min(zb, z1 - z0)))) return rc;
   const ZoneGeom zg = h->geom();

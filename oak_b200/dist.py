@@ -157,18 +157,32 @@ class PeerResult:
         self.dist, self.handle, self.rank, self.world = dist, handle, rank, world
         self.N, self.n = int(N), int(n)
         nel = self.N * self.n + self.n
-        self.base, hd = handle.ipc_alloc(8 * nel)
+        self.base, hd, self.opened, self.bases = None, None, [], []
+        try:
+            import os
+            if os.environ.get("OAK_B200_TEST_PEER_FAIL") == str(rank):   # exercises the collective fall-back
+                raise RuntimeError("forced")
+            self.base, hd = handle.ipc_alloc(8 * nel)
+        except Exception:
+            hd = None
         handles = [None] * world
-        dist.all_gather_object(handles, hd)
-        self.opened = []
-        self.bases = []
-        for r in range(world):
-            if r == rank:
-                self.bases.append(self.base)
-            else:
-                ptr = handle.ipc_open(handles[r])
-                self.opened.append(ptr)
-                self.bases.append(ptr)
+        dist.all_gather_object(handles, hd)        # every rank takes part, also one whose allocation failed
+        if any(x is None for x in handles):
+            self.free()
+            raise RuntimeError("a rank could not allocate its result array")
+        self.failed = None       # set instead of raising once peers may have mapped this rank's array:
+        try:                      # the caller then tears everything down collectively (close_mappings, barrier, free)
+            for r in range(world):
+                if r == rank:
+                    self.bases.append(self.base)
+                else:
+                    ptr = handle.ipc_open(handles[r])
+                    self.opened.append(ptr)
+                    self.bases.append(ptr)
+        except Exception as e:
+            self.failed = str(e)[:80]
+            self.Sa = self.xa = None
+            return
 
         class _Raw:   # __cuda_array_interface__ view of the library's allocation
             def __init__(self, ptr, count):
@@ -188,11 +202,18 @@ class PeerResult:
         hence their stores into this rank's arrays, are complete."""
         self.dist.all_reduce(self._flag)
 
-    def close(self):
+    def close_mappings(self):
         for ptr in self.opened:
             self.handle.ipc_close(ptr)
         self.opened = []
+
+    def free(self):
         if self.base:
-            self.dist.barrier()   # nobody still maps it
             self.handle.ipc_free(self.base)
             self.base = None
+
+    def close(self):
+        """Collective: unmap the peers' arrays, wait until nobody maps this rank's any more, free it."""
+        self.close_mappings()
+        self.dist.barrier()
+        self.free()
