@@ -546,3 +546,15 @@ def test_assim_ensemble_tabulated_anamorphosis(ob, monotone):
                                          obs["var"], anamtype=3, inflation=1.02, anamtable=tab)
     assert ((E < xs[0]).any() and (E > xs[-1]).any())      # the clamping rule is exercised
     assert rel(xf, xfo) < 1e-14 and rel(xa, xao) < RTOL and rel(Ea, Eo) < RTOL
+
+
+@pytest.mark.parametrize("N", [2, 3, 5, 9, 33, 63])
+def test_tiny_and_odd_ensemble_sizes(ob, N):
+    """N = 2 (no Householder step at all), 3 (one), odd sizes and sizes just above / below the padded widths"""
+    from oak_b200 import synthetic
+    c = synthetic.small_case(nx=10, ny=8, nz=2, N=N, m=120, corr=3000.0, maxlen=6000.0, seed=N)
+    with ob.Handle(0) as h:
+        _configure(ob, h, c)
+        xa, Sa, _, st = h.local_analysis(c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], ob.DiagCovar(c["var"]))
+    xo, So, _, mloc = _oracle_loc(c)
+    assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL, (rel(xa, xo), rel(Sa, So), st["zones_fallback"])
