@@ -466,6 +466,16 @@ def main():
                 return tot
 
             e2e_step()  # warm-up
+            if os.environ.get("OAK_B200_CHUNK_MB"):   # experiment: chunk size of the host-streaming path
+                for cm in os.environ["OAK_B200_CHUNK_MB"].split(","):
+                    for p in phases:
+                        p["h"].set_option("chunk_mb", float(cm))
+                    e2e_step()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    e2e_step(); e2e_step()
+                    torch.cuda.synchronize()
+                    print("chunk_mb", cm, "e2e columns/s %.0f" % (nzones / ((time.perf_counter() - t0) / 2)), file=sys.stderr, flush=True)
             barrier()
             t0 = time.perf_counter()
             for _ in range(a.e2e_steps):
