@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
     if (!t_ready) { mbar_wait(&bar, 0); t_ready = true; }
 
     double acc[4][2 * CB];
+    double dm[4] = {0., 0., 0., 0.};  // Sf(rows,:) . ampl for the thread's 4 rows (the mean update rides along)
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -122,6 +123,9 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
       const double2 s01 = *reinterpret_cast<const double2 *>(sS + k * LDS + 4 * ty);
       const double2 s23 = *reinterpret_cast<const double2 *>(sS + k * LDS + 4 * ty + 2);
       const double sv[4] = {s01.x, s01.y, s23.x, s23.y};
+      const double ak = s_ampl[k];
+#pragma unroll
+      for (int a = 0; a < 4; a++) dm[a] = fma(sv[a], ak, dm[a]);
 #pragma unroll
       for (int b = 0; b < CB; b++) {
         const double2 t = *reinterpret_cast<const double2 *>(sT + k * NP + 2 * tx + 32 * b);
@@ -132,13 +136,17 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
         }
       }
     }
-    // mean update for the chunk: one thread per row
-    if (tid < rc) {
-      double d = 0.;
-      for (int k = 0; k < N; k++) d = fma(sS[k * LDS + tid], s_ampl[k], d);
-      const double v = xf[i1 + r0 + tid] + d;
-      xa[i1 + r0 + tid] = v;
-      for (int dd = 0; dd < P.n; dd++) P.xa[dd][ip + r0 + tid] = v;
+    // mean update for the chunk: the threads of column group 0 own 4 rows each
+    if (tx == 0) {
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const int r = 4 * ty + a;
+        if (r < rc) {
+          const double v = xf[i1 + r0 + r] + dm[a];
+          xa[i1 + r0 + r] = v;
+          for (int dd = 0; dd < P.n; dd++) P.xa[dd][ip + r0 + r] = v;
+        }
+      }
     }
     __syncthreads();  // all reads of sS done: reuse it to transpose the results for coalesced stores
 #pragma unroll

@@ -26,7 +26,7 @@
 #include "tridiag_math.cuh"
 
 #ifndef TRI_MINB
-#define TRI_MINB 1   // CTAs per SM requested from the compiler for k_tridiag / k_tvec (register cap)
+#define TRI_MINB 5   // CTAs per SM requested from the compiler for k_tridiag(_tile) (register cap 204: 8.24 -> 7.52 ms per 90 k zones)
 #endif
 #ifndef TRI_TILE
 #define TRI_TILE 1   // 1 = k_tridiag_tile (8 x 8 cyclic register tiles), 0 = k_tridiag (row per thread)
