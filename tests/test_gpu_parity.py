@@ -558,3 +558,21 @@ def test_tiny_and_odd_ensemble_sizes(ob, N):
         xa, Sa, _, st = h.local_analysis(c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], ob.DiagCovar(c["var"]))
     xo, So, _, mloc = _oracle_loc(c)
     assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL, (rel(xa, xo), rel(Sa, So), st["zones_fallback"])
+
+
+def test_committed_golden_fixture(ob, handle):
+    """the CUDA path against tests/golden/rrsqrt_known_answers.npz (closed-form known answers of
+    test/test_rrsqrt.F90 + the oracle's Sa for the Gaspari-Cohn local case; tools/make_golden.py)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rrsqrt_known_answers.npz"))
+    c = rrsqrt_case()
+    zs = [1] * c["n"]
+    xa, Sa, _ = ob.locanalysis(zs, _sel(ob, c, zs, 1, c["length"], 1e30), c["xf"], c["Hxf"], c["y"], c["Sf"],
+                               c["HSf"], ob.DiagCovar(c["var"]), handle=handle)
+    assert np.abs(xa - g["xa_gc_local"]).max() < TOL_REF
+    assert rel(xa, g["xa_gc_local_oracle"]) < RTOL and rel(Sa, g["Sa_gc_local_oracle"]) < RTOL
+    zs = [c["n"]]
+    xa, Sa, _ = ob.locanalysis(zs, _sel(ob, c, zs, 2, 1.0, 1e30), c["xf"], c["Hxf"], c["y"], c["Sf"],
+                               c["HSf"], ob.DiagCovar(c["var"]), handle=handle)
+    assert np.abs(xa - g["xa_global"]).max() < TOL_REF and np.abs(Sa @ Sa.T - g["Pa_global"]).max() < TOL_REF
+    assert rel(Sa, g["Sa_global_oracle"]) < RTOL

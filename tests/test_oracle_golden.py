@@ -197,3 +197,22 @@ def test_tabulated_anamorphosis_interp1_and_clamping_rule():
     assert oracle.anamtransform(True, 3, [-3.0], tab)[0] == tab[0, 0]         # y(1) = -1 < x(1) = 0  -> x(1)
     assert oracle.anamtransform(True, 3, [50.0], tab)[0] == tab[-1, 0]        # y(end) = 6.19 >= x(1) -> x(end)
     assert (oracle.anamtransform(True, 2, [1.0, np.e], None) == np.log([1.0, np.e])).all()
+
+
+def test_committed_golden_fixture_matches_oracle_and_known_answers():
+    """tests/golden/rrsqrt_known_answers.npz (tools/make_golden.py): the reference's closed-form known answers
+    for test/test_rrsqrt.F90 and the oracle's Sa for the local case"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rrsqrt_known_answers.npz"))
+    c = rrsqrt_case()
+    n, m = c["n"], c["m"]
+    xa_k, Pa_k = kalman_check(c["xf"], c["Sf"], c["H"], c["y"], np.diag(c["var"]))
+    assert np.abs(xa_k - g["xa_global"]).max() < 1e-13 and np.abs(Pa_k - g["Pa_global"]).max() < 1e-13
+    xg, Sg, _ = oracle.analysis(c["xf"], c["Hxf"], c["y"], c["Sf"], c["HSf"], c["var"])
+    assert np.abs(xg - g["xa_global"]).max() < 1e-8 and np.abs(Sg @ Sg.T - g["Pa_global"]).max() < 1e-8
+    obs = oracle.make_obs(m, obsx=c["xobs"], obsy=np.zeros(m), weightfun=1)
+    xo, So, _, mloc = oracle.loc_analysis([1] * n, dict(x=c["xmod"], y=np.zeros(n)), c["length"], 1e30, obs,
+                                          c["xf"], c["Hxf"], c["y"], c["Sf"], c["HSf"], c["var"])
+    assert np.abs(xo - g["xa_gc_local"]).max() < 1e-8          # tolerance of test/test_rrsqrt.F90:20
+    assert (mloc == g["mloc_gc_local"]).all()
+    assert np.abs(So - g["Sa_gc_local_oracle"]).max() < 1e-12 and np.abs(xo - g["xa_gc_local_oracle"]).max() < 1e-12
