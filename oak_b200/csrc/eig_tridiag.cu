@@ -34,6 +34,9 @@
 #ifndef TQL_PWK
 #define TQL_PWK 1    // k_tql: 1 = square-root-free QL (Pal-Walker-Kahan), 0 = plain implicit QL
 #endif
+#ifndef TVEC_TWISTED2
+#define TVEC_TWISTED2 0   // 1: twisted_vector2 (interleaved pivot recurrences, stored reciprocals) - prepared, host-tested,
+#endif                    //    not yet measured on the GPU
 #ifndef TVEC_MINB
 #define TVEC_MINB 1
 #endif
@@ -574,10 +577,15 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
   if (live) {
     const double pivmin = tn * 1e-150;
     double gam;
-    double zz = twisted_vector(N, sd, se, 1, lam, pivmin, W + j, LDW, &gam);
+#if TVEC_TWISTED2
+#define OAK_TWISTED twisted_vector2
+#else
+#define OAK_TWISTED twisted_vector
+#endif
+    double zz = OAK_TWISTED(N, sd, se, 1, lam, pivmin, W + j, LDW, &gam);
     if (!(fabs(gam) <= TRI_RESTOL * tn * sqrt(zz)) || !(zz < 1e300)) {  // one Rayleigh-quotient correction, then give up
       const double lam2 = lam + gam / zz;
-      zz = twisted_vector(N, sd, se, 1, lam2, pivmin, W + j, LDW, &gam);
+      zz = OAK_TWISTED(N, sd, se, 1, lam2, pivmin, W + j, LDW, &gam);
       if (!(fabs(gam) <= TRI_RESTOL * tn * sqrt(zz)) || !(zz < 1e300)) bad = true;
     }
     const double sc_ = rsqrt(zz);

@@ -234,3 +234,116 @@ OAK_HD double twisted_vector(int n, const double *d, const double *e, int sd, do
   *gam = gbest;
   return zz;
 }
+
+// twisted_vector2 — the same vector with about a third of the dependent reciprocal chain (prepared for k_tvec,
+// -DTVEC_TWISTED2=1; checked on the host against twisted_vector, tests/test_tridiag_host.py).
+//   phase 1  forward pivots p_0..p_{h-1} and backward pivots q_{n-1}..q_h run in ONE loop (two independent chains);
+//            their RECIPROCALS are stored in w (forward ones below h = n/2, backward ones from h up)
+//   phase 2  both recurrences continue into the other half, where the stored reciprocals give gamma_i on the fly
+//            (gamma_i = p_i - e_i^2 / q_{i+1} = q_i - e_{i-1}^2 / p_{i-1}); nothing is stored; r = argmin |gamma_i|
+//   phase 3  the |r - h| reciprocals still missing on the far side of the twist are recomputed from the pivot
+//            saved at the crossing
+//   phase 4  z_{i-1} = -e_{i-1} z_i (1/p_{i-1}) upwards and z_{i+1} = -e_i z_i (1/q_{i+1}) downwards: one
+//            dependent multiplication per step, the two directions interleaved
+// Chain: n/2 + n/2 + |r-h| reciprocal steps (two chains wide in phases 1-2) instead of 2n + (n-r) + n.
+OAK_HD double twisted_vector2(int n, const double *d, const double *e, int sd, double lam, double pivmin,
+                              double *w, int sw, double *gam) {
+  if (n == 1) { w[0] = 1.; *gam = d[0] - lam; return 1.; }
+  const int h = n / 2;  // forward reciprocals live in w[0..h), backward ones in w[h..n)
+  // ---- phase 1 ----
+  double p = d[0] - lam, q = d[(n - 1) * sd] - lam;
+  {
+    int i = 0, j = n - 1;
+    while (i < h || j >= h) {
+      if (i < h) {
+        if (fabs(p) < pivmin) p = -pivmin;
+        const double ip = oak_rcp(p);
+        w[i * sw] = ip;
+        const double ei = e[i * sd];
+        p = fma(-ei * ei, ip, d[(i + 1) * sd] - lam);  // p_{i+1}; i+1 <= h <= n-1
+        i++;
+      }
+      if (j >= h) {
+        if (fabs(q) < pivmin) q = -pivmin;
+        const double iq = oak_rcp(q);
+        w[j * sw] = iq;
+        if (j > 0) {
+          const double ej = e[(j - 1) * sd];
+          q = fma(-ej * ej, iq, d[(j - 1) * sd] - lam);  // q_{j-1}
+        }
+        j--;
+      }
+    }
+  }
+  const double p_h = p, q_hm1 = q;  // p_h and q_{h-1} (q_{h-1} only meaningful for h >= 1, true for n >= 2)
+  // ---- phase 2 ----
+  double best = 1e300, gbest = 0.;
+  int r = 0;
+  {
+    int i = h, j = h - 1;
+    while (i < n || j >= 0) {
+      if (i < n) {
+        if (fabs(p) < pivmin) p = -pivmin;
+        double gm = p;
+        if (i < n - 1) {
+          const double ei = e[i * sd];
+          gm = fma(-ei * ei, w[(i + 1) * sw], p);          // gamma_i = p_i - e_i^2 / q_{i+1}
+          p = fma(-ei * ei, oak_rcp(p), d[(i + 1) * sd] - lam);
+        }
+        if (fabs(gm) < best) { best = fabs(gm); gbest = gm; r = i; }
+        i++;
+      }
+      if (j >= 0) {
+        if (fabs(q) < pivmin) q = -pivmin;
+        double gm = q;
+        if (j > 0) {
+          const double ej = e[(j - 1) * sd];
+          gm = fma(-ej * ej, w[(j - 1) * sw], q);          // gamma_j = q_j - e_{j-1}^2 / p_{j-1}
+          q = fma(-ej * ej, oak_rcp(q), d[(j - 1) * sd] - lam);
+        }
+        if (fabs(gm) < best) { best = fabs(gm); gbest = gm; r = j; }
+        j--;
+      }
+    }
+  }
+  // ---- phase 3 ----
+  if (r >= h) {           // forward reciprocals for h <= i < r
+    p = p_h;
+    for (int i = h; i < r; i++) {
+      if (fabs(p) < pivmin) p = -pivmin;
+      const double ip = oak_rcp(p);
+      w[i * sw] = ip;
+      const double ei = e[i * sd];
+      p = fma(-ei * ei, ip, d[(i + 1) * sd] - lam);
+    }
+  } else {                // backward reciprocals for r < j <= h-1
+    q = q_hm1;
+    for (int j = h - 1; j > r; j--) {
+      if (fabs(q) < pivmin) q = -pivmin;
+      const double iq = oak_rcp(q);
+      w[j * sw] = iq;
+      const double ej = e[(j - 1) * sd];
+      q = fma(-ej * ej, iq, d[(j - 1) * sd] - lam);
+    }
+  }
+  // ---- phase 4 ----
+  double zz = 1., zu = 1., zd = 1.;
+  int iu = r, id = r;
+  while (iu > 0 || id < n - 1) {
+    if (iu > 0) {
+      zu = -e[(iu - 1) * sd] * w[(iu - 1) * sw] * zu;
+      w[(iu - 1) * sw] = zu;
+      zz = fma(zu, zu, zz);
+      iu--;
+    }
+    if (id < n - 1) {
+      zd = -e[id * sd] * w[(id + 1) * sw] * zd;
+      w[(id + 1) * sw] = zd;
+      zz = fma(zd, zd, zz);
+      id++;
+    }
+  }
+  w[r * sw] = 1.;
+  *gam = gbest;
+  return zz;
+}

@@ -23,9 +23,9 @@ def hostlib(tmp_path_factory):
     dp = ctypes.POINTER(ctypes.c_double)
     for f in (lib.host_tql, lib.host_pwk):
         f.argtypes = [ctypes.c_int, dp, dp, ctypes.c_int, ctypes.c_double]
-    lib.host_twisted.restype = ctypes.c_double
-    lib.host_twisted.argtypes = [ctypes.c_int, dp, dp, ctypes.c_int, ctypes.c_double, ctypes.c_double, dp,
-                                 ctypes.c_int, dp]
+    for f in (lib.host_twisted, lib.host_twisted2):
+        f.restype = ctypes.c_double
+        f.argtypes = [ctypes.c_int, dp, dp, ctypes.c_int, ctypes.c_double, ctypes.c_double, dp, ctypes.c_int, dp]
     return lib
 
 
@@ -100,3 +100,29 @@ def test_numpy_prototype_of_the_route(hostlib, monkeypatch):
         Mr = p.ref_M(G)
         worst = max(worst, np.abs(M - Mr).max() / np.abs(Mr).max())
     assert worst < 1e-11
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 16, 33, 64])
+def test_twisted_vector2_equals_twisted_vector(hostlib, n):
+    """the variant with interleaved pivot recurrences and stored reciprocals (prepared for k_tvec,
+    -DTVEC_TWISTED2=1) gives the same vectors and residuals"""
+    dp = ctypes.POINTER(ctypes.c_double)
+    if n == 1:
+        d, e = np.array([2.5]), np.zeros(0)
+    else:
+        d, e, _ = _tridiag(n, 31 + n)
+    T = np.diag(d) + (np.diag(e, 1) + np.diag(e, -1) if n > 1 else 0.0)
+    lam = np.linalg.eigvalsh(T)
+    tn = max(np.abs(d).max(), np.abs(e).max() if n > 1 else 0.0)
+    eb = np.ascontiguousarray(np.concatenate([e, [0.0]]))
+    for j in range(n):
+        out = []
+        for f in (hostlib.host_twisted, hostlib.host_twisted2):
+            w = np.zeros(n * 2); gam = ctypes.c_double()
+            zz = f(n, np.ascontiguousarray(d).ctypes.data_as(dp), eb.ctypes.data_as(dp), 1, lam[j], tn * 1e-150,
+                   w.ctypes.data_as(dp), 2, ctypes.byref(gam))
+            out.append((w[::2] / np.sqrt(zz), abs(gam.value) / np.sqrt(zz)))
+        (z1, r1), (z2, r2) = out
+        assert r2 <= 1e-13 * tn and np.abs(T @ z2 - lam[j] * z2).max() <= 1e-13 * tn
+        gapj = min([abs(lam[j] - lam[k]) for k in range(n) if k != j] + [tn]) / tn
+        assert min(np.abs(z1 - z2).max(), np.abs(z1 + z2).max()) <= 1e-13 / max(gapj, 1e-12)

@@ -7,3 +7,7 @@ extern "C" double host_twisted(int n, const double *d, const double *e, int sd, 
   return twisted_vector(n, d, e, sd, lam, pivmin, w, sw, gam);
 }
 extern "C" int host_pwk(int n, double *d, double *e, int s, double tn) { return pwk_eigenvalues(n, d, e, s, tn); }
+extern "C" double host_twisted2(int n, const double *d, const double *e, int sd, double lam, double pivmin,
+                                double *w, int sw, double *gam) {
+  return twisted_vector2(n, d, e, sd, lam, pivmin, w, sw, gam);
+}
