@@ -67,9 +67,19 @@ OAKB200_API int oakb200_version(void);
 OAKB200_API int oakb200_create(int device, oakb200_handle **h);
 OAKB200_API int oakb200_destroy(oakb200_handle *h);
 
-/* Options (all optional): "eig_kernel" 4 = Householder tridiagonalisation + QL + twisted factorisation
- * (default for N <= 64; flagged zones fall back to 0), 0 = register-resident block Jacobi, 1 = simple
- * shared-memory Jacobi (cross-check); "zones_per_batch"; "jacobi_tol"; "max_sweeps"; "profile". */
+/* Options (all optional; a key the library does not know is an error):
+ *   "eig_kernel"      4 = Householder tridiagonalisation + QL + twisted factorisation (default for N <= 64;
+ *                     flagged zones fall back to 0), 0 = register-resident block Jacobi (N > 64), 1 = simple
+ *                     shared-memory Jacobi (cross-check), 2 / 3 = measured variants of 0
+ *   "tri_orthtol"     route 4: accepted loss of orthogonality between neighbouring eigenvectors (default 1e-11)
+ *   "tri_maxgroup"    route 4: largest group of close eigenvalues orthogonalised in place (default 6; 0 sends
+ *                     every zone with a close pair to the Jacobi kernel)
+ *   "jacobi_tol", "max_sweeps", "fixed_sweeps"   stopping rule of the Jacobi kernels
+ *   "zones_per_batch" zones per kernel batch (default: from the workspace budget), "pad_to" padded ensemble size
+ *   "chunk_mb"        host-buffer entry points: size of the state chunks streamed through the device (256)
+ *   "profile"         1: batches serialised, CUDA-event time per kernel family in the statistics
+ *   "async", "order_after_caller", "stream_priority"   see oakb200_synchronize
+ *   "peer_mode"       see oakb200_set_peer_outputs: 1 copy engines (default), 0 stores of the apply kernel */
 OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key, double value);
 
 /* Zones = the partition of the (zone-permuted) state vector (assimilation.F90:578-641).
