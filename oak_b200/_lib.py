@@ -75,6 +75,10 @@ def lib():
             f"{LIB_PATH} is missing: build it with `python -m oak_b200.build` (needs nvcc). "
             "oak_b200 has no CPU fallback.")
     L = C.CDLL(LIB_PATH)
+    if hasattr(L, "oakb200_emulated") and os.environ.get("OAK_B200_TEST_EMU") != "1":
+        raise RuntimeError(
+            f"{LIB_PATH} is the CPU emulation build of the kernels (tools/cuemu, a test harness); it is never a "
+            "product library: oak_b200 has no CPU fallback.")
     for name, (res, args) in SIGNATURES.items():
         f = getattr(L, name)  # AttributeError if the symbol is not exported
         f.restype = res

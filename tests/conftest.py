@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "needs_torch_cuda: GPU test that also needs torch.cuda (device tensors, NCCL)")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -19,6 +20,14 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         has_gpu = False
     if has_gpu:
+        return
+    if os.environ.get("OAK_B200_TEST_EMU") == "1":
+        # tests/test_emulated_kernels.py re-runs GPU parity tests against the CPU emulation build of the kernel
+        # sources (tools/cuemu) in a subprocess with this variable set: only tests needing torch.cuda stay skipped
+        skip_cuda = pytest.mark.skip(reason="needs torch.cuda (not available in the CPU emulation of the kernels)")
+        for it in items:
+            if "needs_torch_cuda" in it.keywords:
+                it.add_marker(skip_cuda)
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for it in items:

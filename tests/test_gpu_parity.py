@@ -250,6 +250,7 @@ def test_edge_cases_empty_zones_all_relevant_excluded_obs_ragged_zones(ob, handl
     assert (xa0 == c["xf"]).all() and (Sa0 == c["Sf"]).all() and st0["zones_skipped"] == zs.size
 
 
+@pytest.mark.needs_torch_cuda
 def test_in_place_chunked_and_device_resident_paths_agree(ob):
     import torch
     from oak_b200 import synthetic
@@ -475,6 +476,7 @@ def test_degenerate_spectrum_falls_back_to_jacobi(ob, N):
         assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL, (rel(xa, xo), rel(Sa, So))
 
 
+@pytest.mark.needs_torch_cuda
 def test_fused_gather_peer_outputs_receive_the_slab(ob):
     """oakb200_set_peer_outputs: the apply kernel stores this rank's rows (analysed and untouched zones) into
     every destination array at row0 (here two arrays on the same device, allocated through oakb200_ipc_alloc;
