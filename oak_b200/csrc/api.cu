@@ -88,6 +88,7 @@ struct oakb200_handle {
   int device = 0;
   // options
   int eig_kernel = 4;
+  int gram_kernel = 0;        // 0: k_gram (DFMA register tiles); 1 / 2: k_gram_mma (DMMA, 4 / 2 warps per zone; NP = 64)
   double tri_orthtol = 0.;  // tridiagonal route: accepted loss of orthogonality between neighbouring eigenvectors (0: default)
   int tri_maxgroup = -1;
   DevBuf d_anam;              // tabulated anamorphosis (K x 2), oakb200_set_anamorphosis_table
@@ -220,7 +221,11 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
   for (int b0 = z0; b0 < z1; b0 += zb) {
     const int nz = std::min(zb, z1 - b0);
     if (prof) CUDA_TRY(cudaEventRecord(s.ev[0], s.st));
-    if ((rc = oak_launch_gram(s.st, NP, zg, h->og, orows, b0, nz, s.G.as<double>(), s.c.as<double>(), mloc, ctr))) return rc;
+    if (h->gram_kernel > 0 && NP == 64)
+      rc = oak_launch_gram_mma(s.st, h->gram_kernel, NP, zg, h->og, orows, b0, nz, s.G.as<double>(), s.c.as<double>(), mloc, ctr);
+    else
+      rc = oak_launch_gram(s.st, NP, zg, h->og, orows, b0, nz, s.G.as<double>(), s.c.as<double>(), mloc, ctr);
+    if (rc) return rc;
     if (prof) CUDA_TRY(cudaEventRecord(s.ev[1], s.st));
     if (h->eig_kernel == 4 && NP <= 64) {
       // tridiagonal route; the zones it flags (close eigenvalue groups it could not orthogonalise, ...) are
@@ -476,6 +481,10 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   if (!h || !key) { oak_set_error("null argument"); return OAK_ERR_ARG; }
   const std::string k(key);
   if (k == "eig_kernel") h->eig_kernel = (int)value;
+  else if (k == "gram_kernel") {
+    if (value != 0. && value != 1. && value != 2.) { oak_set_error("gram_kernel = %g (expected 0, 1 or 2)", value); return OAK_ERR_ARG; }
+    h->gram_kernel = (int)value;
+  }
   else if (k == "tri_orthtol") h->tri_orthtol = value;
   else if (k == "tri_maxgroup") h->tri_maxgroup = (int)value;
   else if (k == "peer_mode") h->peer_mode = (int)value;

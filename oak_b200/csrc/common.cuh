@@ -290,6 +290,9 @@ int oak_launch_select(cudaStream_t st, const ZoneGeom &zg, const ObsGrid &og, in
                       const int64_t *offsets, int32_t *counts, int32_t *idx, double *w, bool fill);
 int oak_launch_gram(cudaStream_t st, int NP, const ZoneGeom &zg, const ObsGrid &og, const ObsRows &orows,
                     int zone0, int nz, double *G, double *c, int32_t *mloc, DevCounters *ctr);
+int oak_launch_gram_mma(cudaStream_t st, int variant, int NP, const ZoneGeom &zg, const ObsGrid &og,
+                        const ObsRows &orows, int zone0, int nz, double *G, double *c, int32_t *mloc,
+                        DevCounters *ctr);
 int oak_launch_eig(cudaStream_t st, int kernel, int N, int NP, int zone0, int nz, const int32_t *mloc,
                    const double *G, const double *c, double *T, double *ampl, double tol, int max_sweeps,
                    DevCounters *ctr);

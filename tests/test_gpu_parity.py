@@ -209,6 +209,26 @@ def test_local_analysis_matches_oracle(ob, handle, N, m, nx, ny, nz):
     assert np.abs(Sa.sum(axis=1)).max() < 1e-12 * max(1.0, np.abs(Sa).max()) * N
 
 
+@pytest.mark.parametrize("variant", [1, 2], ids=["mma_4warps", "mma_2warps"])
+@pytest.mark.parametrize("N,m,maxlen", [(64, 900, 6000.0), (40, 700, 9000.0), (64, 60, 4000.0)])
+def test_gram_tensor_core_variants_match_the_register_tile_kernel(ob, variant, N, m, maxlen):
+    # option gram_kernel = 1 / 2: G and c accumulated by mma.m8n8k4.f64 on the lower 8 x 8 tiles (gram_mma.cu).
+    # Segments of every length 0..32 occur (k-steps of 4 rows padded with coef = 0), several chunks per zone at
+    # the larger radius, zones without observations at the smaller one; N = 40 exercises the zero padding to 64.
+    from oak_b200 import synthetic
+    c = synthetic.small_case(nx=14, ny=12, nz=3, N=N, m=m, corr=maxlen / 2, maxlen=maxlen, seed=11 * N + m)
+    xo, So, _, mloc = _oracle_loc(c)
+    out = {}
+    for gk in (0, variant):
+        with ob.Handle(0, gram_kernel=gk, pad_to=64) as h:
+            _configure(ob, h, c)
+            xa, Sa, _, st = h.local_analysis(c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], ob.DiagCovar(c["var"]))
+        assert st["obs_relevant_sum"] == mloc.sum() and st["zones_skipped"] == (mloc == 0).sum()
+        assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL, (gk, rel(xa, xo), rel(Sa, So))
+        out[gk] = (xa, Sa)
+    assert rel(out[variant][0], out[0][0]) < 1e-11 and rel(out[variant][1], out[0][1]) < 1e-11
+
+
 def test_edge_cases_empty_zones_all_relevant_excluded_obs_ragged_zones(ob, handle):
     from oak_b200 import synthetic
     c = synthetic.small_case(nx=30, ny=10, nz=4, N=24, m=200, corr=2500.0, maxlen=5000.0, seed=3)
