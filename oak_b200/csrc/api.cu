@@ -88,6 +88,7 @@ struct oakb200_handle {
   int device = 0;
   // options
   int eig_kernel = 4;
+  int fuse_apply = 0;         // 1: tridiagonal route, k_tvec updates the zone rows from the factored transform (no T, no k_apply)
   int gram_kernel = 0;        // 0: k_gram (DFMA register tiles); 1 / 2: k_gram_mma (DMMA, 4 / 2 warps per zone; NP = 64)
   double tri_orthtol = 0.;  // tridiagonal route: accepted loss of orthogonality between neighbouring eigenvectors (0: default)
   int tri_maxgroup = -1;
@@ -227,13 +228,19 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
       rc = oak_launch_gram(s.st, NP, zg, h->og, orows, b0, nz, s.G.as<double>(), s.c.as<double>(), mloc, ctr);
     if (rc) return rc;
     if (prof) CUDA_TRY(cudaEventRecord(s.ev[1], s.st));
+    const int32_t *only_flagged = nullptr;
     if (h->eig_kernel == 4 && NP <= 64) {
       // tridiagonal route; the zones it flags (close eigenvalue groups it could not orthogonalise, ...) are
       // recomputed by the Jacobi kernel, which skips the zones whose flag is 0
       int32_t *flags = nullptr;
+      // fused apply: not with the store flavour of the fused all-gather (k_apply is the kernel that stores to the peers)
+      const bool fuse = h->fuse_apply && !(use_peers && h->peer_mode == 0);
+      const FusedApplyArgs fa{zg.zstart + b0, rowbase, xf, Sf, xa, Sa, ldS, ldSa};
       if ((rc = oak_launch_eig_tridiag(s.st, N, NP, nz, mloc + b0, s.G.as<double>(), s.c.as<double>(),
                                        s.T.as<double>(), s.ampl.as<double>(), s.tri.p, &flags, ctr,
-                                       prof ? &s.ev[8] : nullptr, h->tri_orthtol, h->tri_maxgroup))) return rc;
+                                       prof ? &s.ev[8] : nullptr, h->tri_orthtol, h->tri_maxgroup,
+                                       fuse ? &fa : nullptr))) return rc;
+      if (fuse) only_flagged = flags;
       if (prof) CUDA_TRY(cudaEventRecord(s.ev[10], s.st));
       if ((rc = oak_launch_eig(s.st, 0, N, NP, 0, nz, flags, s.G.as<double>(), s.c.as<double>(),
                                s.T.as<double>(), s.ampl.as<double>(), h->tol, h->max_sweeps, ctr))) return rc;
@@ -244,7 +251,8 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
     if (prof) CUDA_TRY(cudaEventRecord(s.ev[2], s.st));
     PeerOut none{};
     if ((rc = oak_launch_apply(s.st, N, NP, zg, b0, nz, rowbase, mloc, s.T.as<double>(), s.ampl.as<double>(), xf,
-                               Sf, ldS, xa, Sa, ldSa, (use_peers && h->peer_mode == 0) ? h->peers : none))) return rc;
+                               Sf, ldS, xa, Sa, ldSa, (use_peers && h->peer_mode == 0) ? h->peers : none,
+                               only_flagged))) return rc;
     if (use_peers && h->peer_mode == 1) {
       // fused all-gather, copy-engine flavour: as soon as the batch is applied its rows go to every peer's
       // array (strided 2-D peer copies over NVLink, no SM involved), overlapping the kernels of the next batches
@@ -481,6 +489,7 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   if (!h || !key) { oak_set_error("null argument"); return OAK_ERR_ARG; }
   const std::string k(key);
   if (k == "eig_kernel") h->eig_kernel = (int)value;
+  else if (k == "fuse_apply") h->fuse_apply = value != 0.;
   else if (k == "gram_kernel") {
     if (value != 0. && value != 1. && value != 2.) { oak_set_error("gram_kernel = %g (expected 0, 1 or 2)", value); return OAK_ERR_ARG; }
     h->gram_kernel = (int)value;

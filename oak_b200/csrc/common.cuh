@@ -274,6 +274,15 @@ struct PeerOut {
   int32_t n;
 };
 
+// state arrays of the batch for the apply fused into the transform kernel (option "fuse_apply")
+struct FusedApplyArgs {
+  const int64_t *zstart;   // prefix sums of the zone sizes, offset to the first zone of the batch
+  int64_t rowbase;         // global row of the first row held in xf / Sf / xa / Sa
+  const double *xf, *Sf;
+  double *xa, *Sa;
+  int64_t ldS, ldSa;
+};
+
 struct DevCounters {      // device-side statistics / status
   unsigned long long relevant, candidates, sweeps, skipped;
   int nan_flag;
@@ -300,11 +309,13 @@ size_t oak_eig_tridiag_ws_bytes(int NP, int nz);
 int oak_launch_eig_tridiag(cudaStream_t st, int N, int NP, int nz, const int32_t *mloc, const double *G,
                            const double *c, double *T, double *ampl, void *ws, int32_t **flags_out,
                            DevCounters *ctr, cudaEvent_t *ev /* optional: [0] after k_tridiag, [1] after k_tql */,
-                           double orthtol /* <= 0: default */, int maxgroup /* < 0: default */);
+                           double orthtol /* <= 0: default */, int maxgroup /* < 0: default */,
+                           const FusedApplyArgs *fuse /* NULL: k_tvec writes T */);
 int oak_launch_apply(cudaStream_t st, int N, int NP, const ZoneGeom &zg, int zone0, int nz,
                      int64_t rowbase, const int32_t *mloc, const double *T, const double *ampl,
                      const double *xf, const double *Sf, int64_t ldS, double *xa, double *Sa,
-                     int64_t ldSa, const PeerOut &peers);
+                     int64_t ldSa, const PeerOut &peers,
+                     const int32_t *only_flagged = nullptr /* batch-local flags: analysed zones with flag 0 are skipped */);
 int oak_fp64_peak(int mode, double *tflops);
 
 // ensemble prologue / epilogue (assimilation.F90:3106-3134, :3301-3357)

@@ -529,14 +529,107 @@ struct BackTile {
   }
 };
 
+
+// ---------------------------------------------------------------------------------------------------
+// Fused apply (option "fuse_apply"): the zone's rows are updated by k_tvec itself from the FACTORED transform,
+//     Sa_z = ((Sf_z - (Sf_z Y) Y^T) - a1 u_v^T) D - a2 u_w^T ,  a1 = Sf_z g1 hv, a2 = Sf_z g2 hw ,  xa_z = xf_z + Sf_z ampl
+// (the rows of T = (M - g1 hv u_v^T) D - g2 hw u_w^T, M = I - Y Y^T, are never formed).  For a zone of nr rows
+// that is 4 nr N^2 flops instead of 2 N^3 + 2 nr N^2, no 8 N^2-byte round trip of T through HBM and no k_apply
+// launch; it pays while nr < N (water columns: 30 rows, N = 64).  Both products run on the fp64 tensor cores
+// (mma.m8n8k4): per chunk of 8 rows, P = S Y (A = S chunk, B = Y^T read from the transposed store Yt) with one
+// extra tile whose B columns are (g1 hv, g2 hw, ampl), then Q = P Y^T.  Row strides of NP + 4 doubles make every
+// fragment load conflict-free.  The chunk is staged completely before its results are stored: Sa may alias Sf.
+// ---------------------------------------------------------------------------------------------------
 template <int NP>
+struct FusedApply {
+  static constexpr int NW = NP / 32, NB = NP / 8, LD = NP + 4, RC = 8, TPW = NB / NW;
+  static constexpr int SMEM_DOUBLES = 2 * RC * LD + 3 * RC;  // sS, sP, per-row sums
+  static_assert(RC == 8, "row index = idx & 7");
+
+  static __device__ __forceinline__ void run(int N, int tid, const double *Yt /* [NP][LD] */, double *sS, double *sP,
+                                             double *s_row, const double *s_g1h, const double *s_g2h,
+                                             const double *s_amp, const double *suv, const double *suw, double dNN,
+                                             int64_t i1, int nrow, const double *__restrict__ xf, const double *Sf,
+                                             int64_t ldS, double *__restrict__ xa, double *Sa, int64_t ldSa) {
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int NK = (N + 3) & ~3;  // members >= N are zero in S, Y and P
+    for (int r0 = 0; r0 < nrow; r0 += RC) {
+      const int rc = min(RC, nrow - r0);
+      // stage S[r][k] = Sf(i1 + r0 + r, k), zero padded
+      for (int idx = tid; idx < RC * NP; idx += NP) {
+        const int r = idx & (RC - 1), k = idx >> 3;
+        sS[r * LD + k] = (r < rc && k < N) ? Sf[i1 + r0 + r + ldS * k] : 0.;
+      }
+      __syncthreads();
+      // P = S Y (+ the three row sums), tiles jb of this warp
+      {
+        double p[TPW][2], e0 = 0., e1 = 0.;
+#pragma unroll
+        for (int b = 0; b < TPW; b++) p[b][0] = p[b][1] = 0.;
+#pragma unroll 2
+        for (int i0 = 0; i0 < NK; i0 += 4) {
+          const double a = sS[g * LD + i0 + t];
+#pragma unroll
+          for (int b = 0; b < TPW; b++)
+            oak_dmma_m8n8k4(p[b][0], p[b][1], a, Yt[(8 * (warp * TPW + b) + g) * LD + i0 + t]);
+          if (warp == 0) {
+            const double bx = g == 0 ? s_g1h[i0 + t] : (g == 1 ? s_g2h[i0 + t] : (g == 2 ? s_amp[i0 + t] : 0.));
+            oak_dmma_m8n8k4(e0, e1, a, bx);
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < TPW; b++)
+          *reinterpret_cast<double2 *>(sP + g * LD + 8 * (warp * TPW + b) + 2 * t) = make_double2(p[b][0], p[b][1]);
+        if (warp == 0) {
+          if (t == 0) { s_row[g] = e0; s_row[RC + g] = e1; }   // a1, a2
+          if (t == 1) s_row[2 * RC + g] = e0;                  // Sf . ampl
+        }
+      }
+      __syncthreads();
+      // Q = P Y^T, tiles kb of this warp, and the finished rows in place of S
+      {
+        double q[TPW][2];
+#pragma unroll
+        for (int b = 0; b < TPW; b++) q[b][0] = q[b][1] = 0.;
+#pragma unroll 2
+        for (int j0 = 0; j0 < NK; j0 += 4) {
+          const double a = sP[g * LD + j0 + t];
+#pragma unroll
+          for (int b = 0; b < TPW; b++)
+            oak_dmma_m8n8k4(q[b][0], q[b][1], a, Yt[(j0 + t) * LD + 8 * (warp * TPW + b) + g]);
+        }
+        const double a1 = s_row[g], a2 = s_row[RC + g];
+#pragma unroll
+        for (int b = 0; b < TPW; b++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int k = 8 * (warp * TPW + b) + 2 * t + e;
+            double v = (sS[g * LD + k] - q[b][e]) - a1 * suv[k];
+            if (k == N - 1) v *= dNN;
+            sS[g * LD + k] = v - a2 * suw[k];
+          }
+      }
+      __syncthreads();
+      for (int idx = tid; idx < RC * NP; idx += NP) {
+        const int r = idx & (RC - 1), k = idx >> 3;
+        if (r < rc && k < N) Sa[i1 + r0 + r + ldSa * k] = sS[r * LD + k];
+      }
+      if (tid < rc) xa[i1 + r0 + tid] = xf[i1 + r0 + tid] + s_row[2 * RC + tid];
+      __syncthreads();
+    }
+  }
+};
+
+// FUSE: see FusedApply above (the zone geometry and the state arrays in `aa` are only used then)
+
+template <int NP, bool FUSE>
 __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__restrict__ mloc,
                                               const double *__restrict__ ws, const double *__restrict__ cin,
                                               double *__restrict__ Tout, double *__restrict__ ampl_out,
                                               int32_t *__restrict__ flags, DevCounters *ctr, double orthtol,
-                                              int maxgroup) {
+                                              int maxgroup, const FusedApplyArgs aa) {
   constexpr int LDW = NP + 1;
-  constexpr int LDY = NP + 2;
+  constexpr int LDY = FUSE ? NP + 4 : NP + 2;  // fused: Yt rows double as mma fragments (conflict-free at NP + 4)
   constexpr int NW = NP / 32;
   constexpr int TR = 8, TC = NP / 8;          // output tile of a thread: TR rows x TC columns
   constexpr int TJ = NP / TC;                 // thread grid: (NP/TR) x TJ = NP threads
@@ -703,6 +796,7 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
     }
     if (am != am) atomicExch(&ctr->nan_flag, 1);
     ampl_out[(int64_t)zl * NP + j] = am;
+    if constexpr (FUSE) sres[j] = am;  // sres is free after the grouping: ampl for the fused apply
   }
   const double vnorm = sqrt(block_sum<NW>(vi * vi, sred, warp, lane));
   const double wN = 1. / sqrt((double)N);
@@ -754,6 +848,18 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
     sg2[j] = gm2 - kappa * g1;
   }
   __syncthreads();
+  if constexpr (FUSE) {
+    // ---- rows of the zone from the factored transform; T itself is not formed ----
+    sa[j] = sg1[j] * hv;   // sa, sb were last read before the barrier above
+    sb[j] = sg2[j] * hw;
+    __syncthreads();
+    double *sS = sm + NP * LDY + 14 * NP, *sP = sS + FusedApply<NP>::RC * FusedApply<NP>::LD;
+    double *s_row = sP + FusedApply<NP>::RC * FusedApply<NP>::LD;
+    const int64_t i1 = aa.zstart[zl] - aa.rowbase;
+    const int nrow = (int)(aa.zstart[zl + 1] - aa.zstart[zl]);
+    FusedApply<NP>::run(N, j, Yt, sS, sP, s_row, sa, sb, sres, suv, suw, dNN, i1, nrow, aa.xf, aa.Sf, aa.ldS, aa.xa,
+                        aa.Sa, aa.ldSa);
+  } else
   // ---- T[i][k] = (M[i][k] - g1[i] hv u_v[k]) D_k - g2[i] hw u_w[k] , row-major ----
   {
     const int ti = j / TJ, tj = j % TJ;
@@ -802,16 +908,25 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
   if (j == 0) flags[zl] = 0;
 }
 
-template <int NP>
-int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G, const double *c, double *T,
-           double *ampl, double *ws, int32_t *flags, DevCounters *ctr, cudaEvent_t *ev, double orthtol, int maxgroup) {
-  constexpr int LDW = NP + 1;
-  const size_t smem = sizeof(double) * (NP * (NP + 2) + 14 * NP);
+template <int NP, bool FUSE>
+int launch_tvec(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *c, double *T, double *ampl,
+                double *ws, int32_t *flags, DevCounters *ctr, double orthtol, int maxgroup, const FusedApplyArgs &aa) {
+  const size_t smem = sizeof(double) * (NP * (NP + (FUSE ? 4 : 2)) + 14 * NP + (FUSE ? FusedApply<NP>::SMEM_DOUBLES : 0));
   static bool attr_done = false;
   if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(k_tvec<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_tvec<NP, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
+  k_tvec<NP, FUSE><<<nz, NP, smem, st>>>(N, mloc, ws, c, T, ampl, flags, ctr, orthtol > 0. ? orthtol : TRI_ORTHTOL,
+                                         maxgroup >= 0 ? maxgroup : TRI_MAXGROUP, aa);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+template <int NP>
+int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G, const double *c, double *T,
+           double *ampl, double *ws, int32_t *flags, DevCounters *ctr, cudaEvent_t *ev, double orthtol, int maxgroup,
+           const FusedApplyArgs *fuse) {
 #if TRI_TILE
   k_tridiag_tile<NP><<<nz, 64, 0, st>>>(N, mloc, G, T, ws);
 #else
@@ -822,10 +937,8 @@ int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G,
   k_tql<NP><<<(nz + 31) / 32, 32, 0, st>>>(N, nz, mloc, ws, flags);
   CUDA_TRY(cudaGetLastError());
   if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
-  k_tvec<NP><<<nz, NP, smem, st>>>(N, mloc, ws, c, T, ampl, flags, ctr, orthtol > 0. ? orthtol : TRI_ORTHTOL,
-                                   maxgroup >= 0 ? maxgroup : TRI_MAXGROUP);
-  CUDA_TRY(cudaGetLastError());
-  return 0;
+  if (fuse) return launch_tvec<NP, true>(st, N, nz, mloc, c, T, ampl, ws, flags, ctr, orthtol, maxgroup, *fuse);
+  return launch_tvec<NP, false>(st, N, nz, mloc, c, T, ampl, ws, flags, ctr, orthtol, maxgroup, FusedApplyArgs{});
 }
 
 }  // namespace
@@ -837,15 +950,18 @@ size_t oak_eig_tridiag_ws_bytes(int NP, int nz) {
 
 // Enqueues k_tridiag, k_tql, k_tvec; on return (stream order) flags[zl] = mloc[zl] for the zones that must be
 // recomputed by the Jacobi kernel and 0 for the others.  V (the reflectors) lives in T until k_tvec replaces it.
+// fuse != NULL: k_tvec also updates the rows of its zones (FusedApply) and writes no T; the caller then applies
+// only the zones k_tvec did not finish (not analysed, or flagged and recomputed by the Jacobi kernel).
 int oak_launch_eig_tridiag(cudaStream_t st, int N, int NP, int nz, const int32_t *mloc, const double *G,
                            const double *c, double *T, double *ampl, void *ws, int32_t **flags_out,
-                           DevCounters *ctr, cudaEvent_t *ev, double orthtol, int maxgroup) {
+                           DevCounters *ctr, cudaEvent_t *ev, double orthtol, int maxgroup,
+                           const FusedApplyArgs *fuse) {
   double *wsd = reinterpret_cast<double *>(ws);
   int32_t *flags = reinterpret_cast<int32_t *>(wsd + 4 * (size_t)NP * nz);
   *flags_out = flags;
   switch (NP) {
-    case 32: return launch<32>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup);
-    case 64: return launch<64>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup);
+    case 32: return launch<32>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup, fuse);
+    case 64: return launch<64>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup, fuse);
   }
   oak_set_error("eig_tridiag: unsupported padded ensemble size %d", NP);
   return OAK_ERR_UNSUPPORTED;

@@ -53,3 +53,9 @@ def test_kernels_under_a_permuted_thread_schedule(emu_lib):
 
 def test_tensor_core_gram_variants(emu_lib):
     _run(emu_lib, "gram_tensor_core and 64-60")
+
+
+def test_fused_apply_in_the_transform_kernel(emu_lib):
+    # option fuse_apply (k_tvec updates the zone rows from the factored transform on mma tiles), incl. the zones it
+    # leaves to k_apply (no observation / Jacobi fallback)
+    _run(emu_lib, "fused_apply and (N20 or degenerate)")

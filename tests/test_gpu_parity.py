@@ -496,6 +496,59 @@ def test_degenerate_spectrum_falls_back_to_jacobi(ob, N):
         assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL, (rel(xa, xo), rel(Sa, So))
 
 
+@pytest.mark.parametrize("N,nz,m,gram", [(64, 30, 500, 0), (40, 13, 400, 1), (20, 5, 300, 0), (64, 3, 6, 0)],
+                         ids=["N64_30rows", "N40_13rows_mma_gram", "N20_np32", "degenerate_fallback"])
+def test_fused_apply_from_the_factored_transform(ob, N, nz, m, gram):
+    """Option fuse_apply: k_tvec updates the zone rows itself, Sa_z = ((Sf_z - (Sf_z Y) Y^T) - a1 u_v^T) D - a2 u_w^T
+    on mma.m8n8k4 tiles, without forming T; k_apply only serves the zones k_tvec did not finish (no observation,
+    or handed to the Jacobi kernel).  Chunks of 8 rows: zone sizes 30 (3 full + 6), 13, 5, 3 and ragged 1..11;
+    in place (Sa aliases Sf) as the Fortran caller does."""
+    from oak_b200 import synthetic
+    degenerate = m == 6
+    if degenerate:
+        c = synthetic.small_case(nx=6, ny=5, nz=nz, N=N, m=6, corr=1e9, maxlen=1e12, seed=5)
+        Q, _ = np.linalg.qr(np.random.default_rng(3).normal(size=(N, 6)))
+        rows = Q.T.copy()
+        rows[:3] *= 2.0
+        rows[5] *= 0.5
+        c["HSf"] = np.asfortranarray(rows)
+        c["var"] = np.full(6, 0.25)
+        zs = None
+    else:
+        c = synthetic.small_case(nx=14, ny=6, nz=nz, N=N, m=m, corr=2500.0, maxlen=5000.0, seed=N + nz)
+        # keep the observations of the left part only: zones on the right have none and keep the forecast
+        keep = c["obs"]["ox"] < 5500.0
+        for k in ("Hxf", "yo", "var"):
+            c[k] = c[k][keep]
+        c["HSf"] = np.asfortranarray(c["HSf"][keep])
+        c["obs"] = {k: (v[..., keep] if v.ndim > 1 else v[keep]) for k, v in c["obs"].items()}
+        c["m"] = int(keep.sum())
+        zs = None
+        if N == 40:  # ragged zones 1..11 rows with their own positions
+            zs, left, k = [], c["Sf"].shape[0], 0
+            while left > 0:
+                sz = min(left, 1 + (k % 11)); zs.append(sz); left -= sz; k += 1
+            zs = np.array(zs, np.int32)
+            rng = np.random.default_rng(1)
+            c["zx"] = rng.uniform(0, 14000, zs.size); c["zy"] = rng.uniform(0, 6000, zs.size)
+            c["corr"] = np.full(zs.size, 2500.0); c["maxlen"] = np.full(zs.size, 5000.0)
+    xo, So, _, mloc = _oracle_loc(c, zs)
+    assert degenerate or ((mloc == 0).any() and (mloc > 0).any())
+    with ob.Handle(0, eig_kernel=4, fuse_apply=1, gram_kernel=gram, pad_to=64 if gram else 0) as h:
+        _configure(ob, h, c, zs)
+        if degenerate:
+            h.set_option("tri_maxgroup", 0)  # every zone goes to the Jacobi kernel and then through k_apply
+        buf = np.asfortranarray(c["Sf"].copy())
+        xa, Sa, _, st = h.local_analysis(c["xf"], c["Hxf"], c["yo"], buf, c["HSf"], ob.DiagCovar(c["var"]), out_Sa=buf)
+    assert Sa is buf
+    if degenerate:
+        assert st["zones_fallback"] == len(mloc)
+    assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL, (rel(xa, xo), rel(Sa, So))
+    start = np.concatenate([[0], np.cumsum(c["zoneSize"] if zs is None else zs)])
+    for z in np.nonzero(mloc == 0)[0]:
+        assert (Sa[start[z]:start[z + 1]] == c["Sf"][start[z]:start[z + 1]]).all()
+
+
 @pytest.mark.needs_torch_cuda
 def test_fused_gather_peer_outputs_receive_the_slab(ob):
     """oakb200_set_peer_outputs: the apply kernel stores this rank's rows (analysed and untouched zones) into
