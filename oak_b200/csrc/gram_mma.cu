@@ -14,7 +14,8 @@
 //   NW = 4 warps: LL triangle (10 tiles) | HH triangle (10) | HL rows 4,5 (8) | HL rows 6,7 (8)
 //   NW = 2 warps: LL + HL rows 4,5 (18 tiles) | HH + HL rows 6,7 (18)
 // Staged rows have a stride of NP + 4 doubles: the 16 lanes of a half-warp then read 16 different 8-byte banks.
-// Rows beyond a segment's count enter with coef = 0; the row buffers are zeroed once so that 0 x stale is 0.
+// The rows the two evaluating warps found are merged into one dense list when they are staged; the rows that pad
+// the last k-step of a chunk enter with coef = 0, and the row buffers are zeroed once so that 0 x stale is 0.
 #include "common.cuh"
 
 namespace {
@@ -72,13 +73,15 @@ struct GramMma {
   using TM = TileMap<NW, W>;
   static constexpr int NB = NP / 8, LDR = NP + 4;
 
-  // rows [0, cnt) of one 32-slot segment of a staged chunk
-  static __device__ __forceinline__ void segment(double (&acc)[TM::NACC][2], const double *rows, const double *coef,
-                                                 int cnt, int g, int t) {
+  // the `total` staged rows of a chunk; the coefficient of merged row q sits in list slot q (q < cnt0, found by
+  // warp 0) or 32 + q - cnt0 (found by warp 1); the rows that pad the last k-step enter with coefficient 0
+  static __device__ __forceinline__ void chunk(double (&acc)[TM::NACC][2], const double *rows, const double *coef,
+                                               int cnt0, int total, int g, int t) {
 #pragma unroll 2
-    for (int k0 = 0; k0 < cnt; k0 += 4) {
-      const double *r = rows + (k0 + t) * LDR + g;
-      const double cf = coef[k0 + t];
+    for (int k0 = 0; k0 < total; k0 += 4) {
+      const int qr = k0 + t;
+      const double *r = rows + qr * LDR + g;
+      const double cf = qr < total ? coef[qr < cnt0 ? qr : 32 + qr - cnt0] : 0.;
       double v[NB];
 #pragma unroll
       for (int b = 0; b < NB; b++)
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
   long long ncand_total = 0;
   for (int i = tid; i < 2 * GRAM_CH * LDR; i += NT) rowbuf[i] = 0.;  // 0 x (never written) must be 0, not NaN
 
-  // E(c): warps 0 and 1, 32 candidates each, into list buffer lb (as k_gram); unused slots get coef 0
+  // E(c): warps 0 and 1, 32 candidates each, into list buffer lb (as k_gram)
   auto eval = [&](int c, int lb, int total) {
     if (warp < 2) {
       int qq = c * GRAM_CH + warp * 32 + lane;
@@ -164,47 +167,45 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
         s_coef[lb][slot] = coef;
         s_cd[lb][slot] = coef * orows.delta[p];
       }
-      if (lane >= cnt) s_coef[lb][warp * 32 + lane] = 0.;
       if (lane == 0) s_cnt[lb][warp] = cnt;
     }
   };
-  // L(c): rows of list buffer lb into row buffer rb (one 16-byte cp.async per lane and row)
+  // L(c): rows of list buffer lb into row buffer rb (one 16-byte cp.async per lane and row); the two warps'
+  // finds are merged here: row buffer slot = r (warp 0's) or cnt0 + r (warp 1's), so the k-steps of four rows
+  // run over one dense list
   auto load_rows = [&](int lb, int rb) {
     double *dstb = rowbuf + (size_t)rb * GRAM_CH * LDR;
+    const int cnt0 = s_cnt[lb][0];
 #pragma unroll
     for (int seg = 0; seg < 2; seg++) {
       const int cnt = s_cnt[lb][seg];
       for (int r = warp; r < cnt; r += NW) {
-        const int slot = seg * 32 + r;
-        const double *src = orows.rows + (int64_t)s_pos[lb][slot] * NP;
-        for (int cidx = lane * 2; cidx < NP; cidx += 64) cp_async16(dstb + slot * LDR + cidx, src + cidx);
+        const double *src = orows.rows + (int64_t)s_pos[lb][seg * 32 + r] * NP;
+        double *dst = dstb + (seg * cnt0 + r) * LDR;
+        for (int cidx = lane * 2; cidx < NP; cidx += 64) cp_async16(dst + cidx, src + cidx);
       }
     }
   };
   // F(c)
   auto fma_rows = [&](int lb, int rb) {
-    const double *srcb = rowbuf + (size_t)rb * GRAM_CH * LDR;
-#pragma unroll
-    for (int seg = 0; seg < 2; seg++) {
-      const int cnt = s_cnt[lb][seg];
-      nrel_total += cnt;
-      const double *rows = srcb + seg * 32 * LDR;
-      const double *coef = s_coef[lb] + seg * 32;
-      if constexpr (NW == 4) {
-        switch (warp) {
-          case 0: GramMma<NP, NW, 0>::segment(acc, rows, coef, cnt, g, t); break;
-          case 1: GramMma<NP, NW, 1>::segment(acc, rows, coef, cnt, g, t); break;
-          case 2: GramMma<NP, NW, 2>::segment(acc, rows, coef, cnt, g, t); break;
-          default: GramMma<NP, NW, 3>::segment(acc, rows, coef, cnt, g, t); break;
-        }
-      } else {
-        if (warp == 0) GramMma<NP, NW, 0>::segment(acc, rows, coef, cnt, g, t);
-        else GramMma<NP, NW, 1>::segment(acc, rows, coef, cnt, g, t);
+    const double *rows = rowbuf + (size_t)rb * GRAM_CH * LDR;
+    const double *coef = s_coef[lb];
+    const int cnt0 = s_cnt[lb][0], total = cnt0 + s_cnt[lb][1];
+    nrel_total += total;
+    if constexpr (NW == 4) {
+      switch (warp) {
+        case 0: GramMma<NP, NW, 0>::chunk(acc, rows, coef, cnt0, total, g, t); break;
+        case 1: GramMma<NP, NW, 1>::chunk(acc, rows, coef, cnt0, total, g, t); break;
+        case 2: GramMma<NP, NW, 2>::chunk(acc, rows, coef, cnt0, total, g, t); break;
+        default: GramMma<NP, NW, 3>::chunk(acc, rows, coef, cnt0, total, g, t); break;
       }
-      if (tid < NP) {
-        const double *cd = s_cd[lb] + seg * 32;
-        for (int r = 0; r < cnt; r++) cacc = fma(cd[r], rows[r * LDR + tid], cacc);
-      }
+    } else {
+      if (warp == 0) GramMma<NP, NW, 0>::chunk(acc, rows, coef, cnt0, total, g, t);
+      else GramMma<NP, NW, 1>::chunk(acc, rows, coef, cnt0, total, g, t);
+    }
+    if (tid < NP) {
+      const double *cd = s_cd[lb];
+      for (int r = 0; r < total; r++) cacc = fma(cd[r < cnt0 ? r : 32 + r - cnt0], rows[r * LDR + tid], cacc);
     }
   };
 
