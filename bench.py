@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--eig-kernel", type=int, default=4)
+    ap.add_argument("--gram-kernel", type=int, default=0, help="0 = DFMA register tiles (default), 1 / 2 = mma.m8n8k4 tiles (4 / 2 warps per zone)")
+    ap.add_argument("--fuse-apply", type=int, default=0, help="1 = the transform kernel updates the zone rows from the factored transform (no T, no k_apply)")
     ap.add_argument("--jacobi-tol", type=float, default=0.0, help="experiment: override the Jacobi stopping tolerance")
     ap.add_argument("--sync-phases", action="store_true", help="N>1: blocking library calls instead of the asynchronous pipeline")
     ap.add_argument("--phases", type=int, default=0, help="pipeline phases for N>1 (0: 1 with the fused gather, 4 with --nccl-gather)")
@@ -243,7 +245,7 @@ def main():
     for j, first in enumerate(ranges):
         d = build_rank_data(a, rank, world, dev, first=first, obs_np=obs_np)
         plan = d["plan"]
-        h = oak_b200.Handle(local, eig_kernel=a.eig_kernel)
+        h = oak_b200.Handle(local, eig_kernel=a.eig_kernel, gram_kernel=a.gram_kernel, fuse_apply=a.fuse_apply)
         if os.environ.get("OAK_B200_FIXED_SWEEPS"):  # kernel timing experiments only (tools/ab.py)
             h.set_option("fixed_sweeps", float(os.environ["OAK_B200_FIXED_SWEEPS"]))
         if os.environ.get("OAK_B200_ZB"):  # pipeline experiments (tools/ab.py)
@@ -439,7 +441,8 @@ def main():
                "config": {"workload": workload_name(a), "zones": nzones, "parallelism": f"zone-range x{world}" + (((", all-gather replaced by peer copies of every finished batch into every rank's result array (copy engines over NVLink, CUDA IPC mappings); " if a.peer_mode == 1 else ", all-gather fused into the apply kernel (stores into every rank's result array over NVLink, CUDA IPC); ") + str(fused_note)) if fused else (f", {nphase} pipelined phases (all-gather of phase j overlaps analysis of j+1; " + ("asynchronous, stream priorities" if use_async else "blocking calls") + ")" + (("; " + fused_note) if fused_note else "") if world > 1 else "")),
                           "l2": "inputs (>= 15 GB state) exceed L2; no explicit flush",
                           "mean_relevant_obs_per_column": mloc_mean, "mean_candidates_per_column": cand_mean,
-                          "mean_jacobi_sweeps": sweeps_mean, "eig_kernel": a.eig_kernel},
+                          "mean_jacobi_sweeps": sweeps_mean, "eig_kernel": a.eig_kernel,
+                          "gram_kernel": a.gram_kernel, "fuse_apply": a.fuse_apply},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
 
     # ---- end to end through the host-buffer entry point (pinned host memory, H2D + D2H inside the timed region)
