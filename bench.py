@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--eig-kernel", type=int, default=4)
-    ap.add_argument("--gram-kernel", type=int, default=0, help="0 = DFMA register tiles (default), 1 / 2 = mma.m8n8k4 tiles (4 / 2 warps per zone)")
+    ap.add_argument("--gram-kernel", type=int, default=0, help="0 = DFMA register tiles (default), 1 / 2 = mma.m8n8k4 tiles (4 / 2 warps per zone), 3 / 4 = same with 32-candidate chunks")
     ap.add_argument("--fuse-apply", type=int, default=0, help="1 = the transform kernel updates the zone rows from the factored transform (no T, no k_apply)")
     ap.add_argument("--jacobi-tol", type=float, default=0.0, help="experiment: override the Jacobi stopping tolerance")
     ap.add_argument("--sync-phases", action="store_true", help="N>1: blocking library calls instead of the asynchronous pipeline")

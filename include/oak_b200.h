@@ -72,7 +72,8 @@ OAKB200_API int oakb200_destroy(oakb200_handle *h);
  *                     flagged zones fall back to 0), 0 = register-resident block Jacobi (N > 64), 1 = simple
  *                     shared-memory Jacobi (cross-check), 2 / 3 = measured variants of 0
  *   "gram_kernel"     0 = DFMA register tiles (default), 1 / 2 = fp64 tensor-core tiles (mma.m8n8k4, 4 / 2 warps per
- *                     zone; padded ensemble size 64 only, other sizes keep 0)
+ *                     zone), 3 / 4 = the same with chunks of 32 instead of 64 candidates (half the shared memory);
+ *                     padded ensemble size 64 only, other sizes keep 0
  *   "fuse_apply"      route 4: 1 = the transform kernel updates the zone rows itself from the factored transform
  *                     (no T written, k_apply only for the zones it did not finish); pays while zone sizes < N. Default 0
  *   "tri_orthtol"     route 4: accepted loss of orthogonality between neighbouring eigenvectors (default 1e-11)

@@ -89,7 +89,7 @@ struct oakb200_handle {
   // options
   int eig_kernel = 4;
   int fuse_apply = 0;         // 1: tridiagonal route, k_tvec updates the zone rows from the factored transform (no T, no k_apply)
-  int gram_kernel = 0;        // 0: k_gram (DFMA register tiles); 1 / 2: k_gram_mma (DMMA, 4 / 2 warps per zone; NP = 64)
+  int gram_kernel = 0;        // 0: k_gram (DFMA register tiles); 1 / 2: k_gram_mma (DMMA, 4 / 2 warps per zone; NP = 64); 3 / 4: same, 32-candidate chunks
   double tri_orthtol = 0.;  // tridiagonal route: accepted loss of orthogonality between neighbouring eigenvectors (0: default)
   int tri_maxgroup = -1;
   DevBuf d_anam;              // tabulated anamorphosis (K x 2), oakb200_set_anamorphosis_table
@@ -491,7 +491,7 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   if (k == "eig_kernel") h->eig_kernel = (int)value;
   else if (k == "fuse_apply") h->fuse_apply = value != 0.;
   else if (k == "gram_kernel") {
-    if (value != 0. && value != 1. && value != 2.) { oak_set_error("gram_kernel = %g (expected 0, 1 or 2)", value); return OAK_ERR_ARG; }
+    if (!(value >= 0. && value <= 4.) || value != (int)value) { oak_set_error("gram_kernel = %g (expected 0 .. 4)", value); return OAK_ERR_ARG; }
     h->gram_kernel = (int)value;
   }
   else if (k == "tri_orthtol") h->tri_orthtol = value;

@@ -44,7 +44,7 @@ __device__ __forceinline__ void oak_dmma_m8n8k4(double &c0, double &c1, double a
 }
 #else
 __device__ __forceinline__ void oak_dmma_m8n8k4(double &c0, double &c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }

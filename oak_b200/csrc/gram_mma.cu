@@ -20,7 +20,7 @@
 
 namespace {
 
-constexpr int GRAM_CH = 64;    // candidates examined per chunk (warps 0 and 1, one per lane)
+constexpr int GRAM_CHMAX = 64; // candidates examined per chunk: 64 (warps 0 and 1, one per lane) or 32 (warp 0)
 constexpr int GRAM_MAXR = 64;  // cell ranges per row group
 
 #ifdef OAK_CUEMU
@@ -115,16 +115,20 @@ struct GramMma {
   }
 };
 
-template <int NP, int NW>
+// CH = 64: two evaluating warps, 2 x 64 staged rows (70 KB: 3 CTAs per SM); CH = 32: one evaluating warp, 2 x 32
+// rows (35 KB: 6 CTAs per SM, twice the barriers per zone)
+template <int NP, int NW, int CH>
 __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, ObsRows orows, int zone0, int nz,
                                                       double *__restrict__ G, double *__restrict__ cvec,
                                                       int32_t *__restrict__ mloc, DevCounters *ctr) {
   static_assert(NP == 64 && (NW == 2 || NW == 4), "tile map is written for 8 x 8 blocks");
+  static_assert(CH == 32 || CH == 64, "one or two evaluating warps");
+  constexpr int GRAM_CH = CH;
   constexpr int NT = 32 * NW, LDR = NP + 4;
   constexpr int NACC = NW == 4 ? 10 : 18;
   extern __shared__ __align__(16) double rowbuf[];  // [2][GRAM_CH][LDR]
-  __shared__ double s_coef[3][GRAM_CH], s_cd[3][GRAM_CH];
-  __shared__ int s_pos[3][GRAM_CH];
+  __shared__ double s_coef[3][GRAM_CHMAX], s_cd[3][GRAM_CHMAX];
+  __shared__ int s_pos[3][GRAM_CHMAX];
   __shared__ int s_cnt[3][2];
   __shared__ int s_rstart[GRAM_MAXR], s_rlen[GRAM_MAXR];
   __shared__ int s_total;
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
 
   // E(c): warps 0 and 1, 32 candidates each, into list buffer lb (as k_gram)
   auto eval = [&](int c, int lb, int total) {
-    if (warp < 2) {
+    if (warp < GRAM_CH / 32) {
       int qq = c * GRAM_CH + warp * 32 + lane;
       bool rel = false;
       double w = 0.;
@@ -167,7 +171,10 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
         s_coef[lb][slot] = coef;
         s_cd[lb][slot] = coef * orows.delta[p];
       }
-      if (lane == 0) s_cnt[lb][warp] = cnt;
+      if (lane == 0) {
+        s_cnt[lb][warp] = cnt;
+        if (GRAM_CH == 32) s_cnt[lb][1] = 0;
+      }
     }
   };
   // L(c): rows of list buffer lb into row buffer rb (one 16-byte cp.async per lane and row); the two warps'
@@ -279,28 +286,33 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
   }
 }
 
-template <int NP, int NW>
+template <int NP, int NW, int CH>
 int launch(cudaStream_t st, const ZoneGeom &zg, const ObsGrid &og, const ObsRows &orows, int zone0, int nz,
            double *G, double *c, int32_t *mloc, DevCounters *ctr) {
-  const size_t smem = sizeof(double) * 2 * GRAM_CH * (NP + 4);
+  const size_t smem = sizeof(double) * 2 * CH * (NP + 4);
   static bool attr_done = false;
   if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(k_gram_mma<NP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_gram_mma<NP, NW, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  k_gram_mma<NP, NW><<<nz, 32 * NW, smem, st>>>(zg, og, orows, zone0, nz, G, c, mloc, ctr);
+  k_gram_mma<NP, NW, CH><<<nz, 32 * NW, smem, st>>>(zg, og, orows, zone0, nz, G, c, mloc, ctr);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
 }  // namespace
 
-// variant 1: four warps per zone, 2: two warps per zone.  Only NP = 64 (the caller keeps k_gram for the rest).
+// variant 1: four warps per zone, 2: two warps per zone (chunks of 64 candidates); 3, 4: the same with chunks of 32
+// candidates (half the shared memory, twice the CTAs per SM).  Only NP = 64 (the caller keeps k_gram for the rest).
 int oak_launch_gram_mma(cudaStream_t st, int variant, int NP, const ZoneGeom &zg, const ObsGrid &og,
                         const ObsRows &orows, int zone0, int nz, double *G, double *c, int32_t *mloc,
                         DevCounters *ctr) {
   if (nz <= 0) return 0;
   if (NP != 64) { oak_set_error("gram_mma: padded ensemble size %d (only 64)", NP); return OAK_ERR_UNSUPPORTED; }
-  if (variant == 2) return launch<64, 2>(st, zg, og, orows, zone0, nz, G, c, mloc, ctr);
-  return launch<64, 4>(st, zg, og, orows, zone0, nz, G, c, mloc, ctr);
+  switch (variant) {
+    case 2: return launch<64, 2, 64>(st, zg, og, orows, zone0, nz, G, c, mloc, ctr);
+    case 3: return launch<64, 4, 32>(st, zg, og, orows, zone0, nz, G, c, mloc, ctr);
+    case 4: return launch<64, 2, 32>(st, zg, og, orows, zone0, nz, G, c, mloc, ctr);
+  }
+  return launch<64, 4, 64>(st, zg, og, orows, zone0, nz, G, c, mloc, ctr);
 }

@@ -209,7 +209,7 @@ def test_local_analysis_matches_oracle(ob, handle, N, m, nx, ny, nz):
     assert np.abs(Sa.sum(axis=1)).max() < 1e-12 * max(1.0, np.abs(Sa).max()) * N
 
 
-@pytest.mark.parametrize("variant", [1, 2], ids=["mma_4warps", "mma_2warps"])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4], ids=["mma_4warps", "mma_2warps", "mma_4warps_ch32", "mma_2warps_ch32"])
 @pytest.mark.parametrize("N,m,maxlen", [(64, 900, 6000.0), (40, 700, 9000.0), (64, 60, 4000.0)])
 def test_gram_tensor_core_variants_match_the_register_tile_kernel(ob, variant, N, m, maxlen):
     # option gram_kernel = 1 / 2: G and c accumulated by mma.m8n8k4.f64 on the lower 8 x 8 tiles (gram_mma.cu).
