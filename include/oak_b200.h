@@ -84,7 +84,9 @@ OAKB200_API int oakb200_destroy(oakb200_handle *h);
  *   "chunk_mb"        host-buffer entry points: size of the state chunks streamed through the device (256)
  *   "profile"         1: batches serialised, CUDA-event time per kernel family in the statistics
  *   "async", "order_after_caller", "stream_priority"   see oakb200_synchronize
- *   "peer_mode"       see oakb200_set_peer_outputs: 1 copy engines (default), 0 stores of the apply kernel */
+ *   "peer_mode"       see oakb200_set_peer_outputs: 1 copy engines (default), 0 stores of the apply kernel
+ *   "push_pieces"     peer_mode 1: the apply of a batch runs in this many launches, each pushed to the peers as soon
+ *                     as it is done (shorter exposed tail at the end of a call); default 1 */
 OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key, double value);
 
 /* Zones = the partition of the (zone-permuted) state vector (assimilation.F90:578-641).

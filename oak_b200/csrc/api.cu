@@ -97,6 +97,7 @@ struct oakb200_handle {
   PeerOut peers{};            // fused all-gather destinations (oakb200_set_peer_outputs); n = 0: none
   cudaStream_t pstream[OAKB200_MAX_PEERS] = {};  // one copy stream per destination (created on first use)
   cudaEvent_t pev[OAKB200_MAX_PEERS] = {};
+  int push_pieces = 1;        // peer_mode 1: the apply of a batch is launched in this many pieces, each pushed as soon as it is done
   int peer_mode = 1;          // 1: copy engines push every finished batch (no SM time); 0: stores of k_apply    // ... largest group of close eigenvalues orthogonalised in place (-1: default)
   int zones_per_batch = 0;
   double tol = 2e-11;  // bound on the remaining non-orthogonality (eig_common.cuh: jacobi_converged)
@@ -250,14 +251,22 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
                                     h->tol, h->max_sweeps, ctr))) return rc;
     if (prof) CUDA_TRY(cudaEventRecord(s.ev[2], s.st));
     PeerOut none{};
-    if ((rc = oak_launch_apply(s.st, N, NP, zg, b0, nz, rowbase, mloc, s.T.as<double>(), s.ampl.as<double>(), xf,
-                               Sf, ldS, xa, Sa, ldSa, (use_peers && h->peer_mode == 0) ? h->peers : none,
-                               only_flagged))) return rc;
-    if (use_peers && h->peer_mode == 1) {
-      // fused all-gather, copy-engine flavour: as soon as the batch is applied its rows go to every peer's
-      // array (strided 2-D peer copies over NVLink, no SM involved), overlapping the kernels of the next batches
+    // fused all-gather, copy-engine flavour: as soon as (a piece of) the batch is applied its rows go to every
+    // peer's array (strided 2-D peer copies over NVLink, no SM involved), overlapping the kernels of the next
+    // batches.  What stays exposed at the end of a call is the push of the last piece of every stream slot, so
+    // "push_pieces" > 1 launches the apply of a batch in pieces and pushes each one behind it.
+    const bool push = use_peers && h->peer_mode == 1;
+    const int npiece = push ? std::max(1, std::min(h->push_pieces, nz)) : 1;
+    for (int pc = 0; pc < npiece; pc++) {
+      const int o0 = (int)((int64_t)nz * pc / npiece), o1 = (int)((int64_t)nz * (pc + 1) / npiece);
+      if ((rc = oak_launch_apply(s.st, N, NP, zg, b0 + o0, o1 - o0, rowbase, mloc, s.T.as<double>() + (size_t)o0 * NP * NP,
+                                 s.ampl.as<double>() + (size_t)o0 * NP, xf, Sf, ldS, xa, Sa, ldSa,
+                                 (use_peers && h->peer_mode == 0) ? h->peers : none,
+                                 only_flagged ? only_flagged + o0 : nullptr))) return rc;
+      if (pc > 0) *launches += 1;
+      if (!push) continue;
       const PeerOut &P = h->peers;
-      const int64_t r0 = h->h_zstart[b0], r1 = h->h_zstart[b0 + nz];
+      const int64_t r0 = h->h_zstart[b0 + o0], r1 = h->h_zstart[b0 + o1];
       if (r1 > r0) {
         // one stream per destination: the copies to different peers run on different copy engines / links
         CUDA_TRY(cudaEventRecord(s.ev[11], s.st));
@@ -497,6 +506,7 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   else if (k == "tri_orthtol") h->tri_orthtol = value;
   else if (k == "tri_maxgroup") h->tri_maxgroup = (int)value;
   else if (k == "peer_mode") h->peer_mode = (int)value;
+  else if (k == "push_pieces") h->push_pieces = std::max(1, (int)value);
   else if (k == "zones_per_batch") h->zones_per_batch = (int)value;
   else if (k == "jacobi_tol") h->tol = value;
   else if (k == "max_sweeps") h->max_sweeps = (int)value;

@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "emu_only: runs only against the CPU emulation build (tools/cuemu)")
     config.addinivalue_line("markers", "needs_torch_cuda: GPU test that also needs torch.cuda (device tensors, NCCL)")
 
 
@@ -20,6 +21,10 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         has_gpu = False
     if has_gpu:
+        skip_emu = pytest.mark.skip(reason="written for the CPU emulation of the kernels (host pointers as device pointers)")
+        for it in items:
+            if "emu_only" in it.keywords:
+                it.add_marker(skip_emu)
         return
     if os.environ.get("OAK_B200_TEST_EMU") == "1":
         # tests/test_emulated_kernels.py re-runs GPU parity tests against the CPU emulation build of the kernel

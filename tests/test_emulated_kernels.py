@@ -59,3 +59,8 @@ def test_fused_apply_in_the_transform_kernel(emu_lib):
     # option fuse_apply (k_tvec updates the zone rows from the factored transform on mma tiles), incl. the zones it
     # leaves to k_apply (no observation / Jacobi fallback)
     _run(emu_lib, "fused_apply and (N20 or degenerate)")
+
+
+def test_pushes_to_the_peers_in_pieces(emu_lib):
+    # host logic of the fused gather (copy-engine flavour) with option push_pieces, alone and with fuse_apply
+    _run(emu_lib, "pushes_in_pieces")

@@ -549,6 +549,46 @@ def test_fused_apply_from_the_factored_transform(ob, N, nz, m, gram):
         assert (Sa[start[z]:start[z + 1]] == c["Sf"][start[z]:start[z + 1]]).all()
 
 
+@pytest.mark.emu_only
+@pytest.mark.parametrize("pieces,fuse", [(1, 0), (3, 0), (4, 1)])
+def test_pushes_in_pieces_under_emulation(ob, pieces, fuse):
+    """Copy-engine flavour of the fused gather with the apply of a batch launched in pieces (option push_pieces),
+    also combined with fuse_apply.  Host logic (piece ranges, pointer offsets into T / ampl / flags, the rows each
+    push covers): checked under the CPU emulation, where device pointers are host pointers, so that numpy arrays
+    can stand for the peers' result arrays.  The device version of this test is
+    test_fused_gather_peer_outputs_receive_the_slab."""
+    import ctypes as C
+    from oak_b200 import synthetic, _lib
+    c = synthetic.small_case(nx=14, ny=5, nz=4, N=24, m=150, corr=2500.0, maxlen=5000.0, seed=9)
+    keep = c["obs"]["ox"] < 5500.0
+    for k in ("Hxf", "yo", "var"):
+        c[k] = c[k][keep]
+    c["HSf"] = np.asfortranarray(c["HSf"][keep])
+    c["obs"] = {k: (v[..., keep] if v.ndim > 1 else v[keep]) for k, v in c["obs"].items()}
+    c["m"] = int(keep.sum())
+    xo, So, _, mloc = _oracle_loc(c)
+    n, N, m = c["Sf"].shape[0], 24, c["m"]
+    row0, ntot = 17, n + 40                       # this rank's rows start at row 17 of the assembled arrays
+    peers = [np.full((ntot, N), 7.0, order="F") for _ in range(2)]
+    peers_x = [np.full(ntot, 7.0) for _ in range(2)]
+    with ob.Handle(0, eig_kernel=4, fuse_apply=fuse, push_pieces=pieces, zones_per_batch=20) as h:
+        _configure(ob, h, c)
+        h.set_peer_outputs([p.ctypes.data for p in peers], [p.ctypes.data for p in peers_x], ntot, row0)
+        Sf = np.asfortranarray(c["Sf"].copy())
+        xa, Sa = np.empty(n), np.empty((n, N), order="F")
+        ptr = lambda a: C.c_void_p(np.ascontiguousarray(a).ctypes.data) if not a.flags.f_contiguous else C.c_void_p(a.ctypes.data)
+        arrs = [np.ascontiguousarray(c[k], dtype=np.float64) for k in ("xf", "Hxf", "yo")]
+        HSf, var = np.asfortranarray(c["HSf"]), np.ascontiguousarray(c["var"])
+        st = _lib.Stats()
+        rc = h._L.oakb200_local_analysis_dev(h._h, n, N, m, ptr(arrs[0]), ptr(arrs[1]), ptr(arrs[2]), ptr(Sf), n, ptr(HSf),
+                                             max(m, 1), ptr(var), None, ptr(xa), ptr(Sa), n, None, None, C.byref(st))
+        assert rc == 0, h._L.oakb200_last_error()
+    assert (mloc == 0).any() and rel(xa, xo) < RTOL and rel(Sa, So) < RTOL
+    for P, px in zip(peers, peers_x):
+        assert (P[row0:row0 + n] == Sa).all() and (px[row0:row0 + n] == xa).all()
+        assert (P[:row0] == 7.0).all() and (P[row0 + n:] == 7.0).all() and (px[:row0] == 7.0).all()
+
+
 @pytest.mark.needs_torch_cuda
 def test_fused_gather_peer_outputs_receive_the_slab(ob):
     """oakb200_set_peer_outputs: the apply kernel stores this rank's rows (analysed and untouched zones) into
