@@ -34,6 +34,9 @@
 #ifndef TQL_PWK
 #define TQL_PWK 1    // k_tql: 1 = square-root-free QL (Pal-Walker-Kahan), 0 = plain implicit QL
 #endif
+#ifndef TQL_LOCAL
+#define TQL_LOCAL 0    // k_tql: 1 = d, e in per-thread local memory (L1) instead of 33 KB of shared memory per warp, so
+#endif                 //    that its CTAs fit next to any other kernel's - prepared, emulation-checked, not yet measured
 #ifndef TVEC_TWISTED2
 #define TVEC_TWISTED2 0   // 1: twisted_vector2 (interleaved pivot recurrences, stored reciprocals) - prepared, host-tested,
 #endif                    //    not yet measured on the GPU
@@ -404,6 +407,34 @@ __global__ void __launch_bounds__(64, TRI_MINB) k_tridiag_tile(int N, const int3
 // ---------------------------------------------------------------------------------------------------
 // k_tql : one thread per zone; d, e transposed into shared memory with an odd stride
 // ---------------------------------------------------------------------------------------------------
+#if TQL_LOCAL
+template <int NP>
+__global__ void __launch_bounds__(32) k_tql(int N, int nz, const int32_t *__restrict__ mloc,
+                                             double *__restrict__ ws, int32_t *__restrict__ flags) {
+  const int zl = blockIdx.x * 32 + threadIdx.x;
+  if (zl >= nz) return;
+  int rot = 0;
+  if (mloc[zl] != 0) {
+    double d[NP], e[NP];  // dynamically indexed: local memory, interleaved over the lanes (one line per warp access)
+    double *wz = ws_zone(ws, NP, zl);
+    double tn = 0.;
+    for (int i = 0; i < NP; i++) {
+      d[i] = wz[i];
+      e[i] = wz[NP + i];
+      if (i < N) tn = fmax(tn, fmax(fabs(d[i]), fabs(e[i])));
+    }
+#if TQL_PWK
+    rot = pwk_eigenvalues(N, d, e, 1, tn);
+#else
+    rot = tql_eigenvalues(N, d, e, 1, tn);
+#endif
+    for (int i = 0; i < N; i++)
+      if (!(fabs(d[i]) <= 4. * tn)) rot = -1;
+    for (int i = 0; i < NP; i++) wz[3 * NP + i] = d[i];
+  }
+  flags[zl] = (rot < 0) ? 1 : 0;
+}
+#else
 template <int NP>
 __global__ void __launch_bounds__(32) k_tql(int N, int nz, const int32_t *__restrict__ mloc,
                                              double *__restrict__ ws, int32_t *__restrict__ flags) {
@@ -443,6 +474,7 @@ __global__ void __launch_bounds__(32) k_tql(int N, int nz, const int32_t *__rest
     for (int i = lane; i < NP; i += 32) wz[3 * NP + i] = sd[i * S + z];
   }
 }
+#endif  // TQL_LOCAL
 
 // ---------------------------------------------------------------------------------------------------
 // k_tvec

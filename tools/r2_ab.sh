@@ -26,6 +26,12 @@ print(build_variant("/tmp/liboak_tw2.so", ["TVEC_TWISTED2=1"]))
 PY
 echo "== TVEC_TWISTED2=1 (gram 0, fuse 0)" | tee -a $LOG
 OAK_B200_LIB=/tmp/liboak_tw2.so timeout 600 python bench.py $small 2>>gpurun_out/r2_ab.err | tail -1 | cut -c1-400 | tee -a $LOG
+python - <<'PY' 2>&1 | tail -3 | tee -a $LOG
+from oak_b200.build import build_variant
+print(build_variant("/tmp/liboak_tqll.so", ["TQL_LOCAL=1"]))
+PY
+echo "== TQL_LOCAL=1 (k_tql without shared memory; gram 0, fuse 0)" | tee -a $LOG
+OAK_B200_LIB=/tmp/liboak_tqll.so timeout 600 python bench.py $small 2>>gpurun_out/r2_ab.err | tail -1 | cut -c1-400 | tee -a $LOG
 echo "== full C3 line with gram_kernel 1 + fuse_apply 1 (compare with profiles/r1_bench_c3_1gpu.json)" | tee -a $LOG
 timeout 900 python bench.py --steps 3 --warmup 3 --gram-kernel 1 --fuse-apply 1 --no-cpu > gpurun_out/r2_bench_c3_g1f1.json 2>>gpurun_out/r2_ab.err
 cut -c1-600 gpurun_out/r2_bench_c3_g1f1.json | tee -a $LOG
