@@ -76,6 +76,8 @@ OAKB200_API int oakb200_destroy(oakb200_handle *h);
  *                     padded ensemble size 64 only, other sizes keep 0
  *   "fuse_apply"      route 4: 1 = the transform kernel updates the zone rows itself from the factored transform
  *                     (no T written, k_apply only for the zones it did not finish); pays while zone sizes < N. Default 0
+ *   "tvec_split"      route 4: 1 = the eigenvector kernel runs as two kernels (vectors of T with few registers and
+ *                     high occupancy | back-transformation and the rest), 32 KB more workspace per zone. Default 0
  *   "tri_orthtol"     route 4: accepted loss of orthogonality between neighbouring eigenvectors (default 1e-11)
  *   "tri_maxgroup"    route 4: largest group of close eigenvalues orthogonalised in place (default 6; 0 sends
  *                     every zone with a close pair to the Jacobi kernel)

@@ -77,6 +77,7 @@ struct DevBuf {
 struct Slot {
   cudaStream_t st = nullptr;
   cudaStream_t cst = nullptr;  // copy-engine pushes of finished batches to the peers (peer_mode 1)
+  DevBuf Wv;                   // option tvec_split: eigenvectors of T between the two halves of k_tvec
   DevBuf G, T, c, ampl, tri;   // batch workspace (tri: d, e, tau, lambda, flags of the tridiagonal route)
   DevBuf S, xf, xa;            // host-streaming chunk buffers
   cudaEvent_t ev[12] = {};
@@ -88,6 +89,7 @@ struct oakb200_handle {
   int device = 0;
   // options
   int eig_kernel = 4;
+  int tvec_split = 0;         // 1: tridiagonal route, k_tvec as two kernels (eigenvectors of T | back-transformation and the rest)
   int fuse_apply = 0;         // 1: tridiagonal route, k_tvec updates the zone rows from the factored transform (no T, no k_apply)
   int gram_kernel = 0;        // 0: k_gram (DFMA register tiles); 1 / 2: k_gram_mma (DMMA, 4 / 2 warps per zone; NP = 64); 3 / 4: same, 32-candidate chunks
   double tri_orthtol = 0.;  // tridiagonal route: accepted loss of orthogonality between neighbouring eigenvectors (0: default)
@@ -166,6 +168,7 @@ int ensure_ws(oakb200_handle *h, Slot &s, int NP, int zb) {
   if ((rc = s.c.ensure(sizeof(double) * (size_t)zb * NP))) return rc;
   if ((rc = s.ampl.ensure(sizeof(double) * (size_t)zb * NP))) return rc;
   if (h->eig_kernel == 4 && NP <= 64 && (rc = s.tri.ensure(oak_eig_tridiag_ws_bytes(NP, zb)))) return rc;
+  if (h->eig_kernel == 4 && NP <= 64 && h->tvec_split && (rc = s.Wv.ensure(sizeof(double) * (size_t)zb * NP * NP))) return rc;
   return 0;
 }
 
@@ -240,7 +243,7 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
       if ((rc = oak_launch_eig_tridiag(s.st, N, NP, nz, mloc + b0, s.G.as<double>(), s.c.as<double>(),
                                        s.T.as<double>(), s.ampl.as<double>(), s.tri.p, &flags, ctr,
                                        prof ? &s.ev[8] : nullptr, h->tri_orthtol, h->tri_maxgroup,
-                                       fuse ? &fa : nullptr))) return rc;
+                                       fuse ? &fa : nullptr, h->tvec_split ? s.Wv.as<double>() : nullptr))) return rc;
       if (fuse) only_flagged = flags;
       if (prof) CUDA_TRY(cudaEventRecord(s.ev[10], s.st));
       if ((rc = oak_launch_eig(s.st, 0, N, NP, 0, nz, flags, s.G.as<double>(), s.c.as<double>(),
@@ -395,7 +398,7 @@ extern "C" OAKB200_API int oakb200_destroy(oakb200_handle *h) {
   }
   for (int i = 0; i < NSLOT; i++) {
     Slot &s = h->slot[i];
-    s.G.release(); s.T.release(); s.c.release(); s.ampl.release(); s.tri.release(); s.S.release(); s.xf.release(); s.xa.release();
+    s.Wv.release(); s.G.release(); s.T.release(); s.c.release(); s.ampl.release(); s.tri.release(); s.S.release(); s.xf.release(); s.xa.release();
     for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
     if (s.st) cudaStreamDestroy(s.st);
     if (s.cst) cudaStreamDestroy(s.cst);
@@ -499,6 +502,7 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   const std::string k(key);
   if (k == "eig_kernel") h->eig_kernel = (int)value;
   else if (k == "fuse_apply") h->fuse_apply = value != 0.;
+  else if (k == "tvec_split") h->tvec_split = value != 0.;
   else if (k == "gram_kernel") {
     if (!(value >= 0. && value <= 4.) || value != (int)value) { oak_set_error("gram_kernel = %g (expected 0 .. 4)", value); return OAK_ERR_ARG; }
     h->gram_kernel = (int)value;

@@ -310,7 +310,8 @@ int oak_launch_eig_tridiag(cudaStream_t st, int N, int NP, int nz, const int32_t
                            const double *c, double *T, double *ampl, void *ws, int32_t **flags_out,
                            DevCounters *ctr, cudaEvent_t *ev /* optional: [0] after k_tridiag, [1] after k_tql */,
                            double orthtol /* <= 0: default */, int maxgroup /* < 0: default */,
-                           const FusedApplyArgs *fuse /* NULL: k_tvec writes T */);
+                           const FusedApplyArgs *fuse /* NULL: k_tvec writes T */,
+                           double *Wg /* NULL, or [nz][NP*NP] workspace: k_tvec runs as two kernels (option tvec_split) */);
 int oak_launch_apply(cudaStream_t st, int N, int NP, const ZoneGeom &zg, int zone0, int nz,
                      int64_t rowbase, const int32_t *mloc, const double *T, const double *ampl,
                      const double *xf, const double *Sf, int64_t ldS, double *xa, double *Sa,

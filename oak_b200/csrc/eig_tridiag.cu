@@ -654,20 +654,24 @@ struct FusedApply {
 
 // FUSE: see FusedApply above (the zone geometry and the state arrays in `aa` are only used then)
 
-template <int NP, bool FUSE>
+// PART 0: the whole kernel.  Option "tvec_split": PART 1 = eigenvectors of T only (twisted factorisations and the
+// grouping: serial reciprocal chains, few registers, so 4 x the zones in flight of the full kernel), W to global
+// memory; PART 2 = everything from U = Q W on, starting from that W.
+template <int NP, bool FUSE, int PART>
 __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__restrict__ mloc,
                                               const double *__restrict__ ws, const double *__restrict__ cin,
                                               double *__restrict__ Tout, double *__restrict__ ampl_out,
                                               int32_t *__restrict__ flags, DevCounters *ctr, double orthtol,
-                                              int maxgroup, const FusedApplyArgs aa) {
-  constexpr int LDW = NP + 1;
+                                              int maxgroup, const FusedApplyArgs aa, double *__restrict__ Wg) {
+  constexpr int LDW = PART == 1 ? NP : NP + 1;  // part 1 builds W directly in global memory (no shared-memory matrix)
   constexpr int LDY = FUSE ? NP + 4 : NP + 2;  // fused: Yt rows double as mma fragments (conflict-free at NP + 4)
   constexpr int NW = NP / 32;
   constexpr int TR = 8, TC = NP / 8;          // output tile of a thread: TR rows x TC columns
   constexpr int TJ = NP / TC;                 // thread grid: (NP/TR) x TJ = NP threads
   extern __shared__ __align__(16) double sm[];
-  double *W = sm;                      // [NP][LDW] : W[i*LDW + j] = element i of vector j ; later V, then Y
-  double *sd = sm + NP * LDY;
+  // [NP][LDW] : W[i*LDW + j] = element i of vector j ; later V, then Y
+  double *W = PART == 1 ? Wg + (int64_t)blockIdx.x * NP * NP : sm;
+  double *sd = PART == 1 ? sm : sm + NP * LDY;
   double *se = sd + NP, *slam = se + NP, *stau = slam + NP, *sc = stau + NP;
   double *sa = sc + NP, *sb = sa + NP, *suv = sb + NP, *sdw = suv + NP, *suw = sdw + NP;
   double *sg1 = suw + NP, *sg2 = sg1 + NP, *sgj = sg2 + NP, *sres = sgj + NP;
@@ -680,6 +684,17 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
   if (ml == 0) { if (threadIdx.x == 0) flags[zl] = 0; return; }
   const int j = threadIdx.x, warp = j >> 5, lane = j & 31;
   const double *wz = ws + (int64_t)zl * 4 * NP;
+  if constexpr (PART == 2) {
+    if (flags[zl] != 0) return;  // part 1 handed the zone to the Jacobi kernel
+    stau[j] = wz[2 * NP + j];
+    const double lam2 = wz[3 * NP + j];
+    slam[j] = lam2;
+    sc[j] = cin[(int64_t)zl * NP + j];
+    sgj[j] = (j < N) ? 1. - 1. / sqrt(1. + fmax(lam2, 0.)) : 0.;
+    const double *Wz = Wg + (int64_t)zl * NP * NP;
+    for (int i = 0; i < NP; i++) W[i * LDW + j] = Wz[i * NP + j];
+    __syncthreads();
+  } else {
   sd[j] = wz[j];
   se[j] = wz[NP + j];
   stau[j] = wz[2 * NP + j];
@@ -758,6 +773,8 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
     if (j == 0) { flags[zl] = ml; atomicAdd(&ctr->fallback, 1ull); }
     return;
   }
+  if constexpr (PART == 1) return;  // W is in place in Wg; flags[zl] is 0 (k_tql's verdict, unchanged)
+  }  // PART != 2
 
   // ---- U = Q W : 2 columns x NP/2 rows per thread in registers, reflectors from shared memory ----
   const int cp = j >> 1, rh = j & 1;
@@ -942,15 +959,26 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
 
 template <int NP, bool FUSE>
 int launch_tvec(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *c, double *T, double *ampl,
-                double *ws, int32_t *flags, DevCounters *ctr, double orthtol, int maxgroup, const FusedApplyArgs &aa) {
+                double *ws, int32_t *flags, DevCounters *ctr, double orthtol, int maxgroup, const FusedApplyArgs &aa,
+                double *Wg) {
+  const size_t smem0 = sizeof(double) * 14 * NP;
   const size_t smem = sizeof(double) * (NP * (NP + (FUSE ? 4 : 2)) + 14 * NP + (FUSE ? FusedApply<NP>::SMEM_DOUBLES : 0));
   static bool attr_done = false;
   if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(k_tvec<NP, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_tvec<NP, FUSE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_tvec<NP, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+    CUDA_TRY(cudaFuncSetAttribute(k_tvec<NP, FUSE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  k_tvec<NP, FUSE><<<nz, NP, smem, st>>>(N, mloc, ws, c, T, ampl, flags, ctr, orthtol > 0. ? orthtol : TRI_ORTHTOL,
-                                         maxgroup >= 0 ? maxgroup : TRI_MAXGROUP, aa);
+  const double ot = orthtol > 0. ? orthtol : TRI_ORTHTOL;
+  const int mg = maxgroup >= 0 ? maxgroup : TRI_MAXGROUP;
+  if (Wg) {
+    k_tvec<NP, false, 1><<<nz, NP, smem0, st>>>(N, mloc, ws, c, T, ampl, flags, ctr, ot, mg, FusedApplyArgs{}, Wg);
+    CUDA_TRY(cudaGetLastError());
+    k_tvec<NP, FUSE, 2><<<nz, NP, smem, st>>>(N, mloc, ws, c, T, ampl, flags, ctr, ot, mg, aa, Wg);
+  } else {
+    k_tvec<NP, FUSE, 0><<<nz, NP, smem, st>>>(N, mloc, ws, c, T, ampl, flags, ctr, ot, mg, aa, nullptr);
+  }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -958,7 +986,7 @@ int launch_tvec(cudaStream_t st, int N, int nz, const int32_t *mloc, const doubl
 template <int NP>
 int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G, const double *c, double *T,
            double *ampl, double *ws, int32_t *flags, DevCounters *ctr, cudaEvent_t *ev, double orthtol, int maxgroup,
-           const FusedApplyArgs *fuse) {
+           const FusedApplyArgs *fuse, double *Wg) {
 #if TRI_TILE
   k_tridiag_tile<NP><<<nz, 64, 0, st>>>(N, mloc, G, T, ws);
 #else
@@ -969,8 +997,8 @@ int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G,
   k_tql<NP><<<(nz + 31) / 32, 32, 0, st>>>(N, nz, mloc, ws, flags);
   CUDA_TRY(cudaGetLastError());
   if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
-  if (fuse) return launch_tvec<NP, true>(st, N, nz, mloc, c, T, ampl, ws, flags, ctr, orthtol, maxgroup, *fuse);
-  return launch_tvec<NP, false>(st, N, nz, mloc, c, T, ampl, ws, flags, ctr, orthtol, maxgroup, FusedApplyArgs{});
+  if (fuse) return launch_tvec<NP, true>(st, N, nz, mloc, c, T, ampl, ws, flags, ctr, orthtol, maxgroup, *fuse, Wg);
+  return launch_tvec<NP, false>(st, N, nz, mloc, c, T, ampl, ws, flags, ctr, orthtol, maxgroup, FusedApplyArgs{}, Wg);
 }
 
 }  // namespace
@@ -987,13 +1015,13 @@ size_t oak_eig_tridiag_ws_bytes(int NP, int nz) {
 int oak_launch_eig_tridiag(cudaStream_t st, int N, int NP, int nz, const int32_t *mloc, const double *G,
                            const double *c, double *T, double *ampl, void *ws, int32_t **flags_out,
                            DevCounters *ctr, cudaEvent_t *ev, double orthtol, int maxgroup,
-                           const FusedApplyArgs *fuse) {
+                           const FusedApplyArgs *fuse, double *Wg) {
   double *wsd = reinterpret_cast<double *>(ws);
   int32_t *flags = reinterpret_cast<int32_t *>(wsd + 4 * (size_t)NP * nz);
   *flags_out = flags;
   switch (NP) {
-    case 32: return launch<32>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup, fuse);
-    case 64: return launch<64>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup, fuse);
+    case 32: return launch<32>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup, fuse, Wg);
+    case 64: return launch<64>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup, fuse, Wg);
   }
   oak_set_error("eig_tridiag: unsupported padded ensemble size %d", NP);
   return OAK_ERR_UNSUPPORTED;

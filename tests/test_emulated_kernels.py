@@ -64,3 +64,8 @@ def test_fused_apply_in_the_transform_kernel(emu_lib):
 def test_pushes_to_the_peers_in_pieces(emu_lib):
     # host logic of the fused gather (copy-engine flavour) with option push_pieces, alone and with fuse_apply
     _run(emu_lib, "pushes_in_pieces")
+
+
+def test_eigenvector_kernel_split(emu_lib):
+    # option tvec_split: vectors of T from a low-register kernel of their own, incl. its hand-over of flagged zones
+    _run(emu_lib, "split_in_two and 24")

@@ -549,6 +549,34 @@ def test_fused_apply_from_the_factored_transform(ob, N, nz, m, gram):
         assert (Sa[start[z]:start[z + 1]] == c["Sf"][start[z]:start[z + 1]]).all()
 
 
+@pytest.mark.parametrize("N,fuse", [(64, 0), (40, 1), (24, 0)])
+def test_eigenvector_kernel_split_in_two(ob, N, fuse):
+    """Option tvec_split: the eigenvectors of T (twisted factorisations, grouping of close eigenvalues) come from a
+    kernel of their own that builds W in global memory; the back-transformation and everything after it start from
+    that W.  Same results as the single kernel, including zones the first half hands to the Jacobi kernel."""
+    from oak_b200 import synthetic
+    c = synthetic.small_case(nx=12, ny=6, nz=5, N=N, m=260, corr=2500.0, maxlen=5000.0, seed=3 * N)
+    xo, So, _, mloc = _oracle_loc(c)
+    out = []
+    for split in (0, 1):
+        with ob.Handle(0, eig_kernel=4, tvec_split=split, fuse_apply=fuse) as h:
+            _configure(ob, h, c)
+            xa, Sa, _, st = h.local_analysis(c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], ob.DiagCovar(c["var"]))
+        assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL, (split, rel(xa, xo), rel(Sa, So))
+        out.append((xa, Sa, st["zones_fallback"]))
+    assert rel(out[1][0], out[0][0]) < 1e-12 and rel(out[1][1], out[0][1]) < 1e-12 and out[0][2] == out[1][2]
+    # degenerate spectrum: every zone is flagged by the first half and recomputed by the Jacobi kernel
+    d = synthetic.small_case(nx=5, ny=4, nz=2, N=N, m=6, corr=1e9, maxlen=1e12, seed=5)
+    Q, _ = np.linalg.qr(np.random.default_rng(3).normal(size=(N, 6)))
+    rows = Q.T.copy(); rows[:3] *= 2.0; rows[5] *= 0.5
+    d["HSf"] = np.asfortranarray(rows); d["var"] = np.full(6, 0.25)
+    xo, So, _, mloc = _oracle_loc(d)
+    with ob.Handle(0, eig_kernel=4, tvec_split=1, fuse_apply=fuse, tri_maxgroup=0) as h:
+        _configure(ob, h, d)
+        xa, Sa, _, st = h.local_analysis(d["xf"], d["Hxf"], d["yo"], d["Sf"], d["HSf"], ob.DiagCovar(d["var"]))
+    assert st["zones_fallback"] == len(mloc) and rel(xa, xo) < RTOL and rel(Sa, So) < RTOL
+
+
 @pytest.mark.emu_only
 @pytest.mark.parametrize("pieces,fuse", [(1, 0), (3, 0), (4, 1)])
 def test_pushes_in_pieces_under_emulation(ob, pieces, fuse):

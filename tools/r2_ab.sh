@@ -9,12 +9,20 @@ cd "$(dirname "$0")/.."
 LOG=gpurun_out/r2_ab.log
 : > $LOG
 echo "== parity of the new options on the device" | tee -a $LOG
-timeout 900 python -m pytest tests/test_gpu_parity.py -q -x -p no:cacheprovider -k "gram_tensor_core or fused_apply" 2>&1 | tail -5 | tee -a $LOG
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -x -p no:cacheprovider -k "gram_tensor_core or fused_apply or split_in_two" 2>&1 | tail -5 | tee -a $LOG
 small="--nx 300 --ny 300 --nz 30 --nobs 90000 --steps 3 --warmup 2 --no-cpu --no-e2e"
 for combo in "0 0" "1 0" "2 0" "3 0" "4 0" "0 1" "1 1" "3 1"; do
   set -- $combo
   echo "== gram_kernel $1 fuse_apply $2" | tee -a $LOG
   timeout 600 python bench.py $small --gram-kernel $1 --fuse-apply $2 2>>gpurun_out/r2_ab.err | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('value %.0f columns/s  ms/step %.2f' % (d['value'], d['ms_per_step']), d['roofline']['kernel_ms_per_step'])" | tee -a $LOG
+done
+for sp in "0 0" "0 1" "1 1"; do
+  set -- $sp
+  echo "== tvec_split 1, gram_kernel $1 fuse_apply $2" | tee -a $LOG
+  timeout 600 python bench.py $small --tvec-split 1 --gram-kernel $1 --fuse-apply $2 2>>gpurun_out/r2_ab.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('value %.0f columns/s  ms/step %.2f' % (d['value'], d['ms_per_step']), d['roofline']['kernel_ms_per_step'])" | tee -a $LOG
