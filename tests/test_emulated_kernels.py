@@ -25,7 +25,8 @@ def emu_lib():
 def _run(emu_lib, expr, extra_env=None):
     env = dict(os.environ, OAK_B200_LIB=emu_lib, OAK_B200_TEST_EMU="1")
     env.update(extra_env or {})
-    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-x",
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"),
+                        os.path.join(ROOT, "tests", "test_variants_gpu.py"), "-q", "-x",
                         "-p", "no:cacheprovider", "-k", expr], env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
     assert " passed" in p.stdout and "failed" not in p.stdout, p.stdout[-2000:]

@@ -9,7 +9,7 @@ cd "$(dirname "$0")/.."
 LOG=gpurun_out/r2_ab.log
 : > $LOG
 echo "== parity of the new options on the device" | tee -a $LOG
-timeout 900 python -m pytest tests/test_gpu_parity.py -q -x -p no:cacheprovider -k "gram_tensor_core or fused_apply or split_in_two" 2>&1 | tail -5 | tee -a $LOG
+timeout 900 python -m pytest tests/test_variants_gpu.py -q -p no:cacheprovider 2>&1 | tail -5 | tee -a $LOG
 small="--nx 300 --ny 300 --nz 30 --nobs 90000 --steps 3 --warmup 2 --no-cpu --no-e2e"
 for combo in "0 0" "1 0" "2 0" "3 0" "4 0" "0 1" "1 1" "3 1"; do
   set -- $combo
