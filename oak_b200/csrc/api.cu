@@ -248,7 +248,7 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
       if (prof) CUDA_TRY(cudaEventRecord(s.ev[10], s.st));
       if ((rc = oak_launch_eig(s.st, 0, N, NP, 0, nz, flags, s.G.as<double>(), s.c.as<double>(),
                                s.T.as<double>(), s.ampl.as<double>(), h->tol, h->max_sweeps, ctr))) return rc;
-      *launches += 3;
+      *launches += 3 + (h->tvec_split ? 1 : 0);
     } else if ((rc = oak_launch_eig(s.st, h->eig_kernel == 4 ? 0 : h->eig_kernel, N, NP, b0, nz, mloc,
                                     s.G.as<double>(), s.c.as<double>(), s.T.as<double>(), s.ampl.as<double>(),
                                     h->tol, h->max_sweeps, ctr))) return rc;
