@@ -408,11 +408,19 @@ def main():
         if tri:
             stages["k_tridiag"] = (stp["ms_tridiag"], 4.0 / 3.0 * N3)
             stages["k_tql+k_tvec"] = (stp["ms_tql"] + stp["ms_tvec"], (9 - 4.0 / 3.0) * N3 + 2 * N3 + 4 * a.N * a.N)
+            if a.fuse_apply:
+                # the apply runs inside k_tvec (k_apply only serves the zones it did not finish): one stage, the
+                # credited flops of both
+                ms_a, fl_a = stages.pop("k_apply")
+                ms_t, fl_t = stages.pop("k_tql+k_tvec")
+                stages["k_tql+k_tvec+apply"] = (ms_t + ms_a, fl_t + fl_a)
         else:
             stages["k_eig_fast"] = (stp["ms_eig"], 9 * N3 + 2 * N3 + 4 * a.N * a.N)
         # dram__bytes_read.sum + dram__bytes_write.sum per zone from the ncu --set full captures under profiles/
         # (r1_ncu_full_tridiag.txt, r1_ncu_full_tvec.txt, r1_ncu_full_gram.txt; 7104-zone launches, N = 64)
         traffic_zone = {"k_gram": 26.1e3, "k_tridiag": 59.5e3, "k_tql+k_tvec": 59.2e3, "k_eig_fast": 39.8e3}
+        if a.gram_kernel or a.fuse_apply or a.tvec_split:
+            traffic_zone = {}   # no ncu capture of the variant kernels yet: traffic is reported as null
         stage_out = {}
         for name, (ms_k, fl) in stages.items():
             ach = fl * z_rank / (ms_k * 1e-3) / 1e12 if ms_k > 0 else 0.0
@@ -424,7 +432,7 @@ def main():
         achieved = dom_fl * (z_rank / nb) / (dom_ms_launch * 1e-3) / 1e12
         roof = {"bound": "fp64", "kernel": dom + " (largest share of the step among: " + ", ".join(stages) + ")",
                 "achieved": achieved, "peak": peak_dfma, "unit": "TFLOP/s", "frac": achieved / peak_dfma,
-                "traffic": traffic_zone.get(dom, 0.0) * (z_rank / nb) if a.N == 64 else None,
+                "traffic": traffic_zone[dom] * (z_rank / nb) if (a.N == 64 and dom in traffic_zone) else None,
                 "peak_source": "DFMA micro-kernel measured in this run (oakb200_fp64_peak); MEASURED_PEAKS.json has no "
                                "fp64 figure; DMMA m8n8k4 measured %.1f TFLOP/s" % peak_dmma,
                 "algorithmic_flops_per_zone_kernel": dom_fl, "launches_per_step": nb,
