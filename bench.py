@@ -393,7 +393,7 @@ def main():
         cand_mean = agg[1].item() / max(nzones, 1)
         sweeps_mean = agg[2].item() / max(analysed, 1)
         tri = a.eig_kernel == 4 and a.N <= 64
-        per_batch = 6 if tri else 3  # kernels per batch: gram, (tridiag, tql, tvec, fallback | eig), apply
+        per_batch = (6 + (1 if a.tvec_split else 0)) if tri else 3  # kernels per batch: gram, (tridiag, tql, tvec [x2 when split], fallback | eig), apply
         nb = max(1, (stp["launches"] - len(phases)) // per_batch)  # batches of this rank in one step
         N3 = a.N ** 3
         fz = flops_per_zone(a.N, a.nz, mloc_mean, cand_mean)
