@@ -135,6 +135,9 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
+  // c = sum coef delta a: element ci per thread; with four warps it is the job of warps 2 and 3, which own 8 tiles
+  // each against the 10 of warps 0 and 1 (which also evaluate the predicate)
+  const int ci = NW == 4 ? tid - 64 : tid;
   const int zl = blockIdx.x;
   if (zl >= nz) return;
   const int zone = zone0 + zl;
@@ -210,9 +213,9 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
       if (warp == 0) GramMma<NP, NW, 0>::chunk(acc, rows, coef, cnt0, total, g, t);
       else GramMma<NP, NW, 1>::chunk(acc, rows, coef, cnt0, total, g, t);
     }
-    if (tid < NP) {
+    if (ci >= 0) {
       const double *cd = s_cd[lb];
-      for (int r = 0; r < total; r++) cacc = fma(cd[r < cnt0 ? r : 32 + r - cnt0], rows[r * LDR + tid], cacc);
+      for (int r = 0; r < total; r++) cacc = fma(cd[r < cnt0 ? r : 32 + r - cnt0], rows[r * LDR + ci], cacc);
     }
   };
 
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
     if (warp == 0) GramMma<NP, NW, 0>::store(acc, Gz, g, t);
     else GramMma<NP, NW, 1>::store(acc, Gz, g, t);
   }
-  if (tid < NP) cvec[(int64_t)zl * NP + tid] = cacc;
+  if (ci >= 0) cvec[(int64_t)zl * NP + ci] = cacc;
   if (tid == 0) {
     mloc[zone] = nrel_total;
     atomicAdd(&ctr->relevant, (unsigned long long)nrel_total);
