@@ -30,7 +30,7 @@ module oak_b200
  use iso_c_binding
  implicit none
  private
- public :: oakb200_setup_zones, oakb200_locanalysis, oakb200_shutdown
+ public :: oakb200_setup_zones, oakb200_locanalysis, oakb200_analysis, oakb200_shutdown
 
  type(c_ptr), save :: handle = c_null_ptr
 
@@ -79,6 +79,17 @@ module oak_b200
    end function
    function oakb200_local_analysis(h, n, N, m, xf, Hxf, yo, Sf, ldSf, HSf, ldHSf, Rdiag, d01, xa, Sa, ldSa, &
         amplitudes, stats) bind(C, name='oakb200_local_analysis') result(rc)
+     import
+     type(c_ptr), value :: h
+     integer(c_int64_t), value :: n, ldSf, ldHSf, ldSa
+     integer(c_int32_t), value :: N, m
+     real(c_double) :: xf(*), Hxf(*), yo(*), Sf(ldSf,*), HSf(ldHSf,*), Rdiag(*), xa(*), Sa(ldSa,*)
+     type(c_ptr), value :: d01, amplitudes      ! optional arrays: c_null_ptr or c_loc(array)
+     type(oakb200_stats) :: stats
+     integer(c_int) :: rc
+   end function
+   function oakb200_global_analysis(h, n, N, m, xf, Hxf, yo, Sf, ldSf, HSf, ldHSf, Rdiag, d01, xa, Sa, ldSa, &
+        amplitudes, stats) bind(C, name='oakb200_global_analysis') result(rc)
      import
      type(c_ptr), value :: h
      integer(c_int64_t), value :: n, ldSf, ldHSf, ldSa
@@ -181,6 +192,44 @@ contains
   call check(oakb200_local_analysis(handle, int(size(xf),c_int64_t), int(size(Sf,2),c_int32_t), int(m,c_int32_t), &
        xf, Hxf, yo, Sf, int(size(Sf,1),c_int64_t), HSf, int(size(HSf,1),c_int64_t), Rdiag, pd01, &
        xa, Sa, int(size(Sa,1),c_int64_t), pamp, stats), 'oakb200_local_analysis')
+ end subroutine
+
+ ! Drop-in for the global scheme: call analysis(xf,Hxf,yo,Sf,HSf,R,xa,Sa,amplitudes)   (rrsqrt.F90:196-208;
+ ! the schemetype = 0 branch of Assim)
+ subroutine oakb200_analysis(xf, Hxf, yo, Sf, HSf, R, xa, Sa, amplitudes)
+  use covariance
+  real(c_double), intent(in) :: xf(:), Hxf(:), yo(:), Sf(:,:), HSf(:,:)
+  class(Covar), intent(in) :: R
+  real(c_double), intent(out) :: xa(:)
+  real(c_double), intent(out), target :: Sa(:,:)
+  real(c_double), intent(out), optional, target :: amplitudes(:)
+  real(c_double), allocatable, target :: Rdiag(:), d01(:)
+  type(c_ptr) :: pd01, pamp
+  type(oakb200_stats) :: stats
+  integer :: m
+
+  m = size(yo)
+  pd01 = c_null_ptr
+  select type (R)
+  type is (DiagCovar)
+    allocate(Rdiag(m)); Rdiag = R%D
+  type is (DCDCovar)
+    allocate(Rdiag(m), d01(m)); d01 = R%D
+    select type (C => R%C)
+    type is (DiagCovar)
+      Rdiag = C%D
+    class default
+      write(stderr,*) 'oak_b200: DCDCovar with a non-diagonal inner covariance is not supported'; ERROR_STOP
+    end select
+    pd01 = c_loc(d01)
+  class default
+    write(stderr,*) 'oak_b200: only diagonal observation error covariances are supported'; ERROR_STOP
+  end select
+  pamp = c_null_ptr
+  if (present(amplitudes)) pamp = c_loc(amplitudes)
+  call check(oakb200_global_analysis(handle, int(size(xf),c_int64_t), int(size(Sf,2),c_int32_t), int(m,c_int32_t), &
+       xf, Hxf, yo, Sf, int(size(Sf,1),c_int64_t), HSf, int(size(HSf,1),c_int64_t), Rdiag, pd01, &
+       xa, Sa, int(size(Sa,1),c_int64_t), pamp, stats), 'oakb200_global_analysis')
  end subroutine
 
  subroutine oakb200_shutdown()

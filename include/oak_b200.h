@@ -136,6 +136,21 @@ OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t n, int32_t
                                const double *d01, double *xa, double *Sa, int64_t ldSa,
                                double *amplitudes, void *stream, oakb200_stats *stats);
 
+/* The global scheme (schemetype = 0, assimilation.F90:292): `analysis` (rrsqrt.F90:196-208), i.e. analysisIncrement
+ * (rrsqrt.F90:100-190) with every observation and weight 1 — one N x N Gram matrix over the m observations, one
+ * transform, applied to all n rows.  Needs neither zones nor observation positions.  Same arguments as the local
+ * entry points; amplitudes[N] (may be NULL) receives ampl (rrsqrt.F90:142,:153), which `analysis` returns.
+ * HOST buffers (the state is streamed through the device in chunks) / DEVICE pointers. */
+OAKB200_API int oakb200_global_analysis(oakb200_handle *h, int64_t n, int32_t N, int32_t m, const double *xf,
+                            const double *Hxf, const double *yo, const double *Sf, int64_t ldSf,
+                            const double *HSf, int64_t ldHSf, const double *Rdiag, const double *d01,
+                            double *xa, double *Sa, int64_t ldSa, double *amplitudes, oakb200_stats *stats);
+OAKB200_API int oakb200_global_analysis_dev(oakb200_handle *h, int64_t n, int32_t N, int32_t m, const double *xf,
+                                const double *Hxf, const double *yo, const double *Sf, int64_t ldSf,
+                                const double *HSf, int64_t ldHSf, const double *Rdiag, const double *d01,
+                                double *xa, double *Sa, int64_t ldSa, double *amplitudes, void *stream,
+                                oakb200_stats *stats);
+
 /* Asynchronous use of oakb200_local_analysis_dev (option "async" = 1): the call returns after enqueueing,
  * `stream` waits for the result (stream-ordered consumers, e.g. an NCCL all-gather, need no host
  * synchronisation); status (NaN, convergence) and statistics are collected here.  One outstanding call per

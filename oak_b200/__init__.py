@@ -4,12 +4,13 @@ Host-side mirror of the reference interface for this path:
 
     locanalysis(zoneSize, selectObservations, xf, Hxf, yo, Sf, HSf, R, ...)      rrsqrt.F90:433
     assim_ensemble(...)   the ensemble branch of Assim around it                  assimilation.F90:3106-3357
+    analysis(xf, Hxf, yo, Sf, HSf, R)   the global scheme on the same primitives                rrsqrt.F90:196
 
 implemented by the CUDA library oak_b200/liboak_b200.so through its C ABI (include/oak_b200.h).
 There is no CPU fallback: importing works anywhere, calling needs the built library and a B200.
 """
-from .api import (DiagCovar, DCDCovar, Handle, OakB200Error, Selector, assim_ensemble, locanalysis,
+from .api import (DiagCovar, DCDCovar, Handle, OakB200Error, Selector, analysis, assim_ensemble, locanalysis,
                   partition_zones)
 
-__all__ = ["Handle", "Selector", "DiagCovar", "DCDCovar", "locanalysis", "assim_ensemble", "partition_zones",
-           "OakB200Error"]
+__all__ = ["Handle", "Selector", "DiagCovar", "DCDCovar", "locanalysis", "analysis", "assim_ensemble",
+           "partition_zones", "OakB200Error"]

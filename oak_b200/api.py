@@ -195,6 +195,47 @@ class Handle:
                                               max(n, 1), _ptr(ampl), C.byref(st)))
         return xa, Sa, ampl, st.asdict()
 
+    def global_analysis(self, xf, Hxf, yo, Sf, HSf, R, out_Sa=None):
+        """analysis (rrsqrt.F90:196-208): the global scheme with host (numpy) arrays; needs neither zones nor
+        observation positions.  Returns xa, Sa, amplitudes (N), stats."""
+        Sf = np.asfortranarray(Sf, dtype=np.float64)
+        HSf = np.asfortranarray(HSf, dtype=np.float64)
+        n, N = Sf.shape
+        m = HSf.shape[0]
+        if HSf.shape[1] != N:
+            raise OakB200Error(-2, f"HSf has {HSf.shape[1]} columns, Sf has {N}")
+        xf = np.ascontiguousarray(xf, dtype=np.float64)
+        Hxf = np.ascontiguousarray(Hxf, dtype=np.float64)
+        yo = np.ascontiguousarray(yo, dtype=np.float64)
+        var, d01 = _flatten_R(R, m)
+        xa = np.empty(n)
+        Sa = out_Sa if out_Sa is not None else np.empty((n, N), order="F")
+        ampl = np.empty(N)
+        st = _lib.Stats()
+        _check(self._L.oakb200_global_analysis(self._h, n, N, m, _ptr(xf), _ptr(Hxf), _ptr(yo), _ptr(Sf), max(n, 1),
+                                               _ptr(HSf), max(m, 1), _ptr(var), _ptr(d01), _ptr(xa), _ptr(Sa),
+                                               max(n, 1), _ptr(ampl), C.byref(st)))
+        return xa, Sa, ampl, st.asdict()
+
+    def global_analysis_dev(self, xf, Hxf, yo, Sf, HSf, Rdiag, xa, Sa, d01=None, ampl=None, stream=None):
+        """The global scheme on CUDA tensors resident on this device (member-major like local_analysis_dev)."""
+        import torch
+        N, n = Sf.shape
+        m = HSf.shape[1]
+        for t in (xf, Hxf, yo, Sf, HSf, Rdiag, xa, Sa) + tuple(x for x in (d01, ampl) if x is not None):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.device.index == self.device):
+                raise OakB200Error(-2, "global_analysis_dev needs contiguous fp64 CUDA tensors on the handle's device")
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        st = _lib.Stats()
+        _check(self._L.oakb200_global_analysis_dev(
+            self._h, n, N, m, C.c_void_p(xf.data_ptr()), C.c_void_p(Hxf.data_ptr()), C.c_void_p(yo.data_ptr()),
+            C.c_void_p(Sf.data_ptr()), max(n, 1), C.c_void_p(HSf.data_ptr()), max(m, 1),
+            C.c_void_p(Rdiag.data_ptr()), None if d01 is None else C.c_void_p(d01.data_ptr()),
+            C.c_void_p(xa.data_ptr()), C.c_void_p(Sa.data_ptr()), max(n, 1),
+            None if ampl is None else C.c_void_p(ampl.data_ptr()), C.c_void_p(stream), C.byref(st)))
+        return st.asdict()
+
     def local_analysis_dev(self, xf, Hxf, yo, Sf, HSf, Rdiag, xa, Sa, d01=None, stream=None):
         """locAnalysis on CUDA tensors resident on this device (fp64).  Matrices are member-major:
         Sf/Sa of shape (N, n) and HSf of shape (N, m), contiguous — the column-major n x N / m x N
@@ -322,6 +363,18 @@ def locanalysis(zoneSize, selectObservations, xf, Hxf, yo, Sf, HSf, R, handle=No
     try:
         h.configure(zoneSize, selectObservations)
         xa, Sa, ampl, _ = h.local_analysis(xf, Hxf, yo, Sf, HSf, R, want_amplitudes=want_amplitudes)
+        return xa, Sa, ampl
+    finally:
+        if own:
+            h.close()
+
+
+def analysis(xf, Hxf, yo, Sf, HSf, R, handle=None, device=0):
+    """analysis (rrsqrt.F90:196-208), the global scheme: returns (xa, Sa, amplitudes)."""
+    own = handle is None
+    h = Handle(device) if own else handle
+    try:
+        xa, Sa, ampl, _ = h.global_analysis(xf, Hxf, yo, Sf, HSf, R)
         return xa, Sa, ampl
     finally:
         if own:

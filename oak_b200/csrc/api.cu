@@ -134,6 +134,7 @@ struct oakb200_handle {
   // ensemble path
   DevBuf d_HE, d_Hi, d_Hj, d_Hs, d_Hshift, d_order, d_rowstart, d_xf, d_xa, d_maxc, d_E;
   DevBuf d_ctr;
+  DevBuf d_gws, d_gzstart;    // global scheme: partial Gram matrices, prefix sums of the row blocks
   Slot slot[NSLOT];
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_user = nullptr;
 
@@ -390,7 +391,7 @@ extern "C" OAKB200_API int oakb200_destroy(oakb200_handle *h) {
                     &h->d_key_in, &h->d_key_out, &h->d_val_in, &h->d_perm, &h->d_cell_start, &h->d_sx, &h->d_sy,
                     &h->d_tmp, &h->d_rows, &h->d_delta, &h->d_scoef, &h->d_HSf, &h->d_yo, &h->d_Hxf, &h->d_R,
                     &h->d_d01, &h->d_ampzero, &h->d_HE, &h->d_Hi, &h->d_Hj, &h->d_Hs, &h->d_Hshift, &h->d_order,
-                    &h->d_rowstart, &h->d_xf, &h->d_xa, &h->d_maxc, &h->d_E, &h->d_ctr, &h->d_anam};
+                    &h->d_rowstart, &h->d_xf, &h->d_xa, &h->d_maxc, &h->d_E, &h->d_ctr, &h->d_anam, &h->d_gws, &h->d_gzstart};
   for (DevBuf *b : bufs) b->release();
   for (int d = 0; d < OAKB200_MAX_PEERS; d++) {
     if (h->pstream[d]) cudaStreamDestroy(h->pstream[d]);
@@ -865,6 +866,193 @@ extern "C" OAKB200_API int oakb200_local_analysis(oakb200_handle *h, int64_t n, 
   CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_a, h->ev_b));
   CUDA_TRY(cudaEventElapsedTime(&msp, h->ev_a, h->slot[0].ev[4]));
   rc = end_call(h, stats, launches, prof, ms, msp);
+  if (stats) { stats->h2d_bytes = h2d; stats->d2h_bytes = d2h; }
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// global scheme (schemetype = 0): analysis, rrsqrt.F90:196-208
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int GLOBAL_BLOCK_ROWS = 512;  // rows of the state one k_apply CTA updates with the shared transform
+
+int global_check(oakb200_handle *h, int64_t n, int N, int m) {
+  if (!h) { oak_set_error("null handle"); return OAK_ERR_ARG; }
+  if (n < 0 || m < 0) { oak_set_error("global_analysis: negative size"); return OAK_ERR_ARG; }
+  if (N < 2) { oak_set_error("ensemble size N = %d < 2", N); return OAK_ERR_ARG; }
+  if (padded(N) < 0) { oak_set_error("ensemble size N = %d > 128 is not supported", N); return OAK_ERR_UNSUPPORTED; }
+  return 0;
+}
+
+// (ampl, T) of the global scheme into slot 0's workspace from device-resident observation-space arrays; enqueued on
+// slot 0's stream.  m > 0.
+int global_transform(oakb200_handle *h, int N, int NP, int m, const double *HSf, int64_t ldH, const double *yo,
+                     const double *Hxf, const double *Rdiag, const double *d01, int64_t *launches) {
+  Slot &s = h->slot[0];
+  int rc;
+  if ((rc = ensure_ws(h, s, NP, 1))) return rc;
+  if ((rc = h->d_mloc.ensure(sizeof(int32_t)))) return rc;
+  const int nparts = oak_global_gram_parts(m);
+  if ((rc = h->d_gws.ensure(oak_global_gram_ws_bytes(NP, nparts)))) return rc;
+  DevCounters *ctr = h->d_ctr.as<DevCounters>();
+  int32_t *mloc = h->d_mloc.as<int32_t>();
+  if ((rc = oak_launch_global_gram(s.st, m, N, NP, HSf, ldH, yo, Hxf, Rdiag, d01, h->d_gws.p, nparts, s.G.as<double>(),
+                                   s.c.as<double>(), mloc))) return rc;
+  *launches += 2;
+  if (h->eig_kernel == 4 && NP <= 64) {
+    int32_t *flags = nullptr;
+    if ((rc = oak_launch_eig_tridiag(s.st, N, NP, 1, mloc, s.G.as<double>(), s.c.as<double>(), s.T.as<double>(),
+                                     s.ampl.as<double>(), s.tri.p, &flags, ctr, nullptr, h->tri_orthtol, h->tri_maxgroup,
+                                     nullptr, nullptr))) return rc;
+    if ((rc = oak_launch_eig(s.st, 0, N, NP, 0, 1, flags, s.G.as<double>(), s.c.as<double>(), s.T.as<double>(),
+                             s.ampl.as<double>(), h->tol, h->max_sweeps, ctr))) return rc;
+    *launches += 4;
+  } else {
+    if ((rc = oak_launch_eig(s.st, h->eig_kernel == 4 ? 0 : h->eig_kernel, N, NP, 0, 1, mloc, s.G.as<double>(),
+                             s.c.as<double>(), s.T.as<double>(), s.ampl.as<double>(), h->tol, h->max_sweeps, ctr))) return rc;
+    *launches += 1;
+  }
+  return 0;
+}
+
+// Sa = Sf T, xa = xf + Sf ampl for the rows [row0, row0 + rows) held in the given buffers (first row = row0, a
+// multiple of GLOBAL_BLOCK_ROWS), on stream slot s; T and ampl are slot 0's.
+int global_apply(oakb200_handle *h, Slot &s, int N, int NP, int64_t n, int64_t row0, int64_t rows, const double *xf,
+                 const double *Sf, int64_t ldS, double *xa, double *Sa, int64_t ldSa, int64_t *launches) {
+  if (rows <= 0) return 0;
+  ZoneGeom zg{};
+  zg.zstart = h->d_gzstart.as<int64_t>();
+  const int b0 = (int)(row0 / GLOBAL_BLOCK_ROWS), b1 = (int)((row0 + rows + GLOBAL_BLOCK_ROWS - 1) / GLOBAL_BLOCK_ROWS);
+  (void)n;
+  PeerOut none{};
+  int rc = oak_launch_apply(s.st, N, NP, zg, b0, b1 - b0, row0, nullptr, h->slot[0].T.as<double>(),
+                            h->slot[0].ampl.as<double>(), xf, Sf, ldS, xa, Sa, ldSa, none, nullptr, true);
+  *launches += 1;
+  return rc;
+}
+
+int global_block_starts(oakb200_handle *h, cudaStream_t st, int64_t n) {
+  const int nblocks = (int)((n + GLOBAL_BLOCK_ROWS - 1) / GLOBAL_BLOCK_ROWS);
+  int rc = h->d_gzstart.ensure(sizeof(int64_t) * ((size_t)nblocks + 1));
+  if (rc) return rc;
+  return oak_launch_block_starts(st, n, GLOBAL_BLOCK_ROWS, nblocks, h->d_gzstart.as<int64_t>());
+}
+
+int global_finish(oakb200_handle *h, oakb200_stats *stats, int64_t launches, int m, float ms) {
+  const int saved = h->nzones;
+  h->nzones = 1;
+  int rc = end_call(h, stats, launches, ProfAcc(), ms, 0.f);
+  h->nzones = saved;
+  if (stats) { stats->obs_relevant_sum = m; stats->zones_skipped = m == 0 ? 1 : 0; }
+  return rc;
+}
+
+}  // namespace
+
+extern "C" OAKB200_API int oakb200_global_analysis_dev(oakb200_handle *h, int64_t n, int32_t N, int32_t m, const double *xf,
+                                           const double *Hxf, const double *yo, const double *Sf, int64_t ldSf,
+                                           const double *HSf, int64_t ldHSf, const double *Rdiag, const double *d01,
+                                           double *xa, double *Sa, int64_t ldSa, double *amplitudes, void *stream,
+                                           oakb200_stats *stats) {
+  int rc = global_check(h, n, N, m);
+  if (rc) return rc;
+  if ((n > 0 && (!xf || !Sf || !xa || !Sa)) || (m > 0 && (!Hxf || !yo || !HSf || !Rdiag))) { oak_set_error("global_analysis: null array"); return OAK_ERR_ARG; }
+  if (ldSf < n || ldSa < n || ldHSf < m) { oak_set_error("global_analysis: leading dimension too small"); return OAK_ERR_ARG; }
+  DeviceGuard guard(h->device);
+  const int NP = padded(h, N);
+  cudaStream_t s0 = h->slot[0].st;
+  CUDA_TRY(cudaEventRecord(h->ev_user, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamWaitEvent(s0, h->ev_user, 0));
+  if (stats) memset(stats, 0, sizeof *stats);
+  CUDA_TRY(cudaMemsetAsync(h->d_ctr.p, 0, sizeof(DevCounters), s0));
+  CUDA_TRY(cudaEventRecord(h->ev_a, s0));
+  int64_t launches = 0;
+  if (m == 0) {  // nothing to assimilate: the increment is zero (G = 0, c = 0)
+    if (n > 0) {
+      if (Sa != Sf) CUDA_TRY(cudaMemcpy2DAsync(Sa, 8 * (size_t)ldSa, Sf, 8 * (size_t)ldSf, 8 * (size_t)n, N, cudaMemcpyDeviceToDevice, s0));
+      CUDA_TRY(cudaMemcpyAsync(xa, xf, 8 * (size_t)n, cudaMemcpyDeviceToDevice, s0));
+    }
+    if (amplitudes) CUDA_TRY(cudaMemsetAsync(amplitudes, 0, sizeof(double) * N, s0));
+  } else {
+    if ((rc = global_transform(h, N, NP, m, HSf, ldHSf, yo, Hxf, Rdiag, d01, &launches))) return rc;
+    if ((rc = global_block_starts(h, s0, n))) return rc;
+    if ((rc = global_apply(h, h->slot[0], N, NP, n, 0, n, xf, Sf, ldSf, xa, Sa, ldSa, &launches))) return rc;
+    launches += 1;
+    if (amplitudes) CUDA_TRY(cudaMemcpyAsync(amplitudes, h->slot[0].ampl.p, sizeof(double) * N, cudaMemcpyDeviceToDevice, s0));
+  }
+  CUDA_TRY(cudaEventRecord(h->ev_b, s0));
+  CUDA_TRY(cudaEventSynchronize(h->ev_b));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_a, h->ev_b));
+  return global_finish(h, stats, launches, m, ms);
+}
+
+extern "C" OAKB200_API int oakb200_global_analysis(oakb200_handle *h, int64_t n, int32_t N, int32_t m, const double *xf,
+                                       const double *Hxf, const double *yo, const double *Sf, int64_t ldSf,
+                                       const double *HSf, int64_t ldHSf, const double *Rdiag, const double *d01,
+                                       double *xa, double *Sa, int64_t ldSa, double *amplitudes, oakb200_stats *stats) {
+  int rc = global_check(h, n, N, m);
+  if (rc) return rc;
+  if ((n > 0 && (!xf || !Sf || !xa || !Sa)) || (m > 0 && (!Hxf || !yo || !HSf || !Rdiag))) { oak_set_error("global_analysis: null array"); return OAK_ERR_ARG; }
+  if (ldSf < n || ldSa < n || ldHSf < m) { oak_set_error("global_analysis: leading dimension too small"); return OAK_ERR_ARG; }
+  DeviceGuard guard(h->device);
+  const int NP = padded(h, N);
+  cudaStream_t s0 = h->slot[0].st;
+  if (stats) memset(stats, 0, sizeof *stats);
+  CUDA_TRY(cudaMemsetAsync(h->d_ctr.p, 0, sizeof(DevCounters), s0));
+  CUDA_TRY(cudaEventRecord(h->ev_a, s0));
+  int64_t launches = 0, h2d = 0, d2h = 0;
+  if (m == 0) {
+    for (int k = 0; k < N && n > 0; k++)
+      if (Sa != Sf) memmove(Sa + (size_t)ldSa * k, Sf + (size_t)ldSf * k, 8 * (size_t)n);
+    if (n > 0) memmove(xa, xf, 8 * (size_t)n);
+    if (amplitudes) memset(amplitudes, 0, sizeof(double) * N);
+  } else {
+    const size_t mb = (size_t)m;
+    if ((rc = h->d_HSf.ensure(8 * mb * N)) || (rc = h->d_yo.ensure(8 * mb)) || (rc = h->d_Hxf.ensure(8 * mb)) ||
+        (rc = h->d_R.ensure(8 * mb)) || (rc = h->d_d01.ensure(8 * mb)))
+      return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(h->d_HSf.p, 8 * mb, HSf, 8 * (size_t)ldHSf, 8 * mb, N, cudaMemcpyHostToDevice, s0));
+    CUDA_TRY(cudaMemcpyAsync(h->d_yo.p, yo, 8 * mb, cudaMemcpyHostToDevice, s0));
+    CUDA_TRY(cudaMemcpyAsync(h->d_Hxf.p, Hxf, 8 * mb, cudaMemcpyHostToDevice, s0));
+    CUDA_TRY(cudaMemcpyAsync(h->d_R.p, Rdiag, 8 * mb, cudaMemcpyHostToDevice, s0));
+    if (d01) CUDA_TRY(cudaMemcpyAsync(h->d_d01.p, d01, 8 * mb, cudaMemcpyHostToDevice, s0));
+    h2d += 8ll * m * (N + 3 + (d01 ? 1 : 0));
+    if ((rc = global_transform(h, N, NP, m, h->d_HSf.as<double>(), m, h->d_yo.as<double>(), h->d_Hxf.as<double>(),
+                               h->d_R.as<double>(), d01 ? h->d_d01.as<double>() : nullptr, &launches))) return rc;
+    if ((rc = global_block_starts(h, s0, n))) return rc;
+    launches += 1;
+    if (amplitudes) CUDA_TRY(cudaMemcpyAsync(amplitudes, h->slot[0].ampl.p, sizeof(double) * N, cudaMemcpyDeviceToHost, s0));
+    CUDA_TRY(cudaEventRecord(h->slot[0].ev[4], s0));
+    for (int i = 1; i < NSLOT; i++) CUDA_TRY(cudaStreamWaitEvent(h->slot[i].st, h->slot[0].ev[4], 0));
+    // the state streams through the device in chunks of whole row blocks, one stream slot per chunk
+    int64_t rows_target = std::max<int64_t>(1, (int64_t)(h->chunk_mb * 1024. * 1024. / (8. * N)));
+    rows_target = std::max<int64_t>(GLOBAL_BLOCK_ROWS, rows_target / GLOBAL_BLOCK_ROWS * GLOBAL_BLOCK_ROWS);
+    int ci = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += rows_target, ci++) {
+      const int64_t rows = std::min(rows_target, n - r0);
+      Slot &s = h->slot[ci % NSLOT];
+      if ((rc = s.S.ensure(8 * (size_t)rows * N)) || (rc = s.xf.ensure(8 * (size_t)rows)) || (rc = s.xa.ensure(8 * (size_t)rows))) return rc;
+      CUDA_TRY(cudaMemcpy2DAsync(s.S.p, 8 * (size_t)rows, Sf + r0, 8 * (size_t)ldSf, 8 * (size_t)rows, N, cudaMemcpyHostToDevice, s.st));
+      CUDA_TRY(cudaMemcpyAsync(s.xf.p, xf + r0, 8 * (size_t)rows, cudaMemcpyHostToDevice, s.st));
+      if ((rc = global_apply(h, s, N, NP, n, r0, rows, s.xf.as<double>(), s.S.as<double>(), rows, s.xa.as<double>(),
+                             s.S.as<double>(), rows, &launches))) return rc;
+      CUDA_TRY(cudaMemcpy2DAsync(Sa + r0, 8 * (size_t)ldSa, s.S.p, 8 * (size_t)rows, 8 * (size_t)rows, N, cudaMemcpyDeviceToHost, s.st));
+      CUDA_TRY(cudaMemcpyAsync(xa + r0, s.xa.p, 8 * (size_t)rows, cudaMemcpyDeviceToHost, s.st));
+      h2d += 8ll * rows * (N + 1);
+      d2h += 8ll * rows * (N + 1);
+    }
+    for (int i = 1; i < NSLOT; i++) {
+      CUDA_TRY(cudaEventRecord(h->slot[i].ev[5], h->slot[i].st));
+      CUDA_TRY(cudaStreamWaitEvent(s0, h->slot[i].ev[5], 0));
+    }
+  }
+  CUDA_TRY(cudaEventRecord(h->ev_b, s0));
+  CUDA_TRY(cudaEventSynchronize(h->ev_b));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_a, h->ev_b));
+  rc = global_finish(h, stats, launches, m, ms);
   if (stats) { stats->h2d_bytes = h2d; stats->d2h_bytes = d2h; }
   return rc;
 }

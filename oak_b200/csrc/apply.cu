@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
                                                const double *__restrict__ T, const double *__restrict__ ampl,
                                                const double *__restrict__ xf, const double *Sf, int64_t ldS,
                                                double *__restrict__ xa, double *Sa, int64_t ldSa,
-                                               const PeerOut P, const int32_t *__restrict__ only_flagged) {
+                                               const PeerOut P, const int32_t *__restrict__ only_flagged,
+                                               int64_t tstride, int astride) {
   extern __shared__ __align__(128) double sm[];
   double *sT = sm;                   // [NP][NP] row-major: sT[k*NP + k']
   double *sS = sm + NP * NP;         // [NP][RC+?] member-major chunk: sS[k*LDS + r]
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
   const int zone = zone0 + zl;
   const int64_t i1 = zg.zstart[zone] - rowbase;
   const int nrow = (int)(zg.zstart[zone + 1] - zg.zstart[zone]);
-  const bool analysed = mloc[zone] != 0;
+  const bool analysed = !mloc || mloc[zone] != 0;  // mloc == NULL: row blocks of the global scheme, all analysed
   if (nrow <= 0) return;
   if (only_flagged && analysed && only_flagged[zl] == 0) return;  // already updated by the fused transform kernel
   const int64_t ip = P.row0 + zg.zstart[zone];  // first row of the zone in the peers' (global) arrays
@@ -102,9 +103,9 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
   if (tid == 0) {
     constexpr uint32_t bytes = NP * NP * sizeof(double);
     mbar_expect_tx(&bar, bytes);
-    bulk_g2s(sT, T + (int64_t)zl * NP * NP, bytes, &bar);
+    bulk_g2s(sT, T + (int64_t)zl * tstride, bytes, &bar);
   }
-  if (tid < NP) s_ampl[tid] = ampl[(int64_t)zl * NP + tid];
+  if (tid < NP) s_ampl[tid] = ampl[(int64_t)zl * astride + tid];
 
   // thread tile of the chunk product: rows 4*ty.., columns 2*tx + 32*b (+1)
   const int ty = tid >> 4, tx = tid & 15;  // 8 x 16
@@ -181,14 +182,15 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
 template <int NP>
 int launch(cudaStream_t st, int N, const ZoneGeom &zg, int zone0, int nz, int64_t rowbase, const int32_t *mloc,
            const double *T, const double *ampl, const double *xf, const double *Sf, int64_t ldS, double *xa,
-           double *Sa, int64_t ldSa, const PeerOut &peers, const int32_t *only_flagged) {
+           double *Sa, int64_t ldSa, const PeerOut &peers, const int32_t *only_flagged, bool shared_transform) {
   const size_t smem = sizeof(double) * (NP * NP + NP * (RC + 2) + NP);
   static bool attr_done = false;
   if (!attr_done) {
     CUDA_TRY(cudaFuncSetAttribute(k_apply<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  k_apply<NP><<<nz, 128, smem, st>>>(N, zg, zone0, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged);
+  k_apply<NP><<<nz, 128, smem, st>>>(N, zg, zone0, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged,
+                                       shared_transform ? 0 : (int64_t)NP * NP, shared_transform ? 0 : NP);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -198,12 +200,12 @@ int launch(cudaStream_t st, int N, const ZoneGeom &zg, int zone0, int nz, int64_
 int oak_launch_apply(cudaStream_t st, int N, int NP, const ZoneGeom &zg, int zone0, int nz, int64_t rowbase,
                      const int32_t *mloc, const double *T, const double *ampl, const double *xf,
                      const double *Sf, int64_t ldS, double *xa, double *Sa, int64_t ldSa, const PeerOut &peers,
-                     const int32_t *only_flagged) {
+                     const int32_t *only_flagged, bool shared_transform) {
   if (nz <= 0) return 0;
   switch (NP) {
-    case 32: return launch<32>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged);
-    case 64: return launch<64>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged);
-    case 128: return launch<128>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged);
+    case 32: return launch<32>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged, shared_transform);
+    case 64: return launch<64>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged, shared_transform);
+    case 128: return launch<128>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged, shared_transform);
   }
   oak_set_error("apply: unsupported padded ensemble size %d", NP);
   return OAK_ERR_UNSUPPORTED;

@@ -316,7 +316,15 @@ int oak_launch_apply(cudaStream_t st, int N, int NP, const ZoneGeom &zg, int zon
                      int64_t rowbase, const int32_t *mloc, const double *T, const double *ampl,
                      const double *xf, const double *Sf, int64_t ldS, double *xa, double *Sa,
                      int64_t ldSa, const PeerOut &peers,
-                     const int32_t *only_flagged = nullptr /* batch-local flags: analysed zones with flag 0 are skipped */);
+                     const int32_t *only_flagged = nullptr /* batch-local flags: analysed zones with flag 0 are skipped */,
+                     bool shared_transform = false /* global scheme: every block of rows uses T[0], ampl[0]; mloc may be NULL */);
+// global scheme (global.cu)
+size_t oak_global_gram_ws_bytes(int NP, int nparts);
+int oak_global_gram_parts(int m);
+int oak_launch_global_gram(cudaStream_t st, int m, int N, int NP, const double *HSf, int64_t ldH, const double *yo,
+                           const double *Hxf, const double *Rdiag, const double *d01, void *ws, int nparts, double *G,
+                           double *c, int32_t *mloc);
+int oak_launch_block_starts(cudaStream_t st, int64_t n, int rows_per_block, int nblocks, int64_t *zstart);
 int oak_fp64_peak(int mode, double *tflops);
 
 // ensemble prologue / epilogue (assimilation.F90:3106-3134, :3301-3357)

@@ -70,3 +70,8 @@ def test_pushes_to_the_peers_in_pieces(emu_lib):
 def test_eigenvector_kernel_split(emu_lib):
     # option tvec_split: vectors of T from a low-register kernel of their own, incl. its hand-over of flagged zones
     _run(emu_lib, "split_in_two and 24")
+
+
+def test_global_scheme(emu_lib):
+    # analysis (rrsqrt.F90:196-208): tall-skinny Gram in partial matrices, one transform, apply over row blocks
+    _run(emu_lib, "global_scheme")

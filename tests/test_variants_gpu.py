@@ -151,3 +151,40 @@ def test_pushes_in_pieces_under_emulation(ob, pieces, fuse):
         assert (P[:row0] == 7.0).all() and (P[row0 + n:] == 7.0).all() and (px[:row0] == 7.0).all()
 
 
+
+
+@pytest.mark.parametrize("eig_kernel", [4, 0])
+def test_global_scheme_known_answers_and_oracle(ob, eig_kernel):
+    """analysis (rrsqrt.F90:196-208) through oakb200_global_analysis: the reference's own known answers
+    (test/test_rrsqrt.F90:57-74: Kalman gain form of xa and Pa, tol 1e-8) and the oracle at 1e-9; then a larger case
+    with excluded observations (DCDCovar), several partial Gram matrices, several row blocks and several host chunks."""
+    import oracle
+    from refcases import kalman_check, rrsqrt_case
+    from test_gpu_parity import TOL_REF
+    c = rrsqrt_case()
+    xa_check, Pa_check = kalman_check(c["xf"], c["Sf"], c["H"], c["y"], np.diag(c["var"]))
+    with ob.Handle(0, eig_kernel=eig_kernel, pad_to=64) as h:
+        xa, Sa, ampl, st = h.global_analysis(c["xf"], c["Hxf"], c["y"], c["Sf"], c["HSf"], ob.DiagCovar(c["var"]))
+    assert np.abs(xa - xa_check).max() < TOL_REF and np.abs(Sa @ Sa.T - Pa_check).max() < TOL_REF
+    xo, So, ao = oracle.analysis(c["xf"], c["Hxf"], c["y"], c["Sf"], c["HSf"], c["var"])
+    assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL and rel(ampl, ao) < 1e-8
+    assert st["obs_relevant_sum"] == c["m"]
+
+    from oak_b200 import synthetic
+    for N in (40, 100):
+        d = synthetic.small_case(nx=21, ny=17, nz=4, N=N, m=700, corr=3000.0, maxlen=6000.0, seed=N)
+        e01 = (np.random.default_rng(1).uniform(size=d["m"]) > 0.25).astype(np.float64)
+        var = np.where(e01 > 0, d["var"], 1e300)    # an excluded observation = infinite variance for the oracle
+        xo, So, ao = oracle.analysis(d["xf"], d["Hxf"], d["yo"], d["Sf"], d["HSf"], var)
+        with ob.Handle(0, eig_kernel=eig_kernel, chunk_mb=0.2) as h:
+            buf = np.asfortranarray(d["Sf"].copy())
+            xa, Sa, ampl, st = h.global_analysis(d["xf"], d["Hxf"], d["yo"], buf, d["HSf"],
+                                                 ob.DCDCovar(e01, ob.DiagCovar(d["var"])), out_Sa=buf)
+            assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL, (N, rel(xa, xo), rel(Sa, So))
+            # no observation: the forecast comes back unchanged
+            xa0, Sa0, a0, st0 = h.global_analysis(d["xf"], np.zeros(0), np.zeros(0), d["Sf"], np.zeros((0, N)),
+                                                  ob.DiagCovar(np.zeros(0)))
+            assert (xa0 == d["xf"]).all() and (Sa0 == d["Sf"]).all() and (a0 == 0).all()
+    # the module-level mirror of the reference call
+    xa, Sa, ampl = ob.analysis(c["xf"], c["Hxf"], c["y"], c["Sf"], c["HSf"], ob.DiagCovar(c["var"]))
+    assert np.abs(xa - xa_check).max() < TOL_REF
