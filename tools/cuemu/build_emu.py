@@ -1,7 +1,11 @@
 """Builds tools/cuemu/_build/liboak_b200_emu.so: the library's own .cu sources compiled with g++ against the
 CPU emulation of the CUDA execution model (cuemu.h).  TEST HARNESS ONLY — see cuemu.h.
 
-    python tools/cuemu/build_emu.py [--force] [-D NAME=VALUE ...] [--out path]
+    python tools/cuemu/build_emu.py [--force] [--asan] [-D NAME=VALUE ...] [--out path]
+
+--asan builds with AddressSanitizer (shared-memory arrays are globals / heap blocks there, so out-of-bounds
+indexing inside a kernel is reported); run the tests with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
+ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0.
 
 Source rewriting (the only things g++ cannot parse): `kernel<<<grid, block, smem, stream>>>(args);` becomes
 `cuemu::launch(grid, block, smem, [&]() { kernel(args); });` and `extern __shared__ T name[];` becomes a pointer
@@ -55,9 +59,11 @@ def split_top(s):
     return out
 
 
-def build(force=False, defines=(), out=None):
+def build(force=False, defines=(), out=None, asan=False):
     os.makedirs(BUILD, exist_ok=True)
-    out = out or os.path.join(BUILD, "liboak_b200_emu.so")
+    out = out or os.path.join(BUILD, "liboak_b200_emu_asan.so" if asan else "liboak_b200_emu.so")
+    cxxflags = CXXFLAGS + (["-O1", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else [])
+    defines = list(defines) + (["CUEMU_ASAN=1"] if asan else [])
     tag = hashlib.sha256(repr(sorted(defines)).encode()).hexdigest()[:8]
     h = hashlib.sha256()
     for root in (CSRC, HERE, os.path.join(HERE, "shim"), os.path.join(HERE, "shim", "cub"), os.path.join(ROOT, "include")):
@@ -85,7 +91,7 @@ def build(force=False, defines=(), out=None):
         cpp = os.path.join(fake, src.replace(".cu", ".emu.cpp"))
         open(cpp, "w").write(rewrite(open(os.path.join(CSRC, src)).read()))
         obj = cpp.replace(".cpp", ".o")
-        cmd = ["g++"] + CXXFLAGS + ["-D" + d for d in defines] + ["-c", cpp, "-o", obj]
+        cmd = ["g++"] + cxxflags + ["-D" + d for d in defines] + ["-c", cpp, "-o", obj]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError(f"g++ failed on {src}:\n{p.stderr[:6000]}")
@@ -94,8 +100,8 @@ def build(force=False, defines=(), out=None):
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(one, SOURCES))
     rt = os.path.join(gen, "cuemu_rt.o")
-    subprocess.check_call(["g++"] + CXXFLAGS + ["-c", os.path.join(HERE, "cuemu_rt.cpp"), "-o", rt])
-    subprocess.check_call(["g++", "-shared", "-o", out] + objs + [rt])
+    subprocess.check_call(["g++"] + cxxflags + ["-c", os.path.join(HERE, "cuemu_rt.cpp"), "-o", rt])
+    subprocess.check_call(["g++", "-shared", "-o", out] + objs + [rt] + (["-fsanitize=address"] if asan else []))
     open(stamp_file, "w").write(h.hexdigest())
     return out
 
@@ -103,4 +109,4 @@ def build(force=False, defines=(), out=None):
 if __name__ == "__main__":
     defs = [sys.argv[i + 1] for i, a in enumerate(sys.argv) if a == "-D"]
     o = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
-    print(build(force="--force" in sys.argv, defines=defs, out=o))
+    print(build(force="--force" in sys.argv, defines=defs, out=o, asan="--asan" in sys.argv))
