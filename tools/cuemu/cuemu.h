@@ -222,7 +222,7 @@ static inline cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *
 static inline cudaError_t cudaMalloc(void **p, size_t bytes) {
   void *q = nullptr;
   if (posix_memalign(&q, 256, bytes ? bytes : 256) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
-  memset(q, 0xA5, bytes ? bytes : 256);  // uninitialised device memory is not zero
+  memset(q, 0xFF, bytes ? bytes : 256);  // uninitialised device memory is not zero: NaN pattern, -1 as an integer
   *p = q;
   return cudaSuccess;
 }

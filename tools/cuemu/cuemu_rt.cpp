@@ -178,7 +178,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
         bs.bidx = uint3{bx, by, bz};
         bs.alive = nt;
         bs.bar_arrived = 0;
-        memset(smem, 0xA5, smem_bytes);  // shared memory is not zero-initialised
+        memset(smem, 0xFF, smem_bytes);  // shared memory is not zero-initialised: NaN pattern
         for (auto &w : bs.warps) { w.arrived = 0; }
         for (int t = 0; t < nt; t++) {
           Fiber &f = bs.fibers[t];
