@@ -68,6 +68,8 @@ OAKB200_API int oakb200_create(int device, oakb200_handle **h);
 OAKB200_API int oakb200_destroy(oakb200_handle *h);
 
 /* Options (all optional; a key the library does not know is an error):
+ *   "scheme"          oakb200_assim_ensemble[_dev]: 1 = local scheme (default), 0 = global scheme (schemetype of the init
+ *                     file, assimilation.F90:292,:3227; zones and observation positions are then not needed)
  *   "eig_kernel"      4 = Householder tridiagonalisation + QL + twisted factorisation (default for N <= 64;
  *                     flagged zones fall back to 0), 0 = register-resident block Jacobi (N > 64), 1 = simple
  *                     shared-memory Jacobi (cross-check), 2 / 3 = measured variants of 0

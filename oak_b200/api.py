@@ -383,11 +383,16 @@ def analysis(xf, Hxf, yo, Sf, HSf, R, handle=None, device=0):
 
 def assim_ensemble(zoneSize, selectObservations, E, Hi, Hj, Hs, Hshift, yo, R, anamtype=1, inflation=1.0,
                    maxCorrection=None, handle=None, device=0, anamtable=None):
-    """Ensemble in, analysed ensemble out (assimilation.F90:3106-3134,:3235-3236,:3301-3357,:3558-3562)."""
+    """Ensemble in, analysed ensemble out (assimilation.F90:3106-3134,:3235-3236,:3301-3357,:3558-3562).
+    zoneSize = None selects the global scheme (schemetype = 0: `analysis` instead of `locanalysis`)."""
     own = handle is None
     h = Handle(device) if own else handle
     try:
-        h.configure(zoneSize, selectObservations)
+        if zoneSize is None:          # global scheme (schemetype = 0): no zones, no observation positions
+            h.set_option("scheme", 0)
+        else:
+            h.set_option("scheme", 1)
+            h.configure(zoneSize, selectObservations)
         Ea, xf, xa, _ = h.assim_ensemble(E, Hi, Hj, Hs, Hshift, yo, R, anamtype, inflation, maxCorrection,
                                          anamtable=anamtable)
         return Ea, xf, xa

@@ -89,6 +89,7 @@ struct oakb200_handle {
   int device = 0;
   // options
   int eig_kernel = 4;
+  int scheme = 1;             // ensemble entry points: 1 = local scheme (default), 0 = global scheme (schemetype, assimilation.F90:292)
   int tvec_split = 0;         // 1: tridiagonal route, k_tvec as two kernels (eigenvectors of T | back-transformation and the rest)
   int fuse_apply = 0;         // 1: tridiagonal route, k_tvec updates the zone rows from the factored transform (no T, no k_apply)
   int gram_kernel = 0;        // 0: k_gram (DFMA register tiles); 1 / 2: k_gram_mma (DMMA, 4 / 2 warps per zone; NP = 64); 3 / 4: same, 32-candidate chunks
@@ -504,6 +505,10 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   if (k == "eig_kernel") h->eig_kernel = (int)value;
   else if (k == "fuse_apply") h->fuse_apply = value != 0.;
   else if (k == "tvec_split") h->tvec_split = value != 0.;
+  else if (k == "scheme") {
+    if (value != 0. && value != 1.) { oak_set_error("scheme = %g (0 global, 1 local)", value); return OAK_ERR_ARG; }
+    h->scheme = (int)value;
+  }
   else if (k == "gram_kernel") {
     if (!(value >= 0. && value <= 4.) || value != (int)value) { oak_set_error("gram_kernel = %g (expected 0 .. 4)", value); return OAK_ERR_ARG; }
     h->gram_kernel = (int)value;
@@ -1063,7 +1068,7 @@ extern "C" OAKB200_API int oakb200_assim_ensemble_dev(oakb200_handle *h, int64_t
                                           const double *Rdiag, const double *d01, int32_t anamtype, double inflation,
                                           const double *maxCorrection, double *Ea, int64_t ldEa, double *xf_out,
                                           double *xa_out, void *stream, oakb200_stats *stats) {
-  int rc = check_ready(h, n, N, m);
+  int rc = (h && h->scheme == 0) ? global_check(h, n, N, m) : check_ready(h, n, N, m);
   if (rc) return rc;
   if (anamtype < 1 || anamtype > 3) { oak_set_error("assim_ensemble: anamorphosis type %d unknown (1 identity, 2 log, 3 tabulated)", anamtype); return OAK_ERR_ARG; }
   if (anamtype == 3 && h->anam_K < 2) { oak_set_error("assim_ensemble: tabulated anamorphosis without a table (oakb200_set_anamorphosis_table)"); return OAK_ERR_STATE; }
@@ -1091,9 +1096,14 @@ extern "C" OAKB200_API int oakb200_assim_ensemble_dev(oakb200_handle *h, int64_t
   if ((rc = oak_launch_mean_anom(s0, m, N, 1, AnamTab{nullptr, 0, 0}, h->d_HE.as<double>(), m, h->d_Hxf.as<double>(), h->d_HE.as<double>(), m))) return rc;
   if ((rc = oak_launch_mean_anom(s0, n, N, anamtype, at, E, ldE, h->d_xf.as<double>(), Ea, ldEa))) return rc;
   CUDA_TRY(cudaStreamSynchronize(s0));
-  rc = oakb200_local_analysis_dev(h, n, N, m, h->d_xf.as<double>(), h->d_Hxf.as<double>(), yo, Ea, ldEa,
-                                  h->d_HE.as<double>(), m, Rdiag, d01, h->d_xa.as<double>(), Ea, ldEa, nullptr,
-                                  (void *)s0, stats);
+  if (h->scheme == 0)   // Assim's global branch: call analysis(xf,Hxf,yo,Sf,HSf,R,xa,Sa,amplitudes)
+    rc = oakb200_global_analysis_dev(h, n, N, m, h->d_xf.as<double>(), h->d_Hxf.as<double>(), yo, Ea, ldEa,
+                                     h->d_HE.as<double>(), m, Rdiag, d01, h->d_xa.as<double>(), Ea, ldEa, nullptr,
+                                     (void *)s0, stats);
+  else
+    rc = oakb200_local_analysis_dev(h, n, N, m, h->d_xf.as<double>(), h->d_Hxf.as<double>(), yo, Ea, ldEa,
+                                    h->d_HE.as<double>(), m, Rdiag, d01, h->d_xa.as<double>(), Ea, ldEa, nullptr,
+                                    (void *)s0, stats);
   if (rc) return rc;
   if ((rc = oak_launch_epilogue(s0, n, N, anamtype, at, inflation, maxCorrection, h->d_xf.as<double>(), h->d_xa.as<double>(), Ea, ldEa, Ea, ldEa))) return rc;
   if (xf_out) CUDA_TRY(cudaMemcpyAsync(xf_out, h->d_xf.p, 8 * (size_t)n, cudaMemcpyDeviceToDevice, s0));
@@ -1108,7 +1118,7 @@ extern "C" OAKB200_API int oakb200_assim_ensemble(oakb200_handle *h, int64_t n, 
                                       const double *Hshift, const double *yo, const double *Rdiag, const double *d01,
                                       int32_t anamtype, double inflation, const double *maxCorrection, double *Ea,
                                       int64_t ldEa, double *xf_out, double *xa_out, oakb200_stats *stats) {
-  int rc = check_ready(h, n, N, m);
+  int rc = (h && h->scheme == 0) ? global_check(h, n, N, m) : check_ready(h, n, N, m);
   if (rc) return rc;
   if ((n > 0 && (!E || !Ea)) || (nnz > 0 && (!Hi || !Hj || !Hs)) || (m > 0 && (!yo || !Rdiag))) { oak_set_error("assim_ensemble: null array"); return OAK_ERR_ARG; }
   DeviceGuard guard(h->device);

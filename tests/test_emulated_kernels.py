@@ -74,4 +74,4 @@ def test_eigenvector_kernel_split(emu_lib):
 
 def test_global_scheme(emu_lib):
     # analysis (rrsqrt.F90:196-208): tall-skinny Gram in partial matrices, one transform, apply over row blocks
-    _run(emu_lib, "global_scheme")
+    _run(emu_lib, "global_scheme")   # also selects test_assim_case_through_the_global_scheme (BASELINE config 1)

@@ -188,3 +188,25 @@ def test_global_scheme_known_answers_and_oracle(ob, eig_kernel):
     # the module-level mirror of the reference call
     xa, Sa, ampl = ob.analysis(c["xf"], c["Hxf"], c["y"], c["Sf"], c["HSf"], ob.DiagCovar(c["var"]))
     assert np.abs(xa - xa_check).max() < TOL_REF
+
+
+def test_assim_case_through_the_global_scheme(ob):
+    # BASELINE config 1, test/test_assim.F90:96-172 (tol 1e-5): ensemble in, ensemble out with schemetype = 0
+    import oracle
+    from refcases import assim_case, kalman_check
+    c = assim_case()
+    n, N = c["n"], c["N"]
+    xf = c["Ef"].sum(axis=1) / N
+    xa_check, Pa_check = kalman_check(xf, (c["Ef"] - xf[:, None]) / np.sqrt(N - 1.0), c["H"], c["yo"],
+                                      np.diag(c["var"]))
+    Ea, xf_o, xa_o = ob.assim_ensemble(None, None, c["Ef"], [1], [5], [1.0], np.zeros(1), c["yo"],
+                                       ob.DiagCovar(c["var"]))
+    xa = Ea.sum(axis=1) / N
+    Eap = Ea - xa[:, None]
+    assert np.abs(xa - xa_check).max() < 1e-5
+    assert np.abs(Eap @ Eap.T / (N - 1.0) - Pa_check).max() < 1e-5
+    obs = oracle.make_obs(1, obsx=c["obsx"], obsy=c["obsy"], weightfun=2)
+    Eo, xfo, xao = oracle.assim_ensemble([n], dict(x=c["x"][:1], y=c["y"][:1]), 1.0, 1e30, obs, c["Ef"],
+                                         np.array([1], np.int32), np.array([5], np.int32), np.array([1.0]),
+                                         np.zeros(1), c["yo"], c["var"])
+    assert rel(Ea, Eo) < RTOL and rel(xf_o, xfo) < 1e-14 and rel(xa_o, xao) < RTOL
