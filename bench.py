@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--eig-kernel", type=int, default=4)
     ap.add_argument("--gram-kernel", type=int, default=0, help="0 = DFMA register tiles (default), 1 / 2 = mma.m8n8k4 tiles (4 / 2 warps per zone), 3 / 4 = same with 32-candidate chunks")
     ap.add_argument("--fuse-apply", type=int, default=0, help="1 = the transform kernel updates the zone rows from the factored transform (no T, no k_apply)")
+    ap.add_argument("--apply-kernel", type=int, default=0, help="1 = k_apply on mma.m8n8k4 tiles (zones the fused transform kernel leaves over; all zones when --fuse-apply 0)")
     ap.add_argument("--tvec-split", type=int, default=0, help="1 = eigenvector kernel as two kernels (vectors of T | back-transformation and the rest)")
     ap.add_argument("--jacobi-tol", type=float, default=0.0, help="experiment: override the Jacobi stopping tolerance")
     ap.add_argument("--sync-phases", action="store_true", help="N>1: blocking library calls instead of the asynchronous pipeline")
@@ -247,7 +248,7 @@ def main():
     for j, first in enumerate(ranges):
         d = build_rank_data(a, rank, world, dev, first=first, obs_np=obs_np)
         plan = d["plan"]
-        h = oak_b200.Handle(local, eig_kernel=a.eig_kernel, gram_kernel=a.gram_kernel, fuse_apply=a.fuse_apply, tvec_split=a.tvec_split)
+        h = oak_b200.Handle(local, eig_kernel=a.eig_kernel, gram_kernel=a.gram_kernel, fuse_apply=a.fuse_apply, tvec_split=a.tvec_split, apply_kernel=a.apply_kernel)
         if os.environ.get("OAK_B200_FIXED_SWEEPS"):  # kernel timing experiments only (tools/ab.py)
             h.set_option("fixed_sweeps", float(os.environ["OAK_B200_FIXED_SWEEPS"]))
         if os.environ.get("OAK_B200_ZB"):  # pipeline experiments (tools/ab.py)
@@ -419,7 +420,7 @@ def main():
         # dram__bytes_read.sum + dram__bytes_write.sum per zone from the ncu --set full captures under profiles/
         # (r1_ncu_full_tridiag.txt, r1_ncu_full_tvec.txt, r1_ncu_full_gram.txt; 7104-zone launches, N = 64)
         traffic_zone = {"k_gram": 26.1e3, "k_tridiag": 59.5e3, "k_tql+k_tvec": 59.2e3, "k_eig_fast": 39.8e3}
-        if a.gram_kernel or a.fuse_apply or a.tvec_split:
+        if a.gram_kernel or a.fuse_apply or a.tvec_split or a.apply_kernel:
             traffic_zone = {}   # no ncu capture of the variant kernels yet: traffic is reported as null
         stage_out = {}
         for name, (ms_k, fl) in stages.items():
@@ -453,7 +454,7 @@ def main():
                           "l2": "inputs (>= 15 GB state) exceed L2; no explicit flush",
                           "mean_relevant_obs_per_column": mloc_mean, "mean_candidates_per_column": cand_mean,
                           "mean_jacobi_sweeps": sweeps_mean, "eig_kernel": a.eig_kernel,
-                          "gram_kernel": a.gram_kernel, "fuse_apply": a.fuse_apply, "tvec_split": a.tvec_split},
+                          "gram_kernel": a.gram_kernel, "fuse_apply": a.fuse_apply, "tvec_split": a.tvec_split, "apply_kernel": a.apply_kernel},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
 
     # ---- end to end through the host-buffer entry point (pinned host memory, H2D + D2H inside the timed region)

@@ -76,6 +76,8 @@ OAKB200_API int oakb200_destroy(oakb200_handle *h);
  *   "gram_kernel"     0 = DFMA register tiles (default), 1 / 2 = fp64 tensor-core tiles (mma.m8n8k4, 4 / 2 warps per
  *                     zone), 3 / 4 = the same with chunks of 32 instead of 64 candidates (half the shared memory);
  *                     padded ensemble size 64 only, other sizes keep 0
+ *   "apply_kernel"    0 = DFMA register tiles (default), 1 = fp64 tensor-core tiles (padded ensemble size 64 only;
+ *                     zones the fused transform kernel leaves over, zones with many rows, the global scheme)
  *   "fuse_apply"      route 4: 1 = the transform kernel updates the zone rows itself from the factored transform
  *                     (no T written, k_apply only for the zones it did not finish); pays while zone sizes < N. Default 0
  *   "tvec_split"      route 4: 1 = the eigenvector kernel runs as two kernels (vectors of T with few registers and

@@ -89,6 +89,7 @@ struct oakb200_handle {
   int device = 0;
   // options
   int eig_kernel = 4;
+  int apply_kernel = 0;       // 0: k_apply (DFMA register tiles); 1: k_apply_mma (DMMA; NP = 64, not with peer_mode 0)
   int scheme = 1;             // ensemble entry points: 1 = local scheme (default), 0 = global scheme (schemetype, assimilation.F90:292)
   int tvec_split = 0;         // 1: tridiagonal route, k_tvec as two kernels (eigenvectors of T | back-transformation and the rest)
   int fuse_apply = 0;         // 1: tridiagonal route, k_tvec updates the zone rows from the factored transform (no T, no k_apply)
@@ -264,10 +265,16 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
     const int npiece = push ? std::max(1, std::min(h->push_pieces, nz)) : 1;
     for (int pc = 0; pc < npiece; pc++) {
       const int o0 = (int)((int64_t)nz * pc / npiece), o1 = (int)((int64_t)nz * (pc + 1) / npiece);
-      if ((rc = oak_launch_apply(s.st, N, NP, zg, b0 + o0, o1 - o0, rowbase, mloc, s.T.as<double>() + (size_t)o0 * NP * NP,
-                                 s.ampl.as<double>() + (size_t)o0 * NP, xf, Sf, ldS, xa, Sa, ldSa,
-                                 (use_peers && h->peer_mode == 0) ? h->peers : none,
-                                 only_flagged ? only_flagged + o0 : nullptr))) return rc;
+      if (h->apply_kernel == 1 && NP == 64 && !(use_peers && h->peer_mode == 0))
+        rc = oak_launch_apply_mma(s.st, N, NP, zg, b0 + o0, o1 - o0, rowbase, mloc, s.T.as<double>() + (size_t)o0 * NP * NP,
+                                  s.ampl.as<double>() + (size_t)o0 * NP, xf, Sf, ldS, xa, Sa, ldSa,
+                                  only_flagged ? only_flagged + o0 : nullptr, false);
+      else
+        rc = oak_launch_apply(s.st, N, NP, zg, b0 + o0, o1 - o0, rowbase, mloc, s.T.as<double>() + (size_t)o0 * NP * NP,
+                              s.ampl.as<double>() + (size_t)o0 * NP, xf, Sf, ldS, xa, Sa, ldSa,
+                              (use_peers && h->peer_mode == 0) ? h->peers : none,
+                              only_flagged ? only_flagged + o0 : nullptr);
+      if (rc) return rc;
       if (pc > 0) *launches += 1;
       if (!push) continue;
       const PeerOut &P = h->peers;
@@ -505,6 +512,10 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   if (k == "eig_kernel") h->eig_kernel = (int)value;
   else if (k == "fuse_apply") h->fuse_apply = value != 0.;
   else if (k == "tvec_split") h->tvec_split = value != 0.;
+  else if (k == "apply_kernel") {
+    if (value != 0. && value != 1.) { oak_set_error("apply_kernel = %g (0 register tiles, 1 tensor-core tiles)", value); return OAK_ERR_ARG; }
+    h->apply_kernel = (int)value;
+  }
   else if (k == "scheme") {
     if (value != 0. && value != 1.) { oak_set_error("scheme = %g (0 global, 1 local)", value); return OAK_ERR_ARG; }
     h->scheme = (int)value;
@@ -931,8 +942,13 @@ int global_apply(oakb200_handle *h, Slot &s, int N, int NP, int64_t n, int64_t r
   const int b0 = (int)(row0 / GLOBAL_BLOCK_ROWS), b1 = (int)((row0 + rows + GLOBAL_BLOCK_ROWS - 1) / GLOBAL_BLOCK_ROWS);
   (void)n;
   PeerOut none{};
-  int rc = oak_launch_apply(s.st, N, NP, zg, b0, b1 - b0, row0, nullptr, h->slot[0].T.as<double>(),
-                            h->slot[0].ampl.as<double>(), xf, Sf, ldS, xa, Sa, ldSa, none, nullptr, true);
+  int rc;
+  if (h->apply_kernel == 1 && NP == 64)
+    rc = oak_launch_apply_mma(s.st, N, NP, zg, b0, b1 - b0, row0, nullptr, h->slot[0].T.as<double>(),
+                              h->slot[0].ampl.as<double>(), xf, Sf, ldS, xa, Sa, ldSa, nullptr, true);
+  else
+    rc = oak_launch_apply(s.st, N, NP, zg, b0, b1 - b0, row0, nullptr, h->slot[0].T.as<double>(),
+                          h->slot[0].ampl.as<double>(), xf, Sf, ldS, xa, Sa, ldSa, none, nullptr, true);
   *launches += 1;
   return rc;
 }

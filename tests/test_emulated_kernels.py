@@ -75,3 +75,8 @@ def test_eigenvector_kernel_split(emu_lib):
 def test_global_scheme(emu_lib):
     # analysis (rrsqrt.F90:196-208): tall-skinny Gram in partial matrices, one transform, apply over row blocks
     _run(emu_lib, "global_scheme")   # also selects test_assim_case_through_the_global_scheme (BASELINE config 1)
+
+
+def test_apply_on_tensor_core_tiles(emu_lib):
+    # option apply_kernel = 1 (k_apply_mma): local zones of 1..75 rows and the row blocks of the global scheme
+    _run(emu_lib, "apply_on_tensor")

@@ -210,3 +210,42 @@ def test_assim_case_through_the_global_scheme(ob):
                                          np.array([1], np.int32), np.array([5], np.int32), np.array([1.0]),
                                          np.zeros(1), c["yo"], c["var"])
     assert rel(Ea, Eo) < RTOL and rel(xf_o, xfo) < 1e-14 and rel(xa_o, xao) < RTOL
+
+
+def test_apply_on_tensor_core_tiles(ob):
+    """Option apply_kernel = 1 (k_apply_mma): local scheme with ragged zones of 1..75 rows (chunks of 32: partial,
+    exact, several), N = 64 and N = 40 (padding), in place, zones without observations; and the global scheme,
+    whose row blocks share one transform."""
+    import oracle
+    from oak_b200 import synthetic
+    for N in (64, 40):
+        c = synthetic.small_case(nx=14, ny=6, nz=25, N=N, m=300, corr=2500.0, maxlen=5000.0, seed=N + 1)
+        keep = c["obs"]["ox"] < 5500.0
+        for k in ("Hxf", "yo", "var"):
+            c[k] = c[k][keep]
+        c["HSf"] = np.asfortranarray(c["HSf"][keep])
+        c["obs"] = {k: (v[..., keep] if v.ndim > 1 else v[keep]) for k, v in c["obs"].items()}
+        c["m"] = int(keep.sum())
+        zs, left, k = [], c["Sf"].shape[0], 0
+        sizes = [1, 7, 31, 32, 33, 64, 75, 12]
+        while left > 0:
+            sz = min(left, sizes[k % len(sizes)]); zs.append(sz); left -= sz; k += 1
+        zs = np.array(zs, np.int32)
+        rng = np.random.default_rng(2)
+        c["zx"] = rng.uniform(0, 14000, zs.size); c["zy"] = rng.uniform(0, 6000, zs.size)
+        c["corr"] = np.full(zs.size, 2500.0); c["maxlen"] = np.full(zs.size, 5000.0)
+        xo, So, _, mloc = _oracle_loc(c, zs)
+        assert (mloc == 0).any() and (mloc > 0).any()
+        with ob.Handle(0, eig_kernel=4, apply_kernel=1, pad_to=64) as h:
+            _configure(ob, h, c, zs)
+            buf = np.asfortranarray(c["Sf"].copy())
+            xa, Sa, _, st = h.local_analysis(c["xf"], c["Hxf"], c["yo"], buf, c["HSf"], ob.DiagCovar(c["var"]), out_Sa=buf)
+        assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL, (N, rel(xa, xo), rel(Sa, So))
+        start = np.concatenate([[0], np.cumsum(zs)])
+        for z in np.nonzero(mloc == 0)[0]:
+            assert (Sa[start[z]:start[z + 1]] == c["Sf"][start[z]:start[z + 1]]).all()
+        # global scheme on the same arrays
+        xo, So, ao = oracle.analysis(c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], c["var"])
+        with ob.Handle(0, apply_kernel=1, pad_to=64, chunk_mb=0.3) as h:
+            xa, Sa, ampl, _ = h.global_analysis(c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], ob.DiagCovar(c["var"]))
+        assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL, (N, rel(xa, xo), rel(Sa, So))

@@ -22,7 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "oak_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
-SOURCES = ["api.cu", "obsgrid.cu", "gram.cu", "gram_mma.cu", "eig_simple.cu", "eig_fast.cu", "eig_tridiag.cu", "apply.cu", "global.cu",
+SOURCES = ["api.cu", "obsgrid.cu", "gram.cu", "gram_mma.cu", "eig_simple.cu", "eig_fast.cu", "eig_tridiag.cu", "apply.cu", "apply_mma.cu", "global.cu",
            "ensemble.cu", "microbench.cu"]
 CXXFLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-ffp-contract=off", "-mfma", "-fno-strict-aliasing",
             "-Wno-attributes", "-Wno-unknown-pragmas", "-DOAK_CUEMU=1", "-I" + os.path.join(HERE, "shim"), "-I" + HERE]

@@ -20,6 +20,11 @@ import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('value %.0f columns/s  ms/step %.2f' % (d['value'], d['ms_per_step']), d['roofline']['kernel_ms_per_step'])" | tee -a $LOG
 done
+echo "== apply_kernel 1 (gram 0, fuse 0)" | tee -a $LOG
+timeout 600 python bench.py $small --apply-kernel 1 2>>gpurun_out/r2_ab.err | tail -1 | cut -c1-400 | tee -a $LOG
+echo "== global scheme, state resident (tools/time_global.py), apply_kernel 0 / 1" | tee -a $LOG
+timeout 600 python tools/time_global.py 2>>gpurun_out/r2_ab.err | tail -1 | tee -a $LOG
+timeout 600 python tools/time_global.py --apply-kernel 1 2>>gpurun_out/r2_ab.err | tail -1 | tee -a $LOG
 for sp in "0 0" "0 1" "1 1"; do
   set -- $sp
   echo "== tvec_split 1, gram_kernel $1 fuse_apply $2" | tee -a $LOG

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--N", type=int, default=64)
     ap.add_argument("--m", type=int, default=1_000_000)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--apply-kernel", type=int, default=0)
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev).manual_seed(20261017)
@@ -32,7 +33,7 @@ def main():
     R = torch.full((a.m,), 0.25, dtype=torch.float64, device=dev)
     xa = torch.empty_like(xf)
     Sa = torch.empty_like(Sf)
-    with oak_b200.Handle(0) as h:
+    with oak_b200.Handle(0, apply_kernel=a.apply_kernel) as h:
         ms = []
         for it in range(a.steps + 2):
             st = h.global_analysis_dev(xf, Hxf, yo, Sf, HSf, R, xa, Sa)
@@ -45,7 +46,7 @@ def main():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    print(json.dumps({"metric": "global analysis, state resident", "ms": t, "rows": a.n, "N": a.N, "m": a.m,
+    print(json.dumps({"metric": "global analysis, state resident", "ms": t, "rows": a.n, "N": a.N, "m": a.m, "apply_kernel": a.apply_kernel,
                       "algorithmic_GB": byt / 1e9, "achieved_GBps": byt / 1e9 / (t * 1e-3), "measured_peaks": peak,
                       "colsum_check": float(Sa.sum(dim=0).abs().max())}))
 
