@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box visit: parity tests, smoke, a reduced bench, optional full bench / ncu passes.
-# usage: tools/gpu_check.sh [tests] [smoke] [sanitize] [benchsmall] [bench] [ncu] [ncufull]
+# usage: tools/gpu_check.sh [tests] [smoke] [sanitize] [benchsmall] [bench] [ncu] [ncufull] [ncuvar]
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.csv 2>&1
@@ -37,6 +37,13 @@ ncutri)
   for kn in k_tridiag k_tvec k_gram k_tql; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kn -s 3 -c 1 -f -o gpurun_out/prof_$kn \
      python bench.py --nx 300 --ny 300 --nobs 90000 --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncufull_$kn.log 2>&1
+  echo "ncufull $kn exit $?"
+  done ;;
+ncuvar)
+  # --set full captures of the kernels behind the round-1-end options (VARIANT = bench flags, e.g. "--gram-kernel 1 --fuse-apply 1")
+  for kn in k_gram_mma k_tvec k_apply_mma; do
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kn -s 3 -c 1 -f -o gpurun_out/prof_var_$kn \
+     python bench.py --nx 300 --ny 300 --nobs 90000 --steps 1 --warmup 1 --no-e2e --no-cpu ${VARIANT:---gram-kernel 1 --fuse-apply 1 --apply-kernel 1} > gpurun_out/ncufull_var_$kn.log 2>&1
   echo "ncufull $kn exit $?"
   done ;;
 ncufull)
