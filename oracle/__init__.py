@@ -129,6 +129,30 @@ def analysis(xf, Hxf, yo, Sf, HSf, var):
     return xa, Sa, ampl
 
 
+def loc_analysis_cellgrid(zoneSize, zone_pos, corrLen, maxLen, obs, xf, Hxf, yo, Sf, HSf, var, e01=None):
+    """locAnalysis with a CPU cell grid in front of the exact predicate (SURVEY 8d: the "fair" CPU baseline;
+    Cartesian metric, Gaussian weights with a finite cut-off only).  Same results as loc_analysis."""
+    Sf = _f(Sf); HSf = _f(HSf)
+    n, N = Sf.shape
+    m = obs.m
+    zs = np.ascontiguousarray(zoneSize, dtype=np.int32)
+    nz = zs.size
+    zx, zy = _f(zone_pos["x"]), _f(zone_pos["y"])
+    cl = _f(np.broadcast_to(corrLen, (nz,)).copy())
+    ml = _f(np.broadcast_to(maxLen, (nz,)).copy())
+    xa = np.zeros(n); Sa = np.zeros((n, N), order="F")
+    mloc = np.zeros(nz, dtype=np.int32)
+    xf, Hxf, yo, var, e01 = [_f(a) for a in (xf, Hxf, yo, var, e01)]
+    f = lib().oracle_loc_analysis_cellgrid
+    f.restype = C.c_int
+    rc = f(C.c_int(nz), _ip(zs), _dp(zx), _dp(zy), _dp(cl), _dp(ml), C.byref(obs), C.c_int(n), C.c_int(N), _dp(xf),
+           _dp(Hxf), _dp(yo), _dp(Sf), C.c_int(n), _dp(HSf), C.c_int(max(m, 1)), _dp(var), _dp(e01), _dp(xa), _dp(Sa),
+           C.c_int(n), _ip(mloc))
+    if rc:
+        raise RuntimeError(f"oracle_loc_analysis_cellgrid status {rc}")
+    return xa, Sa, None, mloc
+
+
 def loc_analysis(zoneSize, zone_pos, corrLen, maxLen, obs, xf, Hxf, yo, Sf, HSf, var, e01=None,
                  local_obs=True, zone_list=None, want_ampl=False):
     """locAnalysis — rrsqrt.F90:433-466.  zone_pos = dict(x=,y=,z=,t=) of per-zone arrays."""

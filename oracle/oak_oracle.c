@@ -421,6 +421,128 @@ int oracle_loc_analysis(int nzones, const int32_t *zoneSize, const double *zx, c
 }
 
 /* ---------------------------------------------------------------------------
+ * The same local analysis with a CPU cell grid in front of the exact predicate instead of the O(m) scan of
+ * assimilation.F90:3745-3757 per zone: the "fair" CPU baseline of SURVEY.md 8(d)(ii) (what the reference's own
+ * CELLGRID_SEARCH variant, ndgrid.F90:1489-1691, is for).  The predicate, the weights, the pack order
+ * (increasing observation number, rrsqrt.F90:395-404) and analysisIncrement are the ones above, so the result is
+ * the one of oracle_loc_analysis.  Only the case the benchmark uses: horizontal localisation, Cartesian metric,
+ * Gaussian weights with a finite cut-off (returns -11 otherwise); local_obs branch only.
+ * ------------------------------------------------------------------------- */
+static int cmp_i32(const void *a, const void *b) {
+  const int32_t x = *(const int32_t *)a, y = *(const int32_t *)b;
+  return (x > y) - (x < y);
+}
+
+int oracle_loc_analysis_cellgrid(int nzones, const int32_t *zoneSize, const double *zx, const double *zy,
+                                 const double *corrLen, const double *maxLen, const oracle_obs_t *obs, int n,
+                                 int N, const double *xf, const double *Hxf, const double *yo, const double *Sf,
+                                 int ldS, const double *HSf, int ldH, const double *var, const double *e01,
+                                 double *xa, double *Sa, int ldSa, int32_t *mloc_out) {
+  const int m = obs->m;
+  if (obs->loctype != 1 || obs->metrictype != 0 || obs->weightfun != 0 || !zy || !obs->obsy) return -11;
+  double rmax = 0;
+  for (int z = 0; z < nzones; z++) {
+    if (!(maxLen[z] < 1e300)) return -11;
+    if (maxLen[z] > rmax) rmax = maxLen[z];
+  }
+  int64_t *start = malloc(sizeof(int64_t) * (nzones + 1));
+  start[0] = 0;
+  for (int z = 0; z < nzones; z++) start[z + 1] = start[z] + zoneSize[z];
+  if (start[nzones] != n) { free(start); return -10; }
+  for (int i = 0; i < n; i++) xa[i] = 0;
+  for (int k = 0; k < N; k++) memcpy(Sa + (size_t)ldSa * k, Sf + (size_t)ldS * k, sizeof(double) * n);
+  if (mloc_out) memset(mloc_out, 0, sizeof(int32_t) * nzones);
+  /* buckets of edge rmax (at most ~4 m cells), observation numbers ascending inside a bucket */
+  double x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+  for (int l = 0; l < m; l++) {
+    const double x = obs->obsx[l], y = obs->obsy[l];
+    if (l == 0) { x0 = x1 = x; y0 = y1 = y; }
+    x0 = fmin(x0, x); x1 = fmax(x1, x);
+    y0 = fmin(y0, y); y1 = fmax(y1, y);
+  }
+  double cs = rmax > 0 ? rmax : 1.;
+  while (((x1 - x0) / cs + 1.) * ((y1 - y0) / cs + 1.) > 4. * (m > 1024 ? m : 1024)) cs *= 2.;
+  const int ncx = (int)floor((x1 - x0) / cs) + 1, ncy = (int)floor((y1 - y0) / cs) + 1;
+  int32_t *cstart = calloc((size_t)ncx * ncy + 1, sizeof(int32_t));
+  int32_t *cell = malloc(sizeof(int32_t) * (m > 0 ? m : 1));
+  int32_t *perm = malloc(sizeof(int32_t) * (m > 0 ? m : 1));
+  for (int l = 0; l < m; l++) {
+    int cx = (int)floor((obs->obsx[l] - x0) / cs), cy = (int)floor((obs->obsy[l] - y0) / cs);
+    cx = cx < 0 ? 0 : (cx >= ncx ? ncx - 1 : cx);
+    cy = cy < 0 ? 0 : (cy >= ncy ? ncy - 1 : cy);
+    cell[l] = cy * ncx + cx;
+    cstart[cell[l] + 1]++;
+  }
+  for (int c = 0; c < ncx * ncy; c++) cstart[c + 1] += cstart[c];
+  {
+    int32_t *fill = malloc(sizeof(int32_t) * ((size_t)ncx * ncy + 1));
+    memcpy(fill, cstart, sizeof(int32_t) * ((size_t)ncx * ncy + 1));
+    for (int l = 0; l < m; l++) perm[fill[cell[l]]++] = l;
+    free(fill);
+  }
+  int status = 0;
+#pragma omp parallel
+  {
+    int32_t *sel = malloc(sizeof(int32_t) * (m > 0 ? m : 1));
+    double *yoz = malloc(sizeof(double) * (m > 0 ? m : 1));
+    double *Hxfz = malloc(sizeof(double) * (m > 0 ? m : 1));
+    double *wz = malloc(sizeof(double) * (m > 0 ? m : 1));
+    double *varz = malloc(sizeof(double) * (m > 0 ? m : 1));
+    double *ez = malloc(sizeof(double) * (m > 0 ? m : 1));
+    double *HSfz = NULL;
+    size_t HSfz_cap = 0;
+#pragma omp for schedule(dynamic)
+    for (int zi = 0; zi < nzones; zi++) {
+      const double px = zx[zi], py = zy[zi], R = maxLen[zi];
+      const double slack = R * 1e-9 + 1e-12 * (fabs(px) + fabs(py) + fabs(x0) + fabs(y0));
+      int cx0 = (int)floor((px - R - slack - x0) / cs), cx1 = (int)floor((px + R + slack - x0) / cs);
+      int cy0 = (int)floor((py - R - slack - y0) / cs), cy1 = (int)floor((py + R + slack - y0) / cs);
+      cx0 = cx0 < 0 ? 0 : cx0;
+      cy0 = cy0 < 0 ? 0 : cy0;
+      cx1 = cx1 >= ncx ? ncx - 1 : cx1;
+      cy1 = cy1 >= ncy ? ncy - 1 : cy1;
+      int nb = 0;
+      for (int cy = cy0; cy <= cy1; cy++)
+        for (int q = cstart[cy * ncx + cx0]; cx0 <= cx1 && q < cstart[cy * ncx + cx1 + 1]; q++) {
+          const int l = perm[q];
+          const double d = oracle_distance(0, obs->trig, obs->obsx[l], obs->obsy[l], px, py);
+          if (d <= R) sel[nb++] = l; /* assimilation.F90:3756 */
+        }
+      if (mloc_out) mloc_out[zi] = nb;
+      if (nb == 0) continue; /* rrsqrt.F90:370-371 */
+      qsort(sel, nb, sizeof(int32_t), cmp_i32); /* pack() keeps the observation order :395-404 */
+      if ((size_t)nb * N > HSfz_cap) {
+        free(HSfz);
+        HSfz_cap = (size_t)nb * N * 2;
+        HSfz = malloc(sizeof(double) * HSfz_cap);
+      }
+      for (int q = 0; q < nb; q++) {
+        const int j = sel[q];
+        const double d = oracle_distance(0, obs->trig, obs->obsx[j], obs->obsy[j], px, py);
+        const double t = d / corrLen[zi];
+        yoz[q] = yo[j];
+        Hxfz[q] = Hxf[j];
+        wz[q] = exp(-(t * t)); /* assimilation.F90:3767 */
+        varz[q] = var[j];
+        ez[q] = e01 ? e01[j] : 1.;
+        for (int k = 0; k < N; k++) HSfz[q + (size_t)nb * k] = HSf[j + (size_t)ldH * k];
+      }
+      const int64_t i1 = start[zi];
+      const int info = oracle_analysis_increment(nb, zoneSize[zi], N, Hxfz, yoz, Sf + i1, ldS, HSfz, nb, wz, ez,
+                                                 varz, xa + i1, Sa + i1, ldSa, NULL);
+      if (info != 0) {
+#pragma omp critical
+        if (!status) status = info;
+      }
+    }
+    free(sel); free(yoz); free(Hxfz); free(wz); free(varz); free(ez); free(HSfz);
+  }
+  for (int i = 0; i < n; i++) xa[i] = xf[i] + xa[i];
+  free(start); free(cstart); free(cell); free(perm);
+  return status;
+}
+
+/* ---------------------------------------------------------------------------
  * obsoper: COO SpMV  Hx(i(k)) += s(k) * x(j(k)) then + Hshift
  * assimilation.F90:2836-2898 ; matoper_inc.F90:220-242.  Indices 1-based as
  * stored by the Fortran code; entries with j<=0 (out-of-grid obs,

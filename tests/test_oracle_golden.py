@@ -216,3 +216,22 @@ def test_committed_golden_fixture_matches_oracle_and_known_answers():
     assert np.abs(xo - g["xa_gc_local"]).max() < 1e-8          # tolerance of test/test_rrsqrt.F90:20
     assert (mloc == g["mloc_gc_local"]).all()
     assert np.abs(So - g["Sa_gc_local_oracle"]).max() < 1e-12 and np.abs(xo - g["xa_gc_local_oracle"]).max() < 1e-12
+
+
+def test_cellgrid_variant_of_the_oracle_equals_the_scan():
+    """The "fair" CPU baseline (SURVEY 8d ii): a CPU cell grid in front of the exact predicate must give the index
+    sets and the analysis of the O(m) scan of assimilation.F90:3745-3757 (same predicate, same pack order)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oak_b200 import synthetic
+    for (nx, ny, m, maxlen) in ((24, 20, 500, 6000.0), (12, 9, 40, 2500.0), (8, 8, 300, 50000.0)):
+        c = synthetic.small_case(nx=nx, ny=ny, nz=3, N=16, m=m, corr=maxlen / 2, maxlen=maxlen, seed=m)
+        obs = oracle.make_obs(c["m"], obsx=c["obs"]["ox"], obsy=c["obs"]["oy"])
+        pos = dict(x=c["zx"], y=c["zy"])
+        e01 = (np.random.default_rng(0).uniform(size=c["m"]) > 0.2).astype(np.float64)
+        args = (c["zoneSize"], pos, c["corr"], c["maxlen"], obs, c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], c["var"])
+        xa0, Sa0, _, ml0 = oracle.loc_analysis(*args, e01=e01)
+        xa1, Sa1, _, ml1 = oracle.loc_analysis_cellgrid(*args, e01=e01)
+        assert (ml0 == ml1).all()
+        assert np.abs(xa0 - xa1).max() <= 1e-14 * np.abs(xa0).max()
+        assert np.abs(Sa0 - Sa1).max() <= 1e-14 * np.abs(Sa0).max()
