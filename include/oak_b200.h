@@ -79,7 +79,8 @@ OAKB200_API int oakb200_destroy(oakb200_handle *h);
  *   "apply_kernel"    0 = DFMA register tiles (default), 1 = fp64 tensor-core tiles (padded ensemble size 64 only;
  *                     zones the fused transform kernel leaves over, zones with many rows, the global scheme)
  *   "fuse_apply"      route 4: 1 = the transform kernel updates the zone rows itself from the factored transform
- *                     (no T written, k_apply only for the zones it did not finish); pays while zone sizes < N. Default 0
+ *                     (no T written, k_apply only for the zones it did not finish); used while every zone has at most
+ *                     N (padded) rows, where the factored form is the cheaper one. Default 0
  *   "tvec_split"      route 4: 1 = the eigenvector kernel runs as two kernels (vectors of T with few registers and
  *                     high occupancy | back-transformation and the rest), 32 KB more workspace per zone. Default 0
  *   "tri_orthtol"     route 4: accepted loss of orthogonality between neighbouring eigenvectors (default 1e-11)

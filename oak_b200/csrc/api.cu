@@ -118,6 +118,7 @@ struct oakb200_handle {
   bool zones_set = false;
   int nzones = 0;
   int64_t nrows = 0;
+  int max_zone_rows = 0;
   int loctype = 1, metrictype = 0, weightfun = 0;
   std::vector<int64_t> h_zstart;
   double rmax = 0.;     // largest finite search radius
@@ -241,7 +242,8 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
       // recomputed by the Jacobi kernel, which skips the zones whose flag is 0
       int32_t *flags = nullptr;
       // fused apply: not with the store flavour of the fused all-gather (k_apply is the kernel that stores to the peers)
-      const bool fuse = h->fuse_apply && !(use_peers && h->peer_mode == 0);
+      // ... and only while the factored form is the cheaper one (4 nr N^2 against 2 N^3 + 2 nr N^2: zones of at most N rows)
+      const bool fuse = h->fuse_apply && !(use_peers && h->peer_mode == 0) && h->max_zone_rows <= NP;
       const FusedApplyArgs fa{zg.zstart + b0, rowbase, xf, Sf, xa, Sa, ldS, ldSa};
       if ((rc = oak_launch_eig_tridiag(s.st, N, NP, nz, mloc + b0, s.G.as<double>(), s.c.as<double>(),
                                        s.T.as<double>(), s.ampl.as<double>(), s.tri.p, &flags, ctr,
@@ -581,6 +583,8 @@ extern "C" OAKB200_API int oakb200_set_zones(oakb200_handle *h, int32_t nzones, 
     if (zoneSize[z] < 0) { oak_set_error("set_zones: negative zone size"); return OAK_ERR_ARG; }
     h->h_zstart[z + 1] = h->h_zstart[z] + zoneSize[z];
   }
+  h->max_zone_rows = 0;
+  for (int z = 0; z < nzones; z++) h->max_zone_rows = std::max(h->max_zone_rows, (int)zoneSize[z]);
   h->nrows = h->h_zstart[nzones];
   h->rmax = 0.; h->any_unbounded = false; h->zlat_absmax = 0.;
   std::vector<double> zeros;
