@@ -15,19 +15,6 @@
 
 namespace {
 
-#ifdef OAK_CUEMU
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) { memcpy(smem_dst, gmem_src, 16); }
-__device__ __forceinline__ void cp_async_commit() {}
-__device__ __forceinline__ void cp_async_wait_all() {}
-#else
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-#endif
-
 constexpr int RC = 32;  // rows per chunk
 
 template <int NP>
@@ -85,7 +72,7 @@ __global__ void __launch_bounds__(128) k_apply_mma(int N, ZoneGeom zg, int zone0
         sS[r * LD + i] = (r < rc && i < N) ? Sf[i1 + r0 + r + ldS * i] : 0.;
       }
     }
-    cp_async_wait_all();
+    cp_async_wait<0>();
     __syncthreads();
 
     double acc[4][2][2], e0 = 0., e1 = 0.;  // [rb][kb - 2 warp][col]

@@ -51,6 +51,24 @@ __device__ __forceinline__ void oak_dmma_m8n8k4(double &c0, double &c1, double a
 #endif
 
 // ---------------------------------------------------------------------------------------
+// 16-byte asynchronous global -> shared copies (LDGSTS); the emulation copies at once
+// ---------------------------------------------------------------------------------------
+#ifdef OAK_CUEMU
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) { memcpy(smem_dst, gmem_src, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
+#else
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
+
+// ---------------------------------------------------------------------------------------
 // Zone / observation-grid descriptors passed by value to kernels
 // ---------------------------------------------------------------------------------------
 struct ZoneGeom {

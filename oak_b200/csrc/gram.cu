@@ -35,22 +35,6 @@ __device__ __forceinline__ void lds_vec(double *dst, const double *src) {
   }
 }
 
-// OAK_CUEMU: functional CPU emulation of the kernels for tests (tools/cuemu); never defined in the product build
-#ifdef OAK_CUEMU
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) { memcpy(smem_dst, gmem_src, 16); }
-__device__ __forceinline__ void cp_async_commit() {}
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {}
-#else
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-#endif
-
 // Software pipeline over chunks of GRAM_CH candidates (per group of cell rows):
 //   E(c)  warps 0,1 evaluate the exact predicate on 32 candidates each and compact the relevant ones
 //         (per-warp segment of the list: position, coef = w^2 d01^2/R, coef*delta)

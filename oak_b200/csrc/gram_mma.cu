@@ -23,21 +23,6 @@ namespace {
 constexpr int GRAM_CHMAX = 64; // candidates examined per chunk: 64 (warps 0 and 1, one per lane) or 32 (warp 0)
 constexpr int GRAM_MAXR = 64;  // cell ranges per row group
 
-#ifdef OAK_CUEMU
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) { memcpy(smem_dst, gmem_src, 16); }
-__device__ __forceinline__ void cp_async_commit() {}
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {}
-#else
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-#endif
-
 // ---- static tile map (NB = 8 blocks per side, HB = 4) ----
 template <int NW, int W>
 struct TileMap {
