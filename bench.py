@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--eig-kernel", type=int, default=4)
-    ap.add_argument("--gram-kernel", type=int, default=0, help="0 = DFMA register tiles (default), 1 / 2 = mma.m8n8k4 tiles (4 / 2 warps per zone), 3 / 4 = same with 32-candidate chunks")
+    ap.add_argument("--gram-kernel", type=int, default=1, help="1 = mma.m8n8k4 tiles, 4 warps per zone (default), 2 = 2 warps per zone, 3 / 4 = same with 32-candidate chunks, 0 = DFMA register tiles")
     ap.add_argument("--fuse-apply", type=int, default=0, help="1 = the transform kernel updates the zone rows from the factored transform (no T, no k_apply)")
     ap.add_argument("--apply-kernel", type=int, default=0, help="1 = k_apply on mma.m8n8k4 tiles (zones the fused transform kernel leaves over; all zones when --fuse-apply 0)")
     ap.add_argument("--tvec-split", type=int, default=0, help="1 = eigenvector kernel as two kernels (vectors of T | back-transformation and the rest)")
@@ -162,6 +162,20 @@ def build_rank_data(a, rank, world, dev, first=None, obs_np=None):
                 var=sub["var"].contiguous(), ox=obs_np["ox"][plan.obs_idx], oy=obs_np["oy"][plan.obs_idx])
 
 
+def load_traffic(a):
+    """{stage: DRAM bytes per zone} from profiles/ncu_traffic.json, for the kernel options of this run only."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            t = json.load(fh)
+        opt = t.get("options", {})
+        same = (opt.get("N") == a.N and opt.get("gram_kernel") == a.gram_kernel and opt.get("fuse_apply") == a.fuse_apply
+                and opt.get("tvec_split") == a.tvec_split and opt.get("apply_kernel") == a.apply_kernel
+                and opt.get("eig_kernel") == a.eig_kernel)
+        return {k: float(v) for k, v in t.get("bytes_per_zone", {}).items()} if same else {}
+    except Exception:
+        return {}
+
+
 def flops_per_zone(N, nz, mloc_mean, cand_mean):
     """algorithmic work per zone: Gram + eigendecomposition (LAPACK count) + transform +
     amplitudes + apply + selection"""
@@ -185,14 +199,34 @@ def cpu_sample_problem(a, d, nsample):
     return dict(zl=zl, Sf=Sf, xf=xf, zx=zx, zy=zy, zs=np.full(zl.size, a.nz, np.int32))
 
 
-def run_oracle_sample(a, host, sp, count, cellgrid=False):
+def run_oracle_sample(a, host, sp, count, cellgrid=False, keep=None):
+    """The oracle on the first `count` sampled columns; `keep` (a dict) receives its xa, Sa (rows of those columns)."""
     import oracle
     obs = oracle.make_obs(host["m"], obsx=host["ox"], obsy=host["oy"])
     k = count * a.nz
     t0 = time.perf_counter()
-    (oracle.loc_analysis_cellgrid if cellgrid else oracle.loc_analysis)(sp["zs"][:count], dict(x=sp["zx"][:count], y=sp["zy"][:count]), a.corr, a.maxlen, obs,
+    r = (oracle.loc_analysis_cellgrid if cellgrid else oracle.loc_analysis)(sp["zs"][:count], dict(x=sp["zx"][:count], y=sp["zy"][:count]), a.corr, a.maxlen, obs,
                         sp["xf"][:k], host["Hxf"], host["yo"], sp["Sf"][:k], host["HSf"], host["var"])
-    return time.perf_counter() - t0
+    t = time.perf_counter() - t0
+    if keep is not None:
+        keep.update(count=count, xa=r[0], Sa=r[1], scan=not cellgrid)
+    return t
+
+
+def parity_vs_oracle(a, d, sp, kept):
+    """Relative error (max norm over the sampled columns, as the parity tests measure it) of the GPU result of THIS
+    run (d["xa"], d["Sa"], left there by the timed steps) against what the oracle computed for the same columns."""
+    import torch
+    count = kept["count"]
+    rows = (sp["zl"][:count, None] * a.nz + np.arange(a.nz)[None, :]).ravel()
+    rt = torch.from_numpy(rows).to(d["Sa"].device)
+    Sg = d["Sa"][:, rt].cpu().numpy().T
+    xg = d["xa"][rt].cpu().numpy()
+    eS = float(np.abs(Sg - kept["Sa"]).max() / np.abs(kept["Sa"]).max())
+    ex = float(np.abs(xg - kept["xa"]).max() / np.abs(kept["xa"]).max())
+    return {"cols": int(count), "max_rel_Sa": eS, "max_rel_xa": ex, "tol": 1e-9, "ok": bool(eS < 1e-9 and ex < 1e-9),
+            "against": "oracle port (dsyev/dgemm), " + ("O(m) scan" if kept["scan"] else "cell-grid selection") +
+                       " on randomly sampled columns of this run's workload"}
 
 
 def host_obs_arrays(d):
@@ -203,12 +237,13 @@ def host_obs_arrays(d):
 def cpu_baseline(a, d, seconds):
     import oracle
     host = host_obs_arrays(d)
-    cores = oracle.max_threads()
+    cores = oracle.set_threads(0)   # every online processor, whatever OMP_NUM_THREADS the launcher exported
     sp = cpu_sample_problem(a, d, 200000)
     probe = max(cores * 2, 16)
     t = run_oracle_sample(a, host, sp, probe)
     count = int(min(sp["zl"].size, max(probe, probe * seconds / max(t, 1e-6))))
-    t = run_oracle_sample(a, host, sp, count)
+    kept = {}
+    t = run_oracle_sample(a, host, sp, count, keep=kept)
     out = {"value": count / t, "unit": "columns/s", "cores": cores, "kind": "port",
            "sample": f"{count} random columns of the same workload (all {host['m']} observations scanned per "
                      f"column as assimilation.F90:3745-3757 does, OpenBLAS dgemm/dsyev, OpenMP dynamic over "
@@ -223,7 +258,19 @@ def cpu_baseline(a, d, seconds):
                                  "sample": f"{cf} random columns, cell-grid selection instead of the O(m) scan, {tf:.1f} s"}
     except Exception as e:  # reported, never fatal for the bench line
         out["with_cell_grid"] = {"value": None, "note": str(e)[:120]}
-    return out, (host, sp)
+    return out, (host, sp, kept)
+
+
+def quick_parity(a, d, ncols=2000):
+    """Parity of this run against the oracle when the CPU baseline leg is off (N > 1, --no-cpu): the cell-grid
+    variant of the port (equal to the scan, tests/test_oracle_golden.py) on a small random sample."""
+    import oracle
+    oracle.set_threads(0)
+    host = host_obs_arrays(d)
+    sp = cpu_sample_problem(a, d, ncols)
+    kept = {}
+    run_oracle_sample(a, host, sp, sp["zl"].size, cellgrid=True, keep=kept)
+    return parity_vs_oracle(a, d, sp, kept)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -244,7 +291,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("OAK_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL_DEBUG is the caller's (the driver reads NCCL's rank lines from it); NCCL logs to stderr / its own file,
+        # the one JSON line goes to stdout
         dist.init_process_group("nccl", device_id=dev)
     from oak_b200 import synthetic as S
     from oak_b200.dist import phase_ranges
@@ -428,11 +476,10 @@ def main():
                 stages["k_tql+k_tvec+apply"] = (ms_t + ms_a, fl_t + fl_a)
         else:
             stages["k_eig_fast"] = (stp["ms_eig"], 9 * N3 + 2 * N3 + 4 * a.N * a.N)
-        # dram__bytes_read.sum + dram__bytes_write.sum per zone from the ncu --set full captures under profiles/
-        # (r1_ncu_full_tridiag.txt, r1_ncu_full_tvec.txt, r1_ncu_full_gram.txt; 7104-zone launches, N = 64)
-        traffic_zone = {"k_gram": 26.1e3, "k_tridiag": 59.5e3, "k_tql+k_tvec": 59.2e3, "k_eig_fast": 39.8e3}
-        if a.gram_kernel or a.fuse_apply or a.tvec_split or a.apply_kernel:
-            traffic_zone = {}   # no ncu capture of the variant kernels yet: traffic is reported as null
+        # dram__bytes_read.sum + dram__bytes_write.sum per zone and kernel: parsed by tools/ncu_traffic.py from the
+        # ncu --set full captures of the build named in that file (profiles/ncu_traffic.json: kernel options, git
+        # hash, zones per launch); null when there is no capture for the kernel or the options differ
+        traffic_zone = load_traffic(a)
         stage_out = {}
         for name, (ms_k, fl) in stages.items():
             ach = fl * z_rank / (ms_k * 1e-3) / 1e12 if ms_k > 0 else 0.0
@@ -444,7 +491,8 @@ def main():
         achieved = dom_fl * (z_rank / nb) / (dom_ms_launch * 1e-3) / 1e12
         roof = {"bound": "fp64", "kernel": dom + " (largest share of the step among: " + ", ".join(stages) + ")",
                 "achieved": achieved, "peak": peak_dfma, "unit": "TFLOP/s", "frac": achieved / peak_dfma,
-                "traffic": traffic_zone[dom] * (z_rank / nb) if (a.N == 64 and dom in traffic_zone) else None,
+                "traffic": traffic_zone[dom] * (z_rank / nb) if dom in traffic_zone else None,
+                "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch / zones per launch)" if dom in traffic_zone else None,
                 "peak_source": "DFMA micro-kernel measured in this run (oakb200_fp64_peak); MEASURED_PEAKS.json has no "
                                "fp64 figure; DMMA m8n8k4 measured %.1f TFLOP/s" % peak_dmma,
                 "algorithmic_flops_per_zone_kernel": dom_fl, "launches_per_step": nb,
@@ -487,6 +535,8 @@ def main():
             def e2e_step():
                 tot = {}
                 for p, q in zip(phases, hb):
+                    # what the Fortran shim does on every Assim: positions to the device + cell-grid build
+                    p["h"].set_observations(obs_x=p["ox"], obs_y=p["oy"])
                     add_stats(tot, p["h"].local_analysis_pinned(q["xf"], q["Hxf"], q["yo"], q["Sf"], q["HSf"], q["var"],
                                                                 q["xa"], q["Sa"]))
                 return tot
@@ -514,7 +564,7 @@ def main():
             ok = bool(torch.equal(hb[0]["Sa"][:, :1000].to(dev), phases[0]["Sa"][:, :1000]))
             e2e = {"value": nzones / float(tt.item()), "unit": "columns/s", "h2d_bytes_per_step": ste["h2d_bytes"],
                    "d2h_bytes_per_step": ste["d2h_bytes"], "steps": a.e2e_steps,
-                   "note": "oakb200_local_analysis on pinned host buffers; state streamed in zone chunks; "
+                   "note": "oakb200_set_observations + oakb200_local_analysis on pinned host buffers; state streamed in zone chunks; "
                            "bytes are per rank; no all-gather of host buffers" + ("" if ok else "; MISMATCH vs resident run")}
             del hb
         except Exception as ex:  # e.g. not enough pinnable host memory
@@ -522,12 +572,18 @@ def main():
                    "error": repr(ex)[:300]}
     if rank == 0:
         out["e2e"] = e2e
-        if world == 1 and not a.no_cpu:
-            try:
-                out["cpu_baseline"], _ = cpu_baseline(a, d, a.cpu_seconds)
-            except Exception as ex:
-                out["cpu_baseline"] = {"value": None, "unit": "columns/s", "cores": None, "kind": "port",
-                                       "sample": "failed: " + repr(ex)[:200]}
+        # parity of THIS run's device result (left in d["xa"], d["Sa"] by the timed steps and the profile pass, which
+        # analyse the same inputs) against the oracle, on the columns the CPU baseline analyses anyway
+        try:
+            if world == 1 and not a.no_cpu:
+                out["cpu_baseline"], (_, sp_, kept_) = cpu_baseline(a, d, a.cpu_seconds)
+                out["parity"] = parity_vs_oracle(a, d, sp_, kept_)
+            else:
+                out["parity"] = quick_parity(a, d)
+        except Exception as ex:
+            out.setdefault("cpu_baseline", {"value": None, "unit": "columns/s", "cores": None, "kind": "port",
+                                            "sample": "failed: " + repr(ex)[:200]})
+            out["parity"] = {"cols": 0, "ok": False, "error": repr(ex)[:200]}
         print(json.dumps(out))
     if peer is not None:
         Sa_full = None
@@ -549,7 +605,8 @@ def reference_arm(a, rank, world):
     d = build_rank_data(a, 0, 1, dev)
     import oracle
     host = host_obs_arrays(d)
-    cores = oracle.max_threads()
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its children: the baseline uses every online processor
+    cores = oracle.set_threads(0)
     sp = cpu_sample_problem(a, d, 100000)
     probe = max(cores * 2, 16)
     t = run_oracle_sample(a, host, sp, probe)

@@ -40,6 +40,21 @@ void oak_set_error(const char *fmt, ...) {
   va_end(ap);
   g_err = buf;
 }
+
+#include <map>
+#include <mutex>
+int oak_func_smem_impl(const void *func, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void *, int>, int> done;  // (kernel, device) -> bytes granted
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = done.find({func, dev});
+  if (it != done.end() && it->second >= bytes) return 0;
+  CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done[{func, dev}] = bytes;
+  return 0;
+}
 extern "C" OAKB200_API const char *oakb200_last_error(void) { return g_err.c_str(); }
 extern "C" OAKB200_API int oakb200_version(void) { return 100; }
 #ifdef OAK_CUEMU
@@ -93,7 +108,7 @@ struct oakb200_handle {
   int scheme = 1;             // ensemble entry points: 1 = local scheme (default), 0 = global scheme (schemetype, assimilation.F90:292)
   int tvec_split = 0;         // 1: tridiagonal route, k_tvec as two kernels (eigenvectors of T | back-transformation and the rest)
   int fuse_apply = 0;         // 1: tridiagonal route, k_tvec updates the zone rows from the factored transform (no T, no k_apply)
-  int gram_kernel = 0;        // 0: k_gram (DFMA register tiles); 1 / 2: k_gram_mma (DMMA, 4 / 2 warps per zone; NP = 64); 3 / 4: same, 32-candidate chunks
+  int gram_kernel = 1;        // 1 (default since round 2: 8.6 -> 5.7 ms per 90 k zones) / 2: k_gram_mma (DMMA, 4 / 2 warps per zone; NP = 64); 3 / 4: same, 32-candidate chunks; 0: k_gram (DFMA register tiles)
   double tri_orthtol = 0.;  // tridiagonal route: accepted loss of orthogonality between neighbouring eigenvectors (0: default)
   int tri_maxgroup = -1;
   DevBuf d_anam;              // tabulated anamorphosis (K x 2), oakb200_set_anamorphosis_table

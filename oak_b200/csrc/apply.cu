@@ -184,11 +184,7 @@ int launch(cudaStream_t st, int N, const ZoneGeom &zg, int zone0, int nz, int64_
            const double *T, const double *ampl, const double *xf, const double *Sf, int64_t ldS, double *xa,
            double *Sa, int64_t ldSa, const PeerOut &peers, const int32_t *only_flagged, bool shared_transform) {
   const size_t smem = sizeof(double) * (NP * NP + NP * (RC + 2) + NP);
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(k_apply<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  { int rc_ = oak_func_smem(k_apply<NP>, (size_t)((int)smem)); if (rc_) return rc_; }
   k_apply<NP><<<nz, 128, smem, st>>>(N, zg, zone0, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged,
                                        shared_transform ? 0 : (int64_t)NP * NP, shared_transform ? 0 : NP);
   CUDA_TRY(cudaGetLastError());

@@ -131,11 +131,7 @@ int oak_launch_apply_mma(cudaStream_t st, int N, int NP, const ZoneGeom &zg, int
   if (NP != 64) { oak_set_error("apply_mma: padded ensemble size %d (only 64)", NP); return OAK_ERR_UNSUPPORTED; }
   constexpr int NPc = 64;
   const size_t smem = sizeof(double) * (NPc * (NPc + 4) + RC * (NPc + 4) + NPc);
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(k_apply_mma<NPc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  { int rc_ = oak_func_smem(k_apply_mma<NPc>, (size_t)((int)smem)); if (rc_) return rc_; }
   k_apply_mma<NPc><<<nz, 128, smem, st>>>(N, zg, zone0, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, only_flagged,
                                           shared_transform ? 0 : (int64_t)NPc * NPc, shared_transform ? 0 : NPc);
   CUDA_TRY(cudaGetLastError());

@@ -23,6 +23,12 @@
 
 void oak_set_error(const char *fmt, ...);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: handles on several GPUs in one process each
+// need it, so the "already set" record is keyed by (kernel, device) and guarded by a mutex.
+int oak_func_smem_impl(const void *func, int bytes);
+template <class F>
+inline int oak_func_smem(F *func, size_t bytes) { return oak_func_smem_impl(reinterpret_cast<const void *>(func), (int)bytes); }
+
 #define CUDA_TRY(expr)                                                                     \
   do {                                                                                     \
     cudaError_t _e = (expr);                                                               \

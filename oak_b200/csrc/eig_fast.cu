@@ -674,11 +674,7 @@ int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G,
   const size_t smem = sizeof(double) * (NP * C::LDW + 9 * NP);
   static_assert((C::NG + 1) * KB * C::LDX <= NP * C::LDW && (KB == 2 ? 7 : 3) * (C::NG + 1) <= 2 * NP, "exchange buffer fits");
   static_assert(2 * C::NG * NP <= NP * C::LDW, "partial-sum buffer fits");
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(k_eig_fast<NP, TL, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  { int rc_ = oak_func_smem(k_eig_fast<NP, TL, KB>, (size_t)((int)smem)); if (rc_) return rc_; }
   k_eig_fast<NP, TL, KB><<<nz, C::NTH, smem, st>>>(N, mloc, G, c, T, ampl, (float)tol, max_sweeps, ctr);
   CUDA_TRY(cudaGetLastError());
   return 0;

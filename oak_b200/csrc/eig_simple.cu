@@ -226,11 +226,7 @@ template <int NP>
 int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G, const double *c, double *T,
            double *ampl, double tol, int max_sweeps, DevCounters *ctr) {
   const size_t smem = sizeof(double) * (NP * NP + 8 * NP);
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(k_eig_simple<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  { int rc_ = oak_func_smem(k_eig_simple<NP>, (size_t)((int)smem)); if (rc_) return rc_; }
   k_eig_simple<NP><<<nz, 128, smem, st>>>(N, mloc, G, c, T, ampl, tol, max_sweeps, ctr);
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -963,13 +963,9 @@ int launch_tvec(cudaStream_t st, int N, int nz, const int32_t *mloc, const doubl
                 double *Wg) {
   const size_t smem0 = sizeof(double) * 14 * NP;
   const size_t smem = sizeof(double) * (NP * (NP + (FUSE ? 4 : 2)) + 14 * NP + (FUSE ? FusedApply<NP>::SMEM_DOUBLES : 0));
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(k_tvec<NP, FUSE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_tvec<NP, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-    CUDA_TRY(cudaFuncSetAttribute(k_tvec<NP, FUSE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  { int rc_ = oak_func_smem(k_tvec<NP, FUSE, 0>, (size_t)((int)smem)); if (rc_) return rc_; }
+  { int rc_ = oak_func_smem(k_tvec<NP, false, 1>, (size_t)((int)smem0)); if (rc_) return rc_; }
+  { int rc_ = oak_func_smem(k_tvec<NP, FUSE, 2>, (size_t)((int)smem)); if (rc_) return rc_; }
   const double ot = orthtol > 0. ? orthtol : TRI_ORTHTOL;
   const int mg = maxgroup >= 0 ? maxgroup : TRI_MAXGROUP;
   if (Wg) {

@@ -169,11 +169,7 @@ int oak_launch_mean_anom(cudaStream_t st, int64_t rows, int N, int anamtype, Ana
                          double *mean, double *S, int64_t ldS) {
   if (rows == 0) return 0;
   const size_t smem = sizeof(double) * 64 * N;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(k_mean_anom, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 128 * 8));
-    attr_done = true;
-  }
+  { int rc_ = oak_func_smem(k_mean_anom, (size_t)(64 * 128 * 8)); if (rc_) return rc_; }
   const double scaling = sqrt((double)N - 1.);
   k_mean_anom<<<(unsigned)((rows + 63) / 64), 256, smem, st>>>(rows, N, anamtype, at, E, ldE, mean, S, ldS, scaling);
   CUDA_TRY(cudaGetLastError());

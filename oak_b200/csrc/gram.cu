@@ -224,11 +224,7 @@ template <int NP, int NT, bool SYM = false>
 int launch(cudaStream_t st, const ZoneGeom &zg, const ObsGrid &og, const ObsRows &orows, int zone0, int nz,
            double *G, double *c, int32_t *mloc, DevCounters *ctr) {
   const size_t smem = sizeof(double) * 2 * GRAM_CH * NP;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(k_gram<NP, NT, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  { int rc_ = oak_func_smem(k_gram<NP, NT, SYM>, (size_t)((int)smem)); if (rc_) return rc_; }
   k_gram<NP, NT, SYM><<<nz, NT, smem, st>>>(zg, og, orows, zone0, nz, G, c, mloc, ctr);
   CUDA_TRY(cudaGetLastError());
   return 0;

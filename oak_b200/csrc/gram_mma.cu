@@ -278,11 +278,7 @@ template <int NP, int NW, int CH>
 int launch(cudaStream_t st, const ZoneGeom &zg, const ObsGrid &og, const ObsRows &orows, int zone0, int nz,
            double *G, double *c, int32_t *mloc, DevCounters *ctr) {
   const size_t smem = sizeof(double) * 2 * CH * (NP + 4);
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(k_gram_mma<NP, NW, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  { int rc_ = oak_func_smem(k_gram_mma<NP, NW, CH>, (size_t)((int)smem)); if (rc_) return rc_; }
   k_gram_mma<NP, NW, CH><<<nz, 32 * NW, smem, st>>>(zg, og, orows, zone0, nz, G, c, mloc, ctr);
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -66,6 +66,8 @@ def lib():
     L.oracle_assim_ensemble.restype = C.c_int
     L.oracle_analysis_increment.restype = C.c_int
     L.oracle_max_threads.restype = C.c_int
+    L.oracle_set_threads.restype = C.c_int
+    L.oracle_set_threads.argtypes = [C.c_int]
     _LIB = L
     return L
 
@@ -244,3 +246,8 @@ def init_partition(partition, nzones):
 
 def max_threads():
     return lib().oracle_max_threads()
+
+
+def set_threads(n=0):
+    """OpenMP threads of the zone loop (n <= 0: all online processors, whatever OMP_NUM_THREADS says)."""
+    return lib().oracle_set_threads(int(n))

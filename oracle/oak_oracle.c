@@ -79,6 +79,19 @@ int oracle_max_threads(void) {
 #endif
 }
 
+/* The launcher of a multi-process run (torch.distributed.run) exports OMP_NUM_THREADS=1; the CPU baseline of the
+ * bench sets the zone-loop thread count explicitly (and reports it).  n <= 0: every online processor. */
+int oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n <= 0) n = omp_get_num_procs();
+  omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
+
 /* ---------------------------------------------------------------------------
  * locfun — Gaspari–Cohn 5th-order piecewise rational, Horner form
  * covariance.F90:645-667
