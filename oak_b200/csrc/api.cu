@@ -366,8 +366,8 @@ int end_call(oakb200_handle *h, oakb200_stats *stats, int64_t launches, const Pr
     stats->ms_tridiag = prof.tridiag; stats->ms_tql = prof.tql; stats->ms_tvec = prof.tvec;
   }
   if (getenv("OAKB200_DEBUG"))
-    fprintf(stderr, "[oak_b200] fallback %llu (ql %llu, residual %llu, group %llu, parallel %llu), gram-schmidt projections %llu, sweeps %llu\n",
-            ctr.fallback, ctr.fb_reason[0], ctr.fb_reason[1], ctr.fb_reason[2], ctr.fb_reason[3], ctr.gs_pairs, ctr.sweeps);
+    fprintf(stderr, "[oak_b200] fallback %llu (ql %llu, residual %llu, group %llu, parallel %llu), gram-schmidt projections %llu, pivot-form vectors %llu, sweeps %llu\n",
+            ctr.fallback, ctr.fb_reason[0], ctr.fb_reason[1], ctr.fb_reason[2], ctr.fb_reason[3], ctr.gs_pairs, ctr.tw_fallback, ctr.sweeps);
   if (ctr.nan_flag) { oak_set_error("NaN in the analysis amplitudes (rrsqrt.F90:145-149)"); return OAK_ERR_NAN; }
   if (ctr.not_converged) { oak_set_error("Jacobi eigensolve did not converge in %d sweeps for %d zones", h->max_sweeps, ctr.not_converged); return OAK_ERR_NAN; }
   return 0;

@@ -314,6 +314,7 @@ struct DevCounters {      // device-side statistics / status
   unsigned long long fallback;  // zones the tridiagonal route handed to the Jacobi kernel
   unsigned long long fb_reason[4];  // ... because of: QL iterations, residual test, group size, parallel vectors
   unsigned long long gs_pairs;      // Gram-Schmidt projections done inside close groups
+  unsigned long long tw_fallback;   // eigenvectors of T computed by the pivot form because the Sturm products underflowed
 };
 
 int oak_launch_pack_obs(cudaStream_t st, int m, int N, int NP, const int32_t *perm, const double *HSf,

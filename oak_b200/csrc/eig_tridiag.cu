@@ -40,6 +40,9 @@
 #ifndef TVEC_TWISTED2
 #define TVEC_TWISTED2 0   // 1: twisted_vector2 (interleaved pivot recurrences, stored reciprocals) - prepared, host-tested,
 #endif                    //    not yet measured on the GPU
+#ifndef TVEC_PRODUCT
+#define TVEC_PRODUCT 1    // 1: twisted_vector3 (division-free Sturm-product recurrences), pivot form as fallback
+#endif
 #ifndef TVEC_MINB
 #define TVEC_MINB 1
 #endif
@@ -675,6 +678,8 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
   double *se = sd + NP, *slam = se + NP, *stau = slam + NP, *sc = stau + NP;
   double *sa = sc + NP, *sb = sa + NP, *suv = sb + NP, *sdw = suv + NP, *suw = sdw + NP;
   double *sg1 = suw + NP, *sg2 = sg1 + NP, *sgj = sg2 + NP, *sres = sgj + NP;
+  double *sds = sres + NP, *se2 = sds + NP, *sen = se2 + NP;   // s d_i, (s e_i)^2, -s e_i of the Sturm-product recurrences
+  constexpr int NVEC = 17;                                       // NP-vectors of shared memory after the matrix
   __shared__ double sred[8];
   __shared__ unsigned sclose[NW];
   __shared__ int sflag;
@@ -706,6 +711,15 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
   // ---- eigenvector j of T ----
   double tn = 0.;
   for (int i = 0; i < N; i++) tn = fmax(tn, fmax(fabs(sd[i]), fabs(se[i])));
+  // power-of-two scale of the Sturm-product recurrences: |s (d - lam)| < 1/2, |s e| < 1/8
+  const double tscale = tn > 0. ? scalbn(1., -(ilogb(tn) + 4)) : 1.;
+#if TVEC_PRODUCT
+  {
+    const double es = (j < N - 1) ? tscale * se[j] : 0.;
+    sds[j] = tscale * sd[j]; se2[j] = es * es; sen[j] = -es;
+  }
+  __syncthreads();
+#endif
   const double lam = (j < N) ? slam[j] : 0.;
   const double lamc = fmax(lam, 0.);
   const double sig = sqrt(1. + lamc);
@@ -722,10 +736,19 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
 #else
 #define OAK_TWISTED twisted_vector
 #endif
-    double zz = OAK_TWISTED(N, sd, se, 1, lam, pivmin, W + j, LDW, &gam);
+#if TVEC_PRODUCT
+    // division-free (Sturm-product) form; the pivot form only where the products underflow
+#define OAK_TWISTED_CALL(lam_)                                                  \
+    zz = twisted_vector3(N, sds, se2, sen, tscale * (lam_), 1. / tscale, W + j, LDW, &gam); \
+    if (zz < 0.) { atomicAdd(&ctr->tw_fallback, 1ull); zz = OAK_TWISTED(N, sd, se, 1, lam_, pivmin, W + j, LDW, &gam); }
+#else
+#define OAK_TWISTED_CALL(lam_) zz = OAK_TWISTED(N, sd, se, 1, lam_, pivmin, W + j, LDW, &gam);
+#endif
+    double zz;
+    OAK_TWISTED_CALL(lam)
     if (!(fabs(gam) <= TRI_RESTOL * tn * sqrt(zz)) || !(zz < 1e300)) {  // one Rayleigh-quotient correction, then give up
       const double lam2 = lam + gam / zz;
-      zz = OAK_TWISTED(N, sd, se, 1, lam2, pivmin, W + j, LDW, &gam);
+      OAK_TWISTED_CALL(lam2)
       if (!(fabs(gam) <= TRI_RESTOL * tn * sqrt(zz)) || !(zz < 1e300)) bad = true;
     }
     const double sc_ = rsqrt(zz);
@@ -902,7 +925,7 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
     sa[j] = sg1[j] * hv;   // sa, sb were last read before the barrier above
     sb[j] = sg2[j] * hw;
     __syncthreads();
-    double *sS = sm + NP * LDY + 14 * NP, *sP = sS + FusedApply<NP>::RC * FusedApply<NP>::LD;
+    double *sS = sm + NP * LDY + NVEC * NP, *sP = sS + FusedApply<NP>::RC * FusedApply<NP>::LD;
     double *s_row = sP + FusedApply<NP>::RC * FusedApply<NP>::LD;
     const int64_t i1 = aa.zstart[zl] - aa.rowbase;
     const int nrow = (int)(aa.zstart[zl + 1] - aa.zstart[zl]);
@@ -961,8 +984,8 @@ template <int NP, bool FUSE>
 int launch_tvec(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *c, double *T, double *ampl,
                 double *ws, int32_t *flags, DevCounters *ctr, double orthtol, int maxgroup, const FusedApplyArgs &aa,
                 double *Wg) {
-  const size_t smem0 = sizeof(double) * 14 * NP;
-  const size_t smem = sizeof(double) * (NP * (NP + (FUSE ? 4 : 2)) + 14 * NP + (FUSE ? FusedApply<NP>::SMEM_DOUBLES : 0));
+  const size_t smem0 = sizeof(double) * 17 * NP;
+  const size_t smem = sizeof(double) * (NP * (NP + (FUSE ? 4 : 2)) + 17 * NP + (FUSE ? FusedApply<NP>::SMEM_DOUBLES : 0));
   { int rc_ = oak_func_smem(k_tvec<NP, FUSE, 0>, (size_t)((int)smem)); if (rc_) return rc_; }
   { int rc_ = oak_func_smem(k_tvec<NP, false, 1>, (size_t)((int)smem0)); if (rc_) return rc_; }
   { int rc_ = oak_func_smem(k_tvec<NP, FUSE, 2>, (size_t)((int)smem)); if (rc_) return rc_; }

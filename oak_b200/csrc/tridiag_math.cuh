@@ -347,3 +347,132 @@ OAK_HD double twisted_vector2(int n, const double *d, const double *e, int sd, d
   *gam = gbest;
   return zz;
 }
+
+// twisted_vector3 — the same vector WITHOUT a division in any recurrence (default in k_tvec since round 2; the
+// pivot form above stays as the fallback for the cases below).  With delta_i = s (d_i - lam), eps_i = s e_i (s a
+// power of two that makes |delta| < 1/2, |eps| < 1/8) the pivots are ratios of the Sturm polynomials,
+//   forward   F_0 = 1, F_1 = delta_0,       F_{i+1} = delta_i F_i - eps_{i-1}^2 F_{i-1}     (F_i = P_{i-1}, p_i = F_{i+1}/F_i)
+//   backward  B_{n-1} = 1, B_{n-2} = delta_{n-1}, B_{i-1} = delta_i B_i - eps_i^2 B_{i+1}   (B_i = Q_{i+1}, q_i = B_{i-1}/B_i)
+// and gamma_i = det(T - lam) / (F_i B_i) (1/gamma_i is the i-th diagonal entry of the inverse), so that the twist is
+// r = argmax |F_i B_i| and, with z_r = 1,
+//   z_i = (F_i / F_r) prod_{j=i}^{r-1} (-eps_j)  (i < r) ,   z_i = (B_i / B_r) prod_{j=r}^{i-1} (-eps_j)  (i > r) ,
+//   gamma_r = (F_{r+1} B_r - eps_r^2 F_r B_{r+1}) / (F_r B_r) / s .
+// Every recurrence step is ONE dependent FMA (the second product only needs the value of two steps ago) instead of
+// the reciprocal + FMA (~70 cycles) of a pivot step, and forward and backward chains run interleaved: the serial
+// chain of a vector is ~2.5 n FMAs instead of ~3.5 n reciprocal steps.  Rounding: each step perturbs delta_i and
+// eps_{i-1}^2 by a few ulp, exactly as a pivot step does.  The scaled polynomials only ever decay (|F_{i+1}| <=
+// |F_i|/2 + |F_{i-1}|/64), so nothing overflows; if F_r B_r underflows (a long run of diagonal entries within
+// ~1e-5 |T| of lam ...) the function reports failure (returns -1) and the caller uses the pivot form.
+//   phase 1  F_i for i < h = n/2 and B_i for i >= h, stored in w
+//   phase 2  both recurrences continue into the other half; |F_i B_i| on the fly, r = argmax
+//   phase 3  the |r - h| values of the far side of the twist that are still missing are recomputed
+//   phase 4  the products towards both ends, z, |z|^2
+// scale = s (the same for every vector of the matrix: exp2(-(ilogb(tn) + 4)), tn = max(|d|, |e|)).
+OAK_HD double twisted_vector3(int n, const double *ds /* s d_i */, const double *e2 /* (s e_i)^2 */,
+                              const double *en /* -s e_i */, double sl /* s lam */, double inv_scale /* 1/s */,
+                              double *w, int sw, double *gam) {
+  // ds, e2, en are per-matrix arrays (unit stride, shared by all the vectors of the matrix); e2[n-1] = en[n-1] = 0
+  if (n == 1) { w[0] = 1.; *gam = (ds[0] - sl) * inv_scale; return 1.; }
+  const int h = n / 2;
+  // ---- phase 1 ----  (uniform trip count: no divergence between the vectors of a warp)
+  double f1 = 1., f0 = 0.;     // F_i, F_{i-1}
+  double b1 = 1., b0 = 0.;     // B_j, B_{j+1}
+  {
+    double fe = 0., be = 0.;   // eps_{i-1}^2 F_{i-1} ; eps_j^2 B_{j+1}   (one step ahead of the chain)
+    double *wf = w, *wb = w + (n - 1) * sw;
+    const double *df = ds, *db = ds + (n - 1), *ef = e2, *eb = e2 + (n - 2);
+#pragma unroll 4
+    for (int i = 0; i < h; i++) {
+      *wf = f1; wf += sw;
+      const double fn = fma(*df - sl, f1, -fe);
+      fe = *ef * f1; f0 = f1; f1 = fn; df++; ef++;
+      *wb = b1; wb -= sw;
+      const double bn = fma(*db - sl, b1, -be);
+      be = *eb * b1; b0 = b1; b1 = bn; db--; eb--;
+    }
+    if (n & 1) {               // the backward half is one longer
+      *wb = b1;
+      const double bn = fma(*db - sl, b1, -be);
+      b0 = b1; b1 = bn;
+    }
+  }
+  // now f1 = F_h, f0 = F_{h-1}; b1 = B_{h-1}, b0 = B_h
+  const double fh1 = f1, fh0 = f0, bh1 = b1, bh0 = b0;
+  // ---- phase 2 ----
+  double best = -1.;
+  int r = 0;
+  {
+    const double *wf = w + h * sw, *wb = w + (h - 1) * sw;
+    const double *df = ds + h, *db = ds + (h - 1), *ef = e2 + (h - 1), *eb = e2 + (h - 1);
+#pragma unroll 4
+    for (int t = 0; t < h; t++) {   // forward at i = h + t, backward at j = h - 1 - t
+      const double kf = fabs(f1 * *wf), kb = fabs(b1 * *wb);
+      if (kf > best) { best = kf; r = h + t; }
+      if (kb > best) { best = kb; r = h - 1 - t; }
+      const double fn = fma(*df - sl, f1, -(*ef * f0));
+      f0 = f1; f1 = fn; wf += sw; df++; ef++;
+      const double bn = fma(*db - sl, b1, -(*eb * b0));
+      b0 = b1; b1 = bn; wb -= sw; db--; eb--;
+    }
+    if (n & 1) {                    // forward at i = n - 1
+      const double kf = fabs(f1 * *wf);
+      if (kf > best) { best = kf; r = n - 1; }
+    }
+  }
+  if (!(best > 1e-250)) return -1.;   // also keeps det = gamma_r F_r B_r (~1e-16 smaller) out of the denormals
+  // ---- phase 3 ----  one loop for both directions: x1, x0 = the recurrence pair at idx, moving by step towards r
+  double fr, fr1, br, br1;
+  {
+    const bool up = r >= h;
+    const int step = up ? 1 : -1, cnt = up ? r - h : h - 1 - r;
+    int idx = up ? h : h - 1;
+    double x1 = up ? fh1 : bh1, x0 = up ? fh0 : bh0;
+    const double *eo = e2 + (up ? -1 : 0);   // forward steps use eps_{idx-1}^2, backward ones eps_idx^2
+    for (int t = 0; t < cnt; t++) {
+      w[idx * sw] = x1;
+      const double xn = fma(ds[idx] - sl, x1, -(eo[idx] * x0));
+      x0 = x1; x1 = xn; idx += step;
+    }
+    // idx == r : x1 = F_r (B_r), x0 = F_{r-1} (B_{r+1})
+    if (up) {
+      fr = x1;
+      fr1 = fma(ds[r] - sl, x1, -((r >= 1 ? e2[r - 1] : 0.) * x0));
+      br = w[r * sw];
+      br1 = r + 1 < n ? w[(r + 1) * sw] : 0.;
+    } else {
+      br = x1; br1 = x0;
+      fr = w[r * sw];
+      fr1 = fma(ds[r] - sl, fr, -((r >= 1 ? e2[r - 1] * w[(r - 1) * sw] : 0.)));
+    }
+  }
+  const double invF = oak_rcp(fr), invB = oak_rcp(br);
+  {
+    const double D = fma(fr1, br, -(e2[r] * fr) * br1);   // e2[n-1] = 0
+    *gam = D * invF * invB * inv_scale;
+  }
+  // ---- phase 4 ----
+  double zz = 1.;
+  {
+    double pu = invF, pd = invB;
+    const int nu = r, nd = n - 1 - r, nt = nu > nd ? nu : nd;
+    double *wu = w + (r - 1) * sw, *wd = w + (r + 1) * sw;
+    const double *eu = en + (r - 1), *ed = en + r;
+    for (int t = 0; t < nt; t++) {
+      if (t < nu) {
+        pu *= *eu;
+        const double z = *wu * pu;
+        *wu = z;
+        zz = fma(z, z, zz);
+      }
+      if (t < nd) {
+        pd *= *ed;
+        const double z = *wd * pd;
+        *wd = z;
+        zz = fma(z, z, zz);
+      }
+      wu -= sw; eu--; wd += sw; ed++;
+    }
+  }
+  w[r * sw] = 1.;
+  return zz;
+}
