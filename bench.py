@@ -312,6 +312,9 @@ def main():
             h.set_option("fixed_sweeps", float(os.environ["OAK_B200_FIXED_SWEEPS"]))
         if os.environ.get("OAK_B200_ZB"):  # pipeline experiments (tools/ab.py)
             h.set_option("zones_per_batch", float(os.environ["OAK_B200_ZB"]))
+        for kv in os.environ.get("OAK_B200_OPTIONS", "").split(","):   # experiments: key=value,... library options
+            if "=" in kv:
+                h.set_option(kv.split("=")[0], float(kv.split("=")[1]))
         if a.jacobi_tol > 0:
             h.set_option("jacobi_tol", a.jacobi_tol)
         h.set_zones(plan.zoneSize, zone_x=plan.zx, zone_y=plan.zy, corrLen=plan.corrLen, maxLen=plan.maxLen,

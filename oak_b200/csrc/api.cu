@@ -92,6 +92,8 @@ struct DevBuf {
 struct Slot {
   cudaStream_t st = nullptr;
   cudaStream_t cst = nullptr;  // copy-engine pushes of finished batches to the peers (peer_mode 1)
+  cudaStream_t qst = nullptr;  // option tql_side: k_tql on a high-priority stream of its own
+  cudaEvent_t qev[2] = {};
   DevBuf Wv;                   // option tvec_split: eigenvectors of T between the two halves of k_tvec
   DevBuf G, T, c, ampl, tri;   // batch workspace (tri: d, e, tau, lambda, flags of the tridiagonal route)
   DevBuf S, xf, xa;            // host-streaming chunk buffers
@@ -108,6 +110,7 @@ struct oakb200_handle {
   int scheme = 1;             // ensemble entry points: 1 = local scheme (default), 0 = global scheme (schemetype, assimilation.F90:292)
   int tvec_split = 0;         // 1: tridiagonal route, k_tvec as two kernels (eigenvectors of T | back-transformation and the rest)
   int fuse_apply = 0;         // 1: tridiagonal route, k_tvec updates the zone rows from the factored transform (no T, no k_apply)
+  int tql_side = 1;           // 1 (default: 286.7 -> 280.9 ms per C3 step): k_tql on the slot's high-priority side stream
   int gram_kernel = 1;        // 1 (default since round 2: 8.6 -> 5.7 ms per 90 k zones) / 2: k_gram_mma (DMMA, 4 / 2 warps per zone; NP = 64); 3 / 4: same, 32-candidate chunks; 0: k_gram (DFMA register tiles)
   double tri_orthtol = 0.;  // tridiagonal route: accepted loss of orthogonality between neighbouring eigenvectors (0: default)
   int tri_maxgroup = -1;
@@ -260,10 +263,12 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
       // ... and only while the factored form is the cheaper one (4 nr N^2 against 2 N^3 + 2 nr N^2: zones of at most N rows)
       const bool fuse = h->fuse_apply && !(use_peers && h->peer_mode == 0) && h->max_zone_rows <= NP;
       const FusedApplyArgs fa{zg.zstart + b0, rowbase, xf, Sf, xa, Sa, ldS, ldSa};
+      const TqlSide tside{s.qst, s.qev[0], s.qev[1]};
       if ((rc = oak_launch_eig_tridiag(s.st, N, NP, nz, mloc + b0, s.G.as<double>(), s.c.as<double>(),
                                        s.T.as<double>(), s.ampl.as<double>(), s.tri.p, &flags, ctr,
                                        prof ? &s.ev[8] : nullptr, h->tri_orthtol, h->tri_maxgroup,
-                                       fuse ? &fa : nullptr, h->tvec_split ? s.Wv.as<double>() : nullptr))) return rc;
+                                       fuse ? &fa : nullptr, h->tvec_split ? s.Wv.as<double>() : nullptr,
+                                       (h->tql_side && !prof) ? &tside : nullptr))) return rc;
       if (fuse) only_flagged = flags;
       if (prof) CUDA_TRY(cudaEventRecord(s.ev[10], s.st));
       if ((rc = oak_launch_eig(s.st, 0, N, NP, 0, nz, flags, s.G.as<double>(), s.c.as<double>(),
@@ -397,6 +402,8 @@ extern "C" OAKB200_API int oakb200_create(int device, oakb200_handle **out) {
   for (int i = 0; i < NSLOT; i++) {
     CUDA_TRY(cudaStreamCreateWithFlags(&h->slot[i].st, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->slot[i].cst, cudaStreamNonBlocking));
+    { int lo = 0, hi = 0; CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CUDA_TRY(cudaStreamCreateWithPriority(&h->slot[i].qst, cudaStreamNonBlocking, hi)); }
+    for (auto &ev : h->slot[i].qev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto &ev : h->slot[i].ev) CUDA_TRY(cudaEventCreate(&ev));
   }
   CUDA_TRY(cudaEventCreate(&h->ev_a));
@@ -428,6 +435,8 @@ extern "C" OAKB200_API int oakb200_destroy(oakb200_handle *h) {
     for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
     if (s.st) cudaStreamDestroy(s.st);
     if (s.cst) cudaStreamDestroy(s.cst);
+    if (s.qst) cudaStreamDestroy(s.qst);
+    for (auto &ev : s.qev) if (ev) cudaEventDestroy(ev);
   }
   if (h->ev_a) cudaEventDestroy(h->ev_a);
   if (h->ev_b) cudaEventDestroy(h->ev_b);
@@ -529,6 +538,7 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   if (k == "eig_kernel") h->eig_kernel = (int)value;
   else if (k == "fuse_apply") h->fuse_apply = value != 0.;
   else if (k == "tvec_split") h->tvec_split = value != 0.;
+  else if (k == "tql_side") h->tql_side = value != 0.;
   else if (k == "apply_kernel") {
     if (value != 0. && value != 1.) { oak_set_error("apply_kernel = %g (0 register tiles, 1 tensor-core tiles)", value); return OAK_ERR_ARG; }
     h->apply_kernel = (int)value;

@@ -22,6 +22,7 @@
 // function: mixing inside a tight group changes f(A) by f' eps |T| only).  Zones where that is not enough
 // (vectors of a group nearly parallel, groups larger than TRI_MAXGROUP, residual test failed, QL not
 // converged) are flagged and recomputed by the Jacobi kernel (eig_fast.cu), which has no such cases.
+#include <cstdlib>
 #include "common.cuh"
 #include "tridiag_math.cuh"
 
@@ -30,6 +31,9 @@
 #endif
 #ifndef TRI_TILE
 #define TRI_TILE 1   // 1 = k_tridiag_tile (8 x 8 cyclic register tiles), 0 = k_tridiag (row per thread)
+#endif
+#ifndef TRI_WARP
+#define TRI_WARP 1   // NP = 64: 1 = k_tridiag_warp (one warp per zone, lower block triangle), 0 = k_tridiag_tile
 #endif
 #ifndef TQL_PWK
 #define TQL_PWK 1    // k_tql: 1 = square-root-free QL (Pal-Walker-Kahan), 0 = plain implicit QL
@@ -406,6 +410,8 @@ __global__ void __launch_bounds__(64, TRI_MINB) k_tridiag_tile(int N, const int3
   __syncthreads();
   if (owner && t == N - 1) { we[N - 2] = x; we[N - 1] = 0.; wd[N - 1] = sx2[N - 1]; }
 }
+
+#include "tridiag_warp.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // k_tql : one thread per zone; d, e transposed into shared memory with an odd stride
@@ -1005,16 +1011,29 @@ int launch_tvec(cudaStream_t st, int N, int nz, const int32_t *mloc, const doubl
 template <int NP>
 int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G, const double *c, double *T,
            double *ampl, double *ws, int32_t *flags, DevCounters *ctr, cudaEvent_t *ev, double orthtol, int maxgroup,
-           const FusedApplyArgs *fuse, double *Wg) {
+           const FusedApplyArgs *fuse, double *Wg, const TqlSide *side) {
 #if TRI_TILE
-  k_tridiag_tile<NP><<<nz, 64, 0, st>>>(N, mloc, G, T, ws);
+  static const int tri_warp = getenv("OAK_B200_TRI_WARP") ? atoi(getenv("OAK_B200_TRI_WARP")) : TRI_WARP;
+  if (NP == 64 && tri_warp) k_tridiag_warp<<<nz, 32, 0, st>>>(N, nz, mloc, G, T, ws);
+  else k_tridiag_tile<NP><<<nz, 64, 0, st>>>(N, mloc, G, T, ws);
 #else
   k_tridiag<NP><<<nz, NP, 0, st>>>(N, mloc, G, T, ws);
 #endif
   CUDA_TRY(cudaGetLastError());
   if (ev) CUDA_TRY(cudaEventRecord(ev[0], st));
+  if (side) {
+    CUDA_TRY(cudaEventRecord(side->e0, st));
+    CUDA_TRY(cudaStreamWaitEvent(side->qst, side->e0, 0));
+    k_tql<NP><<<(nz + 31) / 32, 32, 0, side->qst>>>(N, nz, mloc, ws, flags);
+    CUDA_TRY(cudaEventRecord(side->e1, side->qst));
+    CUDA_TRY(cudaStreamWaitEvent(st, side->e1, 0));
+  } else
   k_tql<NP><<<(nz + 31) / 32, 32, 0, st>>>(N, nz, mloc, ws, flags);
   CUDA_TRY(cudaGetLastError());
+  {  // timing experiment (OAK_B200_TQL_REPEAT=k): the kernel only reads d, e and writes lambda, so it can be repeated
+    static const int rep = getenv("OAK_B200_TQL_REPEAT") ? atoi(getenv("OAK_B200_TQL_REPEAT")) : 0;
+    for (int r = 0; r < rep; r++) k_tql<NP><<<(nz + 31) / 32, 32, 0, st>>>(N, nz, mloc, ws, flags);
+  }
   if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
   if (fuse) return launch_tvec<NP, true>(st, N, nz, mloc, c, T, ampl, ws, flags, ctr, orthtol, maxgroup, *fuse, Wg);
   return launch_tvec<NP, false>(st, N, nz, mloc, c, T, ampl, ws, flags, ctr, orthtol, maxgroup, FusedApplyArgs{}, Wg);
@@ -1034,13 +1053,13 @@ size_t oak_eig_tridiag_ws_bytes(int NP, int nz) {
 int oak_launch_eig_tridiag(cudaStream_t st, int N, int NP, int nz, const int32_t *mloc, const double *G,
                            const double *c, double *T, double *ampl, void *ws, int32_t **flags_out,
                            DevCounters *ctr, cudaEvent_t *ev, double orthtol, int maxgroup,
-                           const FusedApplyArgs *fuse, double *Wg) {
+                           const FusedApplyArgs *fuse, double *Wg, const TqlSide *side) {
   double *wsd = reinterpret_cast<double *>(ws);
   int32_t *flags = reinterpret_cast<int32_t *>(wsd + 4 * (size_t)NP * nz);
   *flags_out = flags;
   switch (NP) {
-    case 32: return launch<32>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup, fuse, Wg);
-    case 64: return launch<64>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup, fuse, Wg);
+    case 32: return launch<32>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup, fuse, Wg, side);
+    case 64: return launch<64>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup, fuse, Wg, side);
   }
   oak_set_error("eig_tridiag: unsupported padded ensemble size %d", NP);
   return OAK_ERR_UNSUPPORTED;
