@@ -185,12 +185,22 @@ OAKB200_API int oakb200_ipc_free(oakb200_handle *h, void *ptr);
  * anamorphosis.F90:304-339 incl. its clamping rule).  One table for the whole state vector.  K = 0 clears it. */
 OAKB200_API int oakb200_set_anamorphosis_table(oakb200_handle *h, int32_t K, const double *table);
 
+/* Per-variable anamorphosis, as anamtransform applies it (assimilation.F90:4531-4567: the variable v of every element
+ * comes from ind2submv, the transform is AnamTrans%anam(v)): vtype[nvar] (1 identity, 2 log, 3 tabulated), vK[nvar]
+ * rows of each tabulated variable's table (ignored otherwise), tables = those K_v x 2 column-major tables one after
+ * the other (HOST), rowvar[n] = 1-based variable number of every row of the zone-permuted state.  Selected by
+ * anamtype = 0 in oakb200_assim_ensemble[_dev].  nvar = 0 clears it. */
+OAKB200_API int oakb200_set_anamorphosis_vars(oakb200_handle *h, int32_t nvar, const int32_t *vtype, const int32_t *vK,
+                                  const double *tables, int64_t n, const int32_t *rowvar);
+
 /* Ensemble branch of Assim around the local scheme (assimilation.F90:3083,:3106-3134 prologue,
  * :3235 analysis, :3301-3357,:3558-3562 epilogue), HOST buffers:
  *   E[n x N] ensemble (zone-permuted), H as COO (Hi,Hj 1-based int32, Hs, nnz; matoper.F90:30-39),
- *   Hshift[m] (may be NULL), yo, Rdiag, d01, anamtype 1 identity / 2 log / 3 tabulated (anamorphosis.F90:78-120,
+ *   Hshift[m] (may be NULL), yo, Rdiag, d01, anamtype 0 per variable (oakb200_set_anamorphosis_vars) / 1 identity / 2 log / 3 tabulated (anamorphosis.F90:78-120,
  *   :304-339; the table comes from oakb200_set_anamorphosis_table),
- *   inflation (inflation.mult), maxCorrection[n] (may be NULL)  ->  Ea[n x N]; xf_out/xa_out[n] optional. */
+ *   inflation (inflation.mult), maxCorrection[n] (may be NULL)  ->  Ea[n x N]; xf_out/xa_out[n] optional:
+ *   xf_out = forecast mean in transformed space (:3127), xa_out = mean of the back-transformed analysis ensemble
+ *   (xa = sum(Sa,2)/size(Sa,2), :3343-3349). */
 OAKB200_API int oakb200_assim_ensemble(oakb200_handle *h, int64_t n, int32_t N, int32_t m, const double *E,
                            int64_t ldE, int64_t nnz, const int32_t *Hi, const int32_t *Hj,
                            const double *Hs, const double *Hshift, const double *yo,

@@ -313,6 +313,16 @@ class Handle:
             raise OakB200Error(-2, "anamorphosis table must be K x 2")
         _check(self._L.oakb200_set_anamorphosis_table(self._h, t.shape[0], _ptr(t)))
 
+    def set_anamorphosis_vars(self, rowvar, specs):
+        """Per-variable anamorphosis (assimilation.F90:4531-4567): rowvar = 1-based variable number of every row of the
+        zone-permuted state, specs = [(type, table or None), ...] per variable.  Select with anamtype=0."""
+        rv = np.ascontiguousarray(rowvar, dtype=np.int32)
+        vt = np.array([t for t, _ in specs], dtype=np.int32)
+        tabs = [np.asfortranarray(tb, dtype=np.float64) if tb is not None else np.zeros((0, 2), order="F") for _, tb in specs]
+        vK = np.array([tb.shape[0] for tb in tabs], dtype=np.int32)
+        flat = np.concatenate([tb.ravel(order="F") for tb in tabs] + [np.zeros(1)])
+        _check(self._L.oakb200_set_anamorphosis_vars(self._h, len(specs), _ptr(vt), _ptr(vK), _ptr(flat), rv.size, _ptr(rv)))
+
     def assim_ensemble(self, E, Hi, Hj, Hs, Hshift, yo, R, anamtype=1, inflation=1.0, maxCorrection=None,
                        anamtable=None):
         """Ensemble branch of Assim (local scheme) with host arrays. Returns Ea, xf, xa, stats."""
@@ -352,15 +362,17 @@ def partition_zones(nzones, nranks):
 
 
 def locanalysis(zoneSize, selectObservations, xf, Hxf, yo, Sf, HSf, R, handle=None, device=0,
-                want_amplitudes=True):
+                want_amplitudes=True, localise_obs=True):
     """locAnalysis (rrsqrt.F90:433-466): returns (xa, Sa, amplitudes).
 
     `selectObservations` is a Selector (the Fortran callback reads the same data from module
     globals); `R` a DiagCovar or DCDCovar.  amplitudes is zero, as in the reference's default
-    local_obs branch (rrsqrt.F90:324)."""
+    local_obs branch (rrsqrt.F90:324); with localise_obs=False (rrsqrt.F90:374-385) every analysed zone uses all
+    observations with their weights and amplitudes(:, zone) is filled."""
     own = handle is None
     h = Handle(device) if own else handle
     try:
+        h.set_option("localise_obs", 1.0 if localise_obs else 0.0)
         h.configure(zoneSize, selectObservations)
         xa, Sa, ampl, _ = h.local_analysis(xf, Hxf, yo, Sf, HSf, R, want_amplitudes=want_amplitudes)
         return xa, Sa, ampl
@@ -382,7 +394,7 @@ def analysis(xf, Hxf, yo, Sf, HSf, R, handle=None, device=0):
 
 
 def assim_ensemble(zoneSize, selectObservations, E, Hi, Hj, Hs, Hshift, yo, R, anamtype=1, inflation=1.0,
-                   maxCorrection=None, handle=None, device=0, anamtable=None):
+                   maxCorrection=None, handle=None, device=0, anamtable=None, anamvars=None):
     """Ensemble in, analysed ensemble out (assimilation.F90:3106-3134,:3235-3236,:3301-3357,:3558-3562).
     zoneSize = None selects the global scheme (schemetype = 0: `analysis` instead of `locanalysis`)."""
     own = handle is None
@@ -393,6 +405,9 @@ def assim_ensemble(zoneSize, selectObservations, E, Hi, Hj, Hs, Hshift, yo, R, a
         else:
             h.set_option("scheme", 1)
             h.configure(zoneSize, selectObservations)
+        if anamvars is not None:      # per-variable transforms: (rowvar 1-based, [(type, table or None), ...])
+            h.set_anamorphosis_vars(*anamvars)
+            anamtype = 0
         Ea, xf, xa, _ = h.assim_ensemble(E, Hi, Hj, Hs, Hshift, yo, R, anamtype, inflation, maxCorrection,
                                          anamtable=anamtable)
         return Ea, xf, xa

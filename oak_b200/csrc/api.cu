@@ -110,12 +110,15 @@ struct oakb200_handle {
   int scheme = 1;             // ensemble entry points: 1 = local scheme (default), 0 = global scheme (schemetype, assimilation.F90:292)
   int tvec_split = 0;         // 1: tridiagonal route, k_tvec as two kernels (eigenvectors of T | back-transformation and the rest)
   int fuse_apply = 0;         // 1: tridiagonal route, k_tvec updates the zone rows from the factored transform (no T, no k_apply)
+  int localise_obs = 1;       // 0: locAnalysis(..., localise_obs=.false.) (rrsqrt.F90:374-385): all observations with their weights, amplitudes filled
   int tql_side = 1;           // 1 (default: 286.7 -> 280.9 ms per C3 step): k_tql on the slot's high-priority side stream
   int gram_kernel = 1;        // 1 (default since round 2: 8.6 -> 5.7 ms per 90 k zones) / 2: k_gram_mma (DMMA, 4 / 2 warps per zone; NP = 64); 3 / 4: same, 32-candidate chunks; 0: k_gram (DFMA register tiles)
   double tri_orthtol = 0.;  // tridiagonal route: accepted loss of orthogonality between neighbouring eigenvectors (0: default)
   int tri_maxgroup = -1;
   DevBuf d_anam;              // tabulated anamorphosis (K x 2), oakb200_set_anamorphosis_table
   int anam_K = 0, anam_monotone = 0;
+  DevBuf d_rowvar, d_vdesc, d_vtab;   // per-variable transforms (oakb200_set_anamorphosis_vars)
+  int anam_nvar = 0; int64_t anam_rows = 0;
   PeerOut peers{};            // fused all-gather destinations (oakb200_set_peer_outputs); n = 0: none
   cudaStream_t pstream[OAKB200_MAX_PEERS] = {};  // one copy stream per destination (created on first use)
   cudaEvent_t pev[OAKB200_MAX_PEERS] = {};
@@ -165,6 +168,7 @@ struct oakb200_handle {
     z.corrLen = d_corr.as<double>(); z.maxLen = d_maxl.as<double>();
     z.zstart = d_zstart.as<int64_t>();
     z.loctype = loctype; z.metrictype = metrictype; z.weightfun = weightfun;
+    z.noloc = localise_obs ? 0 : 1;
     return z;
   }
 };
@@ -226,12 +230,19 @@ int pack_obs(oakb200_handle *h, cudaStream_t st, int N, int NP, const double *HS
                              h->d_delta.as<double>(), h->d_scoef.as<double>());
 }
 
+// amplitudes(:, zone) of the zones of a batch (localise_obs = .false.; zero for the zones that were skipped)
+__global__ void k_copy_ampl(int N, int NP, int nz, const int32_t *__restrict__ mloc, const double *__restrict__ ampl,
+                            double *__restrict__ out) {
+  const int z = blockIdx.x, j = threadIdx.x;
+  if (z < nz && j < N) out[(int64_t)z * N + j] = mloc[z] != 0 ? ampl[(int64_t)z * NP + j] : 0.;
+}
+
 struct ProfAcc { double gram = 0, eig = 0, apply = 0, tridiag = 0, tql = 0, tvec = 0; };
 
 // Runs zones [z0, z1) on slot s. The state buffers hold rows starting at global row `rowbase`.
 int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t rowbase, const double *xf,
               const double *Sf, int64_t ldS, double *xa, double *Sa, int64_t ldSa, int64_t *launches,
-              ProfAcc *prof, bool use_peers = false) {
+              ProfAcc *prof, bool use_peers = false, double *ampl_out = nullptr /* device, [N x nzones] */) {
   int zb = batch_size(h, NP, h->nzones);
   if (h->zones_per_batch <= 0 && z1 - z0 > zb) {
     // a chunk of the host path holds a little more than one batch: split it evenly instead of one full batch
@@ -277,6 +288,11 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
     } else if ((rc = oak_launch_eig(s.st, h->eig_kernel == 4 ? 0 : h->eig_kernel, N, NP, b0, nz, mloc,
                                     s.G.as<double>(), s.c.as<double>(), s.T.as<double>(), s.ampl.as<double>(),
                                     h->tol, h->max_sweeps, ctr))) return rc;
+    if (ampl_out && !h->localise_obs) {
+      k_copy_ampl<<<nz, NP, 0, s.st>>>(N, NP, nz, mloc + b0, s.ampl.as<double>(), ampl_out + (int64_t)b0 * N);
+      CUDA_TRY(cudaGetLastError());
+      *launches += 1;
+    }
     if (prof) CUDA_TRY(cudaEventRecord(s.ev[2], s.st));
     PeerOut none{};
     // fused all-gather, copy-engine flavour: as soon as (a piece of) the batch is applied its rows go to every
@@ -423,7 +439,7 @@ extern "C" OAKB200_API int oakb200_destroy(oakb200_handle *h) {
                     &h->d_key_in, &h->d_key_out, &h->d_val_in, &h->d_perm, &h->d_cell_start, &h->d_sx, &h->d_sy,
                     &h->d_tmp, &h->d_rows, &h->d_delta, &h->d_scoef, &h->d_HSf, &h->d_yo, &h->d_Hxf, &h->d_R,
                     &h->d_d01, &h->d_ampzero, &h->d_HE, &h->d_Hi, &h->d_Hj, &h->d_Hs, &h->d_Hshift, &h->d_order,
-                    &h->d_rowstart, &h->d_xf, &h->d_xa, &h->d_maxc, &h->d_E, &h->d_ctr, &h->d_anam, &h->d_gws, &h->d_gzstart};
+                    &h->d_rowstart, &h->d_xf, &h->d_xa, &h->d_maxc, &h->d_E, &h->d_ctr, &h->d_anam, &h->d_gws, &h->d_gzstart, &h->d_rowvar, &h->d_vdesc, &h->d_vtab};
   for (DevBuf *b : bufs) b->release();
   for (int d = 0; d < OAKB200_MAX_PEERS; d++) {
     if (h->pstream[d]) cudaStreamDestroy(h->pstream[d]);
@@ -461,6 +477,44 @@ extern "C" OAKB200_API int oakb200_set_anamorphosis_table(oakb200_handle *h, int
   CUDA_TRY(cudaMemcpy(h->d_anam.p, table, sizeof(double) * 2 * (size_t)K, cudaMemcpyHostToDevice));
   h->anam_K = K;
   h->anam_monotone = mono;
+  return 0;
+}
+
+extern "C" OAKB200_API int oakb200_set_anamorphosis_vars(oakb200_handle *h, int32_t nvar, const int32_t *vtype,
+                                                         const int32_t *vK, const double *tables, int64_t n,
+                                                         const int32_t *rowvar) {
+  if (!h) { oak_set_error("null handle"); return OAK_ERR_ARG; }
+  if (nvar == 0) { h->anam_nvar = 0; h->anam_rows = 0; return 0; }
+  if (nvar < 0 || !vtype || !vK || n < 0 || (n > 0 && !rowvar)) { oak_set_error("set_anamorphosis_vars: invalid argument"); return OAK_ERR_ARG; }
+  std::vector<int32_t> desc(4 * (size_t)nvar);
+  int64_t off = 0;
+  for (int v = 0; v < nvar; v++) {
+    if (vtype[v] < 1 || vtype[v] > 3) { oak_set_error("set_anamorphosis_vars: variable %d has unknown type %d", v + 1, vtype[v]); return OAK_ERR_ARG; }
+    const int K = vtype[v] == 3 ? vK[v] : 0;
+    if (vtype[v] == 3 && (K < 2 || !tables)) { oak_set_error("set_anamorphosis_vars: variable %d is tabulated but has no table", v + 1); return OAK_ERR_ARG; }
+    int mono = 1;
+    for (int c = 0; c < 2 && K > 0; c++)
+      for (int i = 0; i + 1 < K; i++) {
+        const double a = tables[off + (int64_t)c * K + i], b = tables[off + (int64_t)c * K + i + 1];
+        if (!(a == a) || !(b == b)) { oak_set_error("set_anamorphosis_vars: NaN in the table of variable %d", v + 1); return OAK_ERR_ARG; }
+        if (!(a < b)) mono = 0;
+      }
+    desc[4 * v] = vtype[v]; desc[4 * v + 1] = K; desc[4 * v + 2] = (int32_t)off; desc[4 * v + 3] = mono;
+    off += 2 * (int64_t)K;
+  }
+  std::vector<int32_t> rv((size_t)n);
+  for (int64_t i = 0; i < n; i++) {   // 1-based variable numbers, as ind2submv returns them (assimilation.F90:1822-1858)
+    if (rowvar[i] < 1 || rowvar[i] > nvar) { oak_set_error("set_anamorphosis_vars: row %lld has variable %d (1..%d)", (long long)i + 1, rowvar[i], nvar); return OAK_ERR_ARG; }
+    rv[(size_t)i] = rowvar[i] - 1;
+  }
+  DeviceGuard guard(h->device);
+  int rc;
+  if ((rc = h->d_vdesc.ensure(sizeof(int32_t) * desc.size())) || (rc = h->d_vtab.ensure(sizeof(double) * (size_t)std::max<int64_t>(off, 1))) ||
+      (rc = h->d_rowvar.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(n, 1)))) return rc;
+  CUDA_TRY(cudaMemcpy(h->d_vdesc.p, desc.data(), sizeof(int32_t) * desc.size(), cudaMemcpyHostToDevice));
+  if (off > 0) CUDA_TRY(cudaMemcpy(h->d_vtab.p, tables, sizeof(double) * (size_t)off, cudaMemcpyHostToDevice));
+  if (n > 0) CUDA_TRY(cudaMemcpy(h->d_rowvar.p, rv.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice));
+  h->anam_nvar = nvar; h->anam_rows = n;
   return 0;
 }
 
@@ -539,6 +593,7 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   else if (k == "fuse_apply") h->fuse_apply = value != 0.;
   else if (k == "tvec_split") h->tvec_split = value != 0.;
   else if (k == "tql_side") h->tql_side = value != 0.;
+  else if (k == "localise_obs") h->localise_obs = value != 0.;
   else if (k == "apply_kernel") {
     if (value != 0. && value != 1.) { oak_set_error("apply_kernel = %g (0 register tiles, 1 tensor-core tiles)", value); return OAK_ERR_ARG; }
     h->apply_kernel = (int)value;
@@ -795,7 +850,7 @@ extern "C" OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t
     Slot &s = h->slot[h->profile ? 0 : bi % NSLOT];
     const int z1 = std::min(h->nzones, z0 + zb);
     if ((rc = run_zones(h, s, N, NP, z0, z1, 0, xf, Sf, ldSf, xa, Sa, ldSa, &launches, h->profile ? &prof : nullptr,
-                        h->peers.n > 0))) return rc;
+                        h->peers.n > 0, amplitudes))) return rc;
   }
   for (int i = 1; i < NSLOT; i++) {
     CUDA_TRY(cudaEventRecord(h->slot[i].ev[5], h->slot[i].st));
@@ -874,6 +929,11 @@ extern "C" OAKB200_API int oakb200_local_analysis(oakb200_handle *h, int64_t n, 
   CUDA_TRY(cudaEventRecord(h->slot[0].ev[4], s0));
   for (int i = 1; i < NSLOT; i++) CUDA_TRY(cudaStreamWaitEvent(h->slot[i].st, h->slot[0].ev[4], 0));
   if (amplitudes) memset(amplitudes, 0, sizeof(double) * (size_t)N * h->nzones);  // rrsqrt.F90:324
+  double *d_ampl_out = nullptr;
+  if (amplitudes && !h->localise_obs) {
+    if ((rc = h->d_ampzero.ensure(sizeof(double) * (size_t)N * std::max(h->nzones, 1)))) return rc;
+    d_ampl_out = h->d_ampzero.as<double>();
+  }
   // chunks of whole zones
   const int64_t rows_target = std::max<int64_t>(1, (int64_t)(h->chunk_mb * 1024. * 1024. / (8. * N)));
   int64_t launches = 1;
@@ -892,7 +952,7 @@ extern "C" OAKB200_API int oakb200_local_analysis(oakb200_handle *h, int64_t n, 
       h2d += 8ll * rows * (N + 1);
     }
     if ((rc = run_zones(h, s, N, NP, z0, z1, r0, s.xf.as<double>(), s.S.as<double>(), rows, s.xa.as<double>(),
-                        s.S.as<double>(), rows, &launches, h->profile ? &prof : nullptr)))
+                        s.S.as<double>(), rows, &launches, h->profile ? &prof : nullptr, false, d_ampl_out)))
       return rc;
     if (rows > 0) {
       CUDA_TRY(cudaMemcpy2DAsync(Sa + r0, 8 * (size_t)ldSa, s.S.p, 8 * (size_t)rows, 8 * (size_t)rows, N, cudaMemcpyDeviceToHost, s.st));
@@ -905,6 +965,7 @@ extern "C" OAKB200_API int oakb200_local_analysis(oakb200_handle *h, int64_t n, 
     CUDA_TRY(cudaEventRecord(h->slot[i].ev[5], h->slot[i].st));
     CUDA_TRY(cudaStreamWaitEvent(s0, h->slot[i].ev[5], 0));
   }
+  if (d_ampl_out) CUDA_TRY(cudaMemcpyAsync(amplitudes, d_ampl_out, sizeof(double) * (size_t)N * h->nzones, cudaMemcpyDeviceToHost, s0));
   CUDA_TRY(cudaEventRecord(h->ev_b, s0));
   CUDA_TRY(cudaEventSynchronize(h->ev_b));
   float ms = 0.f, msp = 0.f;
@@ -1115,9 +1176,10 @@ extern "C" OAKB200_API int oakb200_assim_ensemble_dev(oakb200_handle *h, int64_t
                                           double *xa_out, void *stream, oakb200_stats *stats) {
   int rc = (h && h->scheme == 0) ? global_check(h, n, N, m) : check_ready(h, n, N, m);
   if (rc) return rc;
-  if (anamtype < 1 || anamtype > 3) { oak_set_error("assim_ensemble: anamorphosis type %d unknown (1 identity, 2 log, 3 tabulated)", anamtype); return OAK_ERR_ARG; }
+  if (anamtype < 0 || anamtype > 3) { oak_set_error("assim_ensemble: anamorphosis type %d unknown (0 per variable, 1 identity, 2 log, 3 tabulated)", anamtype); return OAK_ERR_ARG; }
   if (anamtype == 3 && h->anam_K < 2) { oak_set_error("assim_ensemble: tabulated anamorphosis without a table (oakb200_set_anamorphosis_table)"); return OAK_ERR_STATE; }
-  const AnamTab at{h->d_anam.as<double>(), h->anam_K, h->anam_monotone};
+  if (anamtype == 0 && (h->anam_nvar < 1 || h->anam_rows != n)) { oak_set_error("assim_ensemble: per-variable anamorphosis needs oakb200_set_anamorphosis_vars for the %lld rows of this state", (long long)n); return OAK_ERR_STATE; }
+  const AnamTab at{h->d_anam.as<double>(), h->anam_K, h->anam_monotone, h->d_rowvar.as<int32_t>(), h->d_vdesc.as<int32_t>(), h->d_vtab.as<double>()};
   if ((n > 0 && (!E || !Ea)) || (nnz > 0 && (!Hi || !Hj || !Hs)) || (m > 0 && (!yo || !Rdiag))) { oak_set_error("assim_ensemble: null array"); return OAK_ERR_ARG; }
   DeviceGuard guard(h->device);
   cudaStream_t s0 = h->slot[0].st;
@@ -1138,7 +1200,7 @@ extern "C" OAKB200_API int oakb200_assim_ensemble_dev(oakb200_handle *h, int64_t
   // HE = H E + Hshift on the untransformed state (assimilation.F90:3112-3114)
   if ((rc = oak_launch_obsoper_rows(s0, m, N, h->d_rowstart.as<int32_t>(), h->d_order.as<int32_t>(), Hj, Hs, Hshift, E, ldE, h->d_HE.as<double>()))) return rc;
   // Hxf, HSf (in place in HE) ; xf, Sf (into Ea)
-  if ((rc = oak_launch_mean_anom(s0, m, N, 1, AnamTab{nullptr, 0, 0}, h->d_HE.as<double>(), m, h->d_Hxf.as<double>(), h->d_HE.as<double>(), m))) return rc;
+  if ((rc = oak_launch_mean_anom(s0, m, N, 1, AnamTab{nullptr, 0, 0, nullptr, nullptr, nullptr}, h->d_HE.as<double>(), m, h->d_Hxf.as<double>(), h->d_HE.as<double>(), m))) return rc;
   if ((rc = oak_launch_mean_anom(s0, n, N, anamtype, at, E, ldE, h->d_xf.as<double>(), Ea, ldEa))) return rc;
   CUDA_TRY(cudaStreamSynchronize(s0));
   if (h->scheme == 0)   // Assim's global branch: call analysis(xf,Hxf,yo,Sf,HSf,R,xa,Sa,amplitudes)

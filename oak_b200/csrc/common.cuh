@@ -82,6 +82,8 @@ struct ZoneGeom {
   const double *corrLen, *maxLen;
   const int64_t *zstart;      // [nzones+1] prefix sums of zoneSize
   int32_t loctype, metrictype, weightfun;
+  int32_t noloc;              // 1: localise_obs = .false. (rrsqrt.F90:374-385): every observation enters with its weight;
+                              //    the relevance predicate only decides whether the zone is analysed at all
 };
 
 struct ObsGrid {
@@ -150,7 +152,7 @@ __device__ __forceinline__ double oak_locfun(double r) {
 
 struct ZoneQuery {
   double x, y, corr, maxl;
-  int32_t loctype, metrictype, weightfun;
+  int32_t loctype, metrictype, weightfun, noloc;
 };
 
 // the callback body for one (zone, observation) pair: relevance flag + weight
@@ -201,7 +203,7 @@ __device__ __forceinline__ CellBox oak_zone_box(const ObsGrid &g, const ZoneQuer
   b.xb0 = 1; b.xb1 = 0;
   double R = (q.weightfun == OAKB200_WEIGHT_GAUSSIAN) ? q.maxl
              : (q.weightfun == OAKB200_WEIGHT_GASPARI_COHN ? 2. * q.corr : INFINITY);
-  const bool all = !(R < 1e300) || !(R == R);
+  const bool all = !(R < 1e300) || !(R == R) || q.noloc;
   if (all || (g.ncx == 1 && g.ncy == 1)) {
     b.cy0 = 0; b.cy1 = g.ncy - 1; b.xa0 = 0; b.xa1 = g.ncx - 1;
     return b;
@@ -269,7 +271,7 @@ __device__ __forceinline__ ZoneQuery oak_zone_query(const ZoneGeom &zg, int32_t 
   q.y = zg.zy ? zg.zy[zone] : 0.;
   q.corr = zg.corrLen[zone];
   q.maxl = zg.maxLen[zone];
-  q.loctype = zg.loctype; q.metrictype = zg.metrictype; q.weightfun = zg.weightfun;
+  q.loctype = zg.loctype; q.metrictype = zg.metrictype; q.weightfun = zg.weightfun; q.noloc = zg.noloc;
   return q;
 }
 
@@ -288,6 +290,10 @@ struct AnamTab {
   const double *tab;   // [0..K) physical values, [K..2K) transformed values
   int32_t K;
   int32_t monotone;    // both columns strictly increasing: the bracket search may bisect
+  // per-variable transforms (anamtype 0; assimilation.F90:4531-4535 looks AnamTrans%anam(v) up for every element):
+  const int32_t *rowvar;   // [n] 0-based variable of each (zone-permuted) row
+  const int32_t *vdesc;    // [nvar][4] : type, K, offset of the K x 2 table in vtab (doubles), monotone
+  const double *vtab;
 };
 
 // destinations of the fused all-gather (oakb200_set_peer_outputs), passed by value to k_apply

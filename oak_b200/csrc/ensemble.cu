@@ -53,6 +53,15 @@ __device__ __forceinline__ double oak_anam(int type, bool forward, const AnamTab
   return x;
 }
 
+// anamtype 0: the transform of the row's own variable
+__device__ __forceinline__ double oak_anam_row(int type, bool forward, const AnamTab &at, int64_t row, double x) {
+  if (type != 0) return oak_anam(type, forward, at, x);
+  const int32_t *d = at.vdesc + 4 * at.rowvar[row];
+  AnamTab sub = at;
+  sub.tab = at.vtab + d[2]; sub.K = d[1]; sub.monotone = d[3];
+  return oak_anam(d[0], forward, sub, x);
+}
+
 // ---- COO -> row-sorted (stable: the entries of a row keep the caller's order, so the sum is
 // accumulated in the same order as the sequential loop of matoper_inc.F90:238-240) ----
 __global__ void k_coo_keys(int64_t nnz, int m, const int32_t *Hi, const int32_t *Hj, uint32_t *key,
@@ -91,7 +100,7 @@ __global__ void __launch_bounds__(256) k_mean_anom(int64_t rows, int N, int anam
   const int64_t r0 = (int64_t)blockIdx.x * 64;
   const int tid = threadIdx.x, lr = tid & 63, kq = tid >> 6;  // 4 members in flight
   const int64_t row = r0 + lr;
-  for (int k = kq; k < N; k += 4) tile[k * 64 + lr] = row < rows ? oak_anam(anamtype, true, at, E[row + ldE * k]) : 0.;
+  for (int k = kq; k < N; k += 4) tile[k * 64 + lr] = row < rows ? oak_anam_row(anamtype, true, at, row, E[row + ldE * k]) : 0.;
   __syncthreads();
   if (tid < 64) {
     double s = 0.;
@@ -113,19 +122,20 @@ __global__ void k_epilogue(int64_t rows, int N, int anamtype, AnamTab at, double
   const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (row >= rows) return;
   double x = xa[row];
-  if (maxCorr) {  // assimilation.F90:3308-3312
-    double d = x - xf[row];
-    const double mc = maxCorr[row];
-    if (d > mc) d = mc;
-    if (d < -mc) d = -mc;
-    x = xf[row] + d;
+  if (maxCorr) {  // the two `where` statements of assimilation.F90:3311-3312, in their order, xa untouched otherwise
+    const double mc = maxCorr[row], f = xf[row];
+    if (__dsub_rn(x, mc) > f) x = __dadd_rn(f, mc);
+    if (x < __dsub_rn(f, mc)) x = __dsub_rn(f, mc);
   }
-  for (int k = blockIdx.y; k < N; k += gridDim.y) {
+  double sum = 0.;
+  for (int k = 0; k < N; k++) {
     double s = Sa[row + ldSa * k];
     if (inflation != 1.) s = __dmul_rn(s, inflation);               // :3301-3304
-    Ea[row + ldEa * k] = oak_anam(anamtype, false, at, __dadd_rn(x, __dmul_rn(s, scaling)));  // :3318-3326
+    const double ea = oak_anam_row(anamtype, false, at, row, __dadd_rn(x, __dmul_rn(s, scaling)));  // :3318-3326
+    Ea[row + ldEa * k] = ea;
+    sum = __dadd_rn(sum, ea);
   }
-  if (blockIdx.y == 0) xa[row] = x;
+  xa[row] = sum / (double)N;   // xa = sum(Sa,2)/size(Sa,2) of the back-transformed ensemble (:3343-3349)
 }
 
 }  // namespace

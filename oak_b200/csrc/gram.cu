@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(NT) k_gram(ZoneGeom zg, ObsGrid og, ObsRows or
   __shared__ int s_cnt[3][2];
   __shared__ int s_rstart[GRAM_MAXR], s_rlen[GRAM_MAXR];
   __shared__ int s_total;
+  __shared__ int s_true;   // localise_obs = .false.: observations that pass the relevance predicate
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int zl = blockIdx.x;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(NT) k_gram(ZoneGeom zg, ObsGrid og, ObsRows or
   double cacc = 0.;
   int nrel_total = 0;
   long long ncand_total = 0;
+  if (threadIdx.x == 0) s_true = 0;   // ordered before its first use by the barrier at the head of the cell loop
 
   // E(c): warps 0 and 1, 32 candidates each, into list buffer lb
   auto eval = [&](int c, int lb, int total) {
@@ -96,6 +98,10 @@ __global__ void __launch_bounds__(NT) k_gram(ZoneGeom zg, ObsGrid og, ObsRows or
         while (qq >= s_rlen[r]) { qq -= s_rlen[r]; r++; }
         p = s_rstart[r] + qq;
         rel = oak_obs_relevant(q, og.sx[p], og.sy[p], w);
+        if (q.noloc) {   // localise_obs = .false.: count the relevant ones, take them all
+          if (rel) atomicAdd(&s_true, 1);
+          rel = true;
+        }
       }
       const unsigned bal = __ballot_sync(0xffffffffu, rel);
       if (rel) {
@@ -213,10 +219,12 @@ __global__ void __launch_bounds__(NT) k_gram(ZoneGeom zg, ObsGrid og, ObsRows or
     }
   if (tid < NP) cvec[(int64_t)zl * NP + tid] = cacc;
   if (tid == 0) {
-    mloc[zone] = nrel_total;
-    atomicAdd(&ctr->relevant, (unsigned long long)nrel_total);
+    // localise_obs = .false.: a zone without any relevant observation is still skipped (rrsqrt.F90:371-372)
+    const int used = (q.noloc && s_true == 0) ? 0 : nrel_total;
+    mloc[zone] = used;
+    atomicAdd(&ctr->relevant, (unsigned long long)used);
     atomicAdd(&ctr->candidates, (unsigned long long)ncand_total);
-    if (nrel_total == 0) atomicAdd(&ctr->skipped, 1ull);
+    if (used == 0) atomicAdd(&ctr->skipped, 1ull);
   }
 }
 

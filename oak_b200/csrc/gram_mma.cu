@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
   __shared__ int s_cnt[3][2];
   __shared__ int s_rstart[GRAM_MAXR], s_rlen[GRAM_MAXR];
   __shared__ int s_total;
+  __shared__ int s_true;   // localise_obs = .false.: observations that pass the relevance predicate
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
   double cacc = 0.;
   int nrel_total = 0;
   long long ncand_total = 0;
+  if (threadIdx.x == 0) s_true = 0;   // ordered before its first use by the barrier at the head of the cell loop
   for (int i = tid; i < 2 * GRAM_CH * LDR; i += NT) rowbuf[i] = 0.;  // 0 x (never written) must be 0, not NaN
 
   // E(c): warps 0 and 1, 32 candidates each, into list buffer lb (as k_gram)
@@ -149,6 +151,10 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
         while (qq >= s_rlen[r]) { qq -= s_rlen[r]; r++; }
         p = s_rstart[r] + qq;
         rel = oak_obs_relevant(q, og.sx[p], og.sy[p], w);
+        if (q.noloc) {   // localise_obs = .false.: count the relevant ones, take them all
+          if (rel) atomicAdd(&s_true, 1);
+          rel = true;
+        }
       }
       const unsigned bal = __ballot_sync(0xffffffffu, rel);
       const int cnt = __popc(bal);
@@ -267,10 +273,12 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
   }
   if (ci >= 0) cvec[(int64_t)zl * NP + ci] = cacc;
   if (tid == 0) {
-    mloc[zone] = nrel_total;
-    atomicAdd(&ctr->relevant, (unsigned long long)nrel_total);
+    // localise_obs = .false.: a zone without any relevant observation is still skipped (rrsqrt.F90:371-372)
+    const int used = (q.noloc && s_true == 0) ? 0 : nrel_total;
+    mloc[zone] = used;
+    atomicAdd(&ctr->relevant, (unsigned long long)used);
     atomicAdd(&ctr->candidates, (unsigned long long)ncand_total);
-    if (nrel_total == 0) atomicAdd(&ctr->skipped, 1ull);
+    if (used == 0) atomicAdd(&ctr->skipped, 1ull);
   }
 }
 

@@ -204,10 +204,21 @@ def anamtransform(forward, anamtype, x, table=None):
 
 
 def assim_ensemble(zoneSize, zone_pos, corrLen, maxLen, obs, E, Hi, Hj, Hs, Hshift, yo, var,
-                   e01=None, anamtype=1, inflation=1.0, maxCorrection=None, anamtable=None):
+                   e01=None, anamtype=1, inflation=1.0, maxCorrection=None, anamtable=None, anamvars=None):
     """ensemble branch of Assim with the local scheme — assimilation.F90:3106-3134, :3235, :3301-3357"""
     tab = _f(np.asfortranarray(anamtable)) if anamtable is not None else None
     lib().oracle_set_anam_table(C.c_int(0 if tab is None else tab.shape[0]), _dp(tab))
+    if anamvars is not None:   # per-variable transforms: (rowvar 0-based per row, [(type, table or None), ...]); anamtype 0
+        rowvar, specs = anamvars
+        rv = np.ascontiguousarray(rowvar, dtype=np.int32)
+        vt = np.array([t for t, _ in specs], dtype=np.int32)
+        tabs = [np.asfortranarray(tb, dtype=np.float64) if tb is not None else np.zeros((0, 2), order="F") for _, tb in specs]
+        vK = np.array([tb.shape[0] for tb in tabs], dtype=np.int32)
+        voff = np.concatenate([[0], np.cumsum(2 * vK)[:-1]]).astype(np.int32)
+        flat = np.concatenate([tb.ravel(order="F") for tb in tabs] + [np.zeros(1)])
+        _keep = (rv, vt, voff, vK, flat)
+        lib().oracle_set_anam_vars(_ip(rv), _ip(vt), _ip(voff), _ip(vK), _dp(flat))
+        anamtype = 0
     E = _f(E)
     n, N = E.shape
     zs = np.ascontiguousarray(zoneSize, dtype=np.int32)

@@ -607,8 +607,24 @@ double oracle_anam(int type, int forward, int K, const double *tab, double x) {
 static const double *g_anamtab = 0;  /* table of the tabulated anamorphosis (set by oracle_set_anam_table) */
 static int g_anamK = 0;
 void oracle_set_anam_table(int K, const double *tab) { g_anamtab = tab; g_anamK = K; }
-static inline double anam_fwd(int type, double x) { return oracle_anam(type, 1, g_anamK, g_anamtab, x); }
-static inline double anam_inv(int type, double x) { return oracle_anam(type, 0, g_anamK, g_anamtab, x); }
+/* per-variable transforms (anamtype 0): AnamTrans%anam(v) looked up for every element through ind2submv
+ * (assimilation.F90:4531-4535): rowvar[i] = 0-based variable of (permuted) row i, vtype[v] its type, the K_v x 2
+ * table of a tabulated one at vtab + voff[v] */
+static const int32_t *g_rowvar = 0, *g_vtype = 0, *g_voff = 0, *g_vK = 0;
+static const double *g_vtab = 0;
+void oracle_set_anam_vars(const int32_t *rowvar, const int32_t *vtype, const int32_t *voff, const int32_t *vK,
+                          const double *vtab) {
+  g_rowvar = rowvar; g_vtype = vtype; g_voff = voff; g_vK = vK; g_vtab = vtab;
+}
+static inline double anam_el(int type, int forward, int row, double x) {
+  if (type == 0) {
+    const int v = g_rowvar[row];
+    return oracle_anam(g_vtype[v], forward, g_vK[v], g_vtab + g_voff[v], x);
+  }
+  return oracle_anam(type, forward, g_anamK, g_anamtab, x);
+}
+#define anam_fwd(type, x) anam_el(type, 1, i, x)
+#define anam_inv(type, x) anam_el(type, 0, i, x)
 
 /* ---------------------------------------------------------------------------
  * Ensemble branch of Assim with the local scheme:
@@ -658,17 +674,21 @@ int oracle_assim_ensemble(int nzones, const int32_t *zoneSize, const double *zx,
   /* saturate correction :3308-3312 */
   if (maxCorrection)
     for (int i = 0; i < n; i++) {
-      double d = xa[i] - xf[i];
-      if (d > maxCorrection[i]) d = maxCorrection[i];
-      if (d < -maxCorrection[i]) d = -maxCorrection[i];
-      xa[i] = xf[i] + d;
+      /* where (xa-maxCorrection.gt.xf) xa=xf+maxCorrection ; where (xa.lt.xf-maxCorrection) xa=xf-maxCorrection */
+      if (xa[i] - maxCorrection[i] > xf[i]) xa[i] = xf[i] + maxCorrection[i];
+      if (xa[i] < xf[i] - maxCorrection[i]) xa[i] = xf[i] - maxCorrection[i];
     }
   /* Ea(:,k) = xa + scaling*Sa(:,k) ; inverse anamorphosis  :3318-3326, :3558-3562 */
   for (int k = 0; k < N; k++)
     for (int i = 0; i < n; i++)
       Ea[i + (size_t)ldEa * k] = anam_inv(anamtype, xa[i] + Sa[i + (size_t)n * k] * scaling);
   if (xf_out) memcpy(xf_out, xf, sizeof(double) * n);
-  if (xa_out) memcpy(xa_out, xa, sizeof(double) * n);
+  if (xa_out) {   /* xa = sum(Sa,2)/size(Sa,2) of the back-transformed ensemble :3343-3349 */
+    for (int i = 0; i < n; i++) xa_out[i] = 0.;
+    for (int k = 0; k < N; k++)
+      for (int i = 0; i < n; i++) xa_out[i] += Ea[i + (size_t)ldEa * k];
+    for (int i = 0; i < n; i++) xa_out[i] /= N;
+  }
   free(Sf); free(Sa); free(HSf); free(xf); free(xa); free(Hxf);
   return info;
 }

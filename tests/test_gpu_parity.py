@@ -209,6 +209,34 @@ def test_local_analysis_matches_oracle(ob, handle, N, m, nx, ny, nz):
     assert np.abs(Sa.sum(axis=1)).max() < 1e-12 * max(1.0, np.abs(Sa).max()) * N
 
 
+@pytest.mark.parametrize("N,m", [(24, 60), (64, 150)])
+def test_localise_obs_false_all_observations_and_amplitudes(ob, N, m):
+    """locAnalysis(..., localise_obs=.false.) (rrsqrt.F90:374-385, exercised by test/test_rrsqrt.F90:162-183): a zone
+    with at least one relevant observation is analysed with ALL observations (Gaussian weights, no cut-off) and its
+    amplitudes are returned; zones without a relevant observation are skipped."""
+    from oak_b200 import synthetic
+    c = synthetic.small_case(nx=12, ny=10, nz=3, N=N, m=m, corr=3000.0, maxlen=4000.0, seed=N + m)
+    keep = c["obs"]["ox"] < 6000.0     # zones on the right have no relevant observation
+    for k in ("Hxf", "yo", "var"):
+        c[k] = c[k][keep]
+    c["HSf"] = np.asfortranarray(c["HSf"][keep])
+    c["obs"] = {k: (v[..., keep] if v.ndim > 1 else v[keep]) for k, v in c["obs"].items()}
+    c["m"] = int(keep.sum())
+    obs = oracle.make_obs(c["m"], obsx=c["obs"]["ox"], obsy=c["obs"]["oy"])
+    xo, So, ao, mloc = oracle.loc_analysis(c["zoneSize"], dict(x=c["zx"], y=c["zy"]), c["corr"], c["maxlen"], obs,
+                                           c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], c["var"], local_obs=False,
+                                           want_ampl=True)
+    for gram_kernel in (1, 0):
+        with ob.Handle(0, localise_obs=0, gram_kernel=gram_kernel) as h:
+            _configure(ob, h, c)
+            xa, Sa, ampl, st = h.local_analysis(c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], ob.DiagCovar(c["var"]),
+                                                want_amplitudes=True)
+        assert 0 < st["zones_skipped"] < c["grid"].nzones
+        assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL, (rel(xa, xo), rel(Sa, So))
+        assert rel(ampl, ao) < RTOL, rel(ampl, ao)
+        assert (ampl[:, np.abs(ao).sum(axis=0) == 0] == 0).all()
+
+
 def test_edge_cases_empty_zones_all_relevant_excluded_obs_ragged_zones(ob, handle):
     from oak_b200 import synthetic
     c = synthetic.small_case(nx=30, ny=10, nz=4, N=24, m=200, corr=2500.0, maxlen=5000.0, seed=3)
@@ -301,7 +329,10 @@ def test_assim_ensemble_with_inflation_anamorphosis_and_saturation(ob, handle):
     Eo, xfo, xao = oracle.assim_ensemble(zs, dict(x=zx, y=zy), 3000.0, 6000.0, oo, E, Hi, Hj, Hs, Hshift, yo,
                                          obs["var"], anamtype=2, inflation=1.05, maxCorrection=maxc)
     assert rel(xf, xfo) < 1e-14 and rel(xa, xao) < RTOL and rel(Ea, Eo) < RTOL
-    assert (np.abs(xa - xf) <= 0.05 * (1 + 1e-12)).all() and (np.abs(xao - xfo) > 0.049).any()
+    # xa is the mean of the back-transformed analysis ensemble (assimilation.F90:3343-3349); the saturation of the
+    # correction (the two `where` statements of :3311-3312) was active
+    assert rel(xa, Ea.mean(axis=1)) < 1e-14
+    assert (np.abs(np.log(Ea).mean(axis=1) - xf) > 0.0499).any()
 
 
 def test_error_behaviour(ob):
@@ -548,6 +579,40 @@ def test_assim_ensemble_tabulated_anamorphosis(ob, monotone):
                                          obs["var"], anamtype=3, inflation=1.02, anamtable=tab)
     assert ((E < xs[0]).any() and (E > xs[-1]).any())      # the clamping rule is exercised
     assert rel(xf, xfo) < 1e-14 and rel(xa, xao) < RTOL and rel(Ea, Eo) < RTOL
+
+
+def test_assim_ensemble_per_variable_anamorphosis(ob):
+    """anamtransform looks the transform up per element through the element's variable (assimilation.F90:4531-4567):
+    zones holding three variables with different transforms (identity, log, tabulated), maxCorrection active."""
+    from oak_b200 import synthetic
+    g = synthetic.Grid(14, 10, 3)
+    N, m = 20, 100
+    rows = np.arange(g.n, dtype=np.int64)
+    E = np.exp(0.4 * synthetic.ensemble_rows(np, g, rows, N, 11)).T.copy(order="F")
+    xs = np.array([0.4, 0.8, 1.0, 1.5, 2.5])
+    tab = np.column_stack([xs, np.sqrt(xs)])
+    rowvar = 1 + (np.arange(g.n) % 3)          # the three rows of a zone belong to variables 1, 2, 3
+    specs = [(1, None), (2, None), (3, tab)]
+    obs = synthetic.observations(np, g, m, 11)
+    Hi, Hj, Hs = synthetic.coo_operator(g, obs)
+    yo = 1.1 + 0.2 * synthetic.normal(np, np.arange(m, dtype=np.int64), 8, 11)
+    zx, zy = g.zone_xy(np, np.arange(g.nzones, dtype=np.int64))
+    zs = np.full(g.nzones, 3, np.int32)
+    sel = ob.Selector(zone_x=zx, zone_y=zy, corrLen=3000.0, maxLen=6000.0, obs_x=obs["ox"], obs_y=obs["oy"],
+                      metrictype=0)
+    maxc = np.full(g.n, 0.08)
+    with ob.Handle(0) as h:
+        with pytest.raises(ob.OakB200Error):       # anamtype 0 without the per-variable description
+            h.configure(zs, sel)
+            h.assim_ensemble(E, Hi, Hj, Hs, None, yo, ob.DiagCovar(obs["var"]), 0, 1.0, None)
+        Ea, xf, xa = ob.assim_ensemble(zs, sel, E, Hi, Hj, Hs, None, yo, ob.DiagCovar(obs["var"]), inflation=1.03,
+                                       maxCorrection=maxc, handle=h, anamvars=(rowvar, specs))
+    oo = oracle.make_obs(m, obsx=obs["ox"], obsy=obs["oy"])
+    Eo, xfo, xao = oracle.assim_ensemble(zs, dict(x=zx, y=zy), 3000.0, 6000.0, oo, E, Hi, Hj, Hs, np.zeros(m), yo,
+                                         obs["var"], inflation=1.03, maxCorrection=maxc, anamvars=(rowvar - 1, specs))
+    assert rel(xf, xfo) < 1e-14 and rel(xa, xao) < RTOL and rel(Ea, Eo) < RTOL
+    assert not np.allclose(xf[1::3], E[1::3].mean(axis=1))     # variable 2 was transformed ...
+    assert rel(xf[0::3], E[0::3].mean(axis=1)) < 1e-14          # ... variable 1 was not
 
 
 @pytest.mark.parametrize("N", [2, 3, 5, 9, 33, 63])
