@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--maxlen", type=float, default=8000.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the e2e legs on pageable host arrays")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--eig-kernel", type=int, default=4)
@@ -569,6 +570,24 @@ def main():
                    "d2h_bytes_per_step": ste["d2h_bytes"], "steps": a.e2e_steps,
                    "note": "oakb200_set_observations + oakb200_local_analysis on pinned host buffers; state streamed in zone chunks; "
                            "bytes are per rank; no all-gather of host buffers" + ("" if ok else "; MISMATCH vs resident run")}
+            # the same call on PAGEABLE host arrays (what a Fortran caller's allocatables are): once with the library
+            # page-locking them for the call (option host_register, the default) and once leaving them pageable
+            if world == 1 and not a.no_pageable:
+                pg = {}
+                q = hb[0]
+                pb = {k: torch.empty_like(v, pin_memory=False).copy_(v) for k, v in q.items()}
+                for mode in (1, 0):
+                    h.set_option("host_register", mode)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    h.set_observations(obs_x=phases[0]["ox"], obs_y=phases[0]["oy"])
+                    h.local_analysis_pinned(pb["xf"], pb["Hxf"], pb["yo"], pb["Sf"], pb["HSf"], pb["var"], pb["xa"], pb["Sa"])
+                    torch.cuda.synchronize()
+                    pg["host_register=%d" % mode] = nzones / (time.perf_counter() - t0)
+                h.set_option("host_register", 1)
+                pg["identical_to_pinned_run"] = bool(torch.equal(pb["Sa"], q["Sa"]))
+                e2e["pageable_columns_per_s"] = pg
+                del pb
             del hb
         except Exception as ex:  # e.g. not enough pinnable host memory
             e2e = {"value": None, "unit": "columns/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,

@@ -73,9 +73,10 @@ OAKB200_API int oakb200_destroy(oakb200_handle *h);
  *   "eig_kernel"      4 = Householder tridiagonalisation + QL + twisted factorisation (default for N <= 64;
  *                     flagged zones fall back to 0), 0 = register-resident block Jacobi (N > 64), 1 = simple
  *                     shared-memory Jacobi (cross-check), 2 / 3 = measured variants of 0
- *   "gram_kernel"     0 = DFMA register tiles (default), 1 / 2 = fp64 tensor-core tiles (mma.m8n8k4, 4 / 2 warps per
- *                     zone), 3 / 4 = the same with chunks of 32 instead of 64 candidates (half the shared memory);
- *                     padded ensemble size 64 only, other sizes keep 0
+ *   "gram_kernel"     1 = fp64 tensor-core tiles (mma.m8n8k4, 4 warps per zone; default since the round-2 timing:
+ *                     8.6 -> 5.7 ms per 90 k zones), 2 = 2 warps per zone, 3 / 4 = the same with chunks of 32 instead of
+ *                     64 candidates (half the shared memory), 0 = DFMA register tiles; padded ensemble size 64 only,
+ *                     other sizes use 0
  *   "apply_kernel"    0 = DFMA register tiles (default), 1 = fp64 tensor-core tiles (padded ensemble size 64 only;
  *                     zones the fused transform kernel leaves over, zones with many rows, the global scheme)
  *   "fuse_apply"      route 4: 1 = the transform kernel updates the zone rows itself from the factored transform
@@ -83,6 +84,12 @@ OAKB200_API int oakb200_destroy(oakb200_handle *h);
  *                     N (padded) rows, where the factored form is the cheaper one. Default 0
  *   "tvec_split"      route 4: 1 = the eigenvector kernel runs as two kernels (vectors of T with few registers and
  *                     high occupancy | back-transformation and the rest), 32 KB more workspace per zone. Default 0
+ *   "tql_side"        route 4: 1 (default) = the QL eigenvalue kernel runs on a high-priority side stream of its slot
+ *   "localise_obs"    1 (default) = locAnalysis' default branch; 0 = localise_obs=.false. (rrsqrt.F90:374-385): a zone with
+ *                     at least one relevant observation is analysed with ALL observations (their weights, no cut-off)
+ *                     and amplitudes(:,zone) is returned
+ *   "host_register"   host-buffer entry points: 1 (default) = pageable caller arrays are page-locked (cudaHostRegister)
+ *                     for the duration of the call so that the chunked copies are asynchronous; 0 = left as they are
  *   "tri_orthtol"     route 4: accepted loss of orthogonality between neighbouring eigenvectors (default 1e-11)
  *   "tri_maxgroup"    route 4: largest group of close eigenvalues orthogonalised in place (default 6; 0 sends
  *                     every zone with a close pair to the Jacobi kernel)

@@ -110,6 +110,7 @@ struct oakb200_handle {
   int scheme = 1;             // ensemble entry points: 1 = local scheme (default), 0 = global scheme (schemetype, assimilation.F90:292)
   int tvec_split = 0;         // 1: tridiagonal route, k_tvec as two kernels (eigenvectors of T | back-transformation and the rest)
   int fuse_apply = 0;         // 1: tridiagonal route, k_tvec updates the zone rows from the factored transform (no T, no k_apply)
+  int host_register = 1;      // host-buffer entry points: page-lock the caller's pageable arrays for the duration of the call
   int localise_obs = 1;       // 0: locAnalysis(..., localise_obs=.false.) (rrsqrt.F90:374-385): all observations with their weights, amplitudes filled
   int tql_side = 1;           // 1 (default: 286.7 -> 280.9 ms per C3 step): k_tql on the slot's high-priority side stream
   int gram_kernel = 1;        // 1 (default since round 2: 8.6 -> 5.7 ms per 90 k zones) / 2: k_gram_mma (DMMA, 4 / 2 warps per zone; NP = 64); 3 / 4: same, 32-candidate chunks; 0: k_gram (DFMA register tiles)
@@ -180,6 +181,23 @@ int padded(const oakb200_handle *h, int N) {
   const int np = padded(N);
   return (np > 0 && h->pad_to > np && h->pad_to <= 128) ? padded(h->pad_to) : np;
 }
+
+// Page-locks pageable caller arrays for the duration of a host-buffer call (a Fortran caller's Sf is ordinary
+// allocatable memory: asynchronous copies from it would be staged synchronously by the driver) and releases them when
+// the call returns, on every path.  Arrays that are already pinned or registered are left alone.
+struct HostPins {
+  std::vector<void *> regs;
+  void pin(const void *p, size_t bytes) {
+    if (!p || bytes < (1u << 20)) return;   // small arrays: not worth a system call
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return; }
+    if (a.type != cudaMemoryTypeUnregistered) return;
+    for (void *q : regs) if (q == p) return;
+    if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterPortable) == cudaSuccess) regs.push_back(const_cast<void *>(p));
+    else cudaGetLastError();                 // not fatal: the copies fall back to the driver's staging
+  }
+  ~HostPins() { for (void *q : regs) cudaHostUnregister(q); }
+};
 
 struct DeviceGuard {
   int prev = -1;
@@ -594,6 +612,7 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   else if (k == "tvec_split") h->tvec_split = value != 0.;
   else if (k == "tql_side") h->tql_side = value != 0.;
   else if (k == "localise_obs") h->localise_obs = value != 0.;
+  else if (k == "host_register") h->host_register = value != 0.;
   else if (k == "apply_kernel") {
     if (value != 0. && value != 1.) { oak_set_error("apply_kernel = %g (0 register tiles, 1 tensor-core tiles)", value); return OAK_ERR_ARG; }
     h->apply_kernel = (int)value;
@@ -907,6 +926,14 @@ extern "C" OAKB200_API int oakb200_local_analysis(oakb200_handle *h, int64_t n, 
   DeviceGuard guard(h->device);
   const int NP = padded(h, N);
   cudaStream_t s0 = h->slot[0].st;
+  HostPins pins;
+  if (h->host_register) {
+    pins.pin(Sf, sizeof(double) * ((size_t)ldSf * (N - 1) + (size_t)n));
+    if (Sa != Sf) pins.pin(Sa, sizeof(double) * ((size_t)ldSa * (N - 1) + (size_t)n));
+    pins.pin(HSf, sizeof(double) * ((size_t)ldHSf * (N - 1) + (size_t)m));
+    pins.pin(xf, sizeof(double) * (size_t)n);
+    pins.pin(xa, sizeof(double) * (size_t)n);
+  }
   if ((rc = begin_call(h, stats))) return rc;
   CUDA_TRY(cudaEventRecord(h->ev_a, s0));
   int64_t h2d = 0, d2h = 0;
