@@ -584,7 +584,7 @@ def main():
                     h.local_analysis_pinned(pb["xf"], pb["Hxf"], pb["yo"], pb["Sf"], pb["HSf"], pb["var"], pb["xa"], pb["Sa"])
                     torch.cuda.synchronize()
                     pg["host_register=%d" % mode] = nzones / (time.perf_counter() - t0)
-                h.set_option("host_register", 1)
+                h.set_option("host_register", 0)
                 pg["identical_to_pinned_run"] = bool(torch.equal(pb["Sa"], q["Sa"]))
                 e2e["pageable_columns_per_s"] = pg
                 del pb

@@ -47,6 +47,18 @@ module oak_b200_iface
      real(c_double), value :: val
      integer(c_int) :: rc
    end function
+   ! page-locked host memory for Sf / Sa / HSf: call c_f_pointer(ptr, Sf, [n, N]) on the result
+   function oakb200_host_alloc(bytes, ptr) bind(C, name='oakb200_host_alloc') result(rc)
+     import
+     integer(c_int64_t), value :: bytes
+     type(c_ptr) :: ptr
+     integer(c_int) :: rc
+   end function
+   function oakb200_host_free(ptr) bind(C, name='oakb200_host_free') result(rc)
+     import
+     type(c_ptr), value :: ptr
+     integer(c_int) :: rc
+   end function
    function oakb200_set_zones(h, nzones, zoneSize, zx, zy, zz, zt, corrLen, maxLen, loctype, metrictype, &
         weightfun) bind(C, name='oakb200_set_zones') result(rc)
      import

@@ -88,8 +88,9 @@ OAKB200_API int oakb200_destroy(oakb200_handle *h);
  *   "localise_obs"    1 (default) = locAnalysis' default branch; 0 = localise_obs=.false. (rrsqrt.F90:374-385): a zone with
  *                     at least one relevant observation is analysed with ALL observations (their weights, no cut-off)
  *                     and amplitudes(:,zone) is returned
- *   "host_register"   host-buffer entry points: 1 (default) = pageable caller arrays are page-locked (cudaHostRegister)
- *                     for the duration of the call so that the chunked copies are asynchronous; 0 = left as they are
+ *   "host_register"   host-buffer entry points: 1 = pageable caller arrays are page-locked (cudaHostRegister) for the
+ *                     duration of the call; 0 (default) = left as they are (the driver stages the copies).  Measured on
+ *                     C3: pinned arrays (oakb200_host_alloc) 2.68 M columns/s, pageable 0.40 M, registered per call 0.09 M
  *   "tri_orthtol"     route 4: accepted loss of orthogonality between neighbouring eigenvectors (default 1e-11)
  *   "tri_maxgroup"    route 4: largest group of close eigenvalues orthogonalised in place (default 6; 0 sends
  *                     every zone with a close pair to the Jacobi kernel)
@@ -102,6 +103,11 @@ OAKB200_API int oakb200_destroy(oakb200_handle *h);
  *   "push_pieces"     peer_mode 1: the apply of a batch runs in this many launches, each pushed to the peers as soon
  *                     as it is done (shorter exposed tail at the end of a call); default 1 */
 OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key, double value);
+
+/* Page-locked host memory for the caller's large arrays (Sf / Sa, HSf of assimilation.F90:2987-3000): with it the
+ * host-buffer entry points overlap the chunked copies with the kernels.  Fortran: c_f_pointer on the returned pointer. */
+OAKB200_API int oakb200_host_alloc(int64_t bytes, void **ptr);
+OAKB200_API int oakb200_host_free(void *ptr);
 
 /* Zones = the partition of the (zone-permuted) state vector (assimilation.F90:578-641).
  * zoneSize[nzones] as passed to locanalysis; zone z owns rows sum(zoneSize[0..z-1]) ... of the state.

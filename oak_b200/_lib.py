@@ -53,6 +53,8 @@ SIGNATURES = {
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                               C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
     "oakb200_set_anamorphosis_table": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "oakb200_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    "oakb200_host_free": (C.c_int, [C.c_void_p]),
     "oakb200_set_anamorphosis_vars": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                               C.c_void_p]),
     "oakb200_set_peer_outputs": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),

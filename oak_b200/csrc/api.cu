@@ -110,7 +110,9 @@ struct oakb200_handle {
   int scheme = 1;             // ensemble entry points: 1 = local scheme (default), 0 = global scheme (schemetype, assimilation.F90:292)
   int tvec_split = 0;         // 1: tridiagonal route, k_tvec as two kernels (eigenvectors of T | back-transformation and the rest)
   int fuse_apply = 0;         // 1: tridiagonal route, k_tvec updates the zone rows from the factored transform (no T, no k_apply)
-  int host_register = 1;      // host-buffer entry points: page-lock the caller's pageable arrays for the duration of the call
+  int host_register = 0;      // host-buffer entry points: 1 = page-lock the caller's pageable arrays for the duration of the call
+                              // (measured on C3: registering 31 GB per call costs more than the driver's staged copies:
+                              // 0.09 vs 0.40 M columns/s; pinned buffers from oakb200_host_alloc: 2.68 M)
   int localise_obs = 1;       // 0: locAnalysis(..., localise_obs=.false.) (rrsqrt.F90:374-385): all observations with their weights, amplitudes filled
   int tql_side = 1;           // 1 (default: 286.7 -> 280.9 ms per C3 step): k_tql on the slot's high-priority side stream
   int gram_kernel = 1;        // 1 (default since round 2: 8.6 -> 5.7 ms per 90 k zones) / 2: k_gram_mma (DMMA, 4 / 2 warps per zone; NP = 64); 3 / 4: same, 32-candidate chunks; 0: k_gram (DFMA register tiles)
@@ -601,6 +603,26 @@ extern "C" OAKB200_API int oakb200_ipc_free(oakb200_handle *h, void *ptr) {
   if (!h) return 0;
   DeviceGuard guard(h->device);
   if (ptr) CUDA_TRY(cudaFree(ptr));
+  return 0;
+}
+
+// Page-locked host memory for the caller's big arrays (Sf / Sa, HSf): the host-buffer entry points then overlap their
+// chunked copies with the kernels (2.68 M columns/s on C3 against 0.40 M from pageable memory).  A Fortran caller maps
+// the pointer with c_f_pointer.
+extern "C" OAKB200_API int oakb200_host_alloc(int64_t bytes, void **ptr) {
+  if (!ptr || bytes <= 0) { oak_set_error("host_alloc: bad arguments"); return OAK_ERR_ARG; }
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    oak_set_error("host_alloc: cudaHostAlloc of %lld bytes failed", (long long)bytes);
+    return OAK_ERR_NOMEM;
+  }
+  *ptr = p;
+  return 0;
+}
+
+extern "C" OAKB200_API int oakb200_host_free(void *ptr) {
+  if (ptr) CUDA_TRY(cudaFreeHost(ptr));
   return 0;
 }
 
