@@ -91,6 +91,9 @@ OAKB200_API int oakb200_destroy(oakb200_handle *h);
  *   "host_register"   host-buffer entry points: 1 = pageable caller arrays are page-locked (cudaHostRegister) for the
  *                     duration of the call; 0 (default) = left as they are (the driver stages the copies).  Measured on
  *                     C3: pinned arrays (oakb200_host_alloc) 2.68 M columns/s, pageable 0.40 M, registered per call 0.09 M
+ *   "apply_tma"       1 (default) = where every zone has the same even number of rows <= 32 (water columns) and the
+ *                     leading dimensions are even, the apply kernel stages the zone's rows with 2-D tensor copies (TMA:
+ *                     cp.async.bulk.tensor.2d in and out); 0 = always the plain kernel
  *   "tri_orthtol"     route 4: accepted loss of orthogonality between neighbouring eigenvectors (default 1e-11)
  *   "tri_maxgroup"    route 4: largest group of close eigenvalues orthogonalised in place (default 6; 0 sends
  *                     every zone with a close pair to the Jacobi kernel)

@@ -110,6 +110,7 @@ struct oakb200_handle {
   int scheme = 1;             // ensemble entry points: 1 = local scheme (default), 0 = global scheme (schemetype, assimilation.F90:292)
   int tvec_split = 0;         // 1: tridiagonal route, k_tvec as two kernels (eigenvectors of T | back-transformation and the rest)
   int fuse_apply = 0;         // 1: tridiagonal route, k_tvec updates the zone rows from the factored transform (no T, no k_apply)
+  int apply_tma = 1;          // k_apply_tma (zone rows staged by 2-D tensor copies) where its conditions hold, else k_apply
   int host_register = 0;      // host-buffer entry points: 1 = page-lock the caller's pageable arrays for the duration of the call
                               // (measured on C3: registering 31 GB per call costs more than the driver's staged copies:
                               // 0.09 vs 0.40 M columns/s; pinned buffers from oakb200_host_alloc: 2.68 M)
@@ -142,7 +143,7 @@ struct oakb200_handle {
   bool zones_set = false;
   int nzones = 0;
   int64_t nrows = 0;
-  int max_zone_rows = 0;
+  int max_zone_rows = 0, min_zone_rows = 0;
   int loctype = 1, metrictype = 0, weightfun = 0;
   std::vector<int64_t> h_zstart;
   double rmax = 0.;     // largest finite search radius
@@ -262,7 +263,8 @@ struct ProfAcc { double gram = 0, eig = 0, apply = 0, tridiag = 0, tql = 0, tvec
 // Runs zones [z0, z1) on slot s. The state buffers hold rows starting at global row `rowbase`.
 int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t rowbase, const double *xf,
               const double *Sf, int64_t ldS, double *xa, double *Sa, int64_t ldSa, int64_t *launches,
-              ProfAcc *prof, bool use_peers = false, double *ampl_out = nullptr /* device, [N x nzones] */) {
+              ProfAcc *prof, bool use_peers = false, double *ampl_out = nullptr /* device, [N x nzones] */,
+              int64_t rows_in_buffers = 0 /* rows held in Sf / Sa (extent of the TMA tensor maps; 0: no TMA) */) {
   int zb = batch_size(h, NP, h->nzones);
   if (h->zones_per_batch <= 0 && z1 - z0 > zb) {
     // a chunk of the host path holds a little more than one batch: split it evenly instead of one full batch
@@ -331,7 +333,8 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
         rc = oak_launch_apply(s.st, N, NP, zg, b0 + o0, o1 - o0, rowbase, mloc, s.T.as<double>() + (size_t)o0 * NP * NP,
                               s.ampl.as<double>() + (size_t)o0 * NP, xf, Sf, ldS, xa, Sa, ldSa,
                               (use_peers && h->peer_mode == 0) ? h->peers : none,
-                              only_flagged ? only_flagged + o0 : nullptr);
+                              only_flagged ? only_flagged + o0 : nullptr, false,
+                              (h->apply_tma && h->min_zone_rows == h->max_zone_rows) ? h->max_zone_rows : 0, rows_in_buffers);
       if (rc) return rc;
       if (pc > 0) *launches += 1;
       if (!push) continue;
@@ -635,6 +638,7 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   else if (k == "tql_side") h->tql_side = value != 0.;
   else if (k == "localise_obs") h->localise_obs = value != 0.;
   else if (k == "host_register") h->host_register = value != 0.;
+  else if (k == "apply_tma") h->apply_tma = value != 0.;
   else if (k == "apply_kernel") {
     if (value != 0. && value != 1.) { oak_set_error("apply_kernel = %g (0 register tiles, 1 tensor-core tiles)", value); return OAK_ERR_ARG; }
     h->apply_kernel = (int)value;
@@ -705,7 +709,8 @@ extern "C" OAKB200_API int oakb200_set_zones(oakb200_handle *h, int32_t nzones, 
     h->h_zstart[z + 1] = h->h_zstart[z] + zoneSize[z];
   }
   h->max_zone_rows = 0;
-  for (int z = 0; z < nzones; z++) h->max_zone_rows = std::max(h->max_zone_rows, (int)zoneSize[z]);
+  h->min_zone_rows = nzones > 0 ? zoneSize[0] : 0;
+  for (int z = 0; z < nzones; z++) { h->max_zone_rows = std::max(h->max_zone_rows, (int)zoneSize[z]); h->min_zone_rows = std::min(h->min_zone_rows, (int)zoneSize[z]); }
   h->nrows = h->h_zstart[nzones];
   h->rmax = 0.; h->any_unbounded = false; h->zlat_absmax = 0.;
   std::vector<double> zeros;
@@ -891,7 +896,7 @@ extern "C" OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t
     Slot &s = h->slot[h->profile ? 0 : bi % NSLOT];
     const int z1 = std::min(h->nzones, z0 + zb);
     if ((rc = run_zones(h, s, N, NP, z0, z1, 0, xf, Sf, ldSf, xa, Sa, ldSa, &launches, h->profile ? &prof : nullptr,
-                        h->peers.n > 0, amplitudes))) return rc;
+                        h->peers.n > 0, amplitudes, h->nrows))) return rc;
   }
   for (int i = 1; i < NSLOT; i++) {
     CUDA_TRY(cudaEventRecord(h->slot[i].ev[5], h->slot[i].st));
@@ -1001,7 +1006,7 @@ extern "C" OAKB200_API int oakb200_local_analysis(oakb200_handle *h, int64_t n, 
       h2d += 8ll * rows * (N + 1);
     }
     if ((rc = run_zones(h, s, N, NP, z0, z1, r0, s.xf.as<double>(), s.S.as<double>(), rows, s.xa.as<double>(),
-                        s.S.as<double>(), rows, &launches, h->profile ? &prof : nullptr, false, d_ampl_out)))
+                        s.S.as<double>(), rows, &launches, h->profile ? &prof : nullptr, false, d_ampl_out, rows)))
       return rc;
     if (rows > 0) {
       CUDA_TRY(cudaMemcpy2DAsync(Sa + r0, 8 * (size_t)ldSa, s.S.p, 8 * (size_t)rows, 8 * (size_t)rows, N, cudaMemcpyDeviceToHost, s.st));

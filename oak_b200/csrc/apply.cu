@@ -10,6 +10,9 @@
 // while the threads stage the first chunk of rows.  Rows are processed in chunks of 32; a chunk is
 // fully staged in shared memory before its results are stored, so Sa may alias Sf.
 #include "common.cuh"
+#ifndef OAK_CUEMU
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#endif
 
 namespace {
 
@@ -48,6 +51,23 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#endif
+
+#ifndef OAK_CUEMU
+// 2-D tiled tensor copies (TMA): box = (rows of the zone) x (members), see k_apply_tma
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, const void *src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
 constexpr int RC = 32;  // rows per chunk
@@ -179,6 +199,158 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
   }
 }
 
+
+#ifndef OAK_CUEMU
+// ---------------------------------------------------------------------------------------------------------
+// k_apply_tma : the same update with the zone's rows staged by the TMA engine.  A zone of `nrow` rows is a box of
+// nrow x N doubles of the member-major state (row stride ld*8 bytes): ONE cp.async.bulk.tensor.2d brings it into
+// shared memory ([member][row], dense) and one brings the result back, both issued by a single thread next to the
+// bulk copy of T, all three signalled on / fenced by the same mbarrier and bulk group.  The per-thread 8-byte
+// loads and stores of k_apply (30 of 32 lanes active on 240-byte runs that straddle sectors; long-scoreboard
+// stalls 35 % in ncu) disappear.  Conditions (checked by the launcher, otherwise k_apply): every zone has the same
+// even number of rows <= 32, ld even, 16-byte aligned arrays, no peer stores.
+// ---------------------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(128) k_apply_tma(int N, int nrow, ZoneGeom zg, int zone0, int64_t rowbase,
+                                                   const int32_t *__restrict__ mloc, const double *__restrict__ T,
+                                                   const double *__restrict__ ampl, const double *__restrict__ xf,
+                                                   double *__restrict__ xa, const __grid_constant__ CUtensorMap mapS,
+                                                   const __grid_constant__ CUtensorMap mapA, int in_place,
+                                                   const int32_t *__restrict__ only_flagged) {
+  extern __shared__ __align__(128) double sm[];
+  double *sT = sm;                   // [NP][NP] row-major
+  double *sS = sm + NP * NP;         // [N][nrow] dense box (+ slack for the tile reads of rows >= nrow)
+  double *s_ampl = sS + NP * RC + 8;
+  __shared__ __align__(8) uint64_t bar;
+
+  const int tid = threadIdx.x;
+  const int zl = blockIdx.x;
+  const int zone = zone0 + zl;
+  const int64_t i1 = zg.zstart[zone] - rowbase;
+  const bool analysed = mloc[zone] != 0;
+  if (only_flagged && analysed && only_flagged[zl] == 0) return;
+  if (!analysed && in_place) {        // the zone keeps the forecast: only the mean has to be copied
+    for (int r = tid; r < nrow; r += 128) xa[i1 + r] = xf[i1 + r];
+    return;
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t tbytes = analysed ? NP * NP * sizeof(double) : 0u;
+    mbar_expect_tx(&bar, tbytes + (uint32_t)(nrow * N * sizeof(double)));
+    if (analysed) bulk_g2s(sT, T + (int64_t)zl * NP * NP, tbytes, &bar);
+    tma_load_2d(sS, &mapS, (int)i1, 0, &bar);
+  }
+  if (tid < NP) s_ampl[tid] = analysed ? ampl[(int64_t)zl * NP + tid] : 0.;
+  __syncthreads();                    // s_ampl
+  mbar_wait(&bar, 0);
+  const int ty = tid >> 4, tx = tid & 15;  // 8 x 16: rows 4 ty .., columns 2 tx + 32 b (+1)
+  constexpr int CB = NP / 32;
+  if (analysed) {
+    double acc[4][2 * CB];
+    double dm[4] = {0., 0., 0., 0.};
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 2 * CB; b++) acc[a][b] = 0.;
+#pragma unroll 4
+    for (int k = 0; k < N; k++) {
+      const double2 s01 = *reinterpret_cast<const double2 *>(sS + k * nrow + 4 * ty);
+      const double2 s23 = *reinterpret_cast<const double2 *>(sS + k * nrow + 4 * ty + 2);
+      const double sv[4] = {s01.x, s01.y, s23.x, s23.y};   // rows >= nrow: the next member's values, never stored
+      const double ak = s_ampl[k];
+#pragma unroll
+      for (int a = 0; a < 4; a++) dm[a] = fma(sv[a], ak, dm[a]);
+#pragma unroll
+      for (int b = 0; b < CB; b++) {
+        const double2 t = *reinterpret_cast<const double2 *>(sT + k * NP + 2 * tx + 32 * b);
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          acc[a][2 * b] = fma(sv[a], t.x, acc[a][2 * b]);
+          acc[a][2 * b + 1] = fma(sv[a], t.y, acc[a][2 * b + 1]);
+        }
+      }
+    }
+    if (tx == 0) {
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const int r = 4 * ty + a;
+        if (r < nrow) xa[i1 + r] = xf[i1 + r] + dm[a];
+      }
+    }
+    __syncthreads();                  // all reads of the box done: it now receives the results
+#pragma unroll
+    for (int b = 0; b < CB; b++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int kk = 2 * tx + 32 * b + e;
+        if (kk < N) {
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+            if (4 * ty + a < nrow) sS[kk * nrow + 4 * ty + a] = acc[a][2 * b + e];
+        }
+      }
+  } else {
+    for (int r = tid; r < nrow; r += 128) xa[i1 + r] = xf[i1 + r];
+  }
+  fence_proxy_async();                // generic-proxy writes of the box before the async-proxy (TMA) read
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_2d(&mapA, (int)i1, 0, sS);
+    tma_store_commit_wait();          // the box must stay valid until the engine has read it
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// rows x N doubles, row stride ld; box nrow x N
+bool make_state_map(CUtensorMap *map, const double *base, int64_t rows, int64_t ld, int N, int nrow) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)N};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)nrow, (cuuint32_t)N};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int NP>
+int launch_tma(cudaStream_t st, int N, int nrow, int64_t rows_in_buffers, const ZoneGeom &zg, int zone0, int nz,
+               int64_t rowbase, const int32_t *mloc, const double *T, const double *ampl, const double *xf,
+               const double *Sf, int64_t ldS, double *xa, double *Sa, int64_t ldSa, const int32_t *only_flagged,
+               bool *done) {
+  *done = false;
+  CUtensorMap mS, mA;
+  if (!make_state_map(&mS, Sf, rows_in_buffers, ldS, N, nrow) || !make_state_map(&mA, Sa, rows_in_buffers, ldSa, N, nrow))
+    return 0;   // the caller falls back to k_apply
+  const size_t smem = sizeof(double) * (NP * NP + NP * RC + 8 + NP);
+  { int rc_ = oak_func_smem(k_apply_tma<NP>, smem); if (rc_) return rc_; }
+  k_apply_tma<NP><<<nz, 128, smem, st>>>(N, nrow, zg, zone0, rowbase, mloc, T, ampl, xf, xa, mS, mA, Sa == Sf ? 1 : 0,
+                                        only_flagged);
+  CUDA_TRY(cudaGetLastError());
+  *done = true;
+  return 0;
+}
+#endif  // OAK_CUEMU
+
 template <int NP>
 int launch(cudaStream_t st, int N, const ZoneGeom &zg, int zone0, int nz, int64_t rowbase, const int32_t *mloc,
            const double *T, const double *ampl, const double *xf, const double *Sf, int64_t ldS, double *xa,
@@ -196,8 +368,20 @@ int launch(cudaStream_t st, int N, const ZoneGeom &zg, int zone0, int nz, int64_
 int oak_launch_apply(cudaStream_t st, int N, int NP, const ZoneGeom &zg, int zone0, int nz, int64_t rowbase,
                      const int32_t *mloc, const double *T, const double *ampl, const double *xf,
                      const double *Sf, int64_t ldS, double *xa, double *Sa, int64_t ldSa, const PeerOut &peers,
-                     const int32_t *only_flagged, bool shared_transform) {
+                     const int32_t *only_flagged, bool shared_transform, int uniform_rows, int64_t rows_in_buffers) {
   if (nz <= 0) return 0;
+#ifndef OAK_CUEMU
+  // TMA-staged state (k_apply_tma) where a zone is one box: equal, even zone sizes <= 32, even leading dimensions,
+  // 16-byte aligned arrays, local scheme, no stores to peers from the kernel
+  if (uniform_rows > 0 && uniform_rows <= RC && (uniform_rows & 1) == 0 && !shared_transform && peers.n == 0 && mloc &&
+      (ldS & 1) == 0 && (ldSa & 1) == 0 && ((uintptr_t)Sf & 15) == 0 && ((uintptr_t)Sa & 15) == 0 && N >= 2 &&
+      rows_in_buffers > 0 && rows_in_buffers < 0x7fffffffll && (NP == 32 || NP == 64)) {
+    bool done = false;
+    int rc = NP == 64 ? launch_tma<64>(st, N, uniform_rows, rows_in_buffers, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, only_flagged, &done)
+                      : launch_tma<32>(st, N, uniform_rows, rows_in_buffers, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, only_flagged, &done);
+    if (rc || done) return rc;
+  }
+#endif
   switch (NP) {
     case 32: return launch<32>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged, shared_transform);
     case 64: return launch<64>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged, shared_transform);

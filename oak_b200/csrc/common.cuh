@@ -352,7 +352,9 @@ int oak_launch_apply(cudaStream_t st, int N, int NP, const ZoneGeom &zg, int zon
                      const double *xf, const double *Sf, int64_t ldS, double *xa, double *Sa,
                      int64_t ldSa, const PeerOut &peers,
                      const int32_t *only_flagged = nullptr /* batch-local flags: analysed zones with flag 0 are skipped */,
-                     bool shared_transform = false /* global scheme: every block of rows uses T[0], ampl[0]; mloc may be NULL */);
+                     bool shared_transform = false /* global scheme: every block of rows uses T[0], ampl[0]; mloc may be NULL */,
+                     int uniform_rows = 0 /* > 0: every zone has this many rows (enables the TMA-staged kernel) */,
+                     int64_t rows_in_buffers = 0 /* rows held in Sf / Sa from their first element (tensor-map extent) */);
 int oak_launch_apply_mma(cudaStream_t st, int N, int NP, const ZoneGeom &zg, int zone0, int nz, int64_t rowbase,
                          const int32_t *mloc, const double *T, const double *ampl, const double *xf, const double *Sf,
                          int64_t ldS, double *xa, double *Sa, int64_t ldSa, const int32_t *only_flagged,
