@@ -34,6 +34,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5"],
+                    help="c3 = the headline workload (BASELINE configs[2]); c4 = 2000x2000x50, N=128, obs at every surface "
+                         "point, analysed slab by slab in place (configs[3]); c5 = 4-D 256x256x10x4, N=64, inflation + log "
+                         "anamorphosis through the ensemble entry point (configs[4])")
+    ap.add_argument("--slab-rows", type=int, default=50, help="c4: grid rows (of nx zones) per resident slab")
+    ap.add_argument("--max-slabs", type=int, default=0, help="c4: analyse only this many slabs per rank (0 = all) and say so")
     ap.add_argument("--nx", type=int, default=1000)
     ap.add_argument("--ny", type=int, default=1000)
     ap.add_argument("--nz", type=int, default=30)
@@ -284,6 +290,10 @@ def main():
 
     if a.impl == "reference":
         return reference_arm(a, rank, world)
+    if a.config == "c4":
+        return run_c4(a, rank, world, local)
+    if a.config == "c5":
+        return run_c5(a, rank, world, local)
 
     import torch.distributed as dist
     import oak_b200
@@ -615,6 +625,282 @@ def main():
     h.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# BASELINE configs[3] ("C4"): 2000 x 2000 x 50, N = 128, an observation at every surface point, corrLen 10 km /
+# cut-off 20 km (m_loc ~ 1257).  The state is 205 GB: it never exists as a whole.  Every rank walks over its zone
+# range in slabs of `--slab-rows` grid rows; a slab (forecast anomalies, mean, the observations within one search
+# radius) is generated on the device, analysed IN PLACE (Sa = Sf) through oakb200_local_analysis_dev and dropped.
+# Timed: the analysis calls (CUDA events), summed over the slabs of a rank, max over ranks.  No all-gather: the
+# analysed state stays distributed, as in the MPI reference until output (parall.F90:507).
+# --------------------------------------------------------------------------------------------------
+def run_c4(a, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    import oak_b200
+    from oak_b200 import synthetic as S
+    nx, ny, nz, N = (2000, 2000, 50, 128) if a.nx == 1000 else (a.nx, a.ny, a.nz, a.N)
+    corr, maxlen = (10000.0, 20000.0) if a.corr == 4000.0 else (a.corr, a.maxlen)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    g = S.Grid(nx, ny, nz)
+    halo = int(math.ceil(maxlen / g.dx)) + 1
+    j_first = [ny * p // world for p in range(world + 1)]           # parall.F90:176-177 on whole grid rows
+    slabs = [(j, min(j + a.slab_rows, j_first[rank + 1])) for j in range(j_first[rank], j_first[rank + 1], a.slab_rows)]
+    if a.max_slabs > 0:
+        slabs = slabs[:a.max_slabs]
+    h = oak_b200.Handle(local)
+    peak = h.fp64_peak(0)
+
+    def make_slab(j0, j1):
+        zones = torch.arange(j0 * nx, j1 * nx, dtype=torch.int64, device=dev)
+        nzs = zones.numel()
+        n_loc = nzs * nz
+        Sf = torch.empty((N, n_loc), dtype=torch.float64, device=dev)
+        xf = torch.empty(n_loc, dtype=torch.float64, device=dev)
+        step = 1 << 19
+        for s0 in range(0, n_loc, step):
+            e0 = min(n_loc, s0 + step)
+            rows = torch.arange(j0 * nx * nz + s0, j0 * nx * nz + e0, dtype=torch.int64, device=dev)
+            mean, anom = S.anomalies(torch, S.ensemble_rows(torch, g, rows, N, SEED))
+            xf[s0:e0] = mean
+            Sf[:, s0:e0] = anom
+        # observations: one at every surface point of the grid rows within the halo (H = identity on the surface row)
+        jo0, jo1 = max(0, j0 - halo), min(ny, j1 + halo)
+        oz = torch.arange(jo0 * nx, jo1 * nx, dtype=torch.int64, device=dev)
+        ox, oy = g.zone_xy(torch, oz)
+        HE = torch.empty((N, oz.numel()), dtype=torch.float64, device=dev)
+        for s0 in range(0, oz.numel(), step):
+            e0 = min(oz.numel(), s0 + step)
+            HE[:, s0:e0] = S.ensemble_rows(torch, g, oz[s0:e0] * nz, N, SEED)
+        Hxf, HSf = S.anomalies(torch, HE)
+        del HE
+        yo = g.mu_rows(torch, oz * nz) + 0.05 * S.normal(torch, oz, 5, SEED)
+        rm = 0.05 * (1.0 + 0.5 * S.uniform(torch, oz, 4, SEED))
+        zx, zy = g.zone_xy(torch, zones)
+        return dict(nzs=nzs, Sf=Sf, xf=xf, xa=torch.empty_like(xf), HSf=HSf.contiguous(), Hxf=Hxf.contiguous(), yo=yo,
+                    var=(rm * rm).contiguous(), zx=zx.cpu().numpy(), zy=zy.cpu().numpy(), ox=ox.cpu().numpy(),
+                    oy=oy.cpu().numpy())
+
+    def analyse(d):
+        h.set_zones(np.full(d["nzs"], nz, np.int32), zone_x=d["zx"], zone_y=d["zy"], corrLen=corr, maxLen=maxlen,
+                    loctype=1, metrictype=0, weightfun=0)
+        h.set_observations(obs_x=d["ox"], obs_y=d["oy"])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st = h.local_analysis_dev(d["xf"], d["Hxf"], d["yo"], d["Sf"], d["HSf"], d["var"], d["xa"], d["Sf"])  # in place
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), st
+
+    # warm-up: the first slab three times on copies (kernels, workspaces, clocks)
+    d = make_slab(*slabs[0])
+    keep = d["Sf"].clone()
+    for _ in range(max(a.warmup, 1)):
+        d["Sf"].copy_(keep)
+        analyse(d)
+    # parity of the first slab against the oracle on sampled columns (interior of the slab)
+    parity = None
+    if rank == 0:
+        try:
+            import oracle
+            oracle.set_threads(0)
+            d["Sf"].copy_(keep)
+            analyse(d)
+            rng = np.random.default_rng(1)
+            zl = np.sort(rng.choice(d["nzs"], size=min(96, d["nzs"]), replace=False))
+            rows = (zl[:, None] * nz + np.arange(nz)[None, :]).ravel()
+            rt = torch.from_numpy(rows).to(dev)
+            obs = oracle.make_obs(int(d["yo"].numel()), obsx=d["ox"], obsy=d["oy"])
+            xo, So, _, _ = oracle.loc_analysis_cellgrid(np.full(zl.size, nz, np.int32), dict(x=d["zx"][zl], y=d["zy"][zl]), corr, maxlen, obs,
+                                                        d["xf"][rt].cpu().numpy(), d["Hxf"].cpu().numpy(), d["yo"].cpu().numpy(),
+                                                        np.asfortranarray(keep[:, rt].cpu().numpy().T),
+                                                        np.asfortranarray(d["HSf"].cpu().numpy().T), d["var"].cpu().numpy())
+            Sg, xg = d["Sf"][:, rt].cpu().numpy().T, d["xa"][rt].cpu().numpy()
+            eS, ex = float(np.abs(Sg - So).max() / np.abs(So).max()), float(np.abs(xg - xo).max() / np.abs(xo).max())
+            parity = {"cols": int(zl.size), "max_rel_Sa": eS, "max_rel_xa": ex, "tol": 1e-9, "ok": bool(eS < 1e-9 and ex < 1e-9),
+                      "against": "oracle port (dsyev/dgemm, cell-grid selection) on sampled columns of the first slab"}
+        except Exception as ex:
+            parity = {"cols": 0, "ok": False, "error": repr(ex)[:200]}
+    # per-kernel times of the first slab (profile pass: batches serialised)
+    d["Sf"].copy_(keep)
+    h.set_option("profile", 1)
+    _, stp = analyse(d)
+    h.set_option("profile", 0)
+    kernel_ms = {k: stp.get("ms_" + k, 0.0) for k in ("pack", "gram", "eig", "apply")}
+    del keep
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total, zones_done, launches, agg = 0.0, 0, 0, np.zeros(3)
+    t_wall = time.perf_counter()
+    for si, (j0, j1) in enumerate(slabs):
+        if si > 0:
+            del d
+            d = make_slab(j0, j1)
+        else:
+            d = make_slab(j0, j1)
+        ms, st = analyse(d)
+        ms_total += ms
+        zones_done += d["nzs"]
+        launches += st["launches"]
+        agg += [st["obs_relevant_sum"], st["obs_candidate_sum"], st["zones_skipped"]]
+    wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total, float(zones_done), agg[0], agg[1]], dtype=torch.float64, device=dev)
+    tmax = t.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        zones_all = float(t[1].item())
+        ms_step = float(tmax[0].item())
+        value = zones_all / (ms_step * 1e-3)
+        mloc = t[2].item() / max(zones_all, 1)
+        cand = t[3].item() / max(zones_all, 1)
+        fz = flops_per_zone(N, nz, mloc, cand)
+        partial = a.max_slabs > 0
+        out = {"metric": "local-analysis grid columns/sec", "value": value, "unit": "columns/s", "n_gpus": world,
+               "steps": 1, "warmup": max(a.warmup, 1), "ms_per_step": ms_step, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": f"synthetic 3D ocean {nx}x{ny}x{nz}, N={N}, {nx * ny} obs (one per surface point), diagonal R, "
+                                      f"local ETKF (gaussian corrLen {corr:g} m, cut-off {maxlen:g} m, cartesian)",
+                          "zones": int(zones_all), "zones_in_full_grid": nx * ny,
+                          "coverage": ("PARTIAL: %d slabs per rank" % a.max_slabs) if partial else "whole grid",
+                          "parallelism": f"zone-range x{world}; state ({nx * ny * nz * N * 8 / 1e9:.0f} GB) never resident as a whole: slabs of "
+                                         f"{a.slab_rows} grid rows generated on the device, analysed in place, dropped; no gather",
+                          "mean_relevant_obs_per_column": mloc, "mean_candidates_per_column": cand,
+                          "transform": "block Jacobi kernel (the tridiagonal route covers N <= 64)",
+                          "timed": "sum of the oakb200_local_analysis_dev calls (CUDA events), max over ranks; slab generation "
+                                   "and oakb200_set_zones / set_observations outside", "wall_s_with_generation": wall},
+               "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
+               "roofline": {"bound": "fp64", "kernel": "whole step", "peak": peak, "unit": "TFLOP/s",
+                            "achieved": value * fz / 1e12 / world, "frac": value * fz / 1e12 / world / peak,
+                            "algorithmic_flops_per_zone": fz, "traffic": None,
+                            "kernel_ms_first_slab": kernel_ms, "zones_first_slab": (slabs[0][1] - slabs[0][0]) * nx,
+                            "peak_source": "DFMA micro-kernel measured in this run"},
+               "e2e": None, "cpu_baseline": None}
+        print(json.dumps(out))
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# BASELINE configs[4] ("C5"): 4-D grid 256 x 256 x 10 levels x 4 times (a zone = the 40 elements of a column), N = 64,
+# 2e5 observations, inflation.mult = 1.05, log anamorphosis, through the ENSEMBLE entry point (Assim's ensemble
+# branch: H E, forward anamorphosis, mean / anomalies, local analysis, inflation, Ea, inverse anamorphosis).
+# --------------------------------------------------------------------------------------------------
+def run_c5(a, rank, world, local):
+    import torch
+    import oak_b200
+    from oak_b200 import synthetic as S
+    if rank != 0:
+        return
+    nx, ny, nz, N, m = (256, 256, 40, 64, 200000) if a.nx == 1000 else (a.nx, a.ny, a.nz, a.N, a.m)
+    corr, maxlen = a.corr, a.maxlen
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    g = S.Grid(nx, ny, nz)
+    rows = torch.arange(g.n, dtype=torch.int64, device=dev)
+    E = torch.exp(0.3 * S.ensemble_rows(torch, g, rows, N, SEED)).contiguous()       # strictly positive, (N, n)
+    obs = S.observations(np, g, m, SEED)
+    Hi, Hj, Hs = S.coo_operator(g, obs)
+    yo = np.log(1.0 + 0.2 * np.abs(np.asarray(g.mu_rows(np, obs["rows"][0])))) + 1.0 + np.asarray(obs["noise"])
+    zx, zy = g.zone_xy(np, np.arange(g.nzones, dtype=np.int64))
+    zs = np.full(g.nzones, nz, np.int32)
+    t = lambda x, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(x)).to(dev).to(dt)
+    dHi, dHj, dHs, dyo, dvar = t(Hi, torch.int32), t(Hj, torch.int32), t(Hs), t(yo), t(obs["var"])
+    h = oak_b200.Handle(local)
+    h.set_zones(zs, zone_x=zx, zone_y=zy, corrLen=corr, maxLen=maxlen, loctype=1, metrictype=0, weightfun=0)
+    h.set_observations(obs_x=obs["ox"], obs_y=obs["oy"])
+    Ea = torch.empty_like(E)
+    xf = torch.empty(g.n, dtype=torch.float64, device=dev)
+    xa = torch.empty_like(xf)
+    infl = 1.05
+
+    def step():
+        return h.assim_ensemble_dev(E, dHi, dHj, dHs, None, dyo, dvar, Ea, anamtype=2, inflation=infl, xf_out=xf, xa_out=xa)
+
+    for _ in range(max(a.warmup, 3)):
+        st = step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launches = 0
+    for _ in range(a.steps):
+        st = step()
+        launches += st["launches"]
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    clocks = sampler.stop()
+    value = g.nzones / (ms * 1e-3)
+    analysed = g.nzones - st["zones_skipped"]
+    mloc = st["obs_relevant_sum"] / max(analysed, 1)
+    cand = st["obs_candidate_sum"] / max(g.nzones, 1)
+    fz = flops_per_zone(N, nz, mloc, cand)
+    peak = h.fp64_peak(0)
+    # streaming passes of the ensemble branch (H E, mean / anomalies in, epilogue out): algorithmic bytes
+    stream_bytes = 8.0 * g.n * N * 4 + 8.0 * m * N * 3
+    # end to end through the host-buffer entry point (pageable numpy arrays in, analysed ensemble out)
+    e2e = None
+    if not a.no_e2e:
+        Eh = np.asfortranarray(E.cpu().numpy().T)
+        h.assim_ensemble(Eh, Hi, Hj, Hs, None, yo, oak_b200.DiagCovar(obs["var"]), 2, infl, None)
+        t0 = time.perf_counter()
+        for _ in range(a.e2e_steps):
+            h.set_observations(obs_x=obs["ox"], obs_y=obs["oy"])
+            Eah, _, _, ste = h.assim_ensemble(Eh, Hi, Hj, Hs, None, yo, oak_b200.DiagCovar(obs["var"]), 2, infl, None)
+        te = (time.perf_counter() - t0) / a.e2e_steps
+        e2e = {"value": g.nzones / te, "unit": "columns/s", "h2d_bytes_per_step": ste["h2d_bytes"],
+               "d2h_bytes_per_step": ste["d2h_bytes"], "steps": a.e2e_steps,
+               "note": "oakb200_set_observations + oakb200_assim_ensemble on host arrays (E in, Ea out)",
+               "identical_to_resident": bool(np.array_equal(Eah, Ea.cpu().numpy().T))}
+    # parity: the whole configuration through the oracle's ensemble branch (brute-force scan per column)
+    parity, cpu = None, None
+    if not a.no_cpu:
+        try:
+            import oracle
+            cores = oracle.set_threads(0)
+            oo = oracle.make_obs(m, obsx=obs["ox"], obsy=obs["oy"])
+            t0 = time.perf_counter()
+            Eo, xfo, xao = oracle.assim_ensemble(zs, dict(x=zx, y=zy), corr, maxlen, oo, np.asfortranarray(E.cpu().numpy().T), Hi, Hj,
+                                                 Hs, np.zeros(m), yo, obs["var"], anamtype=2, inflation=infl)
+            tc = time.perf_counter() - t0
+            Eg = Ea.cpu().numpy().T
+            eE = float(np.abs(Eg - Eo).max() / np.abs(Eo).max())
+            ex = float(np.abs(xa.cpu().numpy() - xao).max() / np.abs(xao).max())
+            parity = {"cols": int(g.nzones), "max_rel_Ea": eE, "max_rel_xa": ex, "tol": 1e-9, "ok": bool(eE < 1e-9 and ex < 1e-9),
+                      "against": "oracle port of the ensemble branch (O(m) scan, dsyev/dgemm) on EVERY column of this workload"}
+            cpu = {"value": g.nzones / tc, "unit": "columns/s", "cores": cores, "kind": "port",
+                   "sample": f"the whole configuration ({g.nzones} columns, {m} observations scanned per column), {tc:.1f} s"}
+        except Exception as ex:
+            parity = {"cols": 0, "ok": False, "error": repr(ex)[:200]}
+    out = {"metric": "local-analysis grid columns/sec", "value": value, "unit": "columns/s", "n_gpus": 1, "steps": a.steps,
+           "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"synthetic 4-D {nx}x{ny} columns x {nz} elements (10 levels x 4 times), N={N}, {m} obs, diagonal R, "
+                                  f"ensemble entry point: H E, log anamorphosis, local ETKF (gaussian corrLen {corr:g} m, cut-off "
+                                  f"{maxlen:g} m), inflation {infl}, inverse anamorphosis",
+                      "zones": g.nzones, "parallelism": "1 GPU", "mean_relevant_obs_per_column": mloc,
+                      "l2": "ensemble 1.3 GB per pass exceeds L2; no explicit flush"},
+           "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
+           "roofline": {"bound": "fp64", "kernel": "whole step", "peak": peak, "unit": "TFLOP/s",
+                        "achieved": value * fz / 1e12, "frac": value * fz / 1e12 / peak, "algorithmic_flops_per_zone": fz,
+                        "traffic": None, "streaming_passes_algorithmic_bytes": stream_bytes},
+           "e2e": e2e, "cpu_baseline": cpu}
+    print(json.dumps(out))
+    h.close()
 
 
 def reference_arm(a, rank, world):

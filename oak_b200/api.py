@@ -257,6 +257,23 @@ class Handle:
             C.byref(st)))
         return st.asdict()
 
+    def assim_ensemble_dev(self, E, Hi, Hj, Hs, Hshift, yo, Rdiag, Ea, anamtype=1, inflation=1.0, maxCorrection=None,
+                           d01=None, xf_out=None, xa_out=None, stream=None):
+        """Ensemble branch of Assim on CUDA tensors of this device: E, Ea member-major (N, n) (Ea may be E), Hi / Hj
+        int32 1-based COO indices, Hs / Hshift / yo / Rdiag fp64.  Returns the stats dict."""
+        import torch
+        N, n = E.shape
+        m = yo.numel()
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        st = _lib.Stats()
+        _check(self._L.oakb200_assim_ensemble_dev(
+            self._h, n, N, m, p(E), max(n, 1), int(Hs.numel()), p(Hi), p(Hj), p(Hs), p(Hshift), p(yo), p(Rdiag), p(d01),
+            int(anamtype), float(inflation), p(maxCorrection), p(Ea), max(n, 1), p(xf_out), p(xa_out),
+            C.c_void_p(stream), C.byref(st)))
+        return st.asdict()
+
     def set_peer_outputs(self, Sa_ptrs, xa_ptrs, ld, row0):
         """Fused all-gather (oakb200_set_peer_outputs): device pointers (ints) of the (N, n) member-major result
         array and of the mean vector of every destination; rows of this rank start at row0.  [] switches off."""
