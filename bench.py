@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--phases", type=int, default=0, help="pipeline phases for N>1 (0: 1 with the fused gather, 4 with --nccl-gather)")
     ap.add_argument("--peer-mode", type=int, default=1, help="fused gather: 1 = copy engines push each finished batch, 0 = stores of the apply kernel")
     ap.add_argument("--push-pieces", type=int, default=1, help="fused gather, peer mode 1: apply + push of every batch in this many pieces")
+    ap.add_argument("--push-kernel", type=int, default=1, help="fused gather: 1 = rows pushed by a small kernel on a side stream (SM stores over NVLink) instead of copy-engine copies")
+    ap.add_argument("--push-ctas", type=int, default=64)
     ap.add_argument("--nccl-gather", action="store_true", help="N>1: reassemble with NCCL all-gathers instead of the fused peer stores of the apply kernel")
     return ap.parse_args()
 
@@ -363,6 +365,8 @@ def main():
             for p in phases:
                 p["h"].set_option("peer_mode", a.peer_mode)
                 p["h"].set_option("push_pieces", a.push_pieces)
+                p["h"].set_option("push_kernel", a.push_kernel)
+                p["h"].set_option("push_ctas", a.push_ctas)
                 p["h"].set_peer_outputs(Sp, xp, plan.n, p["plan"].r0)
             Sa_full = peer.Sa
         else:

@@ -47,6 +47,9 @@
 #ifndef TVEC_PRODUCT
 #define TVEC_PRODUCT 1    // 1: twisted_vector3 (division-free Sturm-product recurrences), pivot form as fallback
 #endif
+#ifndef TVEC_MMA_T
+#define TVEC_MMA_T 1      // NP = 64: the product M = I - Y Y^T on mma.m8n8k4 tiles (36 lower tiles, mirrored on store)
+#endif
 #ifndef TVEC_MINB
 #define TVEC_MINB 1
 #endif
@@ -571,6 +574,32 @@ struct BackTile {
 };
 
 
+// Tile map of the symmetric 64 x 64 product M = I - Y Y^T on two warps (the map of k_gram_mma's two-warp variant):
+// warp 0 owns the LL triangle and the HL rows 4, 5 (18 tiles), warp 1 the HH triangle and the HL rows 6, 7 (18)
+template <int W>
+struct MTileMap {
+  static constexpr int HB = 4;
+  static __host__ __device__ constexpr bool owns(int bi, int bj) {
+    if (bj > bi) return false;
+    const bool LL = bi < HB, HH = bj >= HB, HL = !LL && !HH;
+    return W == 0 ? (LL || (HL && bi < HB + 2)) : (HH || (HL && bi >= HB + 2));
+  }
+  static __host__ __device__ constexpr int slot(int bi, int bj) {
+    const bool LL = bi < HB, HH = bj >= HB;
+    if (LL) return bi * (bi + 1) / 2 + bj;
+    if (HH) return (bi - HB) * (bi - HB + 1) / 2 + (bj - HB);
+    return 10 + ((bi - HB) & 1) * HB + bj;
+  }
+  static __host__ __device__ constexpr bool needs_row(int b) {
+    for (int jj = 0; jj <= b; jj++) if (owns(b, jj)) return true;
+    return false;
+  }
+  static __host__ __device__ constexpr bool needs_col(int b) {
+    for (int ii = b; ii < 2 * HB; ii++) if (owns(ii, b)) return true;
+    return false;
+  }
+};
+
 // ---------------------------------------------------------------------------------------------------
 // Fused apply (option "fuse_apply"): the zone's rows are updated by k_tvec itself from the FACTORED transform,
 //     Sa_z = ((Sf_z - (Sf_z Y) Y^T) - a1 u_v^T) D - a2 u_w^T ,  a1 = Sf_z g1 hv, a2 = Sf_z g2 hw ,  xa_z = xf_z + Sf_z ampl
@@ -673,7 +702,7 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
                                               int32_t *__restrict__ flags, DevCounters *ctr, double orthtol,
                                               int maxgroup, const FusedApplyArgs aa, double *__restrict__ Wg) {
   constexpr int LDW = PART == 1 ? NP : NP + 1;  // part 1 builds W directly in global memory (no shared-memory matrix)
-  constexpr int LDY = FUSE ? NP + 4 : NP + 2;  // fused: Yt rows double as mma fragments (conflict-free at NP + 4)
+  constexpr int LDY = NP + 4;  // Yt rows double as mma fragments (fused apply, tensor-core M product): conflict-free at NP + 4
   constexpr int NW = NP / 32;
   constexpr int TR = 8, TC = NP / 8;          // output tile of a thread: TR rows x TC columns
   constexpr int TJ = NP / TC;                 // thread grid: (NP/TR) x TJ = NP threads
@@ -939,6 +968,65 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
                         aa.Sa, aa.ldSa);
   } else
   // ---- T[i][k] = (M[i][k] - g1[i] hv u_v[k]) D_k - g2[i] hw u_w[k] , row-major ----
+#if TVEC_MMA_T
+  // M = I - Y Y^T on the fp64 tensor cores: only the 36 tiles (8 x 8) on or below the diagonal are accumulated (Y Y^T
+  // is symmetric), 18 per warp; a k-step of four eigenpairs needs one fragment load per block the warp touches
+  // (lane 4g+t reads Yt[(k0+t)][8b+g]: A fragment of block row b and B fragment of block column b).  The rank-one
+  // terms are applied to the accumulator fragments, the strictly lower tiles are written twice (as they are and
+  // transposed).  ~580 DMMA + ~260 loads per zone instead of 8.2 k DFMA + 1 k loads, 36 instead of 64 accumulators.
+  if constexpr (NP == 64) {
+    const int gq = lane >> 2, tq = lane & 3;
+    const int NK = (N + 3) & ~3;
+    double *Tz = Tout + (int64_t)zl * NP * NP;
+    auto run = [&](auto tm) {
+      using TM = decltype(tm);
+      double acc[18][2];
+#pragma unroll
+      for (int a_ = 0; a_ < 18; a_++) acc[a_][0] = acc[a_][1] = 0.;
+#pragma unroll 2
+      for (int k0 = 0; k0 < NK; k0 += 4) {
+        const double *r = Yt + (k0 + tq) * LDY + gq;
+        double v[8];
+#pragma unroll
+        for (int b = 0; b < 8; b++)
+          if (TM::needs_row(b) || TM::needs_col(b)) v[b] = r[8 * b];
+#pragma unroll
+        for (int bi = 0; bi < 8; bi++)
+#pragma unroll
+          for (int bj = 0; bj <= bi; bj++)
+            if (TM::owns(bi, bj)) oak_dmma_m8n8k4(acc[TM::slot(bi, bj)][0], acc[TM::slot(bi, bj)][1], v[bi], v[bj]);
+      }
+#pragma unroll
+      for (int bi = 0; bi < 8; bi++)
+#pragma unroll
+        for (int bj = 0; bj <= bi; bj++)
+          if (TM::owns(bi, bj)) {
+            const int i = 8 * bi + gq, k = 8 * bj + 2 * tq;
+            const double m0 = (i == k ? 1. : 0.) - acc[TM::slot(bi, bj)][0];
+            const double m1 = (i == k + 1 ? 1. : 0.) - acc[TM::slot(bi, bj)][1];
+            {
+              const double g1i = sg1[i] * hv, g2i = sg2[i] * hw;
+              double t0 = m0 - g1i * suv[k], t1 = m1 - g1i * suv[k + 1];
+              if (k == N - 1) t0 *= dNN;
+              if (k + 1 == N - 1) t1 *= dNN;
+              t0 -= g2i * suw[k];
+              t1 -= g2i * suw[k + 1];
+              *reinterpret_cast<double2 *>(Tz + (int64_t)i * NP + k) = make_double2(t0, t1);
+            }
+            if (bi != bj) {   // the mirrored tile: T[k][i], T[k+1][i] from M[k][i] = M[i][k]
+              const double uvi = suv[i], uwi = suw[i];
+              double t0 = m0 - sg1[k] * hv * uvi, t1 = m1 - sg1[k + 1] * hv * uvi;
+              if (i == N - 1) { t0 *= dNN; t1 *= dNN; }
+              t0 -= sg2[k] * hw * uwi;
+              t1 -= sg2[k + 1] * hw * uwi;
+              Tz[(int64_t)k * NP + i] = t0;
+              Tz[(int64_t)(k + 1) * NP + i] = t1;
+            }
+          }
+    };
+    if (warp == 0) run(MTileMap<0>{}); else run(MTileMap<1>{});
+  } else
+#endif
   {
     const int ti = j / TJ, tj = j % TJ;
     double acc[TR][TC];
@@ -991,7 +1079,7 @@ int launch_tvec(cudaStream_t st, int N, int nz, const int32_t *mloc, const doubl
                 double *ws, int32_t *flags, DevCounters *ctr, double orthtol, int maxgroup, const FusedApplyArgs &aa,
                 double *Wg) {
   const size_t smem0 = sizeof(double) * 17 * NP;
-  const size_t smem = sizeof(double) * (NP * (NP + (FUSE ? 4 : 2)) + 17 * NP + (FUSE ? FusedApply<NP>::SMEM_DOUBLES : 0));
+  const size_t smem = sizeof(double) * (NP * (NP + 4) + 17 * NP + (FUSE ? FusedApply<NP>::SMEM_DOUBLES : 0));
   { int rc_ = oak_func_smem(k_tvec<NP, FUSE, 0>, (size_t)((int)smem)); if (rc_) return rc_; }
   { int rc_ = oak_func_smem(k_tvec<NP, false, 1>, (size_t)((int)smem0)); if (rc_) return rc_; }
   { int rc_ = oak_func_smem(k_tvec<NP, FUSE, 2>, (size_t)((int)smem)); if (rc_) return rc_; }

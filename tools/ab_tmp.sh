@@ -1,2 +1,7 @@
-timeout 900 python bench.py --config c5 --steps 3 --warmup 3 > gpurun_out/r2p_c5.json 2> gpurun_out/r2p_c5.err; echo "c5 exit $?"; tail -3 gpurun_out/r2p_c5.err; cut -c1-1500 gpurun_out/r2p_c5.json
-timeout 900 python bench.py --config c4 --max-slabs 2 --warmup 2 > gpurun_out/r2p_c4.json 2> gpurun_out/r2p_c4.err; echo "c4 exit $?"; tail -3 gpurun_out/r2p_c4.err; cut -c1-2500 gpurun_out/r2p_c4.json
+small="--nx 300 --ny 300 --nz 30 --nobs 90000 --steps 3 --warmup 2 --no-cpu --no-e2e"
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --no-header -p no:cacheprovider 2>&1 | tail -3
+python bench.py $small 2> gpurun_out/ab.err | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('value %.0f  ms/step %.2f' % (d['value'], d['ms_per_step']), d['roofline']['kernel_ms_per_step'], d['parity']['ok'], d['parity']['max_rel_Sa'])"
+tail -2 gpurun_out/ab.err
