@@ -167,7 +167,10 @@ struct WarpSteps {
 
 }  // namespace tw
 
-__global__ void __launch_bounds__(32, 8) k_tridiag_warp(int N, int nz, const int32_t *__restrict__ mloc,
+#ifndef TRIW_MINB
+#define TRIW_MINB 8
+#endif
+__global__ void __launch_bounds__(32, TRIW_MINB) k_tridiag_warp(int N, int nz, const int32_t *__restrict__ mloc,
                                                          const double *__restrict__ G, double *__restrict__ V,
                                                          double *__restrict__ ws) {
   constexpr int NP = 64;
