@@ -62,6 +62,9 @@ def parse():
     ap.add_argument("--phases", type=int, default=0, help="pipeline phases for N>1 (0: 1 with the fused gather, 4 with --nccl-gather)")
     ap.add_argument("--peer-mode", type=int, default=1, help="fused gather: 1 = copy engines push each finished batch, 0 = stores of the apply kernel")
     ap.add_argument("--push-pieces", type=int, default=1, help="fused gather, peer mode 1: apply + push of every batch in this many pieces")
+    ap.add_argument("--gather", default="multicast", choices=["multicast", "peer"],
+                    help="N>1, fused gather: multicast = one multimem store per row, replicated by NVSwitch into every rank's "
+                         "result array (falls back to peer when unsupported); peer = one store / copy per destination")
     ap.add_argument("--push-kernel", type=int, default=1, help="fused gather: 1 = rows pushed by a small kernel on a side stream (SM stores over NVLink) instead of copy-engine copies")
     ap.add_argument("--push-ctas", type=int, default=64)
     ap.add_argument("--nccl-gather", action="store_true", help="N>1: reassemble with NCCL all-gathers instead of the fused peer stores of the apply kernel")
@@ -323,7 +326,7 @@ def main():
         h = oak_b200.Handle(local, eig_kernel=a.eig_kernel, gram_kernel=a.gram_kernel, fuse_apply=a.fuse_apply, tvec_split=a.tvec_split, apply_kernel=a.apply_kernel)
         if os.environ.get("OAK_B200_FIXED_SWEEPS"):  # kernel timing experiments only (tools/ab.py)
             h.set_option("fixed_sweeps", float(os.environ["OAK_B200_FIXED_SWEEPS"]))
-        if os.environ.get("OAK_B200_ZB"):  # pipeline experiments (tools/ab.py)
+        if os.environ.get("OAK_B200_ZB") and os.environ["OAK_B200_ZB"] != "0":  # pipeline experiments (tools/ab.py)
             h.set_option("zones_per_batch", float(os.environ["OAK_B200_ZB"]))
         for kv in os.environ.get("OAK_B200_OPTIONS", "").split(","):   # experiments: key=value,... library options
             if "=" in kv:
@@ -346,21 +349,44 @@ def main():
     d, plan, h = phases[0], phases[0]["plan"], phases[0]["h"]
     n_loc = sum(p["plan"].r1 - p["plan"].r0 for p in phases)
     z_rank = sum(p["plan"].z1 - p["plan"].z0 for p in phases)
-    Sa_full, peer, fused_note = None, None, None
+    Sa_full, peer, fused_note, use_mc = None, None, None, False
     if fused:
         # fused all-gather: every finished batch of this rank goes straight into the result arrays of all ranks
         # (CUDA-IPC mappings over NVLink).  The set-up is collective: if ANY rank cannot map its peers, all ranks
         # fall back together to the NCCL all-gather (same kernels otherwise), so nobody waits in a collective alone.
-        from oak_b200.dist import PeerResult
+        from oak_b200.dist import PeerResult, MulticastResult
         err = None
-        try:
+        use_mc = False
+        if a.gather == "multicast":
+            # collective attempt: all ranks succeed or all fall back to the peer flavour
+            try:
+                mcres = MulticastResult(dist, a.N, plan.n, rank, world, dev)
+                okm = 1.0
+            except Exception as e:
+                mcres, okm, mc_err = None, 0.0, str(e)[:80]
+            okt = torch.tensor([okm], device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            use_mc = okt.item() == 1.0
+            if not use_mc and mcres is not None:
+                mcres.close()
+                mcres = None
+        if use_mc:
+            peer = mcres
+        else:
+          try:
             peer = PeerResult(dist, h, a.N, plan.n, rank, world, dev)
             err = peer.failed
-        except Exception as e:
+          except Exception as e:
             err, peer = str(e)[:80], None
         okf = torch.tensor([0.0 if err else 1.0], device=dev)
         dist.all_reduce(okf, op=dist.ReduceOp.MIN)
-        if okf.item() == 1.0:
+        if okf.item() == 1.0 and use_mc:
+            mS, mx = peer.multicast_pointers()
+            for p in phases:
+                p["h"].set_option("push_ctas", a.push_ctas)
+                p["h"].set_multicast_output(mS, mx, plan.n, p["plan"].r0)
+            Sa_full = peer.Sa
+        elif okf.item() == 1.0:
             Sp, xp = peer.destinations()
             for p in phases:
                 p["h"].set_option("peer_mode", a.peer_mode)
@@ -411,7 +437,9 @@ def main():
             peer.fence()   # readers after the writers of all ranks
         return tot
 
-    if fused and a.peer_mode == 2:
+    if fused and use_mc:
+        pass
+    if fused and a.peer_mode == 2 and not use_mc:
         fused_note = "EXPERIMENT: results not pushed to the peers (compute-only timing, not a valid bench line)"
     elif fused:   # once: the fused result equals the NCCL all-gather of the slabs, bit for bit
         step()
@@ -527,7 +555,7 @@ def main():
         out = {"metric": "local-analysis grid columns/sec", "value": value, "unit": "columns/s", "n_gpus": world,
                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": workload_name(a), "zones": nzones, "parallelism": f"zone-range x{world}" + (((", all-gather replaced by peer copies of every finished batch into every rank's result array (copy engines over NVLink, CUDA IPC mappings); " if a.peer_mode == 1 else ", all-gather fused into the apply kernel (stores into every rank's result array over NVLink, CUDA IPC); ") + str(fused_note)) if fused else (f", {nphase} pipelined phases (all-gather of phase j overlaps analysis of j+1; " + ("asynchronous, stream priorities" if use_async else "blocking calls") + ")" + (("; " + fused_note) if fused_note else "") if world > 1 else "")),
+               "config": {"workload": workload_name(a), "zones": nzones, "parallelism": f"zone-range x{world}" + (((", all-gather replaced by NVSwitch multicast: every finished batch is stored once (multimem.st, k_push_mc on a side stream) and replicated by the switch into every rank's result array (cuMulticast object over the ranks' arrays); " if use_mc else (", all-gather replaced by stores of every finished batch into every rank's result array (k_push on a side stream over NVLink, CUDA IPC mappings); " if (a.peer_mode == 1 and a.push_kernel) else (", all-gather replaced by peer copies of every finished batch into every rank's result array (copy engines over NVLink, CUDA IPC mappings); " if a.peer_mode == 1 else ", all-gather fused into the apply kernel (stores into every rank's result array over NVLink, CUDA IPC); "))) + str(fused_note)) if fused else (f", {nphase} pipelined phases (all-gather of phase j overlaps analysis of j+1; " + ("asynchronous, stream priorities" if use_async else "blocking calls") + ")" + (("; " + fused_note) if fused_note else "") if world > 1 else "")),
                           "l2": "inputs (>= 15 GB state) exceed L2; no explicit flush",
                           "mean_relevant_obs_per_column": mloc_mean, "mean_candidates_per_column": cand_mean,
                           "mean_jacobi_sweeps": sweeps_mean, "eig_kernel": a.eig_kernel,

@@ -196,6 +196,13 @@ OAKB200_API int oakb200_ipc_open(oakb200_handle *h, const unsigned char handle[6
 OAKB200_API int oakb200_ipc_close(oakb200_handle *h, void *ptr);
 OAKB200_API int oakb200_ipc_free(oakb200_handle *h, void *ptr);
 
+/* The same gather through NVSwitch multicast: Sa_mc / xa_mc are the MULTICAST addresses of the result arrays (every rank
+ * has bound its own array at the same offsets of one multicast object: cuMulticastCreate / cuMulticastAddDevice /
+ * cuMulticastBindMem, done by the caller, see oak_b200.dist.MulticastResult).  Every finished batch is then stored once
+ * with multimem.st and replicated by the switch into all ranks' arrays (1/world of the NVLink egress of the peer
+ * flavour).  NULL, NULL switches it off.  Takes precedence over oakb200_set_peer_outputs. */
+OAKB200_API int oakb200_set_multicast_output(oakb200_handle *h, double *Sa_mc, double *xa_mc, int64_t ld, int64_t row0);
+
 /* Table of the tabulated anamorphosis (type 3): AnamTrans%anam(v)%transform, K x 2 column-major HOST array,
  * column 1 = physical values, column 2 = transformed values (assimilation.F90:4539-4567, interp1
  * anamorphosis.F90:304-339 incl. its clamping rule).  One table for the whole state vector.  K = 0 clears it. */

@@ -58,6 +58,7 @@ SIGNATURES = {
     "oakb200_set_anamorphosis_vars": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                               C.c_void_p]),
     "oakb200_set_peer_outputs": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
+    "oakb200_set_multicast_output": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
     "oakb200_ipc_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
     "oakb200_ipc_open": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     "oakb200_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -282,6 +282,12 @@ class Handle:
         arr_x = (C.c_void_p * max(k, 1))(*[C.c_void_p(p) for p in xa_ptrs])
         _check(self._L.oakb200_set_peer_outputs(self._h, k, arr_S, arr_x, int(ld), int(row0)))
 
+    def set_multicast_output(self, Sa_mc, xa_mc, ld, row0):
+        """Fused gather through NVSwitch multicast (oakb200_set_multicast_output): multicast addresses (ints) of the
+        (N, n) member-major result array and of the mean vector; rows of this rank start at row0.  None switches off."""
+        _check(self._L.oakb200_set_multicast_output(self._h, C.c_void_p(Sa_mc) if Sa_mc else None,
+                                                    C.c_void_p(xa_mc) if xa_mc else None, int(ld), int(row0)))
+
     def ipc_alloc(self, nbytes):
         """Device buffer other processes can map: returns (pointer, 64-byte handle)."""
         ptr = C.c_void_p()

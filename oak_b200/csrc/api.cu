@@ -94,7 +94,7 @@ struct Slot {
   cudaStream_t cst = nullptr;  // copy-engine pushes of finished batches to the peers (peer_mode 1)
   bool cst_used = false;
   cudaStream_t qst = nullptr;  // option tql_side: k_tql on a high-priority stream of its own
-  cudaEvent_t qev[2] = {};
+  cudaEvent_t qev[4] = {};
   DevBuf Wv;                   // option tvec_split: eigenvectors of T between the two halves of k_tvec
   DevBuf G, T, c, ampl, tri;   // batch workspace (tri: d, e, tau, lambda, flags of the tridiagonal route)
   DevBuf S, xf, xa;            // host-streaming chunk buffers
@@ -127,6 +127,8 @@ struct oakb200_handle {
   DevBuf d_rowvar, d_vdesc, d_vtab;   // per-variable transforms (oakb200_set_anamorphosis_vars)
   int anam_nvar = 0; int64_t anam_rows = 0;
   PeerOut peers{};            // fused all-gather destinations (oakb200_set_peer_outputs); n = 0: none
+  double *mc_Sa = nullptr, *mc_xa = nullptr;   // multicast addresses of the result arrays (oakb200_set_multicast_output)
+  int64_t mc_ld = 0, mc_row0 = 0;
   cudaStream_t pstream[OAKB200_MAX_PEERS] = {};  // one copy stream per destination (created on first use)
   cudaEvent_t pev[OAKB200_MAX_PEERS] = {};
   int push_pieces = 1;        // peer_mode 1: the apply of a batch is launched in this many pieces, each pushed as soon as it is done
@@ -298,6 +300,44 @@ __global__ void __launch_bounds__(256) k_push(PeerOut P, const double *__restric
   }
 }
 
+// Fused gather, NVSwitch-multicast flavour (oakb200_set_multicast_output): the result arrays of all ranks are bound to one
+// multicast object (cuMulticastCreate / cuMulticastBindMem, set up by the caller: oak_b200.dist.MulticastResult); a
+// 16-byte multimem.st to the multicast address is replicated BY THE SWITCH into every rank's array, so a rank sends its
+// slab once (1.9 GB per C3 step at 8 GPUs) instead of once per peer (13.4 GB).
+#ifndef OAK_CUEMU
+__device__ __forceinline__ void mc_store16(double *p, double2 v) {
+  const float4 f = *reinterpret_cast<const float4 *>(&v);
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w) : "memory");
+}
+__device__ __forceinline__ void mc_store8(double *p, double v) {
+  asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+#else
+__device__ __forceinline__ void mc_store16(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
+__device__ __forceinline__ void mc_store8(double *p, double v) { *p = v; }
+#endif
+__global__ void __launch_bounds__(256) k_push_mc(double *__restrict__ Smc, double *__restrict__ xmc, int64_t ld,
+                                                 const double *__restrict__ Sa, int64_t ldSa,
+                                                 const double *__restrict__ xa, int64_t r0, int64_t g0, int64_t L, int N,
+                                                 int vec) {
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  if (vec) {
+    const int64_t LV = L >> 1, total = LV * (N + 1);
+    for (int64_t i = tid; i < total; i += nth) {
+      const int64_t k = i / LV, v = i - k * LV;
+      if (k < N) mc_store16(Smc + g0 + 2 * v + ld * k, *reinterpret_cast<const double2 *>(Sa + r0 + 2 * v + ldSa * k));
+      else mc_store16(xmc + g0 + 2 * v, *reinterpret_cast<const double2 *>(xa + r0 + 2 * v));
+    }
+  } else {
+    const int64_t total = L * (N + 1);
+    for (int64_t i = tid; i < total; i += nth) {
+      const int64_t k = i / L, v = i - k * L;
+      if (k < N) mc_store8(Smc + g0 + v + ld * k, Sa[r0 + v + ldSa * k]);
+      else mc_store8(xmc + g0 + v, xa[r0 + v]);
+    }
+  }
+}
+
 struct ProfAcc { double gram = 0, eig = 0, apply = 0, tridiag = 0, tql = 0, tvec = 0; };
 
 // Runs zones [z0, z1) on slot s. The state buffers hold rows starting at global row `rowbase`.
@@ -336,7 +376,7 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
       // ... and only while the factored form is the cheaper one (4 nr N^2 against 2 N^3 + 2 nr N^2: zones of at most N rows)
       const bool fuse = h->fuse_apply && !(use_peers && h->peer_mode == 0) && h->max_zone_rows <= NP;
       const FusedApplyArgs fa{zg.zstart + b0, rowbase, xf, Sf, xa, Sa, ldS, ldSa};
-      const TqlSide tside{s.qst, s.qev[0], s.qev[1]};
+      const TqlSide tside{s.qst, s.qev[0], s.qev[1], s.qev[2], s.qev[3]};
       if ((rc = oak_launch_eig_tridiag(s.st, N, NP, nz, mloc + b0, s.G.as<double>(), s.c.as<double>(),
                                        s.T.as<double>(), s.ampl.as<double>(), s.tri.p, &flags, ctr,
                                        prof ? &s.ev[8] : nullptr, h->tri_orthtol, h->tri_maxgroup,
@@ -361,7 +401,8 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
     // peer's array (strided 2-D peer copies over NVLink, no SM involved), overlapping the kernels of the next
     // batches.  What stays exposed at the end of a call is the push of the last piece of every stream slot, so
     // "push_pieces" > 1 launches the apply of a batch in pieces and pushes each one behind it.
-    const bool push = use_peers && h->peer_mode == 1;
+    const bool mcast = h->mc_Sa != nullptr && !prof;
+    const bool push = (use_peers && h->peer_mode == 1) || mcast;
     const int npiece = push ? std::max(1, std::min(h->push_pieces, nz)) : 1;
     for (int pc = 0; pc < npiece; pc++) {
       const int o0 = (int)((int64_t)nz * pc / npiece), o1 = (int)((int64_t)nz * (pc + 1) / npiece);
@@ -379,11 +420,20 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
       if (pc > 0) *launches += 1;
       if (!push) continue;
       const PeerOut &P = h->peers;
-      const int64_t r0 = h->h_zstart[b0 + o0], r1 = h->h_zstart[b0 + o1];
+      const int64_t r0 = h->h_zstart[b0 + o0], r1 = h->h_zstart[b0 + o1];  // rows of the piece (zone prefix sums of this call)
       if (r1 > r0) {
         // one stream per destination: the copies to different peers run on different copy engines / links
         CUDA_TRY(cudaEventRecord(s.ev[11], s.st));
-        if (h->push_kernel) {
+        if (mcast) {
+          CUDA_TRY(cudaStreamWaitEvent(s.cst, s.ev[11], 0));
+          const int64_t L = r1 - r0, lr0 = r0 - rowbase, g0 = h->mc_row0 + r0;
+          const bool vec = ((L | lr0 | g0 | ldSa | h->mc_ld) & 1) == 0 && ((uintptr_t)Sa & 15) == 0 && ((uintptr_t)xa & 15) == 0 &&
+                           ((uintptr_t)h->mc_Sa & 15) == 0 && ((uintptr_t)h->mc_xa & 15) == 0;
+          k_push_mc<<<h->push_ctas, 256, 0, s.cst>>>(h->mc_Sa, h->mc_xa, h->mc_ld, Sa, ldSa, xa, lr0, g0, L, N, vec ? 1 : 0);
+          CUDA_TRY(cudaGetLastError());
+          *launches += 1;
+          s.cst_used = true;
+        } else if (h->push_kernel) {
           CUDA_TRY(cudaStreamWaitEvent(s.cst, s.ev[11], 0));
           const int64_t L = r1 - r0, lr0 = r0 - rowbase, g0 = P.row0 + r0;
           bool vec = ((L | lr0 | g0 | ldSa | P.ld) & 1) == 0 && ((uintptr_t)Sa & 15) == 0 && ((uintptr_t)xa & 15) == 0;
@@ -611,6 +661,13 @@ extern "C" OAKB200_API int oakb200_set_peer_outputs(oakb200_handle *h, int32_t n
       CUDA_TRY(cudaEventCreateWithFlags(&h->pev[d], cudaEventDisableTiming));
     }
   }
+  return 0;
+}
+
+extern "C" OAKB200_API int oakb200_set_multicast_output(oakb200_handle *h, double *Sa_mc, double *xa_mc, int64_t ld, int64_t row0) {
+  if (!h) { oak_set_error("null handle"); return OAK_ERR_ARG; }
+  if ((Sa_mc == nullptr) != (xa_mc == nullptr)) { oak_set_error("set_multicast_output: both addresses or none"); return OAK_ERR_ARG; }
+  h->mc_Sa = Sa_mc; h->mc_xa = xa_mc; h->mc_ld = ld; h->mc_row0 = row0;
   return 0;
 }
 
@@ -953,7 +1010,7 @@ extern "C" OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t
     CUDA_TRY(cudaEventRecord(h->slot[i].ev[5], h->slot[i].st));
     CUDA_TRY(cudaStreamWaitEvent(s0, h->slot[i].ev[5], 0));
   }
-  if (h->peers.n > 0 && h->peer_mode == 1) {
+  if ((h->peers.n > 0 && h->peer_mode == 1) || h->mc_Sa) {
     for (int d = 0; d < h->peers.n; d++) {
       CUDA_TRY(cudaEventRecord(h->pev[d], h->pstream[d]));
       CUDA_TRY(cudaStreamWaitEvent(s0, h->pev[d], 0));

@@ -339,7 +339,7 @@ int oak_launch_eig(cudaStream_t st, int kernel, int N, int NP, int zone0, int nz
 size_t oak_eig_tridiag_ws_bytes(int NP, int nz);
 // k_tql on a stream of its own (experiment / option "tql_side"): it is latency bound (one thread per zone), so it can
 // be given a high-priority stream whose few CTAs are placed as soon as an SM has room
-struct TqlSide { cudaStream_t qst; cudaEvent_t e0, e1; };
+struct TqlSide { cudaStream_t qst; cudaEvent_t e0, e1, e2, e3; };
 int oak_launch_eig_tridiag(cudaStream_t st, int N, int NP, int nz, const int32_t *mloc, const double *G,
                            const double *c, double *T, double *ampl, void *ws, int32_t **flags_out,
                            DevCounters *ctr, cudaEvent_t *ev /* optional: [0] after k_tridiag, [1] after k_tql */,

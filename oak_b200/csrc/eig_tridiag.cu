@@ -22,6 +22,7 @@
 // function: mixing inside a tight group changes f(A) by f' eps |T| only).  Zones where that is not enough
 // (vectors of a group nearly parallel, groups larger than TRI_MAXGROUP, residual test failed, QL not
 // converged) are flagged and recomputed by the Jacobi kernel (eig_fast.cu), which has no such cases.
+#include <algorithm>
 #include <cstdlib>
 #include "common.cuh"
 #include "tridiag_math.cuh"
@@ -34,6 +35,9 @@
 #endif
 #ifndef TRI_WARP
 #define TRI_WARP 1   // NP = 64: 1 = k_tridiag_warp (one warp per zone, lower block triangle), 0 = k_tridiag_tile
+#endif
+#ifndef EIG_HALVES
+#define EIG_HALVES 1   // 2: a batch goes through tridiag / QL / eigenvectors in two software-pipelined halves
 #endif
 #ifndef TQL_PWK
 #define TQL_PWK 1    // k_tql: 1 = square-root-free QL (Pal-Walker-Kahan), 0 = plain implicit QL
@@ -1100,6 +1104,34 @@ template <int NP>
 int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G, const double *c, double *T,
            double *ampl, double *ws, int32_t *flags, DevCounters *ctr, cudaEvent_t *ev, double orthtol, int maxgroup,
            const FusedApplyArgs *fuse, double *Wg, const TqlSide *side) {
+#if TRI_TILE && TRI_WARP
+  // Two halves of the batch, software-pipelined around the latency-bound QL kernel: while the eigenvalues of the first
+  // half are computed on the side stream, the main stream reduces the second half; the eigenvectors of the first half
+  // then overlap the QL of the second.  (The chain of a slot otherwise idles ~1.1 ms per batch inside k_tql.)
+  static const int halves = getenv("OAK_B200_EIG_HALVES") ? atoi(getenv("OAK_B200_EIG_HALVES")) : EIG_HALVES;
+  if (NP == 64 && side && !fuse && !Wg && !ev && halves == 2 && nz >= 4096) {
+    const int h1 = (nz / 2 + 31) / 32 * 32;
+    const cudaEvent_t evs[4] = {side->e0, side->e1, side->e2, side->e3};
+    for (int part = 0; part < 2; part++) {
+      const int z0 = part ? h1 : 0, n1 = part ? nz - h1 : h1;
+      k_tridiag_warp<<<n1, 32, 0, st>>>(N, n1, mloc + z0, G + (size_t)z0 * NP * NP, T + (size_t)z0 * NP * NP, ws + (size_t)z0 * 4 * NP);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaEventRecord(evs[2 * part], st));
+      CUDA_TRY(cudaStreamWaitEvent(side->qst, evs[2 * part], 0));
+      k_tql<NP><<<(n1 + 31) / 32, 32, 0, side->qst>>>(N, n1, mloc + z0, ws + (size_t)z0 * 4 * NP, flags + z0);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaEventRecord(evs[2 * part + 1], side->qst));
+    }
+    for (int part = 0; part < 2; part++) {
+      const int z0 = part ? h1 : 0, n1 = part ? nz - h1 : h1;
+      CUDA_TRY(cudaStreamWaitEvent(st, evs[2 * part + 1], 0));
+      int rc = launch_tvec<NP, false>(st, N, n1, mloc + z0, c + (size_t)z0 * NP, T + (size_t)z0 * NP * NP, ampl + (size_t)z0 * NP,
+                                      ws + (size_t)z0 * 4 * NP, flags + z0, ctr, orthtol, maxgroup, FusedApplyArgs{}, nullptr);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+#endif
 #if TRI_TILE
   static const int tri_warp = getenv("OAK_B200_TRI_WARP") ? atoi(getenv("OAK_B200_TRI_WARP")) : TRI_WARP;
   if (NP == 64 && tri_warp) k_tridiag_warp<<<nz, 32, 0, st>>>(N, nz, mloc, G, T, ws);
@@ -1112,7 +1144,16 @@ int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G,
   if (side) {
     CUDA_TRY(cudaEventRecord(side->e0, st));
     CUDA_TRY(cudaStreamWaitEvent(side->qst, side->e0, 0));
-    k_tql<NP><<<(nz + 31) / 32, 32, 0, side->qst>>>(N, nz, mloc, ws, flags);
+    {
+      // option: the batch in `tql_split` consecutive launches of the side stream (at most one 33 KB warp per SM at a
+      // time then fits beside four k_tvec CTAs instead of displacing two of them)
+      static const int split = getenv("OAK_B200_TQL_SPLIT") ? std::max(1, atoi(getenv("OAK_B200_TQL_SPLIT"))) : 1;
+      const int per = ((nz + split - 1) / split + 31) / 32 * 32;
+      for (int z0 = 0; z0 < nz; z0 += per) {
+        const int n1 = std::min(per, nz - z0);
+        k_tql<NP><<<(n1 + 31) / 32, 32, 0, side->qst>>>(N, n1, mloc + z0, ws + (size_t)z0 * 4 * NP, flags + z0);
+      }
+    }
     CUDA_TRY(cudaEventRecord(side->e1, side->qst));
     CUDA_TRY(cudaStreamWaitEvent(st, side->e1, 0));
   } else

@@ -11,7 +11,7 @@ run() {
     bench.py --gpus $N --steps 3 --warmup 3 --no-cpu --no-e2e "$@" 2>>gpurun_out/r2_mg2.err | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
-print('value %.0f columns/s  ms/step %.2f  %s  parity %s' % (d['value'], d['ms_per_step'], d['config']['parallelism'][-60:], d.get('parity', {}).get('ok')))" | tee -a $LOG
+print('value %.0f columns/s  ms/step %.2f  %s  parity %s' % (d['value'], d['ms_per_step'], d['config']['parallelism'][14:70] + ' ... ' + d['config']['parallelism'][-12:], d.get('parity', {}).get('ok')))" | tee -a $LOG
 }
 IFS=';' read -ra VARS <<< "${2:-;--push-kernel 1;--push-kernel 1 --push-ctas 16;--push-kernel 1 --push-ctas 64}"
 for v in "${VARS[@]}"; do run $v; done
