@@ -66,7 +66,7 @@ def parse():
                     help="N>1, fused gather: multicast = one multimem store per row, replicated by NVSwitch into every rank's "
                          "result array (falls back to peer when unsupported); peer = one store / copy per destination")
     ap.add_argument("--push-kernel", type=int, default=1, help="fused gather: 1 = rows pushed by a small kernel on a side stream (SM stores over NVLink) instead of copy-engine copies")
-    ap.add_argument("--push-ctas", type=int, default=64)
+    ap.add_argument("--push-ctas", type=int, default=24)
     ap.add_argument("--nccl-gather", action="store_true", help="N>1: reassemble with NCCL all-gathers instead of the fused peer stores of the apply kernel")
     return ap.parse_args()
 

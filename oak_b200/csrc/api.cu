@@ -112,7 +112,7 @@ struct oakb200_handle {
   int tvec_split = 0;         // 1: tridiagonal route, k_tvec as two kernels (eigenvectors of T | back-transformation and the rest)
   int fuse_apply = 0;         // 1: tridiagonal route, k_tvec updates the zone rows from the factored transform (no T, no k_apply)
   int push_kernel = 1;        // fused gather: 1 (default: 47.8 -> 46.1 ms per C3 step at 8 GPUs) = k_push on the slot's side stream, 0 = copy-engine copies
-  int push_ctas = 64;
+  int push_ctas = 24;         // CTAs of the push kernels (8 GPUs, multicast: 8 / 16 / 24 / 32 / 64 / 148 CTAs -> 36.7 / 36.2 / 36.2 / 36.3 / 38.4 / 40.4 ms)
   int apply_tma = 1;          // k_apply_tma (zone rows staged by 2-D tensor copies) where its conditions hold, else k_apply
   int host_register = 0;      // host-buffer entry points: 1 = page-lock the caller's pageable arrays for the duration of the call
                               // (measured on C3: registering 31 GB per call costs more than the driver's staged copies:
