@@ -19,6 +19,9 @@
 #ifndef PWK_SHORT_CHAIN
 #define PWK_SHORT_CHAIN 0   // 1: measured equal on a B200 (14.35 vs 14.26 ms per 90 k zones): the lanes of a warp wait for each other, not for the chain
 #endif
+#ifndef PWK_FLAT
+#define PWK_FLAT 1   // pwk_eigenvalues: one loop over sweeps instead of a loop nest over (l, sweeps at l), see there
+#endif
 #ifndef OAK_RCP_NEWTON
 #define OAK_RCP_NEWTON 0
 #endif
@@ -127,6 +130,29 @@ OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) {
   // [l, m] is the current unreduced block: e_m is negligible.  m is found by a scan only when a new block
   // starts; inside a block the sweep itself notices the off-diagonals it makes negligible (a scan per
   // iteration, as in dsterf, would cost as much as the sweep here).
+#if PWK_FLAT
+  // ONE loop over sweeps, l advanced inside it: the 32 zones of a warp then only wait for each other's sweep lengths,
+  // not for the zone that needs the most sweeps at every single l (a nested "for l { repeat until e_l negligible }"
+  // costs a warp sum_l max_lanes(sweeps at l) ~ 2.1 n sweeps where a lane needs ~1.9 n: 7349 -> 4706 rotation trips
+  // per warp on C3-like spectra, tools/sim_tql_divergence.py).  Per zone the operations and their order are unchanged.
+  int m = -1, l = 0, iter = 0;
+  for (;;) {
+    for (; l < n; l++, iter = 0) {
+      if (m < l) {
+        for (m = l; m < n - 1; m++) {
+          const double em = e[m * s];
+          if (em <= abstol2 || em <= eps2 * fabs(d[m * s] * d[(m + 1) * s])) break;
+        }
+      } else {
+        const double el = e[l * s];
+        if (el <= abstol2 || el <= eps2 * fabs(d[l * s] * d[(l + 1) * s])) m = l;
+      }
+      if (m != l) break;
+    }
+    if (l >= n) break;
+    {
+      if (++iter > 60) return -1;
+#else
   int m = -1;
   for (int l = 0; l < n; l++) {
     int iter = 0;
@@ -142,6 +168,7 @@ OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) {
       }
       if (m == l) break;
       if (++iter > 60) return -1;
+#endif
       const double rte = sqrt(e[l * s]);
       double p = d[l * s];
       double sigma = (d[(l + 1) * s] - p) * 0.5 * oak_rcp(rte);

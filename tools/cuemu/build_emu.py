@@ -45,6 +45,7 @@ def rewrite(text):
 
 def split_top(s):
     out, depth, cur = [], 0, ""
+    s = s.replace("->", "\x00")   # a member access is not a closing bracket
     for ch in s:
         if ch in "(<[":
             depth += 1
@@ -56,7 +57,7 @@ def split_top(s):
         else:
             cur += ch
     out.append(cur)
-    return out
+    return [c.replace("\x00", "->") for c in out]
 
 
 def build(force=False, defines=(), out=None, asan=False):

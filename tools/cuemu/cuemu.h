@@ -256,3 +256,12 @@ template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAtt
 static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof *h); memcpy(h, &p, sizeof p); return cudaSuccess; }
 static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, &h, sizeof *p); return cudaSuccess; }
 static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+// page-locked host memory: plain heap memory here (the pointer-attribute query says "unregistered")
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; void *devicePointer; void *hostPointer; };
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p) { a->type = cudaMemoryTypeUnregistered; a->device = 0; a->devicePointer = nullptr; a->hostPointer = const_cast<void *>(p); return cudaSuccess; }
+constexpr unsigned cudaHostRegisterPortable = 1, cudaHostAllocPortable = 1;
+static inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
+static inline cudaError_t cudaHostAlloc(void **p, size_t bytes, unsigned) { *p = malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
