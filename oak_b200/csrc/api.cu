@@ -113,6 +113,9 @@ struct oakb200_handle {
   int fuse_apply = 0;         // 1: tridiagonal route, k_tvec updates the zone rows from the factored transform (no T, no k_apply)
   int push_kernel = 1;        // fused gather: 1 (default: 47.8 -> 46.1 ms per C3 step at 8 GPUs) = k_push on the slot's side stream, 0 = copy-engine copies
   int push_ctas = 24;         // CTAs of the push kernels (8 GPUs, multicast: 8 / 16 / 24 / 32 / 64 / 148 CTAs -> 36.7 / 36.2 / 36.2 / 36.3 / 38.4 / 40.4 ms)
+  int ens_fuse = 1;           // oakb200_assim_ensemble[_dev], local scheme: 1 = prologue (anamorphosis, mean, anomalies) and epilogue (inflation,
+                              // saturation, Ea, inverse anamorphosis) inside the apply kernel: E read once, Ea written once (4 of 6 passes saved)
+  EnsFuse ens{};              // set for the duration of such a call
   int apply_tma = 1;          // k_apply_tma (zone rows staged by 2-D tensor copies) where its conditions hold, else k_apply
   int host_register = 0;      // host-buffer entry points: 1 = page-lock the caller's pageable arrays for the duration of the call
                               // (measured on C3: registering 31 GB per call costs more than the driver's staged copies:
@@ -415,7 +418,8 @@ int run_zones(oakb200_handle *h, Slot &s, int N, int NP, int z0, int z1, int64_t
                               s.ampl.as<double>() + (size_t)o0 * NP, xf, Sf, ldS, xa, Sa, ldSa,
                               (use_peers && h->peer_mode == 0) ? h->peers : none,
                               only_flagged ? only_flagged + o0 : nullptr, false,
-                              (h->apply_tma && h->min_zone_rows == h->max_zone_rows) ? h->max_zone_rows : 0, rows_in_buffers);
+                              (h->apply_tma && h->min_zone_rows == h->max_zone_rows) ? h->max_zone_rows : 0, rows_in_buffers,
+                              h->ens.on ? &h->ens : nullptr);
       if (rc) return rc;
       if (pc > 0) *launches += 1;
       if (!push) continue;
@@ -745,6 +749,7 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   else if (k == "localise_obs") h->localise_obs = value != 0.;
   else if (k == "host_register") h->host_register = value != 0.;
   else if (k == "apply_tma") h->apply_tma = value != 0.;
+  else if (k == "ens_fuse") h->ens_fuse = value != 0.;
   else if (k == "push_kernel") h->push_kernel = value != 0.;
   else if (k == "push_ctas") h->push_ctas = std::max(1, (int)value);
   else if (k == "apply_kernel") {
@@ -1367,8 +1372,21 @@ extern "C" OAKB200_API int oakb200_assim_ensemble_dev(oakb200_handle *h, int64_t
     return rc;
   // HE = H E + Hshift on the untransformed state (assimilation.F90:3112-3114)
   if ((rc = oak_launch_obsoper_rows(s0, m, N, h->d_rowstart.as<int32_t>(), h->d_order.as<int32_t>(), Hj, Hs, Hshift, E, ldE, h->d_HE.as<double>()))) return rc;
-  // Hxf, HSf (in place in HE) ; xf, Sf (into Ea)
+  // Hxf, HSf (in place in HE)
   if ((rc = oak_launch_mean_anom(s0, m, N, 1, AnamTab{nullptr, 0, 0, nullptr, nullptr, nullptr}, h->d_HE.as<double>(), m, h->d_Hxf.as<double>(), h->d_HE.as<double>(), m))) return rc;
+  // fused form (local scheme, matrix form of the apply): the apply kernel reads E and writes Ea, xf, xa itself
+  const bool fuse = h->ens_fuse && h->scheme != 0 && !h->fuse_apply && h->apply_kernel == 0 && n > 0;
+  if (fuse) {
+    CUDA_TRY(cudaStreamSynchronize(s0));
+    h->ens = EnsFuse{1, anamtype, at, inflation, sqrt((double)N - 1.), maxCorrection, h->d_xf.as<double>()};
+    rc = oakb200_local_analysis_dev(h, n, N, m, h->d_xf.as<double>(), h->d_Hxf.as<double>(), yo, E, ldE,
+                                    h->d_HE.as<double>(), m, Rdiag, d01, h->d_xa.as<double>(), Ea, ldEa, nullptr,
+                                    (void *)s0, stats);
+    h->ens.on = 0;
+    if (rc) return rc;
+    if (stats) stats->launches += 3;
+  } else {
+  // xf, Sf (into Ea)
   if ((rc = oak_launch_mean_anom(s0, n, N, anamtype, at, E, ldE, h->d_xf.as<double>(), Ea, ldEa))) return rc;
   CUDA_TRY(cudaStreamSynchronize(s0));
   if (h->scheme == 0)   // Assim's global branch: call analysis(xf,Hxf,yo,Sf,HSf,R,xa,Sa,amplitudes)
@@ -1381,10 +1399,11 @@ extern "C" OAKB200_API int oakb200_assim_ensemble_dev(oakb200_handle *h, int64_t
                                     (void *)s0, stats);
   if (rc) return rc;
   if ((rc = oak_launch_epilogue(s0, n, N, anamtype, at, inflation, maxCorrection, h->d_xf.as<double>(), h->d_xa.as<double>(), Ea, ldEa, Ea, ldEa))) return rc;
+  if (stats) stats->launches += 6;
+  }
   if (xf_out) CUDA_TRY(cudaMemcpyAsync(xf_out, h->d_xf.p, 8 * (size_t)n, cudaMemcpyDeviceToDevice, s0));
   if (xa_out) CUDA_TRY(cudaMemcpyAsync(xa_out, h->d_xa.p, 8 * (size_t)n, cudaMemcpyDeviceToDevice, s0));
   CUDA_TRY(cudaStreamSynchronize(s0));
-  if (stats) stats->launches += 6;
   return 0;
 }
 

@@ -72,6 +72,61 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 constexpr int RC = 32;  // rows per chunk
 
+// ---- ensemble prologue / epilogue on a staged chunk (EnsFuse, common.cuh): sS[k*lds + r], r < rc rows, k < N members.
+// Same operations, in the same order, as k_mean_anom / k_epilogue (ensemble.cu), which remain the unfused form.
+// All threads of the block call both (they contain block barriers).
+template <int NT>
+__device__ __forceinline__ void ens_prologue(const EnsFuse &F, double *sS, int lds, int N, int rc, int64_t grow0,
+                                             double *s_mean, int tid) {
+  if (F.anamtype != 1) {
+    for (int idx = tid; idx < N * rc; idx += NT) {
+      const int k = idx / rc, r = idx - k * rc;
+      sS[k * lds + r] = oak_anam_row(F.anamtype, true, F.at, grow0 + r, sS[k * lds + r]);
+    }
+    __syncthreads();
+  }
+  if (tid < rc) {
+    double s = 0.;
+    for (int k = 0; k < N; k++) s = __dadd_rn(s, sS[k * lds + tid]);   // sum(Sf,2)/N  assimilation.F90:3127
+    s = s / (double)N;
+    s_mean[tid] = s;
+    F.xf_out[grow0 + tid] = s;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < N * rc; idx += NT) {
+    const int k = idx / rc, r = idx - k * rc;
+    sS[k * lds + r] = __ddiv_rn(__dsub_rn(sS[k * lds + r], s_mean[r]), F.scaling);   // :3130
+  }
+  __syncthreads();
+}
+
+// s_x[r]: analysed mean of row r on entry (xf + Sf ampl); on exit the mean of the back-transformed members
+template <int NT>
+__device__ __forceinline__ void ens_epilogue(const EnsFuse &F, double *sS, int lds, int N, int rc, int64_t grow0,
+                                             const double *s_mean, double *s_x, int tid) {
+  if (tid < rc && F.maxCorr) {   // the two `where` statements of assimilation.F90:3311-3312
+    double x = s_x[tid];
+    const double mc = F.maxCorr[grow0 + tid], f = s_mean[tid];
+    if (__dsub_rn(x, mc) > f) x = __dadd_rn(f, mc);
+    if (x < __dsub_rn(f, mc)) x = __dsub_rn(f, mc);
+    s_x[tid] = x;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < N * rc; idx += NT) {
+    const int k = idx / rc, r = idx - k * rc;
+    double s = sS[k * lds + r];
+    if (F.inflation != 1.) s = __dmul_rn(s, F.inflation);                                     // :3301-3304
+    sS[k * lds + r] = oak_anam_row(F.anamtype, false, F.at, grow0 + r, __dadd_rn(s_x[r], __dmul_rn(s, F.scaling)));  // :3318-3326
+  }
+  __syncthreads();
+  if (tid < rc) {
+    double sum = 0.;
+    for (int k = 0; k < N; k++) sum = __dadd_rn(sum, sS[k * lds + tid]);
+    s_x[tid] = sum / (double)N;   // xa = sum(Ea,2)/N of the back-transformed ensemble (:3343-3349)
+  }
+  __syncthreads();
+}
+
 template <int NP>
 __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, int64_t rowbase,
                                                const int32_t *__restrict__ mloc,
@@ -79,13 +134,14 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
                                                const double *__restrict__ xf, const double *Sf, int64_t ldS,
                                                double *__restrict__ xa, double *Sa, int64_t ldSa,
                                                const PeerOut P, const int32_t *__restrict__ only_flagged,
-                                               int64_t tstride, int astride) {
+                                               int64_t tstride, int astride, const EnsFuse F) {
   extern __shared__ __align__(128) double sm[];
   double *sT = sm;                   // [NP][NP] row-major: sT[k*NP + k']
   double *sS = sm + NP * NP;         // [NP][RC+?] member-major chunk: sS[k*LDS + r]
   constexpr int LDS = RC + 2;
   double *s_ampl = sS + NP * LDS;    // [NP]
   __shared__ __align__(8) uint64_t bar;
+  __shared__ double s_mean[RC], s_x[RC];   // ensemble form (F.on): forecast mean and analysed mean of the chunk's rows
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int zl = blockIdx.x;
@@ -97,7 +153,7 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
   if (only_flagged && analysed && only_flagged[zl] == 0) return;  // already updated by the fused transform kernel
   const int64_t ip = P.row0 + zg.zstart[zone];  // first row of the zone in the peers' (global) arrays
 
-  if (!analysed) {
+  if (!analysed && !F.on) {
     // zone keeps the forecast
     for (int r = tid; r < nrow; r += 128) {
       const double v = xf[i1 + r];
@@ -120,12 +176,13 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
     mbar_fence_init();
   }
   __syncthreads();
-  if (tid == 0) {
+  if (tid == 0 && analysed) {
     constexpr uint32_t bytes = NP * NP * sizeof(double);
     mbar_expect_tx(&bar, bytes);
     bulk_g2s(sT, T + (int64_t)zl * tstride, bytes, &bar);
   }
-  if (tid < NP) s_ampl[tid] = ampl[(int64_t)zl * astride + tid];
+  if (tid < NP && analysed) s_ampl[tid] = ampl[(int64_t)zl * astride + tid];
+  const int64_t grow = rowbase + i1;   // global (zone-permuted) index of the zone's first row: per-row arrays of the ensemble form
 
   // thread tile of the chunk product: rows 4*ty.., columns 2*tx + 32*b (+1)
   const int ty = tid >> 4, tx = tid & 15;  // 8 x 16
@@ -141,6 +198,11 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
       sS[k * LDS + lane] = v;
     }
     __syncthreads();
+    if (F.on) ens_prologue<128>(F, sS, LDS, N, rc, grow + r0, s_mean, tid);
+    if (!analysed) {   // ensemble form only: the zone keeps the forecast (Sa = Sf, xa = xf) and still goes through the epilogue
+      if (tid < rc) s_x[tid] = s_mean[tid];
+      __syncthreads();
+    } else {
     if (!t_ready) { mbar_wait(&bar, 0); t_ready = true; }
 
     double acc[4][2 * CB];
@@ -173,6 +235,7 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
       for (int a = 0; a < 4; a++) {
         const int r = 4 * ty + a;
         if (r < rc) {
+          if (F.on) { s_x[r] = s_mean[r] + dm[a]; continue; }
           const double v = xf[i1 + r0 + r] + dm[a];
           xa[i1 + r0 + r] = v;
           for (int dd = 0; dd < P.n; dd++) P.xa[dd][ip + r0 + r] = v;
@@ -189,6 +252,15 @@ __global__ void __launch_bounds__(128) k_apply(int N, ZoneGeom zg, int zone0, in
         *reinterpret_cast<double2 *>(sS + kk * LDS + 4 * ty + 2) = make_double2(acc[2][2 * b + e], acc[3][2 * b + e]);
       }
     __syncthreads();
+    }  // analysed
+    if (F.on) {
+      ens_epilogue<128>(F, sS, LDS, N, rc, grow + r0, s_mean, s_x, tid);
+      if (tid < rc) {
+        const double v = s_x[tid];
+        xa[i1 + r0 + tid] = v;
+        for (int dd = 0; dd < P.n; dd++) P.xa[dd][ip + r0 + tid] = v;
+      }
+    }
     for (int k = warp; k < N; k += 4)
       if (lane < rc) {
         const double v = sS[k * LDS + lane];
@@ -216,12 +288,13 @@ __global__ void __launch_bounds__(128) k_apply_tma(int N, int nrow, ZoneGeom zg,
                                                    const double *__restrict__ ampl, const double *__restrict__ xf,
                                                    double *__restrict__ xa, const __grid_constant__ CUtensorMap mapS,
                                                    const __grid_constant__ CUtensorMap mapA, int in_place,
-                                                   const int32_t *__restrict__ only_flagged) {
+                                                   const int32_t *__restrict__ only_flagged, const EnsFuse F) {
   extern __shared__ __align__(128) double sm[];
   double *sT = sm;                   // [NP][NP] row-major
   double *sS = sm + NP * NP;         // [N][nrow] dense box (+ slack for the tile reads of rows >= nrow)
   double *s_ampl = sS + NP * RC + 8;
   __shared__ __align__(8) uint64_t bar;
+  __shared__ double s_mean[RC], s_x[RC];   // ensemble form (F.on), as in k_apply
 
   const int tid = threadIdx.x;
   const int zl = blockIdx.x;
@@ -229,7 +302,7 @@ __global__ void __launch_bounds__(128) k_apply_tma(int N, int nrow, ZoneGeom zg,
   const int64_t i1 = zg.zstart[zone] - rowbase;
   const bool analysed = mloc[zone] != 0;
   if (only_flagged && analysed && only_flagged[zl] == 0) return;
-  if (!analysed && in_place) {        // the zone keeps the forecast: only the mean has to be copied
+  if (!analysed && in_place && !F.on) {        // the zone keeps the forecast: only the mean has to be copied
     for (int r = tid; r < nrow; r += 128) xa[i1 + r] = xf[i1 + r];
     return;
   }
@@ -249,6 +322,8 @@ __global__ void __launch_bounds__(128) k_apply_tma(int N, int nrow, ZoneGeom zg,
   mbar_wait(&bar, 0);
   const int ty = tid >> 4, tx = tid & 15;  // 8 x 16: rows 4 ty .., columns 2 tx + 32 b (+1)
   constexpr int CB = NP / 32;
+  const int64_t grow = rowbase + i1;
+  if (F.on) ens_prologue<128>(F, sS, nrow, N, nrow, grow, s_mean, tid);
   if (analysed) {
     double acc[4][2 * CB];
     double dm[4] = {0., 0., 0., 0.};
@@ -278,7 +353,10 @@ __global__ void __launch_bounds__(128) k_apply_tma(int N, int nrow, ZoneGeom zg,
 #pragma unroll
       for (int a = 0; a < 4; a++) {
         const int r = 4 * ty + a;
-        if (r < nrow) xa[i1 + r] = xf[i1 + r] + dm[a];
+        if (r < nrow) {
+          if (F.on) s_x[r] = s_mean[r] + dm[a];
+          else xa[i1 + r] = xf[i1 + r] + dm[a];
+        }
       }
     }
     __syncthreads();                  // all reads of the box done: it now receives the results
@@ -293,8 +371,15 @@ __global__ void __launch_bounds__(128) k_apply_tma(int N, int nrow, ZoneGeom zg,
             if (4 * ty + a < nrow) sS[kk * nrow + 4 * ty + a] = acc[a][2 * b + e];
         }
       }
+  } else if (F.on) {
+    if (tid < nrow) s_x[tid] = s_mean[tid];
   } else {
     for (int r = tid; r < nrow; r += 128) xa[i1 + r] = xf[i1 + r];
+  }
+  if (F.on) {
+    __syncthreads();                  // results / s_x of all threads
+    ens_epilogue<128>(F, sS, nrow, N, nrow, grow, s_mean, s_x, tid);
+    if (tid < nrow) xa[i1 + tid] = s_x[tid];
   }
   fence_proxy_async();                // generic-proxy writes of the box before the async-proxy (TMA) read
   __syncthreads();
@@ -336,7 +421,7 @@ template <int NP>
 int launch_tma(cudaStream_t st, int N, int nrow, int64_t rows_in_buffers, const ZoneGeom &zg, int zone0, int nz,
                int64_t rowbase, const int32_t *mloc, const double *T, const double *ampl, const double *xf,
                const double *Sf, int64_t ldS, double *xa, double *Sa, int64_t ldSa, const int32_t *only_flagged,
-               bool *done) {
+               const EnsFuse &ens, bool *done) {
   *done = false;
   CUtensorMap mS, mA;
   if (!make_state_map(&mS, Sf, rows_in_buffers, ldS, N, nrow) || !make_state_map(&mA, Sa, rows_in_buffers, ldSa, N, nrow))
@@ -344,7 +429,7 @@ int launch_tma(cudaStream_t st, int N, int nrow, int64_t rows_in_buffers, const 
   const size_t smem = sizeof(double) * (NP * NP + NP * RC + 8 + NP);
   { int rc_ = oak_func_smem(k_apply_tma<NP>, smem); if (rc_) return rc_; }
   k_apply_tma<NP><<<nz, 128, smem, st>>>(N, nrow, zg, zone0, rowbase, mloc, T, ampl, xf, xa, mS, mA, Sa == Sf ? 1 : 0,
-                                        only_flagged);
+                                        only_flagged, ens);
   CUDA_TRY(cudaGetLastError());
   *done = true;
   return 0;
@@ -354,11 +439,12 @@ int launch_tma(cudaStream_t st, int N, int nrow, int64_t rows_in_buffers, const 
 template <int NP>
 int launch(cudaStream_t st, int N, const ZoneGeom &zg, int zone0, int nz, int64_t rowbase, const int32_t *mloc,
            const double *T, const double *ampl, const double *xf, const double *Sf, int64_t ldS, double *xa,
-           double *Sa, int64_t ldSa, const PeerOut &peers, const int32_t *only_flagged, bool shared_transform) {
+           double *Sa, int64_t ldSa, const PeerOut &peers, const int32_t *only_flagged, bool shared_transform,
+           const EnsFuse &ens) {
   const size_t smem = sizeof(double) * (NP * NP + NP * (RC + 2) + NP);
   { int rc_ = oak_func_smem(k_apply<NP>, (size_t)((int)smem)); if (rc_) return rc_; }
   k_apply<NP><<<nz, 128, smem, st>>>(N, zg, zone0, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged,
-                                       shared_transform ? 0 : (int64_t)NP * NP, shared_transform ? 0 : NP);
+                                       shared_transform ? 0 : (int64_t)NP * NP, shared_transform ? 0 : NP, ens);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -368,8 +454,12 @@ int launch(cudaStream_t st, int N, const ZoneGeom &zg, int zone0, int nz, int64_
 int oak_launch_apply(cudaStream_t st, int N, int NP, const ZoneGeom &zg, int zone0, int nz, int64_t rowbase,
                      const int32_t *mloc, const double *T, const double *ampl, const double *xf,
                      const double *Sf, int64_t ldS, double *xa, double *Sa, int64_t ldSa, const PeerOut &peers,
-                     const int32_t *only_flagged, bool shared_transform, int uniform_rows, int64_t rows_in_buffers) {
+                     const int32_t *only_flagged, bool shared_transform, int uniform_rows, int64_t rows_in_buffers,
+                     const EnsFuse *ens_in) {
   if (nz <= 0) return 0;
+  EnsFuse ens{};
+  if (ens_in) ens = *ens_in;
+  if (ens.on && (shared_transform || !mloc)) { oak_set_error("apply: the ensemble form is for the local scheme"); return OAK_ERR_ARG; }
 #ifndef OAK_CUEMU
   // TMA-staged state (k_apply_tma) where a zone is one box: equal, even zone sizes <= 32, even leading dimensions,
   // 16-byte aligned arrays, local scheme, no stores to peers from the kernel
@@ -377,15 +467,15 @@ int oak_launch_apply(cudaStream_t st, int N, int NP, const ZoneGeom &zg, int zon
       (ldS & 1) == 0 && (ldSa & 1) == 0 && ((uintptr_t)Sf & 15) == 0 && ((uintptr_t)Sa & 15) == 0 && N >= 2 &&
       rows_in_buffers > 0 && rows_in_buffers < 0x7fffffffll && (NP == 32 || NP == 64)) {
     bool done = false;
-    int rc = NP == 64 ? launch_tma<64>(st, N, uniform_rows, rows_in_buffers, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, only_flagged, &done)
-                      : launch_tma<32>(st, N, uniform_rows, rows_in_buffers, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, only_flagged, &done);
+    int rc = NP == 64 ? launch_tma<64>(st, N, uniform_rows, rows_in_buffers, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, only_flagged, ens, &done)
+                      : launch_tma<32>(st, N, uniform_rows, rows_in_buffers, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, only_flagged, ens, &done);
     if (rc || done) return rc;
   }
 #endif
   switch (NP) {
-    case 32: return launch<32>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged, shared_transform);
-    case 64: return launch<64>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged, shared_transform);
-    case 128: return launch<128>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged, shared_transform);
+    case 32: return launch<32>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged, shared_transform, ens);
+    case 64: return launch<64>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged, shared_transform, ens);
+    case 128: return launch<128>(st, N, zg, zone0, nz, rowbase, mloc, T, ampl, xf, Sf, ldS, xa, Sa, ldSa, peers, only_flagged, shared_transform, ens);
   }
   oak_set_error("apply: unsupported padded ensemble size %d", NP);
   return OAK_ERR_UNSUPPORTED;

@@ -296,6 +296,71 @@ struct AnamTab {
   const double *vtab;
 };
 
+// interp1 (anamorphosis.F90:304-339): first bracket x_k <= xi < x_k+1, (1-alpha) y_k + alpha y_k+1; without a
+// bracket y_1 (xi < x_1) or y_K, and `out`.  A strictly increasing x has at most one bracket, found by bisection;
+// otherwise the reference's linear scan.  Explicitly rounded operations (no FMA contraction): same bits as the
+// Fortran expression evaluated in IEEE arithmetic.
+__device__ __forceinline__ double oak_interp1(int K, const double *x, const double *y, bool monotone, double xi, bool &out) {
+  int k = -1;
+  if (monotone) {
+    if (xi >= x[0] && xi < x[K - 1]) {
+      int lo = 0, hi = K - 1;  // x[lo] <= xi < x[hi]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (x[mid] <= xi) lo = mid; else hi = mid;
+      }
+      k = lo;
+    }
+  } else {
+    for (int kp = 0; kp < K - 1; kp++)
+      if (x[kp] <= xi && xi < x[kp + 1]) { k = kp; break; }
+  }
+  out = (k == -1);
+  if (k != -1) {
+    const double alpha = __ddiv_rn(__dsub_rn(xi, x[k]), __dsub_rn(x[k + 1], x[k]));
+    return __dadd_rn(__dmul_rn(__dsub_rn(1., alpha), y[k]), __dmul_rn(alpha, y[k + 1]));
+  }
+  return (xi < x[0]) ? y[0] : y[K - 1];
+}
+
+// anamtransform for one element (assimilation.F90:4516-4576): 1 identity, 2 log/exp, 3 tabulated.  An
+// extrapolated tabulated value is replaced by the first / last entry of the table's INPUT-side column,
+// chosen by comparing the already interpolated value with transform(1,ti) (:4560-4567, reproduced as is).
+__device__ __forceinline__ double oak_anam(int type, bool forward, const AnamTab &at, double x) {
+  if (type == 2) return forward ? log(x) : exp(x);
+  if (type == 3) {
+    const double *ti = forward ? at.tab : at.tab + at.K, *tj = forward ? at.tab + at.K : at.tab;
+    bool out;
+    double v = oak_interp1(at.K, ti, tj, at.monotone != 0, x, out);
+    if (out) v = (v < ti[0]) ? ti[0] : ti[at.K - 1];
+    return v;
+  }
+  return x;
+}
+
+// anamtype 0: the transform of the row's own variable
+__device__ __forceinline__ double oak_anam_row(int type, bool forward, const AnamTab &at, int64_t row, double x) {
+  if (type != 0) return oak_anam(type, forward, at, x);
+  const int32_t *d = at.vdesc + 4 * at.rowvar[row];
+  AnamTab sub = at;
+  sub.tab = at.vtab + d[2]; sub.K = d[1]; sub.monotone = d[3];
+  return oak_anam(d[0], forward, sub, x);
+}
+
+// Ensemble branch of Assim folded into the apply kernel (oakb200_assim_ensemble[_dev], option "ens_fuse"): the array
+// the kernel reads holds the raw ensemble E; per staged chunk of rows it does the prologue (forward anamorphosis,
+// xf = mean, Sf = (E - xf)/scaling; assimilation.F90:3123-3131) before the product and the epilogue (inflation,
+// saturation of the correction, Ea = xa + scaling Sa, inverse anamorphosis, xa = mean(Ea); :3301-3349) after it,
+// with the operations and summation order of k_mean_anom / k_epilogue, so E is read once and Ea written once.
+struct EnsFuse {
+  int32_t on;              // 0: plain apply (the array holds anomalies)
+  int32_t anamtype;
+  AnamTab at;
+  double inflation, scaling;
+  const double *maxCorr;   // [n] or NULL
+  double *xf_out;          // [n] mean of the (transformed) forecast ensemble
+};
+
 // destinations of the fused all-gather (oakb200_set_peer_outputs), passed by value to k_apply
 struct PeerOut {
   double *Sa[OAKB200_MAX_PEERS];
@@ -354,7 +419,8 @@ int oak_launch_apply(cudaStream_t st, int N, int NP, const ZoneGeom &zg, int zon
                      const int32_t *only_flagged = nullptr /* batch-local flags: analysed zones with flag 0 are skipped */,
                      bool shared_transform = false /* global scheme: every block of rows uses T[0], ampl[0]; mloc may be NULL */,
                      int uniform_rows = 0 /* > 0: every zone has this many rows (enables the TMA-staged kernel) */,
-                     int64_t rows_in_buffers = 0 /* rows held in Sf / Sa from their first element (tensor-map extent) */);
+                     int64_t rows_in_buffers = 0 /* rows held in Sf / Sa from their first element (tensor-map extent) */,
+                     const EnsFuse *ens = nullptr /* ensemble prologue / epilogue inside the kernel (Sf = raw ensemble) */);
 int oak_launch_apply_mma(cudaStream_t st, int N, int NP, const ZoneGeom &zg, int zone0, int nz, int64_t rowbase,
                          const int32_t *mloc, const double *T, const double *ampl, const double *xf, const double *Sf,
                          int64_t ldS, double *xa, double *Sa, int64_t ldSa, const int32_t *only_flagged,

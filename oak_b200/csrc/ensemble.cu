@@ -11,56 +11,7 @@
 
 namespace {
 
-// interp1 (anamorphosis.F90:304-339): first bracket x_k <= xi < x_k+1, (1-alpha) y_k + alpha y_k+1; without a
-// bracket y_1 (xi < x_1) or y_K, and `out`.  A strictly increasing x has at most one bracket, found by bisection;
-// otherwise the reference's linear scan.  Explicitly rounded operations (no FMA contraction): same bits as the
-// Fortran expression evaluated in IEEE arithmetic.
-__device__ __forceinline__ double oak_interp1(int K, const double *x, const double *y, bool monotone, double xi, bool &out) {
-  int k = -1;
-  if (monotone) {
-    if (xi >= x[0] && xi < x[K - 1]) {
-      int lo = 0, hi = K - 1;  // x[lo] <= xi < x[hi]
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (x[mid] <= xi) lo = mid; else hi = mid;
-      }
-      k = lo;
-    }
-  } else {
-    for (int kp = 0; kp < K - 1; kp++)
-      if (x[kp] <= xi && xi < x[kp + 1]) { k = kp; break; }
-  }
-  out = (k == -1);
-  if (k != -1) {
-    const double alpha = __ddiv_rn(__dsub_rn(xi, x[k]), __dsub_rn(x[k + 1], x[k]));
-    return __dadd_rn(__dmul_rn(__dsub_rn(1., alpha), y[k]), __dmul_rn(alpha, y[k + 1]));
-  }
-  return (xi < x[0]) ? y[0] : y[K - 1];
-}
-
-// anamtransform for one element (assimilation.F90:4516-4576): 1 identity, 2 log/exp, 3 tabulated.  An
-// extrapolated tabulated value is replaced by the first / last entry of the table's INPUT-side column,
-// chosen by comparing the already interpolated value with transform(1,ti) (:4560-4567, reproduced as is).
-__device__ __forceinline__ double oak_anam(int type, bool forward, const AnamTab &at, double x) {
-  if (type == 2) return forward ? log(x) : exp(x);
-  if (type == 3) {
-    const double *ti = forward ? at.tab : at.tab + at.K, *tj = forward ? at.tab + at.K : at.tab;
-    bool out;
-    double v = oak_interp1(at.K, ti, tj, at.monotone != 0, x, out);
-    if (out) v = (v < ti[0]) ? ti[0] : ti[at.K - 1];
-    return v;
-  }
-  return x;
-}
-
-// anamtype 0: the transform of the row's own variable
-__device__ __forceinline__ double oak_anam_row(int type, bool forward, const AnamTab &at, int64_t row, double x) {
-  if (type != 0) return oak_anam(type, forward, at, x);
-  const int32_t *d = at.vdesc + 4 * at.rowvar[row];
-  AnamTab sub = at;
-  sub.tab = at.vtab + d[2]; sub.K = d[1]; sub.monotone = d[3];
-  return oak_anam(d[0], forward, sub, x);
-}
+// oak_interp1 / oak_anam / oak_anam_row: common.cuh (shared with the fused apply kernel, apply.cu)
 
 // ---- COO -> row-sorted (stable: the entries of a row keep the caller's order, so the sum is
 // accumulated in the same order as the sequential loop of matoper_inc.F90:238-240) ----

@@ -80,3 +80,8 @@ def test_global_scheme(emu_lib):
 def test_apply_on_tensor_core_tiles(emu_lib):
     # option apply_kernel = 1 (k_apply_mma): local zones of 1..75 rows and the row blocks of the global scheme
     _run(emu_lib, "apply_on_tensor")
+
+
+def test_ensemble_prologue_and_epilogue_inside_the_apply_kernel(emu_lib):
+    # option ens_fuse: bit-identical to the three-pass form (k_mean_anom, analysis, k_epilogue) and within 1e-9 of the oracle
+    _run(emu_lib, "fused_in_the_apply")

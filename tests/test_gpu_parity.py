@@ -335,6 +335,56 @@ def test_assim_ensemble_with_inflation_anamorphosis_and_saturation(ob, handle):
     assert (np.abs(np.log(Ea).mean(axis=1) - xf) > 0.0499).any()
 
 
+@pytest.mark.parametrize("zone_rows", [3, 4, "ragged", 40])
+def test_assim_ensemble_fused_in_the_apply_kernel_equals_the_three_pass_form(ob, zone_rows):
+    # option ens_fuse (default 1): prologue (anamorphosis, mean, anomalies) and epilogue (inflation, saturation, Ea,
+    # inverse anamorphosis, mean) of assimilation.F90:3123-3131,:3301-3349 run inside k_apply / k_apply_tma on the staged
+    # rows; same operations in the same order as k_mean_anom / k_epilogue, so the results are IDENTICAL, bit for bit,
+    # to ens_fuse = 0 — for zones of odd size (k_apply), even size (k_apply_tma on the device), unequal sizes, more
+    # rows than one chunk (40 > 32), and zones without any observation (which keep the forecast but are still inflated
+    # and back-transformed).  Both are compared with the oracle as well.
+    from oak_b200 import synthetic
+    nzg = {3: 3, 4: 4, "ragged": 3, 40: 40}[zone_rows]
+    g = synthetic.Grid(10, 8, nzg)
+    N, m = 24, 60
+    rows = np.arange(g.n, dtype=np.int64)
+    E = np.exp(0.3 * synthetic.ensemble_rows(np, g, rows, N, 5)).T.copy(order="F")
+    obs = synthetic.observations(np, g, m, 5)
+    obs["ox"] = 0.45 * obs["ox"]; obs["oy"] = 0.45 * obs["oy"]       # observations in one corner: far zones have none
+    Hi, Hj, Hs = synthetic.coo_operator(g, obs)
+    Hshift = 0.01 * np.arange(m)
+    yo = 1.0 + 0.1 * synthetic.normal(np, np.arange(m, dtype=np.int64), 8, 5)
+    zx, zy = g.zone_xy(np, np.arange(g.nzones, dtype=np.int64))
+    if zone_rows == "ragged":      # merge pairs of columns: sizes 6, 3, 6, 3, ... (first element rule for the position)
+        keep = np.ones(g.nzones, bool); keep[1::3] = False
+        zs = np.where(np.roll(~keep, -1), 2 * nzg, nzg)[keep].astype(np.int32)
+        zx, zy = zx[keep], zy[keep]
+        assert zs.sum() == g.n
+    else:
+        zs = np.full(g.nzones, nzg, np.int32)
+    sel = ob.Selector(zone_x=zx, zone_y=zy, corrLen=1500.0, maxLen=3000.0, obs_x=obs["ox"], obs_y=obs["oy"], metrictype=0)
+    maxc = np.full(g.n, 0.05)
+    out = {}
+    for fuse in (0, 1):
+        h = ob.Handle(0)
+        h.set_option("ens_fuse", fuse)
+        h.set_option("scheme", 1)
+        h.configure(zs, sel)
+        *out[fuse], st = h.assim_ensemble(E, Hi, Hj, Hs, Hshift, yo, ob.DiagCovar(obs["var"]), anamtype=2,
+                                          inflation=1.05, maxCorrection=maxc)
+        assert 0 < st["zones_skipped"] < st["zones_total"]
+        out[fuse].append(st["launches"])
+        h.close()
+    assert out[1].pop() == out[0].pop() - 3     # k_mean_anom (state), k_epilogue and their pass over the state are gone
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    oo = oracle.make_obs(m, obsx=obs["ox"], obsy=obs["oy"])
+    Eo, xfo, xao = oracle.assim_ensemble(zs, dict(x=zx, y=zy), 1500.0, 3000.0, oo, E, Hi, Hj, Hs, Hshift, yo,
+                                         obs["var"], anamtype=2, inflation=1.05, maxCorrection=maxc)
+    Ea, xf, xa = out[1]
+    assert rel(xf, xfo) < 1e-14 and rel(xa, xao) < RTOL and rel(Ea, Eo) < RTOL
+
+
 def test_error_behaviour(ob):
     h = ob.Handle(0)
     with pytest.raises(ob.OakB200Error):      # analysis before configuration
