@@ -877,13 +877,44 @@ def run_c5(a, rank, world, local):
     ms = e0.elapsed_time(e1) / a.steps
     clocks = sampler.stop()
     value = g.nzones / (ms * 1e-3)
+    # the ensemble branch in its two forms, timed the same way: fused (prologue / epilogue inside the apply kernel: 2 passes over
+    # the state) and three-pass (k_mean_anom over E, analysis in place, k_epilogue over Ea: 6 passes); with the log anamorphosis
+    # of this configuration and with none.  Both forms must give identical bits.  The library's default (ens_fuse = -1)
+    # follows this measurement: fused only without anamorphosis.
+    def timed(anam, fuse):
+        h.set_option("ens_fuse", fuse)
+        f = lambda: h.assim_ensemble_dev(E, dHi, dHj, dHs, None, dyo, dvar, Ea, anamtype=anam, inflation=infl, xf_out=xf, xa_out=xa)
+        f(); f()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(a.steps):
+            f()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / a.steps, Ea.clone(), xa.clone()
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        hbm_peak = None
+    saved_bytes = 8.0 * g.n * N * 4
+    ens_fuse = {"passes_over_the_state": {"fused": 2, "three_pass": 6}, "saved_algorithmic_bytes": saved_bytes,
+                "hbm_peak_GBps": hbm_peak, "peak_source": "MEASURED_PEAKS.json (driver-written copy bandwidth)" if hbm_peak else None}
+    for name, anam in (("log_anamorphosis", 2), ("no_anamorphosis", 1)):
+        t1, E1, x1 = timed(anam, 1)
+        t0, E0, x0 = timed(anam, 0)
+        ens_fuse[name] = {"fused_ms_per_step": t1, "three_pass_ms_per_step": t0,
+                          "identical_bits": bool(torch.equal(E1, E0) and torch.equal(x1, x0)),
+                          "saved_passes_GBps": saved_bytes / ((t0 - t1) * 1e-3) / 1e9 if t0 > t1 else None}
+        del E1, E0, x1, x0
+    h.set_option("ens_fuse", -1)
+    step()
     analysed = g.nzones - st["zones_skipped"]
     mloc = st["obs_relevant_sum"] / max(analysed, 1)
     cand = st["obs_candidate_sum"] / max(g.nzones, 1)
     fz = flops_per_zone(N, nz, mloc, cand)
     peak = h.fp64_peak(0)
     # streaming passes of the ensemble branch (H E, mean / anomalies in, epilogue out): algorithmic bytes
-    stream_bytes = 8.0 * g.n * N * 4 + 8.0 * m * N * 3
+    stream_bytes = 8.0 * g.n * N * 2 + 8.0 * m * N * 3
     # end to end through the host-buffer entry point (pageable numpy arrays in, analysed ensemble out)
     e2e = None
     if not a.no_e2e:
@@ -929,7 +960,7 @@ def run_c5(a, rank, world, local):
            "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
            "roofline": {"bound": "fp64", "kernel": "whole step", "peak": peak, "unit": "TFLOP/s",
                         "achieved": value * fz / 1e12, "frac": value * fz / 1e12 / peak, "algorithmic_flops_per_zone": fz,
-                        "traffic": None, "streaming_passes_algorithmic_bytes": stream_bytes},
+                        "traffic": None, "streaming_passes_algorithmic_bytes": stream_bytes, "ens_fuse": ens_fuse},
            "e2e": e2e, "cpu_baseline": cpu}
     print(json.dumps(out))
     h.close()

@@ -113,8 +113,11 @@ struct oakb200_handle {
   int fuse_apply = 0;         // 1: tridiagonal route, k_tvec updates the zone rows from the factored transform (no T, no k_apply)
   int push_kernel = 1;        // fused gather: 1 (default: 47.8 -> 46.1 ms per C3 step at 8 GPUs) = k_push on the slot's side stream, 0 = copy-engine copies
   int push_ctas = 24;         // CTAs of the push kernels (8 GPUs, multicast: 8 / 16 / 24 / 32 / 64 / 148 CTAs -> 36.7 / 36.2 / 36.2 / 36.3 / 38.4 / 40.4 ms)
-  int ens_fuse = 1;           // oakb200_assim_ensemble[_dev], local scheme: 1 = prologue (anamorphosis, mean, anomalies) and epilogue (inflation,
-                              // saturation, Ea, inverse anamorphosis) inside the apply kernel: E read once, Ea written once (4 of 6 passes saved)
+  int ens_fuse = -1;          // oakb200_assim_ensemble[_dev], local scheme: 1 = prologue (anamorphosis, mean, anomalies) and epilogue (inflation,
+                              // saturation, Ea, inverse anamorphosis) inside the apply kernel: E read once, Ea written once (4 of 6 passes saved);
+                              // 0 = three-pass form (k_mean_anom, analysis in place, k_epilogue); -1 (default) = fused when there is no anamorphosis
+                              // (identity): measured on C5 (B200), the 2 x nz x N log / exp per zone cost more inside the fp64-bound apply kernel
+                              // (27.9 ms per step) than under the HBM-bound streaming kernels (27.1 ms)
   EnsFuse ens{};              // set for the duration of such a call
   int apply_tma = 1;          // k_apply_tma (zone rows staged by 2-D tensor copies) where its conditions hold, else k_apply
   int host_register = 0;      // host-buffer entry points: 1 = page-lock the caller's pageable arrays for the duration of the call
@@ -749,7 +752,7 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   else if (k == "localise_obs") h->localise_obs = value != 0.;
   else if (k == "host_register") h->host_register = value != 0.;
   else if (k == "apply_tma") h->apply_tma = value != 0.;
-  else if (k == "ens_fuse") h->ens_fuse = value != 0.;
+  else if (k == "ens_fuse") h->ens_fuse = value < 0. ? -1 : (value != 0.);
   else if (k == "push_kernel") h->push_kernel = value != 0.;
   else if (k == "push_ctas") h->push_ctas = std::max(1, (int)value);
   else if (k == "apply_kernel") {
@@ -1375,7 +1378,7 @@ extern "C" OAKB200_API int oakb200_assim_ensemble_dev(oakb200_handle *h, int64_t
   // Hxf, HSf (in place in HE)
   if ((rc = oak_launch_mean_anom(s0, m, N, 1, AnamTab{nullptr, 0, 0, nullptr, nullptr, nullptr}, h->d_HE.as<double>(), m, h->d_Hxf.as<double>(), h->d_HE.as<double>(), m))) return rc;
   // fused form (local scheme, matrix form of the apply): the apply kernel reads E and writes Ea, xf, xa itself
-  const bool fuse = h->ens_fuse && h->scheme != 0 && !h->fuse_apply && h->apply_kernel == 0 && n > 0;
+  const bool fuse = (h->ens_fuse == 1 || (h->ens_fuse < 0 && anamtype == 1)) && h->scheme != 0 && !h->fuse_apply && h->apply_kernel == 0 && n > 0;
   if (fuse) {
     CUDA_TRY(cudaStreamSynchronize(s0));
     h->ens = EnsFuse{1, anamtype, at, inflation, sqrt((double)N - 1.), maxCorrection, h->d_xf.as<double>()};

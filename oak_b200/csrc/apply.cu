@@ -78,11 +78,11 @@ constexpr int RC = 32;  // rows per chunk
 template <int NT>
 __device__ __forceinline__ void ens_prologue(const EnsFuse &F, double *sS, int lds, int N, int rc, int64_t grow0,
                                              double *s_mean, int tid) {
+  const int r = tid & 31;   // a chunk has at most 32 rows: lane = row, warps stride over the members
   if (F.anamtype != 1) {
-    for (int idx = tid; idx < N * rc; idx += NT) {
-      const int k = idx / rc, r = idx - k * rc;
-      sS[k * lds + r] = oak_anam_row(F.anamtype, true, F.at, grow0 + r, sS[k * lds + r]);
-    }
+    if (r < rc)
+      for (int k = tid >> 5; k < N; k += NT / 32)
+        sS[k * lds + r] = oak_anam_row(F.anamtype, true, F.at, grow0 + r, sS[k * lds + r]);
     __syncthreads();
   }
   if (tid < rc) {
@@ -93,9 +93,9 @@ __device__ __forceinline__ void ens_prologue(const EnsFuse &F, double *sS, int l
     F.xf_out[grow0 + tid] = s;
   }
   __syncthreads();
-  for (int idx = tid; idx < N * rc; idx += NT) {
-    const int k = idx / rc, r = idx - k * rc;
-    sS[k * lds + r] = __ddiv_rn(__dsub_rn(sS[k * lds + r], s_mean[r]), F.scaling);   // :3130
+  if (r < rc) {
+    const double mu = s_mean[r];
+    for (int k = tid >> 5; k < N; k += NT / 32) sS[k * lds + r] = __ddiv_rn(__dsub_rn(sS[k * lds + r], mu), F.scaling);   // :3130
   }
   __syncthreads();
 }
@@ -104,6 +104,7 @@ __device__ __forceinline__ void ens_prologue(const EnsFuse &F, double *sS, int l
 template <int NT>
 __device__ __forceinline__ void ens_epilogue(const EnsFuse &F, double *sS, int lds, int N, int rc, int64_t grow0,
                                              const double *s_mean, double *s_x, int tid) {
+  const int r = tid & 31;
   if (tid < rc && F.maxCorr) {   // the two `where` statements of assimilation.F90:3311-3312
     double x = s_x[tid];
     const double mc = F.maxCorr[grow0 + tid], f = s_mean[tid];
@@ -112,11 +113,13 @@ __device__ __forceinline__ void ens_epilogue(const EnsFuse &F, double *sS, int l
     s_x[tid] = x;
   }
   __syncthreads();
-  for (int idx = tid; idx < N * rc; idx += NT) {
-    const int k = idx / rc, r = idx - k * rc;
-    double s = sS[k * lds + r];
-    if (F.inflation != 1.) s = __dmul_rn(s, F.inflation);                                     // :3301-3304
-    sS[k * lds + r] = oak_anam_row(F.anamtype, false, F.at, grow0 + r, __dadd_rn(s_x[r], __dmul_rn(s, F.scaling)));  // :3318-3326
+  if (r < rc) {
+    const double x = s_x[r];
+    for (int k = tid >> 5; k < N; k += NT / 32) {
+      double s = sS[k * lds + r];
+      if (F.inflation != 1.) s = __dmul_rn(s, F.inflation);                                     // :3301-3304
+      sS[k * lds + r] = oak_anam_row(F.anamtype, false, F.at, grow0 + r, __dadd_rn(x, __dmul_rn(s, F.scaling)));  // :3318-3326
+    }
   }
   __syncthreads();
   if (tid < rc) {

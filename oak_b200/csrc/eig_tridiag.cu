@@ -748,8 +748,18 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
   __syncthreads();
 
   // ---- eigenvector j of T ----
-  double tn = 0.;
-  for (int i = 0; i < N; i++) tn = fmax(tn, fmax(fabs(sd[i]), fabs(se[i])));
+  // tn = max |d_i|, |e_i| : one entry per thread and a block-wide maximum (every thread scanning all of d, e was 6 % of
+  // the kernel's instructions, ncu source page; a maximum does not depend on the order, so tn is the same number)
+  double tn = (j < N) ? fmax(fabs(sd[j]), fabs(se[j])) : 0.;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tn = fmax(tn, __shfl_xor_sync(FULL, tn, o));
+  if constexpr (NW > 1) {
+    if (lane == 0) sred[warp] = tn;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < NW; w++) tn = fmax(tn, sred[w]);
+    __syncthreads();   // sred is reused by the block sums below
+  }
   // power-of-two scale of the Sturm-product recurrences: |s (d - lam)| < 1/2, |s e| < 1/8
   const double tscale = tn > 0. ? scalbn(1., -(ilogb(tn) + 4)) : 1.;
 #if TVEC_PRODUCT
@@ -850,10 +860,14 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
     }
   __syncthreads();
   {
+    // the reflectors (up to 32 KB) come in by 16-byte asynchronous copies, all in flight at once: with plain loads
+    // staged through registers this loop was 1 % of the instructions but 7.8 % of the stall samples (long scoreboard)
     const double2 *Vg = reinterpret_cast<const double2 *>(Tout + (int64_t)zl * NP * NP);
     double2 *Vs2 = reinterpret_cast<double2 *>(W);
     const int nv = max(N - 2, 0) * (NP / 2);
-    for (int idx = j; idx < nv; idx += NP) Vs2[idx] = Vg[idx];
+    for (int idx = j; idx < nv; idx += NP) cp_async16(Vs2 + idx, Vg + idx);
+    cp_async_commit();
+    cp_async_wait<0>();
   }
   __syncthreads();
   BackTile<NP, 0>::run(u, N, rh, W, stau);

@@ -206,7 +206,13 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
     }
     if (ci >= 0) {
       const double *cd = s_cd[lb];
-      for (int r = 0; r < total; r++) cacc = fma(cd[r < cnt0 ? r : 32 + r - cnt0], rows[r * LDR + ci], cacc);
+      // the two evaluating warps' finds one after the other (same order as the merged list, no index select per row)
+      const double *rp = rows + ci;
+#pragma unroll 4
+      for (int r = 0; r < cnt0; r++, rp += LDR) cacc = fma(cd[r], *rp, cacc);
+      const int cnt1 = total - cnt0;
+#pragma unroll 4
+      for (int r = 0; r < cnt1; r++, rp += LDR) cacc = fma(cd[32 + r], *rp, cacc);
     }
   };
 

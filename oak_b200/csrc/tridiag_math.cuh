@@ -20,7 +20,7 @@
 #define PWK_SHORT_CHAIN 0   // 1: measured equal on a B200 (14.35 vs 14.26 ms per 90 k zones): the lanes of a warp wait for each other, not for the chain
 #endif
 #ifndef PWK_FLAT
-#define PWK_FLAT 1   // pwk_eigenvalues: one loop over sweeps instead of a loop nest over (l, sweeps at l), see there
+#define PWK_FLAT 0   // pwk_eigenvalues: 1 = one loop over sweeps instead of a loop nest over (l, sweeps at l): measured slower, see there
 #endif
 #ifndef OAK_RCP_NEWTON
 #define OAK_RCP_NEWTON 0
@@ -127,46 +127,55 @@ OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) {
   const double abstol2 = 0.25 * eps2 * tn * tn;
   for (int i = 0; i < n - 1; i++) { const double ei = e[i * s]; e[i * s] = ei * ei; }
   if (n > 0) e[(n - 1) * s] = 0.;
-  // [l, m] is the current unreduced block: e_m is negligible.  m is found by a scan only when a new block
-  // starts; inside a block the sweep itself notices the off-diagonals it makes negligible (a scan per
-  // iteration, as in dsterf, would cost as much as the sweep here).
+  // [l, mb] is the current unreduced block: e_mb is negligible.  A scan for the end of a block costs as much as a
+  // sweep, and rescanning at every new l (as dsterf does) was 24 % of k_tql's instructions and 35 % of its stall
+  // samples (ncu, profiles/r2_ncu_lines_k_tql.txt), so block ends are TRACKED instead: the sweep notices every
+  // off-diagonal it makes negligible (all entries it rewrites are tested with their final neighbours; e_l is tested at
+  // the head of the next trip), untouched entries cannot change status, hence after d_l has converged the block simply
+  // goes on as [l+1, mb]; a split at msplit < mb leaves [msplit+1, mb] for later (mhi remembers that end).  Only when
+  // more than two ends would have to be remembered (two splits in one sweep, a split inside a split) the bookkeeping
+  // is declared dirty and the next block end is found by the scan again.  The sequence of (l, block end, shift) is
+  // the one of the rescanning form, so the eigenvalues are bit-identical to it.
+  int mb = -1, mhi = -1;
+  bool dirty = false;
+#define PWK_BLOCK_END()                                                                          \
+  if (mb < l) {                                                                                  \
+    if (!dirty && mhi >= l) mb = mhi;                                                            \
+    else {                                                                                       \
+      for (mb = l; mb < n - 1; mb++) {                                                           \
+        const double em = e[mb * s];                                                             \
+        if (em <= abstol2 || em <= eps2 * fabs(d[mb * s] * d[(mb + 1) * s])) break;              \
+      }                                                                                          \
+      mhi = mb; dirty = false;                                                                   \
+    }                                                                                            \
+  }
 #if PWK_FLAT
-  // ONE loop over sweeps, l advanced inside it: the 32 zones of a warp then only wait for each other's sweep lengths,
-  // not for the zone that needs the most sweeps at every single l (a nested "for l { repeat until e_l negligible }"
-  // costs a warp sum_l max_lanes(sweeps at l) ~ 2.1 n sweeps where a lane needs ~1.9 n: 7349 -> 4706 rotation trips
-  // per warp on C3-like spectra, tools/sim_tql_divergence.py).  Per zone the operations and their order are unchanged.
-  int m = -1, l = 0, iter = 0;
+  // ONE loop over sweeps, l advanced inside it (measured on a B200: 8 % SLOWER than the loop nest, k_tql 69.4 -> 75.0 ms
+  // per C3 step, although a warp executes 36 % fewer rotation trips, tools/sim_tql_divergence.py: the lanes of a warp
+  // then work at different rows i of the transposed d, e arrays and collide on the shared-memory banks, 0.3 M -> 13 M
+  // conflicts per 7104 zones; kept as a switch)
+  int l = 0, iter = 0;
   for (;;) {
     for (; l < n; l++, iter = 0) {
-      if (m < l) {
-        for (m = l; m < n - 1; m++) {
-          const double em = e[m * s];
-          if (em <= abstol2 || em <= eps2 * fabs(d[m * s] * d[(m + 1) * s])) break;
-        }
-      } else {
-        const double el = e[l * s];
-        if (el <= abstol2 || el <= eps2 * fabs(d[l * s] * d[(l + 1) * s])) m = l;
-      }
-      if (m != l) break;
+      PWK_BLOCK_END()
+      if (l == mb) continue;
+      const double el = e[l * s];
+      if (el <= abstol2 || el <= eps2 * fabs(d[l * s] * d[(l + 1) * s])) continue;   // d_l converged, the block goes on
+      break;
     }
     if (l >= n) break;
     {
       if (++iter > 60) return -1;
 #else
-  int m = -1;
   for (int l = 0; l < n; l++) {
     int iter = 0;
     for (;;) {
-      if (m < l) {
-        for (m = l; m < n - 1; m++) {
-          const double em = e[m * s];
-          if (em <= abstol2 || em <= eps2 * fabs(d[m * s] * d[(m + 1) * s])) break;
-        }
-      } else {
+      PWK_BLOCK_END()
+      if (l == mb) break;
+      {
         const double el = e[l * s];
-        if (el <= abstol2 || el <= eps2 * fabs(d[l * s] * d[(l + 1) * s])) m = l;
+        if (el <= abstol2 || el <= eps2 * fabs(d[l * s] * d[(l + 1) * s])) break;   // d_l converged, the block goes on
       }
-      if (m == l) break;
       if (++iter > 60) return -1;
 #endif
       const double rte = sqrt(e[l * s]);
@@ -174,15 +183,15 @@ OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) {
       double sigma = (d[(l + 1) * s] - p) * 0.5 * oak_rcp(rte);
       const double r0 = sqrt(fma(sigma, sigma, 1.));
       sigma = p - rte * oak_rcp(sigma + copysign(r0, sigma));
-      double c = 1., sn = 0., gamma = d[m * s] - sigma;
+      double c = 1., sn = 0., gamma = d[mb * s] - sigma;
       p = gamma * gamma;
-      int msplit = m;          // lowest index whose new off-diagonal is negligible
+      int msplit = mb, nsplit = 0;   // lowest index whose new off-diagonal is negligible, number of such indices
       double dnext = 0., enew = 0.;  // d_{i+2} (final) and the new e_{i+1} of the previous trip
-      for (int i = m - 1; i >= l; i--) {
+      for (int i = mb - 1; i >= l; i--) {
         rot++;
         const double bb = e[i * s];
         const double r = p + bb;
-        if (i != m - 1) { enew = sn * r; e[(i + 1) * s] = enew; }
+        if (i != mb - 1) { enew = sn * r; e[(i + 1) * s] = enew; }
         const double oldc = c;
 #if PWK_SHORT_CHAIN
         // gamma = c (alpha - sigma) - sn oldgam = num / r with num = p (alpha - sigma) - bb oldgam, and the next
@@ -197,7 +206,7 @@ OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) {
         gamma = num * ir;
         const double dn = oldgam + (alpha - gamma);
         d[(i + 1) * s] = dn;
-        if (i != m - 1 && (enew <= abstol2 || enew <= eps2 * fabs(dn * dnext))) msplit = i + 1;
+        if (i != mb - 1 && (enew <= abstol2 || enew <= eps2 * fabs(dn * dnext))) { msplit = i + 1; nsplit++; }
         dnext = dn;
         p = (p != 0.) ? (num * num) * irp : oldc * bb;
 #else
@@ -209,16 +218,20 @@ OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) {
         gamma = fma(c, alpha - sigma, -sn * oldgam);
         const double dn = oldgam + (alpha - gamma);
         d[(i + 1) * s] = dn;
-        if (i != m - 1 && (enew <= abstol2 || enew <= eps2 * fabs(dn * dnext))) msplit = i + 1;
+        if (i != mb - 1 && (enew <= abstol2 || enew <= eps2 * fabs(dn * dnext))) { msplit = i + 1; nsplit++; }
         dnext = dn;
         p = (c != 0.) ? gamma * gamma * (r * ip) : oldc * bb;
 #endif
       }
       e[l * s] = sn * p;
       d[l * s] = sigma + gamma;
-      m = msplit;
+      if (nsplit != 0) {
+        if (nsplit > 1 || mhi != mb) dirty = true;   // more block ends than the two that are remembered
+        mb = msplit;
+      }
     }
   }
+#undef PWK_BLOCK_END
   for (int i = 1; i < n; i++) {
     const double v = d[i * s];
     int j = i - 1;
