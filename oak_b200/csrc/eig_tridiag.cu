@@ -1096,8 +1096,11 @@ template <int NP, bool FUSE>
 int launch_tvec(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *c, double *T, double *ampl,
                 double *ws, int32_t *flags, DevCounters *ctr, double orthtol, int maxgroup, const FusedApplyArgs &aa,
                 double *Wg) {
+  // experiment switches OAK_B200_TVEC_PAD / OAK_B200_TRI_PAD: extra (unused) dynamic shared memory per CTA, i.e. fewer
+  // resident CTAs of this kernel per SM, so that CTAs of another stream's kernel fit beside them
+  static const int tvec_pad = getenv("OAK_B200_TVEC_PAD") ? std::max(0, atoi(getenv("OAK_B200_TVEC_PAD"))) : 0;
   const size_t smem0 = sizeof(double) * 17 * NP;
-  const size_t smem = sizeof(double) * (NP * (NP + 4) + 17 * NP + (FUSE ? FusedApply<NP>::SMEM_DOUBLES : 0));
+  const size_t smem = sizeof(double) * (NP * (NP + 4) + 17 * NP + (FUSE ? FusedApply<NP>::SMEM_DOUBLES : 0)) + (size_t)tvec_pad;
   { int rc_ = oak_func_smem(k_tvec<NP, FUSE, 0>, (size_t)((int)smem)); if (rc_) return rc_; }
   { int rc_ = oak_func_smem(k_tvec<NP, false, 1>, (size_t)((int)smem0)); if (rc_) return rc_; }
   { int rc_ = oak_func_smem(k_tvec<NP, FUSE, 2>, (size_t)((int)smem)); if (rc_) return rc_; }
@@ -1148,7 +1151,8 @@ int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G,
 #endif
 #if TRI_TILE
   static const int tri_warp = getenv("OAK_B200_TRI_WARP") ? atoi(getenv("OAK_B200_TRI_WARP")) : TRI_WARP;
-  if (NP == 64 && tri_warp) k_tridiag_warp<<<nz, 32, 0, st>>>(N, nz, mloc, G, T, ws);
+  static const int tri_pad = getenv("OAK_B200_TRI_PAD") ? std::min(40000, std::max(0, atoi(getenv("OAK_B200_TRI_PAD")))) : 0;
+  if (NP == 64 && tri_warp) k_tridiag_warp<<<nz, 32, tri_pad, st>>>(N, nz, mloc, G, T, ws);
   else k_tridiag_tile<NP><<<nz, 64, 0, st>>>(N, mloc, G, T, ws);
 #else
   k_tridiag<NP><<<nz, NP, 0, st>>>(N, mloc, G, T, ws);

@@ -20,7 +20,7 @@
 #define PWK_SHORT_CHAIN 0   // 1: measured equal on a B200 (14.35 vs 14.26 ms per 90 k zones): the lanes of a warp wait for each other, not for the chain
 #endif
 #ifndef PWK_FLAT
-#define PWK_FLAT 0   // pwk_eigenvalues: 1 = one loop over sweeps instead of a loop nest over (l, sweeps at l): measured slower, see there
+#define PWK_FLAT 1   // pwk_eigenvalues: 1 = one loop over sweeps instead of a loop nest over (l, sweeps at l), see there
 #endif
 #ifndef OAK_RCP_NEWTON
 #define OAK_RCP_NEWTON 0
@@ -150,10 +150,12 @@ OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) {
     }                                                                                            \
   }
 #if PWK_FLAT
-  // ONE loop over sweeps, l advanced inside it (measured on a B200: 8 % SLOWER than the loop nest, k_tql 69.4 -> 75.0 ms
-  // per C3 step, although a warp executes 36 % fewer rotation trips, tools/sim_tql_divergence.py: the lanes of a warp
-  // then work at different rows i of the transposed d, e arrays and collide on the shared-memory banks, 0.3 M -> 13 M
-  // conflicts per 7104 zones; kept as a switch)
+  // ONE loop over sweeps, l advanced inside it: the 32 zones of a warp then only wait for each other's sweep lengths,
+  // not for the zone that needs the most sweeps at every single l (the loop nest costs a warp sum_l max_lanes(sweeps at
+  // l) ~ 2.1 n sweeps where a lane needs ~1.9 n: 7349 -> 4706 rotation trips per warp on C3-like spectra,
+  // tools/sim_tql_divergence.py).  Measured on a B200 (k_tql per C3 step): rescanning form 69.4 ms (loop nest) / 75.0 ms
+  // (flat: the desynchronised scans collide on the shared-memory banks); tracked block ends 47.1 ms (loop nest) /
+  // 40.7 ms (flat) -> C3 249.2 -> 234.4 ms per step.
   int l = 0, iter = 0;
   for (;;) {
     for (; l < n; l++, iter = 0) {
