@@ -39,6 +39,13 @@
 #ifndef EIG_HALVES
 #define EIG_HALVES 1   // 2: a batch goes through tridiag / QL / eigenvectors in two software-pipelined halves
 #endif
+#ifndef TQL_GLOBAL
+#define TQL_GLOBAL 1   // k_tql: 1 = d, e of the warp's 32 zones transposed into a GLOBAL scratch array (L1 / L2 resident) and read
+                       // through a register prefetch queue, no shared memory; 0 = transposed into 33 KB of shared memory per warp
+#endif
+#ifndef TQL_PF
+#define TQL_PF 6       // TQL_GLOBAL: rotations of read-ahead
+#endif
 #ifndef TQL_PWK
 #define TQL_PWK 1    // k_tql: 1 = square-root-free QL (Pal-Walker-Kahan), 0 = plain implicit QL
 #endif
@@ -423,10 +430,53 @@ __global__ void __launch_bounds__(64, TRI_MINB) k_tridiag_tile(int N, const int3
 // ---------------------------------------------------------------------------------------------------
 // k_tql : one thread per zone; d, e transposed into shared memory with an odd stride
 // ---------------------------------------------------------------------------------------------------
-#if TQL_LOCAL
+#if TQL_GLOBAL
+// k_tql, no shared memory.  Why: the kernel is a latency-bound scalar chain per zone (~0.7 ms per launch whatever the
+// batch), overlapped with the throughput kernels of the other stream slots.  With d, e in shared memory every resident
+// warp held 33.8 KB of it for that time, 3.5 - 5 warps per SM, i.e. half of the SM's shared memory: the kernel running
+// beside it (k_gram_mma 70 KB, k_tvec 43 KB, k_apply 50 KB per CTA) lost about half of its CTAs, which is where the
+// ~20 ms per C3 step came from that the overlap never hid (the same 20 ms at 63 x 0.65 ms and at 41 x 0.70 ms of k_tql).
+// Here the transposed copy [i][lane] of the warp's 32 problems lives in a global scratch array (32 KB per warp, L2 /
+// L1 resident; lanes at the same i read one 256-byte run), and pwk_eigenvalues_t<PF> loads (d_i, e_i) PF rotations
+// ahead so the load latency is off the dependent chain.  What the warp still takes from its neighbours is registers.
 template <int NP>
 __global__ void __launch_bounds__(32) k_tql(int N, int nz, const int32_t *__restrict__ mloc,
-                                             double *__restrict__ ws, int32_t *__restrict__ flags) {
+                                             double *__restrict__ ws, int32_t *__restrict__ flags, double *__restrict__ scr) {
+  const int lane = threadIdx.x;
+  const int z0 = blockIdx.x * 32;
+  double *gd = scr + (size_t)blockIdx.x * 2 * NP * 32, *ge = gd + NP * 32;
+  for (int z = 0; z < 32; z++) {
+    if (z0 + z >= nz) break;
+    const double *wz = ws_zone(ws, NP, z0 + z);
+    for (int i = lane; i < NP; i += 32) {
+      gd[i * 32 + z] = wz[i];
+      ge[i * 32 + z] = wz[NP + i];
+    }
+  }
+  __syncwarp();
+  const int zl = z0 + lane;
+  const bool active = zl < nz && mloc[zl] != 0;
+  int rot = 0;
+  if (active) {
+    double tn = 0.;
+    for (int i = 0; i < N; i++) tn = fmax(tn, fmax(fabs(gd[i * 32 + lane]), fabs(ge[i * 32 + lane])));
+    rot = pwk_eigenvalues_t<TQL_PF>(N, gd + lane, ge + lane, 32, tn);
+    // the reciprocals of the iteration are not guarded against denormals: verify instead (NaN-safe)
+    for (int i = 0; i < N; i++)
+      if (!(fabs(gd[i * 32 + lane]) <= 4. * tn)) rot = -1;
+  }
+  if (zl < nz) flags[zl] = (rot < 0) ? 1 : 0;
+  __syncwarp();
+  for (int z = 0; z < 32; z++) {
+    if (z0 + z >= nz) break;
+    double *wz = ws_zone(ws, NP, z0 + z);
+    for (int i = lane; i < NP; i += 32) wz[3 * NP + i] = gd[i * 32 + z];
+  }
+}
+#elif TQL_LOCAL
+template <int NP>
+__global__ void __launch_bounds__(32) k_tql(int N, int nz, const int32_t *__restrict__ mloc,
+                                             double *__restrict__ ws, int32_t *__restrict__ flags, double *) {
   const int zl = blockIdx.x * 32 + threadIdx.x;
   if (zl >= nz) return;
   int rot = 0;
@@ -453,7 +503,7 @@ __global__ void __launch_bounds__(32) k_tql(int N, int nz, const int32_t *__rest
 #else
 template <int NP>
 __global__ void __launch_bounds__(32) k_tql(int N, int nz, const int32_t *__restrict__ mloc,
-                                             double *__restrict__ ws, int32_t *__restrict__ flags) {
+                                             double *__restrict__ ws, int32_t *__restrict__ flags, double *) {
   constexpr int S = 33;
   __shared__ double sd[NP * S], se[NP * S];
   const int lane = threadIdx.x;
@@ -1120,7 +1170,9 @@ int launch_tvec(cudaStream_t st, int N, int nz, const int32_t *mloc, const doubl
 template <int NP>
 int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G, const double *c, double *T,
            double *ampl, double *ws, int32_t *flags, DevCounters *ctr, cudaEvent_t *ev, double orthtol, int maxgroup,
-           const FusedApplyArgs *fuse, double *Wg, const TqlSide *side) {
+           const FusedApplyArgs *fuse, double *Wg, const TqlSide *side, double *scr) {
+  // scratch of k_tql: 2 NP doubles per zone, addressed by groups of 32 zones (sub-ranges below start at multiples of 32)
+  auto scr_at = [&](int z0) { return scr + (size_t)(z0 / 32) * 2 * NP * 32; };
 #if TRI_TILE && TRI_WARP
   // Two halves of the batch, software-pipelined around the latency-bound QL kernel: while the eigenvalues of the first
   // half are computed on the side stream, the main stream reduces the second half; the eigenvectors of the first half
@@ -1135,7 +1187,7 @@ int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G,
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaEventRecord(evs[2 * part], st));
       CUDA_TRY(cudaStreamWaitEvent(side->qst, evs[2 * part], 0));
-      k_tql<NP><<<(n1 + 31) / 32, 32, 0, side->qst>>>(N, n1, mloc + z0, ws + (size_t)z0 * 4 * NP, flags + z0);
+      k_tql<NP><<<(n1 + 31) / 32, 32, 0, side->qst>>>(N, n1, mloc + z0, ws + (size_t)z0 * 4 * NP, flags + z0, scr_at(z0));
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaEventRecord(evs[2 * part + 1], side->qst));
     }
@@ -1169,17 +1221,17 @@ int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G,
       const int per = ((nz + split - 1) / split + 31) / 32 * 32;
       for (int z0 = 0; z0 < nz; z0 += per) {
         const int n1 = std::min(per, nz - z0);
-        k_tql<NP><<<(n1 + 31) / 32, 32, 0, side->qst>>>(N, n1, mloc + z0, ws + (size_t)z0 * 4 * NP, flags + z0);
+        k_tql<NP><<<(n1 + 31) / 32, 32, 0, side->qst>>>(N, n1, mloc + z0, ws + (size_t)z0 * 4 * NP, flags + z0, scr_at(z0));
       }
     }
     CUDA_TRY(cudaEventRecord(side->e1, side->qst));
     CUDA_TRY(cudaStreamWaitEvent(st, side->e1, 0));
   } else
-  k_tql<NP><<<(nz + 31) / 32, 32, 0, st>>>(N, nz, mloc, ws, flags);
+  k_tql<NP><<<(nz + 31) / 32, 32, 0, st>>>(N, nz, mloc, ws, flags, scr);
   CUDA_TRY(cudaGetLastError());
   {  // timing experiment (OAK_B200_TQL_REPEAT=k): the kernel only reads d, e and writes lambda, so it can be repeated
     static const int rep = getenv("OAK_B200_TQL_REPEAT") ? atoi(getenv("OAK_B200_TQL_REPEAT")) : 0;
-    for (int r = 0; r < rep; r++) k_tql<NP><<<(nz + 31) / 32, 32, 0, st>>>(N, nz, mloc, ws, flags);
+    for (int r = 0; r < rep; r++) k_tql<NP><<<(nz + 31) / 32, 32, 0, st>>>(N, nz, mloc, ws, flags, scr);
   }
   if (ev) CUDA_TRY(cudaEventRecord(ev[1], st));
   if (fuse) return launch_tvec<NP, true>(st, N, nz, mloc, c, T, ampl, ws, flags, ctr, orthtol, maxgroup, *fuse, Wg);
@@ -1188,9 +1240,11 @@ int launch(cudaStream_t st, int N, int nz, const int32_t *mloc, const double *G,
 
 }  // namespace
 
-// Per-zone workspace of the tridiagonal route: 4 NP doubles (d, e, tau, lambda) + one int32 flag.
+// Per-zone workspace of the tridiagonal route: 4 NP doubles (d, e, tau, lambda) + one int32 flag + k_tql's scratch
+// (transposed d, e: 2 NP doubles per zone, groups of 32 zones).
 size_t oak_eig_tridiag_ws_bytes(int NP, int nz) {
-  return sizeof(double) * 4 * (size_t)NP * nz + sizeof(int32_t) * (size_t)nz + 64;
+  return sizeof(double) * 4 * (size_t)NP * nz + (sizeof(int32_t) * (size_t)nz + 255) / 256 * 256 +
+         sizeof(double) * 2 * (size_t)NP * (((size_t)nz + 31) / 32 * 32) + 64;
 }
 
 // Enqueues k_tridiag, k_tql, k_tvec; on return (stream order) flags[zl] = mloc[zl] for the zones that must be
@@ -1204,9 +1258,10 @@ int oak_launch_eig_tridiag(cudaStream_t st, int N, int NP, int nz, const int32_t
   double *wsd = reinterpret_cast<double *>(ws);
   int32_t *flags = reinterpret_cast<int32_t *>(wsd + 4 * (size_t)NP * nz);
   *flags_out = flags;
+  double *scr = reinterpret_cast<double *>(reinterpret_cast<char *>(flags) + (sizeof(int32_t) * (size_t)nz + 255) / 256 * 256);
   switch (NP) {
-    case 32: return launch<32>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup, fuse, Wg, side);
-    case 64: return launch<64>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup, fuse, Wg, side);
+    case 32: return launch<32>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup, fuse, Wg, side, scr);
+    case 64: return launch<64>(st, N, nz, mloc, G, c, T, ampl, wsd, flags, ctr, ev, orthtol, maxgroup, fuse, Wg, side, scr);
   }
   oak_set_error("eig_tridiag: unsupported padded ensemble size %d", NP);
   return OAK_ERR_UNSUPPORTED;

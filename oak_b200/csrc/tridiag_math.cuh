@@ -121,7 +121,12 @@ OAK_HD int tql_eigenvalues(int n, double *d, double *e, int s, double tn) {
 // LAPACK dsterf): works on e_i^2, one reciprocal chain per rotation instead of an inverse square root plus
 // the longer dependent chain of the plain QL step, i.e. about half the latency per rotation, which is
 // what bounds k_tql (one thread per zone).  Same interface as tql_eigenvalues; e is overwritten by squares.
-OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) {
+// PF > 0 (k_tql with d, e in global memory): the entries a rotation reads, (d_i, e_i), are loaded PF rotations ahead
+// into a register queue, so that the L1 / L2 latency of the loads stays off the dependent chain of the rotations; a
+// sweep only writes entries above the ones it still has to read, so the queue never holds a stale value.  Same
+// operations on the same values as PF = 0.
+template <int PF>
+OAK_HD int pwk_eigenvalues_t(int n, double *d, double *e, int s, double tn) {
   int rot = 0;
   const double eps2 = OAK_DBL_EPS * OAK_DBL_EPS;
   const double abstol2 = 0.25 * eps2 * tn * tn;
@@ -180,18 +185,39 @@ OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) {
       }
       if (++iter > 60) return -1;
 #endif
-      const double rte = sqrt(e[l * s]);
-      double p = d[l * s];
-      double sigma = (d[(l + 1) * s] - p) * 0.5 * oak_rcp(rte);
+      // the loads of a sweep's set-up, issued together (one latency, not four, when d, e live in global memory)
+      const double el_ = e[l * s], dl_ = d[l * s], dl1_ = d[(l + 1) * s], dmb_ = d[mb * s];
+      double qd[PF > 0 ? PF : 1], qe[PF > 0 ? PF : 1];
+      if (PF > 0) {
+#pragma unroll
+        for (int t = 0; t < PF; t++) {
+          const int ip = mb - 1 - t;
+          if (ip >= l) { qd[t] = d[ip * s]; qe[t] = e[ip * s]; }
+        }
+      }
+      const double rte = sqrt(el_);
+      double p = dl_;
+      double sigma = (dl1_ - p) * 0.5 * oak_rcp(rte);
       const double r0 = sqrt(fma(sigma, sigma, 1.));
       sigma = p - rte * oak_rcp(sigma + copysign(r0, sigma));
-      double c = 1., sn = 0., gamma = d[mb * s] - sigma;
+      double c = 1., sn = 0., gamma = dmb_ - sigma;
       p = gamma * gamma;
       int msplit = mb, nsplit = 0;   // lowest index whose new off-diagonal is negligible, number of such indices
       double dnext = 0., enew = 0.;  // d_{i+2} (final) and the new e_{i+1} of the previous trip
-      for (int i = mb - 1; i >= l; i--) {
+      for (int i0 = mb - 1; i0 >= l; i0 -= (PF > 0 ? PF : 1)) {
+#pragma unroll
+       for (int t = 0; t < (PF > 0 ? PF : 1); t++) {
+        const int i = i0 - t;
+        if (i < l) break;
         rot++;
-        const double bb = e[i * s];
+        double bb, alpha;
+        if (PF > 0) {
+          bb = qe[t]; alpha = qd[t];
+          const int ipf = i - PF;
+          if (ipf >= l) { qd[t] = d[ipf * s]; qe[t] = e[ipf * s]; }
+        } else {
+          bb = e[i * s]; alpha = d[i * s];
+        }
         const double r = p + bb;
         if (i != mb - 1) { enew = sn * r; e[(i + 1) * s] = enew; }
         const double oldc = c;
@@ -199,7 +225,7 @@ OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) {
         // gamma = c (alpha - sigma) - sn oldgam = num / r with num = p (alpha - sigma) - bb oldgam, and the next
         // p = gamma^2 r / p = num^2 / (r p): the loop-carried chain p -> p' is add, mul, reciprocal, mul (7 dependent
         // operations with the 4 of the reciprocal) instead of 10; gamma, c, sn hang off a second reciprocal
-        const double oldgam = gamma, alpha = d[i * s];
+        const double oldgam = gamma;
         const double num = fma(p, alpha - sigma, -(bb * oldgam));
         const double irp = oak_rcp(r * p);
         const double ir = oak_rcp(r);
@@ -216,7 +242,7 @@ OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) {
         const double ip = oak_rcp(p);  // independent of ir: the two reciprocals overlap
         c = p * ir;
         sn = bb * ir;
-        const double oldgam = gamma, alpha = d[i * s];
+        const double oldgam = gamma;
         gamma = fma(c, alpha - sigma, -sn * oldgam);
         const double dn = oldgam + (alpha - gamma);
         d[(i + 1) * s] = dn;
@@ -224,6 +250,7 @@ OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) {
         dnext = dn;
         p = (c != 0.) ? gamma * gamma * (r * ip) : oldc * bb;
 #endif
+       }
       }
       e[l * s] = sn * p;
       d[l * s] = sigma + gamma;
@@ -242,6 +269,8 @@ OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) {
   }
   return rot;
 }
+
+OAK_HD int pwk_eigenvalues(int n, double *d, double *e, int s, double tn) { return pwk_eigenvalues_t<0>(n, d, e, s, tn); }
 
 // Eigenvector of T for the eigenvalue lam by the twisted factorisation (Fernando; Parlett & Dhillon):
 //   forward pivots  p_0 = d_0 - lam , p_{i+1} = (d_{i+1} - lam) - e_i^2 / p_i

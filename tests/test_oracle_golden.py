@@ -137,6 +137,40 @@ def test_distance_metrics():
             assert abs(a - b) <= 1e-6 * max(a, 1.0)  # acos near 1 amplifies 1-ulp differences
 
 
+def test_spherical_selection_against_libm_counts_boundary_flips():
+    # The device predicate and the oracle's trig=1 mode share include/oak_b200_math.h, so their index sets agree bit for
+    # bit by construction.  What a gfortran build of the reference evaluates is libm (trig=0 here): the sets can only
+    # differ for observations whose distance lies within rounding of the cut-off.  Count those flips on a realistic
+    # configuration instead of hiding them: they must be (a) rare and (b) all within 1e-9 relative of maxLen, i.e.
+    # observations whose Gaussian weight at the cut-off is the same to 1e-9 either way.
+    rng = np.random.default_rng(20261018)
+    m, nz = 20000, 400
+    ox = rng.uniform(-20, 20, m); oy = rng.uniform(30, 60, m)
+    zx = rng.uniform(-19, 19, nz); zy = rng.uniform(31, 59, nz)
+    flips = checked = 0
+    worst = 0.0
+    for metric in (1, 2):
+        for z in range(nz):
+            maxlen = 150e3
+            # adversarial cut-off: the exact (libm) distance of some observation to this zone
+            k = int(rng.integers(m))
+            if z % 2 == 0:
+                maxlen = oracle.distance(metric, (ox[k], oy[k]), (zx[z], zy[z]), trig=0)
+                if not (1e3 < maxlen < 400e3):
+                    maxlen = 150e3
+            near = np.nonzero((np.abs(ox - zx[z]) < 6) & (np.abs(oy - zy[z]) < 4))[0]
+            for l in near:
+                a = oracle.distance(metric, (ox[l], oy[l]), (zx[z], zy[z]), trig=0)
+                b = oracle.distance(metric, (ox[l], oy[l]), (zx[z], zy[z]), trig=1)
+                checked += 1
+                if (a <= maxlen) != (b <= maxlen):
+                    flips += 1
+                    worst = max(worst, abs(a - maxlen) / maxlen, abs(b - maxlen) / maxlen)
+    assert checked > 100000
+    assert flips <= checked * 1e-4, (flips, checked)
+    assert worst < 1e-9
+
+
 def test_init_partition_is_stable_counting_sort():
     # assimilation.F90:578-641
     part = np.array([2, 1, 2, 3, 1, 3, 3], dtype=np.int32)

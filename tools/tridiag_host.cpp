@@ -22,3 +22,4 @@ extern "C" double host_twisted3(int n, const double *d, const double *e, int sd,
   }
   return twisted_vector3(n, ds, e2, en, scale * lam, 1. / scale, w, sw, gam);
 }
+extern "C" int host_pwk_pf(int n, double *d, double *e, int s, double tn) { return pwk_eigenvalues_t<6>(n, d, e, s, tn); }
