@@ -30,7 +30,8 @@ class ObsT(C.Structure):
 def build(force=False):
     so = os.path.join(_HERE, "liboak_oracle.so")
     src = os.path.join(_HERE, "oak_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    src2 = os.path.join(_HERE, "oak_ndgrid.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(src2)):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "liboak_oracle.so"])
     return so
 
@@ -68,6 +69,14 @@ def lib():
     L.oracle_max_threads.restype = C.c_int
     L.oracle_set_threads.restype = C.c_int
     L.oracle_set_threads.argtypes = [C.c_int]
+    if L.oracle_ndgrid_init(_openblas_path().encode()) != 0:
+        raise RuntimeError("oracle_ndgrid_init failed (dgesvd not found)")
+    L.oracle_ndgrid_create.restype = C.c_void_p
+    L.oracle_ndgrid_create.argtypes = [C.c_int, c_ip, c_dp, c_u8p]
+    L.oracle_ndgrid_destroy.argtypes = [C.c_void_p]
+    L.oracle_cinterp.argtypes = [C.c_void_p, C.c_int, c_dp, c_ip, c_dp, c_ip]
+    L.oracle_ndgrid_nsimplex.restype = C.c_int
+    L.oracle_ndgrid_tetrahedra.argtypes = [C.c_int, c_dp]
     _LIB = L
     return L
 
@@ -262,3 +271,52 @@ def max_threads():
 def set_threads(n=0):
     """OpenMP threads of the zone loop (n <= 0: all online processors, whatever OMP_NUM_THREADS says)."""
     return lib().oracle_set_threads(int(n))
+
+
+# ---------------------------------------------------------------------------------------------------
+# n-dimensional grid interpolation (ndgrid.F90: cinterp), the arithmetic of the observation operator
+# ---------------------------------------------------------------------------------------------------
+def ndgrid_full_coords(gshape, axes=None, coords=None):
+    """Coordinates of every grid point, [n][prod(gshape)] with the first dimension fastest (Fortran order):
+    from separable axes (one 1-D array per dimension) or from explicit arrays of the grid's shape."""
+    gshape = tuple(int(g) for g in gshape)
+    n = len(gshape)
+    total = int(np.prod(gshape))
+    out = np.empty((n, total))
+    for d in range(n):
+        if coords is not None:
+            out[d] = np.asarray(coords[d], dtype=np.float64).reshape(gshape, order="F").ravel(order="F")
+        else:
+            shp = [1] * n
+            shp[d] = gshape[d]
+            out[d] = np.broadcast_to(np.asarray(axes[d], dtype=np.float64).reshape(shp), gshape).ravel(order="F")
+    return out
+
+
+def tetrahedra(n):
+    """tetrahedron(2^n, n+1, nbth) of split (ndgrid.F90:357-435), as [nbth][n+1][2^n]"""
+    L = lib()
+    nb = L.oracle_ndgrid_nsimplex(n)
+    t = np.zeros((nb, n + 1, 1 << n))
+    L.oracle_ndgrid_tetrahedra(n, _dp(t))
+    return t
+
+
+def cinterp(gshape, coord_full, xi, masked=None):
+    """cinterp (ndgrid.F90:1183-1257) for the points xi[m][n]: (indexes[m][2^n][n] 1-based, coeff[m][2^n], nbp[m])"""
+    L = lib()
+    gs = np.ascontiguousarray(gshape, dtype=np.int32)
+    n = gs.size
+    cf = np.ascontiguousarray(coord_full, dtype=np.float64)
+    mk = None if masked is None else np.ascontiguousarray(masked, dtype=np.uint8)
+    xi = np.ascontiguousarray(xi, dtype=np.float64).reshape(-1, n)
+    m = xi.shape[0]
+    idx = np.zeros((m, 1 << n, n), dtype=np.int32)
+    co = np.zeros((m, 1 << n))
+    nbp = np.zeros(m, dtype=np.int32)
+    g = L.oracle_ndgrid_create(n, gs.ctypes.data_as(c_ip), _dp(cf), None if mk is None else mk.ctypes.data_as(c_u8p))
+    try:
+        L.oracle_cinterp(g, m, _dp(xi), idx.ctypes.data_as(c_ip), _dp(co), nbp.ctypes.data_as(c_ip))
+    finally:
+        L.oracle_ndgrid_destroy(g)
+    return idx, co, nbp
