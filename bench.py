@@ -34,10 +34,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5"],
+    ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5", "hgen"],
                     help="c3 = the headline workload (BASELINE configs[2]); c4 = 2000x2000x50, N=128, obs at every surface "
                          "point, analysed slab by slab in place (configs[3]); c5 = 4-D 256x256x10x4, N=64, inflation + log "
-                         "anamorphosis through the ensemble entry point (configs[4])")
+                         "anamorphosis through the ensemble entry point (configs[4]); hgen = interpolation weights of the observation "
+                         "operator (batched cinterp) for 1e6 observations on the C3 grid (SURVEY 8f rank 3)")
     ap.add_argument("--slab-rows", type=int, default=50, help="c4: grid rows (of nx zones) per resident slab")
     ap.add_argument("--max-slabs", type=int, default=0, help="c4: analyse only this many slabs per rank (0 = all) and say so")
     ap.add_argument("--nx", type=int, default=1000)
@@ -299,6 +300,8 @@ def main():
         return run_c4(a, rank, world, local)
     if a.config == "c5":
         return run_c5(a, rank, world, local)
+    if a.config == "hgen":
+        return run_hgen(a, rank, world, local)
 
     import torch.distributed as dist
     import oak_b200
@@ -961,6 +964,110 @@ def run_c5(a, rank, world, local):
            "roofline": {"bound": "fp64", "kernel": "whole step", "peak": peak, "unit": "TFLOP/s",
                         "achieved": value * fz / 1e12, "frac": value * fz / 1e12 / peak, "algorithmic_flops_per_zone": fz,
                         "traffic": None, "streaming_passes_algorithmic_bytes": stream_bytes, "ens_fuse": ens_fuse},
+           "e2e": e2e, "cpu_baseline": cpu}
+    print(json.dumps(out))
+    h.close()
+
+
+# --------------------------------------------------------------------------------------------------
+# interpolation weights of the observation operator (genObservationOper -> cinterp,
+# assimilation.F90:2471-2656, ndgrid.F90:1183-1257) for the observations of the C3 workload on its 3-D grid.
+# metric: observations per second; the kernel is HBM / latency bound: algorithmic bytes per observation =
+# 3 coordinates in + 8 corners x 3 subscripts (int32) + 8 weights + nbp out.
+# --------------------------------------------------------------------------------------------------
+def run_hgen(a, rank, world, local):
+    import torch
+    import oak_b200
+    from oak_b200 import synthetic as S
+    if rank != 0:
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    g = S.Grid(a.nx, a.ny, a.nz)
+    m = a.m
+    gshape = (a.nx, a.ny, a.nz)
+    axes = [g.dx * np.arange(1, a.nx + 1), g.dy * np.arange(1, a.ny + 1), -5.0 * np.arange(a.nz) ** 1.3]   # depth: descending, stretched
+    rng = np.random.default_rng(SEED)
+    lo = np.array([ax.min() for ax in axes]); hi = np.array([ax.max() for ax in axes])
+    xi = lo + (hi - lo) * rng.uniform(-0.01, 1.01, (m, 3))                                   # ~4 % outside the grid
+    masked = None
+    h = oak_b200.Handle(local)
+    t = lambda x, dt: torch.from_numpy(np.ascontiguousarray(x)).to(dev).to(dt)
+    d_ax = t(np.concatenate(axes), torch.float64)
+    d_xi = t(xi, torch.float64)
+    d_idx = torch.empty((m, 8, 3), dtype=torch.int32, device=dev)
+    d_co = torch.empty((m, 8), dtype=torch.float64, device=dev)
+    d_nbp = torch.empty(m, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)                     # > L2 (126 MB)
+    for _ in range(max(a.warmup, 3)):
+        h.cinterp_dev(gshape, d_ax, None, d_xi, d_idx, d_co, d_nbp)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    tot = 0.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(a.steps):
+        flush.zero_()
+        e0.record()
+        h.cinterp_dev(gshape, d_ax, None, d_xi, d_idx, d_co, d_nbp)
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    ms = tot / a.steps
+    clocks = sampler.stop()
+    value = m / (ms * 1e-3)
+    bytes_obs = 3 * 8 + 8 * 3 * 4 + 8 * 8 + 4
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        peak_src = "MEASURED_PEAKS.json (driver-written copy bandwidth)"
+    except Exception:
+        hbm_peak, peak_src = 6548.0, "fallback: the copy bandwidth measured on this pool's B200s in round 1"
+    ach = bytes_obs * m / (ms * 1e-3) / 1e9
+    # end to end: host arrays in, host arrays out (what the Fortran driver calls once per model variable)
+    e2e = None
+    if not a.no_e2e:
+        h.cinterp(gshape, axes, xi[:1000])
+        t0 = time.perf_counter()
+        for _ in range(a.e2e_steps):
+            idx_h, co_h, nbp_h = h.cinterp(gshape, axes, xi)
+        te = (time.perf_counter() - t0) / a.e2e_steps
+        e2e = {"value": m / te, "unit": "observations/s", "h2d_bytes_per_step": int(xi.nbytes + sum(ax.nbytes for ax in axes)),
+               "d2h_bytes_per_step": int(idx_h.nbytes + co_h.nbytes + nbp_h.nbytes), "steps": a.e2e_steps,
+               "note": "oakb200_cinterp on pageable host arrays (positions in; corner subscripts, weights, nbp out)",
+               "identical_to_resident": bool(np.array_equal(idx_h, d_idx.cpu().numpy()) and np.array_equal(co_h, d_co.cpu().numpy()))}
+    parity, cpu = None, None
+    if not a.no_cpu:
+        try:
+            import oracle
+            ns = 20000
+            sel = rng.choice(m, ns, replace=False)
+            coord = oracle.ndgrid_full_coords(gshape, axes=axes)
+            og = oracle.NdGrid(gshape, coord)
+            og.cinterp(xi[sel])                       # builds the part of the databox tree these points need
+            t0 = time.perf_counter()
+            i0, c0, n0 = og.cinterp(xi[sel])
+            tc = time.perf_counter() - t0
+            og.close()
+            gi, gc, gn = d_idx[sel].cpu().numpy(), d_co[sel].cpu().numpy(), d_nbp[sel].cpu().numpy()
+            ins = n0 > 0
+            err = float(np.abs(gc[ins] - c0[ins]).max())
+            parity = {"obs": ns, "nbp_equal": bool(np.array_equal(gn, n0)), "cells_equal": bool(np.array_equal(gi[ins], i0[ins])),
+                      "max_abs_weight_error": err, "tol": 1e-12, "ok": bool(np.array_equal(gn, n0) and np.array_equal(gi[ins], i0[ins]) and err < 1e-12),
+                      "against": "oracle restatement of cinterp (databox tree, simplices, dgetrf-rule elimination) on randomly sampled observations of this run"}
+            cpu = {"value": ns / tc, "unit": "observations/s", "cores": 1, "kind": "port",
+                   "sample": f"{ns} observations of this workload, databox tree already built (the reference runs genObservationOper serially, one observation after the other), {tc:.2f} s"}
+        except Exception as ex:
+            parity = {"obs": 0, "ok": False, "error": repr(ex)[:200]}
+    out = {"metric": "observation-operator rows generated per second (interpolation weights, batched cinterp)", "value": value,
+           "unit": "observations/s", "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"interpolation weights of {m} observations on the {a.nx}x{a.ny}x{a.nz} rectilinear grid of the C3 workload "
+                                  "(stretched descending depth axis), 3-D simplex interpolation as ndgrid.F90:464-665",
+                      "l2": "256 MB written between timed iterations (L2 flush)"},
+           "gpu_launches": int(a.steps), "clocks": clocks, "parity": parity,
+           "roofline": {"bound": "hbm", "kernel": "k_cinterp<3>", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                        "traffic": None, "algorithmic_bytes_per_observation": bytes_obs, "peak_source": peak_src,
+                        "note": "one thread per observation: binary searches on the axes, up to 24 simplices x a 4x4 elimination; latency bound"},
            "e2e": e2e, "cpu_baseline": cpu}
     print(json.dumps(out))
     h.close()

@@ -243,6 +243,31 @@ OAKB200_API int oakb200_assim_ensemble_dev(oakb200_handle *h, int64_t n, int32_t
  * speeds: rank p of P owns zones [first[p], first[p+1]) ; first has P+1 entries (0-based). */
 OAKB200_API int oakb200_partition_zones(int32_t nzones, int32_t nranks, int32_t *first);
 
+/* Observation-operator generation: the batched form of `cinterp`
+ * (ndgrid.F90:1183-1257), the arithmetic inside genObservationOper (assimilation.F90:2471-2656, the calls at
+ * :2569-2585): for each of the m observation positions xi[m][ndim] (row-major, one row per observation) locate the cell
+ * of the model grid that contains it and return the interpolation weights on the 2^ndim corners of that cell, from the
+ * first of the n! 2^(n-1) simplices of the cell (split, ndgrid.F90:357-435) that contains the point
+ * (interp_cube / interp_tetrahedron, :464-665).
+ *   gshape[ndim]            shape of the variable's grid (ndim 1 .. 4)
+ *   axes                    the coordinate axes one after the other (gshape[0] + ... + gshape[ndim-1] values): grids whose
+ *                           coordinate k depends on subscript k only (regular / rectilinear; ascending or descending)
+ *   masked[prod(gshape)]    1 = land / invalid point (first subscript fastest), or NULL
+ *   indexes[m][2^ndim][ndim] 1-based subscripts of the corners (corner j has the upper node in dimension k when bit k of
+ *                           j is set), coeff[m][2^ndim], nbp[m] = 2^ndim, or 0 when the point is outside the grid or a
+ *                           corner is masked (genObservationOper then writes its zero row with index -1, :2597-2611)
+ * Cells with a degenerate simplex (singleton dimension, |det| <= 1e-8) take an SVD branch in the reference
+ * (:527-627) that is not implemented on the device: they get nbp = -1, *ndegenerate counts them and the call returns
+ * OAKB200 error -6 (the other observations are valid).  The name matching of variables and the choice of the finest
+ * grid (hres, :2545-2594) stay in the Fortran driver, which calls this once per model variable. */
+OAKB200_API int oakb200_cinterp(oakb200_handle *h, int32_t ndim, const int32_t *gshape, const double *axes,
+                    const uint8_t *masked, int32_t m, const double *xi, int32_t *indexes, double *coeff,
+                    int32_t *nbp, int32_t *ndegenerate);
+/* Same with DEVICE pointers for axes, masked, xi, indexes, coeff, nbp (gshape and ndegenerate on the host). */
+OAKB200_API int oakb200_cinterp_dev(oakb200_handle *h, int32_t ndim, const int32_t *gshape, const double *axes,
+                        const uint8_t *masked, int32_t m, const double *xi, int32_t *indexes, double *coeff,
+                        int32_t *nbp, int32_t *ndegenerate, void *stream);
+
 /* Measured fp64 pipe peak on this device, used as the roofline denominator:
  * mode 0 = DFMA (register-resident FMA chains), 1 = DMMA (mma.sync.m8n8k4.f64). TFLOP/s. */
 OAKB200_API int oakb200_fp64_peak(oakb200_handle *h, int32_t mode, double *tflops);

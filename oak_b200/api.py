@@ -371,6 +371,40 @@ class Handle:
                                               _ptr(xf), _ptr(xa), C.byref(st)))
         return Ea, xf, xa, st.asdict()
 
+    def cinterp(self, gshape, axes, xi, masked=None):
+        """Batched cinterp (ndgrid.F90:1183-1257) on the device for one model grid with separable axes: returns
+        (indexes[m][2^n][n] 1-based, coeff[m][2^n], nbp[m]).  Raises when observations fall into degenerate cells."""
+        gs = np.ascontiguousarray(gshape, dtype=np.int32)
+        n = gs.size
+        ax = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.float64).ravel() for a in axes]))
+        if ax.size != int(gs.sum()):
+            raise OakB200Error(-2, f"axes hold {ax.size} values, gshape needs {int(gs.sum())}")
+        mk = None if masked is None else np.ascontiguousarray(np.asarray(masked).ravel(order="F"), dtype=np.uint8)
+        if mk is not None and mk.size != int(np.prod(gs)):
+            raise OakB200Error(-2, "mask size does not match gshape")
+        xi = np.ascontiguousarray(xi, dtype=np.float64).reshape(-1, n)
+        m = xi.shape[0]
+        idx = np.zeros((m, 1 << n, n), dtype=np.int32)
+        co = np.zeros((m, 1 << n))
+        nbp = np.zeros(m, dtype=np.int32)
+        ndeg = C.c_int32(0)
+        rc = self._L.oakb200_cinterp(self._h, n, _ptr(gs), _ptr(ax), _ptr(mk), m, _ptr(xi), _ptr(idx), _ptr(co),
+                                     _ptr(nbp), C.byref(ndeg))
+        self.last_cinterp = (idx, co, nbp, ndeg.value)
+        _check(rc)
+        return idx, co, nbp
+
+    def cinterp_dev(self, gshape, axes, masked, xi, indexes, coeff, nbp):
+        """Device-resident form (torch tensors): axes (float64, concatenated), masked (uint8 or None), xi (m x n),
+        indexes (m x 2^n x n int32), coeff (m x 2^n), nbp (m int32).  Returns the number of degenerate observations."""
+        gs = np.ascontiguousarray(gshape, dtype=np.int32)
+        ndeg = C.c_int32(0)
+        dp = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        rc = self._L.oakb200_cinterp_dev(self._h, gs.size, _ptr(gs), dp(axes), dp(masked), int(xi.shape[0]), dp(xi),
+                                         dp(indexes), dp(coeff), dp(nbp), C.byref(ndeg), None)
+        _check(rc)
+        return ndeg.value
+
     def fp64_peak(self, mode=0):
         v = C.c_double()
         _check(self._L.oakb200_fp64_peak(self._h, int(mode), C.byref(v)))
@@ -437,3 +471,28 @@ def assim_ensemble(zoneSize, selectObservations, E, Hi, Hj, Hs, Hshift, yo, R, a
     finally:
         if own:
             h.close()
+
+
+def gen_observation_oper(handle, gshape, axes, xi, masked=None, seaindex=None):
+    """The part of genObservationOper (assimilation.F90:2471-2656) that follows cinterp, for observations of ONE model
+    variable: COO triplets (Hi, Hj, Hs), 1-based, 2^n entries per observation that lies in the grid and a single zero
+    entry with model index -1 otherwise (:2597-2611).  Hj is the linear index of the corner in the variable's grid (first
+    subscript fastest), mapped through `seaindex` (full -> packed, assimilation.F90:2379-2381) when given."""
+    idx, co, nbp = handle.cinterp(gshape, axes, xi, masked)
+    gs = np.asarray(gshape, dtype=np.int64)
+    ioff = np.concatenate([[1], np.cumprod(gs[:-1])])
+    m, twon, n = idx.shape
+    lin = ((idx.astype(np.int64) - 1) * ioff).sum(axis=2) + 1          # [m][2^n], 1-based
+    if seaindex is not None:
+        lin = np.asarray(seaindex, dtype=np.int64)[lin - 1]
+    inside = nbp > 0
+    cnt = np.where(inside, twon, 1)
+    start = np.concatenate([[0], np.cumsum(cnt)])
+    nnz = int(start[-1])
+    Hi = np.repeat(np.arange(1, m + 1, dtype=np.int32), cnt)
+    Hj = np.full(nnz, -1, dtype=np.int32)
+    Hs = np.zeros(nnz)
+    pos = (start[:-1][inside][:, None] + np.arange(twon)[None, :]).ravel()
+    Hj[pos] = lin[inside].ravel()
+    Hs[pos] = co[inside].ravel()
+    return Hi, Hj, Hs

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "liboak_b200.so")
-SOURCES = ["api.cu", "obsgrid.cu", "gram.cu", "gram_mma.cu", "eig_simple.cu", "eig_fast.cu", "eig_tridiag.cu", "apply.cu", "apply_mma.cu", "global.cu", "ensemble.cu",
+SOURCES = ["api.cu", "obsgrid.cu", "gram.cu", "gram_mma.cu", "eig_simple.cu", "eig_fast.cu", "eig_tridiag.cu", "apply.cu", "apply_mma.cu", "global.cu", "ensemble.cu", "hgen.cu",
            "microbench.cu"]
 HEADERS = ["common.cuh", "eig_common.cuh", "tridiag_math.cuh", "tridiag_warp.cuh", "../../include/oak_b200.h", "../../include/oak_b200_math.h"]
 # per-file extra flags (none at present: eig_fast.cu spells its approximate fp32 operations in inline PTX)

@@ -129,6 +129,7 @@ struct oakb200_handle {
   double tri_orthtol = 0.;  // tridiagonal route: accepted loss of orthogonality between neighbouring eigenvectors (0: default)
   int tri_maxgroup = -1;
   DevBuf d_anam;              // tabulated anamorphosis (K x 2), oakb200_set_anamorphosis_table
+  DevBuf d_tet;               // simplex table of the batched cinterp (+ its degenerate-cell counter)
   int anam_K = 0, anam_monotone = 0;
   DevBuf d_rowvar, d_vdesc, d_vtab;   // per-variable transforms (oakb200_set_anamorphosis_vars)
   int anam_nvar = 0; int64_t anam_rows = 0;
@@ -239,7 +240,8 @@ int batch_size(const oakb200_handle *h, int NP, int nzones_call) {
   // the tridiagonal route has a latency-bound kernel (k_tql: one thread per zone, ~1.6 ms whatever the
   // batch size up to ~28 k zones), so its batches are larger: 1 GB of workspace instead of 256 MB
   const bool tri = h->eig_kernel == 4 && NP <= 64;
-  const int cap = (int)((size_t)(tri ? 1024 : 256) * 1024 * 1024 / per_zone);
+  // (round 2, with k_tql at ~0.7 ms per launch: 16.5 k -> 24.3 k zones per batch, C3 234.0 -> 230.1 ms per step)
+  const int cap = (int)((size_t)(tri ? 1536 : 256) * 1024 * 1024 / per_zone);
   const int wave = NP <= 64 ? 592 : 148;
   int zb = nzones_call / (NSLOT * (tri ? 4 : 8));
   // ... and never small when the call is (multi-GPU phases of ~30 k zones): 12 waves per batch, or one batch
@@ -568,7 +570,7 @@ extern "C" OAKB200_API int oakb200_destroy(oakb200_handle *h) {
                     &h->d_key_in, &h->d_key_out, &h->d_val_in, &h->d_perm, &h->d_cell_start, &h->d_sx, &h->d_sy,
                     &h->d_tmp, &h->d_rows, &h->d_delta, &h->d_scoef, &h->d_HSf, &h->d_yo, &h->d_Hxf, &h->d_R,
                     &h->d_d01, &h->d_ampzero, &h->d_HE, &h->d_Hi, &h->d_Hj, &h->d_Hs, &h->d_Hshift, &h->d_order,
-                    &h->d_rowstart, &h->d_xf, &h->d_xa, &h->d_maxc, &h->d_E, &h->d_ctr, &h->d_anam, &h->d_gws, &h->d_gzstart, &h->d_rowvar, &h->d_vdesc, &h->d_vtab};
+                    &h->d_rowstart, &h->d_xf, &h->d_xa, &h->d_maxc, &h->d_E, &h->d_ctr, &h->d_anam, &h->d_tet, &h->d_gws, &h->d_gzstart, &h->d_rowvar, &h->d_vdesc, &h->d_vtab};
   for (DevBuf *b : bufs) b->release();
   for (int d = 0; d < OAKB200_MAX_PEERS; d++) {
     if (h->pstream[d]) cudaStreamDestroy(h->pstream[d]);
@@ -1444,6 +1446,66 @@ extern "C" OAKB200_API int oakb200_assim_ensemble(oakb200_handle *h, int64_t n, 
     if (e == cudaSuccess && xa_out) e = cudaMemcpy(xa_out, dxa.p, 8 * (size_t)n, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { oak_set_error("assim_ensemble: D2H copy failed: %s", cudaGetErrorString(e)); rc = OAK_ERR_CUDA; }
     if (stats) { stats->h2d_bytes = 8ll * n * N + 16ll * nnz + 8ll * m * 4; stats->d2h_bytes = 8ll * n * N; }
+  }
+  cleanup();
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Observation-operator generation: batched cinterp (ndgrid.F90:1183-1257) for one model grid
+// ---------------------------------------------------------------------------------------------------------
+extern "C" OAKB200_API int oakb200_cinterp_dev(oakb200_handle *h, int32_t ndim, const int32_t *gshape, const double *axes,
+                                   const uint8_t *masked, int32_t m, const double *xi, int32_t *indexes, double *coeff,
+                                   int32_t *nbp, int32_t *ndegenerate, void *stream) {
+  if (!h || !gshape || !axes || (m > 0 && (!xi || !indexes || !coeff || !nbp))) { oak_set_error("cinterp: null argument"); return OAK_ERR_ARG; }
+  if (ndim < 1 || ndim > 4) { oak_set_error("cinterp: %d dimensions (1 .. 4 supported)", ndim); return OAK_ERR_UNSUPPORTED; }
+  DeviceGuard guard(h->device);
+  int rc;
+  if ((rc = h->d_tet.ensure(sizeof(double) * oak_cinterp_tet_doubles(ndim) + 64))) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->slot[0].st;
+  int *d_ndeg = reinterpret_cast<int *>(h->d_tet.as<double>() + oak_cinterp_tet_doubles(ndim));
+  if ((rc = oak_launch_cinterp(st, ndim, gshape, axes, masked, h->d_tet.as<double>(), m, xi, indexes, coeff, nbp, d_ndeg))) return rc;
+  int nd = 0;
+  CUDA_TRY(cudaMemcpyAsync(&nd, d_ndeg, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (ndegenerate) *ndegenerate = nd;
+  if (nd > 0) {
+    oak_set_error("cinterp: %d observation(s) fall in a degenerate cell (singleton dimension or |det| <= 1e-8): the SVD branch of "
+                  "interp_tetrahedron (ndgrid.F90:527-627) is not implemented on the device; they are marked nbp = -1", nd);
+    return OAK_ERR_UNSUPPORTED;
+  }
+  return 0;
+}
+
+extern "C" OAKB200_API int oakb200_cinterp(oakb200_handle *h, int32_t ndim, const int32_t *gshape, const double *axes,
+                               const uint8_t *masked, int32_t m, const double *xi, int32_t *indexes, double *coeff,
+                               int32_t *nbp, int32_t *ndegenerate) {
+  if (!h || !gshape || !axes || (m > 0 && (!xi || !indexes || !coeff || !nbp))) { oak_set_error("cinterp: null argument"); return OAK_ERR_ARG; }
+  if (ndim < 1 || ndim > 4) { oak_set_error("cinterp: %d dimensions (1 .. 4 supported)", ndim); return OAK_ERR_UNSUPPORTED; }
+  DeviceGuard guard(h->device);
+  size_t nax = 0, total = 1;
+  for (int k = 0; k < ndim; k++) {
+    if (gshape[k] < 1) { oak_set_error("cinterp: empty dimension"); return OAK_ERR_ARG; }
+    nax += (size_t)gshape[k]; total *= (size_t)gshape[k];
+  }
+  const size_t twon = (size_t)1 << ndim, mb = (size_t)std::max(m, 1);
+  DevBuf dax, dmask, dxi, didx, dco, dnbp;
+  auto cleanup = [&]() { dax.release(); dmask.release(); dxi.release(); didx.release(); dco.release(); dnbp.release(); };
+  int rc;
+  if ((rc = dax.ensure(8 * nax)) || (masked && (rc = dmask.ensure(total))) || (rc = dxi.ensure(8 * mb * ndim)) ||
+      (rc = didx.ensure(4 * mb * twon * ndim)) || (rc = dco.ensure(8 * mb * twon)) || (rc = dnbp.ensure(4 * mb))) { cleanup(); return rc; }
+  cudaStream_t st = h->slot[0].st;
+  cudaError_t e = cudaMemcpyAsync(dax.p, axes, 8 * nax, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && masked) e = cudaMemcpyAsync(dmask.p, masked, total, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && m > 0) e = cudaMemcpyAsync(dxi.p, xi, 8 * (size_t)m * ndim, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) { oak_set_error("cinterp: H2D copy failed: %s", cudaGetErrorString(e)); cleanup(); return OAK_ERR_CUDA; }
+  rc = oakb200_cinterp_dev(h, ndim, gshape, dax.as<double>(), masked ? dmask.as<uint8_t>() : nullptr, m, dxi.as<double>(),
+                           didx.as<int32_t>(), dco.as<double>(), dnbp.as<int32_t>(), ndegenerate, (void *)st);
+  if ((rc == 0 || rc == OAK_ERR_UNSUPPORTED) && m > 0) {
+    e = cudaMemcpy(indexes, didx.p, 4 * (size_t)m * twon * ndim, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(coeff, dco.p, 8 * (size_t)m * twon, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(nbp, dnbp.p, 4 * (size_t)m, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { oak_set_error("cinterp: D2H copy failed: %s", cudaGetErrorString(e)); rc = OAK_ERR_CUDA; }
   }
   cleanup();
   return rc;

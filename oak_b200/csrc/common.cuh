@@ -434,6 +434,12 @@ int oak_launch_global_gram(cudaStream_t st, int m, int N, int NP, const double *
 int oak_launch_block_starts(cudaStream_t st, int64_t n, int rows_per_block, int nblocks, int64_t *zstart);
 int oak_fp64_peak(int mode, double *tflops);
 
+// observation-operator generation: batched cinterp (hgen.cu)
+size_t oak_cinterp_tet_doubles(int n);
+int oak_launch_cinterp(cudaStream_t st, int n, const int32_t *gshape, const double *d_axes, const uint8_t *d_masked,
+                       double *d_tet, int m, const double *d_xi, int32_t *d_indexes, double *d_coeff, int32_t *d_nbp,
+                       int *d_ndeg);
+
 // ensemble prologue / epilogue (assimilation.F90:3106-3134, :3301-3357)
 int oak_launch_obsoper(cudaStream_t st, int m, int N, int64_t nnz, const int32_t *Hi, const int32_t *Hj,
                        const double *Hs, const double *Hshift, const double *E, int64_t ldE, double *HE);

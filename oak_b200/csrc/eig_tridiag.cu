@@ -40,7 +40,7 @@
 #define EIG_HALVES 1   // 2: a batch goes through tridiag / QL / eigenvectors in two software-pipelined halves
 #endif
 #ifndef TQL_GLOBAL
-#define TQL_GLOBAL 1   // k_tql: 1 = d, e of the warp's 32 zones transposed into a GLOBAL scratch array (L1 / L2 resident) and read
+#define TQL_GLOBAL 0   // k_tql: 1 = d, e of the warp's 32 zones transposed into a GLOBAL scratch array (L1 / L2 resident) and read
                        // through a register prefetch queue, no shared memory; 0 = transposed into 33 KB of shared memory per warp
 #endif
 #ifndef TQL_PF

@@ -320,3 +320,31 @@ def cinterp(gshape, coord_full, xi, masked=None):
     finally:
         L.oracle_ndgrid_destroy(g)
     return idx, co, nbp
+
+
+class NdGrid:
+    """Keeps the oracle's grid (and its lazily built databox tree, as the reference keeps it in type(grid)) alive
+    across calls: the CPU baseline of bench.py --config hgen times cinterp with the tree already built."""
+
+    def __init__(self, gshape, coord_full, masked=None):
+        self.L = lib()
+        self.gs = np.ascontiguousarray(gshape, dtype=np.int32)
+        self.n = self.gs.size
+        self.cf = np.ascontiguousarray(coord_full, dtype=np.float64)
+        self.mk = None if masked is None else np.ascontiguousarray(masked, dtype=np.uint8)
+        self.g = self.L.oracle_ndgrid_create(self.n, self.gs.ctypes.data_as(c_ip), _dp(self.cf),
+                                             None if self.mk is None else self.mk.ctypes.data_as(c_u8p))
+
+    def cinterp(self, xi):
+        xi = np.ascontiguousarray(xi, dtype=np.float64).reshape(-1, self.n)
+        m = xi.shape[0]
+        idx = np.zeros((m, 1 << self.n, self.n), dtype=np.int32)
+        co = np.zeros((m, 1 << self.n))
+        nbp = np.zeros(m, dtype=np.int32)
+        self.L.oracle_cinterp(self.g, m, _dp(xi), idx.ctypes.data_as(c_ip), _dp(co), nbp.ctypes.data_as(c_ip))
+        return idx, co, nbp
+
+    def close(self):
+        if self.g:
+            self.L.oracle_ndgrid_destroy(self.g)
+            self.g = None

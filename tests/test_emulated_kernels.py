@@ -85,3 +85,12 @@ def test_apply_on_tensor_core_tiles(emu_lib):
 def test_ensemble_prologue_and_epilogue_inside_the_apply_kernel(emu_lib):
     # option ens_fuse: bit-identical to the three-pass form (k_mean_anom, analysis, k_epilogue) and within 1e-9 of the oracle
     _run(emu_lib, "fused_in_the_apply")
+
+
+def test_observation_operator_weights(emu_lib):
+    # hgen.cu: batched cinterp against the oracle's restatement of ndgrid.F90 (cells, weights, tie-breaking on faces,
+    # degenerate cells reported)
+    env = dict(os.environ, OAK_B200_LIB=emu_lib, OAK_B200_TEST_EMU="1")
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_hgen_gpu.py"), "-q", "-x",
+                        "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and " passed" in p.stdout, p.stdout[-3000:] + p.stderr[-2000:]

@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "oak_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
 SOURCES = ["api.cu", "obsgrid.cu", "gram.cu", "gram_mma.cu", "eig_simple.cu", "eig_fast.cu", "eig_tridiag.cu", "apply.cu", "apply_mma.cu", "global.cu",
-           "ensemble.cu", "microbench.cu"]
+           "ensemble.cu", "hgen.cu", "microbench.cu"]
 CXXFLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-ffp-contract=off", "-mfma", "-fno-strict-aliasing",
             "-Wno-attributes", "-Wno-unknown-pragmas", "-DOAK_CUEMU=1", "-I" + os.path.join(HERE, "shim"), "-I" + HERE]
 
