@@ -133,6 +133,22 @@ module oak_b200_iface
      type(oakb200_stats) :: stats
      integer(c_int) :: rc
    end function
+   ! observation operator: batched cinterp (ndgrid.F90:1183-1257) for one model grid with separable axes; called from
+   ! genObservationOper (assimilation.F90:2569-2585) once per model variable instead of once per observation
+   function oakb200_cinterp(h, ndim, gshape, axes, masked, nobs, xi, indexes, coeff, nbp, ndegenerate) &
+        bind(C, name='oakb200_cinterp') result(rc)
+     import
+     type(c_ptr), value :: h
+     integer(c_int32_t), value :: ndim, nobs
+     integer(c_int32_t) :: gshape(*)            ! ndim entries
+     real(c_double) :: axes(*)                  ! the coordinate axes one after the other
+     type(c_ptr), value :: masked               ! c_loc of an integer(c_int8_t) array, 1 = masked, or c_null_ptr
+     real(c_double) :: xi(ndim, *)              ! xi(:,l) = position of observation l
+     integer(c_int32_t) :: indexes(ndim, 2**ndim, *)   ! 1-based corner subscripts: tmpHindex(7:6+ndim, ...)
+     real(c_double) :: coeff(2**ndim, *)        ! tmpHcoeff
+     integer(c_int32_t) :: nbp(*), ndegenerate  ! nbp = 2**ndim, 0 (out of grid / masked corner), -1 (degenerate cell)
+     integer(c_int) :: rc
+   end function
    ! multi-GPU (replaces parallPartion / parallGather, parall.F90:166-186, :507-566)
    function oakb200_partition_zones(nzones, nranks, first) bind(C, name='oakb200_partition_zones') result(rc)
      import

@@ -94,6 +94,13 @@ OAKB200_API int oakb200_destroy(oakb200_handle *h);
  *   "apply_tma"       1 (default) = where every zone has the same even number of rows <= 32 (water columns) and the
  *                     leading dimensions are even, the apply kernel stages the zone's rows with 2-D tensor copies (TMA:
  *                     cp.async.bulk.tensor.2d in and out); 0 = always the plain kernel
+ *   "ens_fuse"        oakb200_assim_ensemble[_dev], local scheme: 1 = the prologue (forward anamorphosis, mean, anomalies) and the
+ *                     epilogue (inflation, saturation, Ea, inverse anamorphosis, mean) run inside the apply kernel on the
+ *                     staged rows: E is read once and Ea written once; 0 = three passes (k_mean_anom, analysis in place,
+ *                     k_epilogue); -1 (default) = fused when there is no anamorphosis (measured on C5: log / exp inside the
+ *                     fp64-bound apply kernel cost more than the saved passes).  Bit-identical results either way
+ *   "push_kernel", "push_ctas"   fused gather: rows pushed by a small kernel (SM stores / multimem stores) on a side stream
+ *                     instead of copy-engine copies (default 1), its number of CTAs (24)
  *   "tri_orthtol"     route 4: accepted loss of orthogonality between neighbouring eigenvectors (default 1e-11)
  *   "tri_maxgroup"    route 4: largest group of close eigenvalues orthogonalised in place (default 6; 0 sends
  *                     every zone with a close pair to the Jacobi kernel)

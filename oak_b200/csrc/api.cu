@@ -528,6 +528,8 @@ int end_call(oakb200_handle *h, oakb200_stats *stats, int64_t launches, const Pr
 
 }  // namespace
 
+extern "C" OAKB200_API int oakb200_destroy(oakb200_handle *h);
+
 extern "C" OAKB200_API int oakb200_create(int device, oakb200_handle **out) {
   if (!out) { oak_set_error("null output pointer"); return OAK_ERR_ARG; }
   *out = nullptr;
@@ -547,17 +549,21 @@ extern "C" OAKB200_API int oakb200_create(int device, oakb200_handle **out) {
   }
   oakb200_handle *h = new oakb200_handle();
   h->device = device;
-  for (int i = 0; i < NSLOT; i++) {
-    CUDA_TRY(cudaStreamCreateWithFlags(&h->slot[i].st, cudaStreamNonBlocking));
-    { int lo = 0, hi = 0; CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CUDA_TRY(cudaStreamCreateWithPriority(&h->slot[i].qst, cudaStreamNonBlocking, hi)); CUDA_TRY(cudaStreamCreateWithPriority(&h->slot[i].cst, cudaStreamNonBlocking, hi)); }
-    for (auto &ev : h->slot[i].qev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    for (auto &ev : h->slot[i].ev) CUDA_TRY(cudaEventCreate(&ev));
-  }
-  CUDA_TRY(cudaEventCreate(&h->ev_a));
-  CUDA_TRY(cudaEventCreate(&h->ev_b));
-  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming));
-  int rc = h->d_ctr.ensure(sizeof(DevCounters));
-  if (rc) { delete h; return rc; }
+  // every resource is owned by the handle from the moment it exists: a failure below destroys what was created
+  auto build = [&]() -> int {
+    for (int i = 0; i < NSLOT; i++) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&h->slot[i].st, cudaStreamNonBlocking));
+      { int lo = 0, hi = 0; CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CUDA_TRY(cudaStreamCreateWithPriority(&h->slot[i].qst, cudaStreamNonBlocking, hi)); CUDA_TRY(cudaStreamCreateWithPriority(&h->slot[i].cst, cudaStreamNonBlocking, hi)); }
+      for (auto &ev : h->slot[i].qev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      for (auto &ev : h->slot[i].ev) CUDA_TRY(cudaEventCreate(&ev));
+    }
+    CUDA_TRY(cudaEventCreate(&h->ev_a));
+    CUDA_TRY(cudaEventCreate(&h->ev_b));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming));
+    return h->d_ctr.ensure(sizeof(DevCounters));
+  };
+  const int rc = build();
+  if (rc) { oakb200_destroy(h); return rc; }
   *out = h;
   return 0;
 }
@@ -991,6 +997,7 @@ extern "C" OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t
   if (rc) return rc;
   if ((n > 0 && (!xf || !Sf || !xa || !Sa)) || (m > 0 && (!Hxf || !yo || !HSf || !Rdiag))) { oak_set_error("local_analysis: null array"); return OAK_ERR_ARG; }
   if (ldSf < n || ldSa < n || ldHSf < m) { oak_set_error("local_analysis: leading dimension too small"); return OAK_ERR_ARG; }
+  if (n > 0 && xa == xf && !h->ens.on) { oak_set_error("local_analysis: xa must not be the array xf (Sa may be Sf; the mean is read while it is written)"); return OAK_ERR_ARG; }
   DeviceGuard guard(h->device);
   const int NP = padded(h, N);
   cudaStream_t s0 = h->slot[0].st;
@@ -1014,7 +1021,12 @@ extern "C" OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t
     Slot &s = h->slot[h->profile ? 0 : bi % NSLOT];
     const int z1 = std::min(h->nzones, z0 + zb);
     if ((rc = run_zones(h, s, N, NP, z0, z1, 0, xf, Sf, ldSf, xa, Sa, ldSa, &launches, h->profile ? &prof : nullptr,
-                        h->peers.n > 0, amplitudes, h->nrows))) return rc;
+                        h->peers.n > 0, amplitudes, h->nrows))) {
+      // nothing of this call may still be writing the caller's (or the peers') arrays when the error is returned
+      for (int i = 0; i < NSLOT; i++) { cudaStreamSynchronize(h->slot[i].st); cudaStreamSynchronize(h->slot[i].cst); cudaStreamSynchronize(h->slot[i].qst); }
+      for (int d = 0; d < OAKB200_MAX_PEERS; d++) if (h->pstream[d]) cudaStreamSynchronize(h->pstream[d]);
+      return rc;
+    }
   }
   for (int i = 1; i < NSLOT; i++) {
     CUDA_TRY(cudaEventRecord(h->slot[i].ev[5], h->slot[i].st));
