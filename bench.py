@@ -986,7 +986,7 @@ def run_hgen(a, rank, world, local):
     g = S.Grid(a.nx, a.ny, a.nz)
     m = a.m
     gshape = (a.nx, a.ny, a.nz)
-    axes = [g.dx * np.arange(1, a.nx + 1), g.dy * np.arange(1, a.ny + 1), -5.0 * np.arange(a.nz) ** 1.3]   # depth: descending, stretched
+    axes = [g.dx * np.arange(1, a.nx + 1), g.dx * np.arange(1, a.ny + 1), -5.0 * np.arange(a.nz) ** 1.3]   # depth: descending, stretched
     rng = np.random.default_rng(SEED)
     lo = np.array([ax.min() for ax in axes]); hi = np.array([ax.max() for ax in axes])
     xi = lo + (hi - lo) * rng.uniform(-0.01, 1.01, (m, 3))                                   # ~4 % outside the grid

@@ -53,6 +53,10 @@ struct TileMap {
   }
 };
 
+#ifndef GRAM_EVAL_PREFETCH
+#define GRAM_EVAL_PREFETCH 1
+#endif
+
 template <int NP, int NW, int W>
 struct GramMma {
   using TM = TileMap<NW, W>;
@@ -139,18 +143,32 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
   if (threadIdx.x == 0) s_true = 0;   // ordered before its first use by the barrier at the head of the cell loop
   for (int i = tid; i < 2 * GRAM_CH * LDR; i += NT) rowbuf[i] = 0.;  // 0 x (never written) must be 0, not NaN
 
-  // E(c): warps 0 and 1, 32 candidates each, into list buffer lb (as k_gram)
-  auto eval = [&](int c, int lb, int total) {
+  // E(c): warps 0 and 1, 32 candidates each, into list buffer lb (as k_gram), in two halves: the loads of the candidate's
+  // position, coefficient and innovation (global memory, scattered) and the predicate with the list update.  Inside the
+  // chunk loop the loads of chunk c+2 are issued BEFORE the tensor-core burst of chunk c and consumed after it
+  // (GRAM_EVAL_PREFETCH), so their latency is not waited for between the burst and the barrier.
+  int pf_p = 0;
+  bool pf_valid = false;
+  double pf_sx = 0., pf_sy = 0., pf_sc = 0., pf_dl = 0.;
+  auto eval_load = [&](int c, int total) {
     if (warp < GRAM_CH / 32) {
       int qq = c * GRAM_CH + warp * 32 + lane;
-      bool rel = false;
-      double w = 0.;
-      int p = 0;
-      if (qq < total) {
+      pf_valid = qq < total;
+      if (pf_valid) {
         int r = 0;
         while (qq >= s_rlen[r]) { qq -= s_rlen[r]; r++; }
-        p = s_rstart[r] + qq;
-        rel = oak_obs_relevant(q, og.sx[p], og.sy[p], w);
+        pf_p = s_rstart[r] + qq;
+        pf_sx = og.sx[pf_p]; pf_sy = og.sy[pf_p];
+        pf_sc = orows.scoef[pf_p]; pf_dl = orows.delta[pf_p];
+      }
+    }
+  };
+  auto eval_finish = [&](int lb) {
+    if (warp < GRAM_CH / 32) {
+      bool rel = false;
+      double w = 0.;
+      if (pf_valid) {
+        rel = oak_obs_relevant(q, pf_sx, pf_sy, w);
         if (q.noloc) {   // localise_obs = .false.: count the relevant ones, take them all
           if (rel) atomicAdd(&s_true, 1);
           rel = true;
@@ -160,10 +178,10 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
       const int cnt = __popc(bal);
       if (rel) {
         const int slot = warp * 32 + __popc(bal & ((1u << lane) - 1u));
-        const double coef = (w * w) * orows.scoef[p];
-        s_pos[lb][slot] = p;
+        const double coef = (w * w) * pf_sc;
+        s_pos[lb][slot] = pf_p;
         s_coef[lb][slot] = coef;
-        s_cd[lb][slot] = coef * orows.delta[p];
+        s_cd[lb][slot] = coef * pf_dl;
       }
       if (lane == 0) {
         s_cnt[lb][warp] = cnt;
@@ -171,6 +189,7 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
       }
     }
   };
+  auto eval = [&](int c, int lb, int total) { eval_load(c, total); eval_finish(lb); };
   // L(c): rows of list buffer lb into row buffer rb (one 16-byte cp.async per lane and row); the two warps'
   // finds are merged here: row buffer slot = r (warp 0's) or cnt0 + r (warp 1's), so the k-steps of four rows
   // run over one dense list
@@ -259,8 +278,14 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
         cp_async_wait<0>();
       }
       __syncthreads();  // rows of chunk c have landed for every thread
+#if GRAM_EVAL_PREFETCH
+      if (c + 2 < nchunk) eval_load(c + 2, total);
+      fma_rows(lb, rb);
+      if (c + 2 < nchunk) eval_finish((c + 2) % 3);
+#else
       fma_rows(lb, rb);
       if (c + 2 < nchunk) eval(c + 2, (c + 2) % 3, total);
+#endif
       __syncthreads();  // list c+2 visible; row buffer rb free for chunk c+2
     }
   }
