@@ -11,8 +11,7 @@
 //                   to the vertex average, |det| > 1e-8, admissible when -1e-8 <= c <= 1 + 1e-8
 //   c_cube = tetrahedron(:,:,l) c_simplex, corner indices 1-based, nbp = 2^n (0: outside the grid or a masked corner)
 //
-// Here: one thread per observation (the work per observation is a few hundred to a few thousand flops, the kernel is
-// bound by the scattered reads of the axes and the stores of the result), grids whose coordinate k depends on
+// Here: one thread per observation, grids whose coordinate k depends on
 // subscript k only (regular and rectilinear grids: `dependence` diagonal).  For those the tree search has a closed
 // form: a point on a shared face is inside several cells, the tree visits the upper half of a box first
 // (sub-box m = 1 has no lower half, :880-893), so the cell with the HIGHEST subscript in every dimension is the one the
@@ -21,6 +20,8 @@
 // Degenerate simplices (|det| <= 1e-8: singleton dimensions, cells thinner than the tolerance) take the SVD branch
 // in the reference (:527-627); that branch is not on the device: such observations are reported (nbp = -1) and the
 // call fails loudly instead of guessing.
+#include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "common.cuh"
@@ -75,6 +76,64 @@ struct HgenGrid {
   int64_t ioffset[HG_NDMAX];  // linear offset of subscript k in the mask
 };
 
+// Per simplex l, in the coordinates u in [0,1]^n of the cell (device table, built on the host):
+//   B_l ((n+1) x (n+1)) with c = B_l [1; u] the barycentric coordinates of u, det_l the determinant of the vertex matrix
+//   [1; W - mean(W)] of the UNIT cell.
+// A rectilinear cell is the unit cell stretched by h_k along dimension k: barycentric coordinates do not change under
+// an affine map, and the determinant interp_tetrahedron tests (ndgrid.F90:514-516, vertices relative to their
+// mean) is det_l * prod_k h_k.  The reference's inverse of the (n+1) x (n+1) matrix per simplex and observation
+// (matoper_inc.F90:569-602: ~1400 instructions here, the kernel then sits on the fp64 pipe: 533 M warp instructions
+// per 1e6 observations, profiles/r2_ncu_full_k_cinterp_lu.txt) becomes n (n+1) FMAs; the two forms agree to rounding
+// (1e-15), far inside the 1e-8 acceptance band that decides which simplex is taken.
+void simplex_tables(int n, const std::vector<double> &tet, std::vector<double> &B, std::vector<double> &det) {
+  const int twon = 1 << n, K = n + 1, nb = nsimplex(n);
+  B.assign((size_t)nb * K * K, 0.);
+  det.assign(nb, 0.);
+  for (int l = 0; l < nb; l++) {
+    double W[HG_NDMAX][HG_NDMAX + 1], wbar[HG_NDMAX], M[HG_NDMAX + 1][2 * (HG_NDMAX + 1)];
+    for (int k = 0; k < n; k++) {
+      wbar[k] = 0.;
+      for (int j = 0; j < K; j++) {
+        double sacc = 0.;
+        for (int q = 0; q < twon; q++)
+          if (q >> k & 1) sacc += tet[((size_t)l * K + j) * twon + q];
+        W[k][j] = sacc;
+        wbar[k] += sacc;
+      }
+      wbar[k] /= K;
+    }
+    for (int i = 0; i < K; i++)
+      for (int j = 0; j < K; j++) {
+        M[i][j] = i == 0 ? 1. : W[i - 1][j] - wbar[i - 1];
+        M[i][K + j] = i == j ? 1. : 0.;
+      }
+    double d = 1.;
+    for (int j = 0; j < K; j++) {  // Gauss-Jordan with partial pivoting
+      int p = j;
+      for (int i = j + 1; i < K; i++)
+        if (fabs(M[i][j]) > fabs(M[p][j])) p = i;
+      if (p != j) { for (int q = 0; q < 2 * K; q++) std::swap(M[j][q], M[p][q]); d = -d; }
+      const double piv = M[j][j];
+      d *= piv;
+      if (piv == 0.) continue;   // cannot happen: the simplices of the unit cell have volume 1 / (n! 2^(n-1))
+      for (int q = 0; q < 2 * K; q++) M[j][q] /= piv;
+      for (int i = 0; i < K; i++)
+        if (i != j) {
+          const double f = M[i][j];
+          for (int q = 0; q < 2 * K; q++) M[i][q] -= f * M[j][q];
+        }
+    }
+    det[l] = d;
+    // c = Ainv [1; u - wbar]  ->  c_j = (Ainv[j][0] - sum_k Ainv[j][1+k] wbar_k) + sum_k Ainv[j][1+k] u_k
+    for (int j = 0; j < K; j++) {
+      double a0 = M[j][K + 0];
+      for (int k = 0; k < n; k++) a0 -= M[j][K + 1 + k] * wbar[k];
+      B[((size_t)l * K + j) * K + 0] = a0;
+      for (int k = 0; k < n; k++) B[((size_t)l * K + j) * K + 1 + k] = M[j][K + 1 + k];
+    }
+  }
+}
+
 // largest cell subscript i in [0, g-2] whose interval contains v (ascending or descending axis); -1 outside
 __device__ __forceinline__ int locate_axis(const double *__restrict__ x, int g, double v) {
   if (g == 1) return (v == x[0]) ? 0 : -1;   // box test of a singleton dimension: xmin = xmax = x(1)
@@ -82,174 +141,117 @@ __device__ __forceinline__ int locate_axis(const double *__restrict__ x, int g, 
   const double lo = asc ? x[0] : x[g - 1], hi = asc ? x[g - 1] : x[0];
   if (v < lo || v > hi) return -1;
   // ascending: largest i with x[i] <= v ; descending: largest i with x[i] >= v ; both capped at g-2
-  int a = 0, b = g - 1;   // invariant: node a satisfies the predicate, node b is the first known not to (or g-1)
+  int a = 0, b = g - 1;   // node a satisfies the predicate, node b is the first known not to (or g-1)
   while (b - a > 1) {
     const int mid = (a + b) >> 1;
     const bool ok = asc ? (x[mid] <= v) : (x[mid] >= v);
     if (ok) a = mid; else b = mid;
   }
-  return a < g - 1 ? a : g - 2;
+  return a;
 }
 
-// c = M^-1 d by Gaussian elimination with the pivoting rule of dgetrf (largest modulus, first on ties); returns det
-template <int K>
-__device__ __forceinline__ double lu_solve(double (&M)[K][K], double (&c)[K]) {
-  double det = 1.;
-#pragma unroll
-  for (int j = 0; j < K; j++) {
-    int p = j;
-#pragma unroll
-    for (int i = j + 1; i < K; i++)
-      if (fabs(M[i][j]) > fabs(M[p][j])) p = i;
-    if (p != j) {
-#pragma unroll
-      for (int q = 0; q < K; q++) {
-        // row exchange written with selects so that the matrix stays in registers (no dynamically indexed array)
-        double rj = M[j][q], rp = rj;
-#pragma unroll
-        for (int i = j + 1; i < K; i++)
-          if (i == p) rp = M[i][q];
-        M[j][q] = rp;
-#pragma unroll
-        for (int i = j + 1; i < K; i++)
-          if (i == p) M[i][q] = rj;
-      }
-      double cj = c[j], cp = cj;
-#pragma unroll
-      for (int i = j + 1; i < K; i++)
-        if (i == p) cp = c[i];
-      c[j] = cp;
-#pragma unroll
-      for (int i = j + 1; i < K; i++)
-        if (i == p) c[i] = cj;
-      det = -det;
-    }
-    const double piv = M[j][j];
-    det *= piv;
-    if (piv != 0.) {
-#pragma unroll
-      for (int i = j + 1; i < K; i++) {
-        const double f = M[i][j] / piv;
-#pragma unroll
-        for (int q = j + 1; q < K; q++) M[i][q] -= f * M[j][q];
-        c[i] -= f * c[j];
-      }
-    }
-  }
-#pragma unroll
-  for (int j = K - 1; j >= 0; j--) {
-    c[j] /= M[j][j];
-#pragma unroll
-    for (int i = 0; i < j; i++) c[i] -= M[i][j] * c[j];
-  }
-  return det;
-}
-
-template <int N>
-__global__ void __launch_bounds__(128) k_cinterp(HgenGrid g, const double *__restrict__ axes,
-                                                 const uint8_t *__restrict__ masked, const double *__restrict__ tet,
-                                                 int nbth, int m, const double *__restrict__ xi,
-                                                 int32_t *__restrict__ indexes, double *__restrict__ coeff,
-                                                 int32_t *__restrict__ nbp, int *__restrict__ ndegenerate) {
+// One thread per observation; the block's results are staged in shared memory and leave in contiguous runs (the
+// per-observation records are 96 + 64 + 4 bytes in 3-D: written by their own threads every store instruction would
+// touch 32 sectors).
+template <int N, int NT>
+__global__ void __launch_bounds__(NT) k_cinterp(HgenGrid g, const double *__restrict__ axes,
+                                                const uint8_t *__restrict__ masked, const double *__restrict__ tet,
+                                                const double *__restrict__ Btab, const double *__restrict__ dettab,
+                                                int nbth, int m, const double *__restrict__ xi,
+                                                int32_t *__restrict__ indexes, double *__restrict__ coeff,
+                                                int32_t *__restrict__ nbp, int *__restrict__ ndegenerate) {
   constexpr int TWON = 1 << N, K = N + 1;
+  constexpr int LI = TWON * N + 1, LC = TWON + 1;   // odd strides: conflict-free staging
   constexpr double tol = 1e-8;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= m) return;
-  double x[N];
-  int ind[N];
-  bool out = false;
+  __shared__ int32_t s_ix[NT * LI];
+  __shared__ double s_cf[NT * LC];
+  __shared__ int32_t s_nbp[NT];
+  const int tid = threadIdx.x;
+  const int p0 = blockIdx.x * NT;
+  const int p = p0 + tid;
+  int32_t *ix = s_ix + tid * LI;
+  double *cf = s_cf + tid * LC;
+  int mynbp = 0;
 #pragma unroll
-  for (int k = 0; k < N; k++) {
-    x[k] = xi[(size_t)p * N + k];
-    ind[k] = locate_axis(axes + g.axoff[k], g.gshape[k], x[k]);
-    out = out || ind[k] < 0;
-  }
-  int32_t *ix = indexes + (size_t)p * TWON * N;
-  double *cf = coeff + (size_t)p * TWON;
-  if (out) {
-#pragma unroll
-    for (int q = 0; q < TWON * N; q++) ix[q] = 0;
-#pragma unroll
-    for (int q = 0; q < TWON; q++) cf[q] = 0.;
-    nbp[p] = 0;
-    return;
-  }
-  // corners of the cell: lower / upper node per dimension (a singleton dimension has one node), mask
-  double lo[N], hi[N];
-  bool anymasked = false;
-#pragma unroll
-  for (int k = 0; k < N; k++) {
-    const double *ax = axes + g.axoff[k];
-    lo[k] = ax[ind[k]];
-    hi[k] = g.gshape[k] > 1 ? ax[ind[k] + 1] : lo[k];
-  }
-#pragma unroll
-  for (int j = 0; j < TWON; j++) {
-    int64_t lin = 0;
-#pragma unroll
-    for (int k = 0; k < N; k++) {
-      const int c = ((j >> k & 1) && g.gshape[k] > 1) ? ind[k] + 1 : ind[k];
-      ix[j * N + k] = c + 1;
-      lin += c * g.ioffset[k];
-    }
-    if (masked && masked[lin]) anymasked = true;
-  }
+  for (int q = 0; q < TWON * N; q++) ix[q] = 0;
 #pragma unroll
   for (int q = 0; q < TWON; q++) cf[q] = 0.;
-  if (anymasked) { nbp[p] = 0; return; }
-
-  // interp_cube: first simplex that contains the point
-  bool degenerate = false;
-  for (int l = 0; l < nbth; l++) {
-    const double *T = tet + (size_t)l * K * TWON;
-    // vertices X(:,j) = sum_q px(:,q) T(q,j); px(k,q) = hi_k or lo_k by bit k of q
-    double X[N][K];
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-#pragma unroll
-      for (int k = 0; k < N; k++) X[k][j] = 0.;
-#pragma unroll
-      for (int q = 0; q < TWON; q++) {
-        const double t = __ldg(T + j * TWON + q);
-#pragma unroll
-        for (int k = 0; k < N; k++) X[k][j] = fma((q >> k & 1) ? hi[k] : lo[k], t, X[k][j]);
-      }
-    }
-    double M[K][K], c[K];
+  if (p < m) {
+    double x[N];
+    int ind[N];
+    bool out = false;
 #pragma unroll
     for (int k = 0; k < N; k++) {
-      double s = 0.;
-#pragma unroll
-      for (int j = 0; j < K; j++) s += X[k][j];
-      const double xc = s / K;
-#pragma unroll
-      for (int j = 0; j < K; j++) M[1 + k][j] = X[k][j] - xc;
-      c[1 + k] = x[k] - xc;
+      x[k] = xi[(size_t)p * N + k];
+      ind[k] = locate_axis(axes + g.axoff[k], g.gshape[k], x[k]);
+      out = out || ind[k] < 0;
     }
+    if (!out) {
+      // the cell: lower / upper node per dimension (a singleton dimension has one node), position inside it, mask
+      double u[N], vol = 1.;
+      bool anymasked = false;
 #pragma unroll
-    for (int j = 0; j < K; j++) M[0][j] = 1.;
-    c[0] = 1.;
-    const double det = lu_solve<K>(M, c);
-    if (!(fabs(det) > tol)) { degenerate = true; continue; }   // SVD branch of the reference: not on the device
-    bool in = true;
-#pragma unroll
-    for (int j = 0; j < K; j++) in = in && (0. - tol <= c[j] && c[j] <= 1. + tol);
-    if (in) {
-#pragma unroll
-      for (int q = 0; q < TWON; q++) {
-        double s = 0.;
-#pragma unroll
-        for (int j = 0; j < K; j++) s = fma(__ldg(T + j * TWON + q), c[j], s);
-        cf[q] = s;
+      for (int k = 0; k < N; k++) {
+        const double *ax = axes + g.axoff[k];
+        const double lo = ax[ind[k]];
+        const double h = g.gshape[k] > 1 ? ax[ind[k] + 1] - lo : 0.;
+        u[k] = h != 0. ? (x[k] - lo) / h : 0.;
+        vol *= h;
       }
-      nbp[p] = TWON;
-      return;
+#pragma unroll
+      for (int j = 0; j < TWON; j++) {
+        int64_t lin = 0;
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+          const int c = ((j >> k & 1) && g.gshape[k] > 1) ? ind[k] + 1 : ind[k];
+          ix[j * N + k] = c + 1;
+          lin += c * g.ioffset[k];
+        }
+        if (masked && masked[lin]) anymasked = true;
+      }
+      if (!anymasked) {
+        // interp_cube: first simplex that contains the point
+        bool degenerate = false, found = false;
+        for (int l = 0; l < nbth && !found; l++) {
+          if (!(fabs(__ldg(dettab + l) * vol) > tol)) { degenerate = true; continue; }   // SVD branch of the reference
+          const double *B = Btab + (size_t)l * K * K;
+          double c[K];
+          bool in = true;
+#pragma unroll
+          for (int j = 0; j < K; j++) {
+            double sacc = __ldg(B + j * K);
+#pragma unroll
+            for (int k = 0; k < N; k++) sacc = fma(__ldg(B + j * K + 1 + k), u[k], sacc);
+            c[j] = sacc;
+            in = in && (0. - tol <= sacc && sacc <= 1. + tol);
+          }
+          if (in) {
+            const double *T = tet + (size_t)l * K * TWON;
+#pragma unroll
+            for (int q = 0; q < TWON; q++) {
+              double sacc = 0.;
+#pragma unroll
+              for (int j = 0; j < K; j++) sacc = fma(__ldg(T + j * TWON + q), c[j], sacc);
+              cf[q] = sacc;
+            }
+            found = true;
+          }
+        }
+        // no simplex took the point: with a degenerate simplex on the way the reference would have gone through its SVD
+        // branch (reported); otherwise cinterp still returns nbp = 2^n
+        if (!found && degenerate) { mynbp = -1; atomicAdd(ndegenerate, 1); }
+        else mynbp = TWON;
+      }
     }
   }
-  // no simplex took the point.  With a degenerate simplex on the way the reference would have gone through its SVD
-  // branch: report; otherwise cinterp still returns nbp = 2^n with the coefficients it was given (zeros here)
-  if (degenerate) { nbp[p] = -1; atomicAdd(ndegenerate, 1); }
-  else nbp[p] = TWON;
+  s_nbp[tid] = mynbp;
+  __syncthreads();
+  const int nv = min(NT, m - p0);   // observations of this block
+  int32_t *gi = indexes + (size_t)p0 * TWON * N;
+  for (int i = tid; i < nv * TWON * N; i += NT) gi[i] = s_ix[(i / (TWON * N)) * LI + i % (TWON * N)];
+  double *gc = coeff + (size_t)p0 * TWON;
+  for (int i = tid; i < nv * TWON; i += NT) gc[i] = s_cf[(i / TWON) * LC + i % TWON];
+  if (tid < nv) nbp[p0 + tid] = s_nbp[tid];
 }
 
 }  // namespace
@@ -268,22 +270,27 @@ int oak_launch_cinterp(cudaStream_t st, int n, const int32_t *gshape, const doub
     g.gshape[k] = gshape[k]; g.axoff[k] = off; g.ioffset[k] = io;
     off += gshape[k]; io *= gshape[k];
   }
-  const int nb = nsimplex(n);
-  std::vector<double> tet((size_t)nb * (n + 1) * (1 << n), 0.);
-  split_host(n, n, 0u, (1u << (1 << n)) - 1u, tet, 0);   // n <= 4: at most 16 corners
-  CUDA_TRY(cudaMemcpyAsync(d_tet, tet.data(), sizeof(double) * tet.size(), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaStreamSynchronize(st));   // `tet` goes out of scope
+  const int nb = nsimplex(n), K = n + 1, twon = 1 << n;
+  std::vector<double> tab((size_t)nb * K * twon, 0.), B, det;
+  split_host(n, n, 0u, (1u << twon) - 1u, tab, 0);   // n <= 4: at most 16 corners
+  simplex_tables(n, tab, B, det);
+  const size_t ntet = tab.size();
+  tab.insert(tab.end(), B.begin(), B.end());
+  tab.insert(tab.end(), det.begin(), det.end());
+  CUDA_TRY(cudaMemcpyAsync(d_tet, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));   // `tab` goes out of scope
   CUDA_TRY(cudaMemsetAsync(d_ndeg, 0, sizeof(int), st));
   if (m <= 0) return 0;
-  const int grid = (m + 127) / 128;
+  const double *dB = d_tet + ntet, *dD = dB + B.size();
   switch (n) {
-    case 1: k_cinterp<1><<<grid, 128, 0, st>>>(g, d_axes, d_masked, d_tet, nb, m, d_xi, d_indexes, d_coeff, d_nbp, d_ndeg); break;
-    case 2: k_cinterp<2><<<grid, 128, 0, st>>>(g, d_axes, d_masked, d_tet, nb, m, d_xi, d_indexes, d_coeff, d_nbp, d_ndeg); break;
-    case 3: k_cinterp<3><<<grid, 128, 0, st>>>(g, d_axes, d_masked, d_tet, nb, m, d_xi, d_indexes, d_coeff, d_nbp, d_ndeg); break;
-    case 4: k_cinterp<4><<<grid, 128, 0, st>>>(g, d_axes, d_masked, d_tet, nb, m, d_xi, d_indexes, d_coeff, d_nbp, d_ndeg); break;
+    case 1: k_cinterp<1, 128><<<(m + 127) / 128, 128, 0, st>>>(g, d_axes, d_masked, d_tet, dB, dD, nb, m, d_xi, d_indexes, d_coeff, d_nbp, d_ndeg); break;
+    case 2: k_cinterp<2, 128><<<(m + 127) / 128, 128, 0, st>>>(g, d_axes, d_masked, d_tet, dB, dD, nb, m, d_xi, d_indexes, d_coeff, d_nbp, d_ndeg); break;
+    case 3: k_cinterp<3, 128><<<(m + 127) / 128, 128, 0, st>>>(g, d_axes, d_masked, d_tet, dB, dD, nb, m, d_xi, d_indexes, d_coeff, d_nbp, d_ndeg); break;
+    case 4: k_cinterp<4, 64><<<(m + 63) / 64, 64, 0, st>>>(g, d_axes, d_masked, d_tet, dB, dD, nb, m, d_xi, d_indexes, d_coeff, d_nbp, d_ndeg); break;
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
-size_t oak_cinterp_tet_doubles(int n) { return (size_t)nsimplex(n) * (n + 1) * (1 << n); }
+// simplex table + barycentric matrices + determinants
+size_t oak_cinterp_tet_doubles(int n) { return (size_t)nsimplex(n) * ((n + 1) * (1 << n) + (n + 1) * (n + 1) + 1); }
