@@ -155,8 +155,8 @@ __device__ __forceinline__ int locate_axis(const double *__restrict__ x, int g, 
 // touch 32 sectors).
 template <int N, int NT>
 __global__ void __launch_bounds__(NT) k_cinterp(HgenGrid g, const double *__restrict__ axes,
-                                                const uint8_t *__restrict__ masked, const double *__restrict__ tet,
-                                                const double *__restrict__ Btab, const double *__restrict__ dettab,
+                                                const uint8_t *__restrict__ masked, const double *tet,
+                                                const double *Btab, const double *dettab,
                                                 int nbth, int m, const double *__restrict__ xi,
                                                 int32_t *__restrict__ indexes, double *__restrict__ coeff,
                                                 int32_t *__restrict__ nbp, int *__restrict__ ndegenerate) {
@@ -166,7 +166,20 @@ __global__ void __launch_bounds__(NT) k_cinterp(HgenGrid g, const double *__rest
   __shared__ int32_t s_ix[NT * LI];
   __shared__ double s_cf[NT * LC];
   __shared__ int32_t s_nbp[NT];
+  // the simplex tables (9.4 KB in 3-D) in shared memory: the lanes of a warp read them at different simplices (a gather:
+  // through the read-only path this was 49 % long-scoreboard stalls); 4-D (163 KB) keeps them in global memory
+  constexpr bool SMTAB = N <= 3;
+  constexpr int NBTH = N == 1 ? 1 : (N == 2 ? 4 : 24);
+  constexpr int TABD = SMTAB ? NBTH * (K * TWON + K * K + 1) : 1;
+  __shared__ double s_tab[TABD];
   const int tid = threadIdx.x;
+  if (SMTAB) {
+    for (int i = tid; i < NBTH * K * TWON; i += NT) s_tab[i] = tet[i];
+    for (int i = tid; i < NBTH * K * K; i += NT) s_tab[NBTH * K * TWON + i] = Btab[i];
+    for (int i = tid; i < NBTH; i += NT) s_tab[NBTH * (K * TWON + K * K) + i] = dettab[i];
+    __syncthreads();
+    tet = s_tab; Btab = s_tab + NBTH * K * TWON; dettab = s_tab + NBTH * (K * TWON + K * K);
+  }
   const int p0 = blockIdx.x * NT;
   const int p = p0 + tid;
   int32_t *ix = s_ix + tid * LI;
@@ -210,20 +223,25 @@ __global__ void __launch_bounds__(NT) k_cinterp(HgenGrid g, const double *__rest
         if (masked && masked[lin]) anymasked = true;
       }
       if (!anymasked) {
-        // interp_cube: first simplex that contains the point
+        // interp_cube: first simplex (in the order of split) that contains the point.
+        // Fast path: the simplex that contains u follows from the order of |u_k - 1/2| (each level of split cuts the
+        // current face into pyramids over its sub-faces, apex = face centre; the pyramid that holds the point is the one
+        // over the sub-face in the direction of the largest |u_k - 1/2| among the free dimensions).  If the point is inside
+        // that simplex by a margin of 1e-5 in every barycentric coordinate it is outside every other simplex of the
+        // tiling by far more than the acceptance band of 1e-8, so "the first simplex that accepts" is this one and the
+        // ordered search is not needed.  Points closer to a simplex boundary (and degenerate cells) take the ordered loop.
         bool degenerate = false, found = false;
-        for (int l = 0; l < nbth && !found; l++) {
-          if (!(fabs(__ldg(dettab + l) * vol) > tol)) { degenerate = true; continue; }   // SVD branch of the reference
+        auto test = [&](int l, double margin) -> bool {
           const double *B = Btab + (size_t)l * K * K;
           double c[K];
           bool in = true;
 #pragma unroll
           for (int j = 0; j < K; j++) {
-            double sacc = __ldg(B + j * K);
+            double sacc = B[j * K];
 #pragma unroll
-            for (int k = 0; k < N; k++) sacc = fma(__ldg(B + j * K + 1 + k), u[k], sacc);
+            for (int k = 0; k < N; k++) sacc = fma(B[j * K + 1 + k], u[k], sacc);
             c[j] = sacc;
-            in = in && (0. - tol <= sacc && sacc <= 1. + tol);
+            in = in && (margin <= sacc && sacc <= 1. - margin);
           }
           if (in) {
             const double *T = tet + (size_t)l * K * TWON;
@@ -231,11 +249,34 @@ __global__ void __launch_bounds__(NT) k_cinterp(HgenGrid g, const double *__rest
             for (int q = 0; q < TWON; q++) {
               double sacc = 0.;
 #pragma unroll
-              for (int j = 0; j < K; j++) sacc = fma(__ldg(T + j * TWON + q), c[j], sacc);
+              for (int j = 0; j < K; j++) sacc = fma(T[j * TWON + q], c[j], sacc);
               cf[q] = sacc;
             }
-            found = true;
           }
+          return in;
+        };
+        {
+          int lstar = 0, sub = nbth;
+          unsigned fixedm = 0;
+#pragma unroll
+          for (int level = 0; level < N - 1; level++) {
+            int best = 0;
+            double bv = -1.;
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+              const double a = fabs(u[k] - 0.5);
+              if (!(fixedm >> k & 1u) && a > bv) { bv = a; best = k; }
+            }
+            const int pos = __popc(~fixedm & ((1u << best) - 1u));
+            sub /= 2 * (N - level);
+            lstar += (2 * pos + (u[best] > 0.5 ? 1 : 0)) * sub;
+            fixedm |= 1u << best;
+          }
+          if (fabs(dettab[lstar] * vol) > tol) found = test(lstar, 1e-5);
+        }
+        for (int l = 0; l < nbth && !found; l++) {
+          if (!(fabs(dettab[l] * vol) > tol)) { degenerate = true; continue; }   // SVD branch of the reference
+          found = test(l, 0. - tol);
         }
         // no simplex took the point: with a degenerate simplex on the way the reference would have gone through its SVD
         // branch (reported); otherwise cinterp still returns nbp = 2^n

@@ -77,3 +77,26 @@ def test_cinterp_out_of_grid_and_masked_points():
     idx, co, nbp = oracle.cinterp(sz, coord, pts, masked=masked)
     assert list(nbp) == [4, 0, 0, 0, 4, 0]   # inside; outside; (2.5,12.5) and (1.5,11.0) touch the masked node; corner; outside
     assert abs(co[0].sum() - 1) < 1e-12
+
+
+def test_simplex_of_a_point_follows_from_the_order_of_its_offsets_from_the_centre():
+    # what k_cinterp's fast path relies on (oak_b200/csrc/hgen.cu): in the numbering of split (ndgrid.F90:357-435) the
+    # simplex that contains u is found level by level from the free dimension with the largest |u_k - 1/2| and its side
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 4):
+        t = oracle.tetrahedra(n)
+        nb = t.shape[0]
+        corners = np.array([[(q >> k) & 1 for k in range(n)] for q in range(2 ** n)], dtype=float)
+        V = t @ corners                                  # [nb][n+1][n] vertices of the simplices of the unit cell
+        for _ in range(300):
+            u = rng.uniform(0, 1, n)
+            lstar, sub, fixed = 0, nb, 0
+            for level in range(n - 1):
+                free = [k for k in range(n) if not (fixed >> k) & 1]
+                best = max(free, key=lambda k: (abs(u[k] - 0.5), -k))
+                sub //= 2 * (n - level)
+                lstar += (2 * free.index(best) + (1 if u[best] > 0.5 else 0)) * sub
+                fixed |= 1 << best
+            M = np.vstack([np.ones(n + 1), V[lstar].T])
+            c = np.linalg.solve(M, np.concatenate([[1.0], u]))
+            assert (c >= -1e-12).all()
