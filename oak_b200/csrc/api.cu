@@ -141,6 +141,7 @@ struct oakb200_handle {
   int push_pieces = 1;        // peer_mode 1: the apply of a batch is launched in this many pieces, each pushed as soon as it is done
   int peer_mode = 1;          // 1: copy engines push every finished batch (no SM time); 0: stores of k_apply    // ... largest group of close eigenvalues orthogonalised in place (-1: default)
   int zones_per_batch = 0;
+  int taper = 0;              // > 0: batches inside the last (taper + 1) x zones_per_batch zones of a call halve (see local_analysis_dev)
   double tol = 2e-11;  // bound on the remaining non-orthogonality (eig_common.cuh: jacobi_converged)
   int max_sweeps = 30;
   int profile = 0;
@@ -780,6 +781,7 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   else if (k == "peer_mode") h->peer_mode = (int)value;
   else if (k == "push_pieces") h->push_pieces = std::max(1, (int)value);
   else if (k == "zones_per_batch") h->zones_per_batch = (int)value;
+  else if (k == "taper") h->taper = std::max(0, (int)value);
   else if (k == "jacobi_tol") h->tol = value;
   else if (k == "max_sweeps") h->max_sweeps = (int)value;
   else if (k == "fixed_sweeps") { h->max_sweeps = (int)value; h->tol = -1.; }  // timing experiments: no convergence test
@@ -1017,9 +1019,16 @@ extern "C" OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t
   ProfAcc prof;
   const int zb = batch_size(h, NP, h->nzones);
   int bi = 0;
-  for (int z0 = 0; z0 < h->nzones; z0 += zb, bi++) {
+  // option "taper": the last batches of a call get smaller (half of what is left, in whole waves), so that the chain of
+  // kernels that ends the call - which nothing overlaps any more - is short; matters on the small slabs of a multi-GPU run
+  const int wave = NP <= 64 ? 592 : 148;
+  for (int z0 = 0, zn = 0; z0 < h->nzones; z0 += zn, bi++) {
     Slot &s = h->slot[h->profile ? 0 : bi % NSLOT];
-    const int z1 = std::min(h->nzones, z0 + zb);
+    zn = zb;
+    const int left = h->nzones - z0;
+    if (h->taper > 0 && !h->profile && left < (h->taper + 1) * zb && left > 2 * wave)
+      zn = std::min(zb, std::max(wave, (left / 2 + wave - 1) / wave * wave));
+    const int z1 = std::min(h->nzones, z0 + zn);
     if ((rc = run_zones(h, s, N, NP, z0, z1, 0, xf, Sf, ldSf, xa, Sa, ldSa, &launches, h->profile ? &prof : nullptr,
                         h->peers.n > 0, amplitudes, h->nrows))) {
       // nothing of this call may still be writing the caller's (or the peers') arrays when the error is returned

@@ -307,6 +307,29 @@ def test_in_place_chunked_and_device_resident_paths_agree(ob):
     h.close()
 
 
+@pytest.mark.needs_torch_cuda
+def test_tapered_batches_give_the_same_bits(ob):
+    # option taper (device-resident entry point): the last batches of a call halve so that the chain of kernels that
+    # ends the call is short; zones are independent, so any partition into batches must give identical results
+    import torch
+    from oak_b200 import synthetic
+    c = synthetic.small_case(nx=80, ny=64, nz=2, N=16, m=4000, corr=2500.0, maxlen=5000.0, seed=13)   # 5120 zones
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = []
+    for taper in (0, 2):
+        h = ob.Handle(0, zones_per_batch=2368, taper=taper)
+        _configure(ob, h, c)
+        Sf_d, HSf_d = t(c["Sf"].T), t(c["HSf"].T)
+        xa_d, Sa_d = torch.empty(c["Sf"].shape[0], dtype=torch.float64, device=dev), torch.empty_like(Sf_d)
+        st = h.local_analysis_dev(t(c["xf"]), t(c["Hxf"]), t(c["yo"]), Sf_d, HSf_d, t(c["var"]), xa_d, Sa_d)
+        torch.cuda.synchronize()
+        out.append((xa_d.cpu().numpy(), Sa_d.cpu().numpy(), st["launches"]))
+        h.close()
+    assert (out[0][0] == out[1][0]).all() and (out[0][1] == out[1][1]).all()
+    assert out[1][2] > out[0][2]      # more, smaller batches at the end
+
+
 def test_assim_ensemble_with_inflation_anamorphosis_and_saturation(ob, handle):
     from oak_b200 import synthetic
     g = synthetic.Grid(18, 14, 3)

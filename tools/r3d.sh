@@ -14,6 +14,13 @@ import json,sys
 d=json.loads(sys.stdin.read())
 print('value %.0f columns/s  ms/step %.2f  %s  parity %s' % (d['value'], d['ms_per_step'], d['config']['parallelism'][14:60], d.get('parity', {}).get('ok')), {k: round(v,1) for k,v in d['roofline']['kernel_ms_per_step'].items()})" | tee -a $LOG
 }
+if [ "$2" = "second" ]; then
+run taper1 OAK_B200_OPTIONS=taper=1
+run zb5920 OAK_B200_ZB=5920
+run taper1_zb5920 OAK_B200_OPTIONS=taper=1 OAK_B200_ZB=5920
+run nslot8 OAK_B200_LIB=$PWD/oak_b200/variants/liboak_nslot8.so
+else
 run default A=1
 run zb16k OAK_B200_ZB=15984
 run zb10k OAK_B200_ZB=10656
+fi
