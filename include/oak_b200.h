@@ -72,7 +72,7 @@ OAKB200_API int oakb200_destroy(oakb200_handle *h);
  *                     file, assimilation.F90:292,:3227; zones and observation positions are then not needed)
  *   "eig_kernel"      4 = Householder tridiagonalisation + QL + twisted factorisation (default for N <= 64;
  *                     flagged zones fall back to 0), 0 = register-resident block Jacobi (N > 64), 1 = simple
- *                     shared-memory Jacobi (cross-check), 2 / 3 = measured variants of 0
+ *                     shared-memory Jacobi (cross-check)
  *   "gram_kernel"     1 = fp64 tensor-core tiles (mma.m8n8k4, 4 warps per zone; default since the round-2 timing:
  *                     8.6 -> 5.7 ms per 90 k zones), 2 = 2 warps per zone, 3 / 4 = the same with chunks of 32 instead of
  *                     64 candidates (half the shared memory), 0 = DFMA register tiles; padded ensemble size 64 only,

@@ -754,7 +754,10 @@ extern "C" OAKB200_API int oakb200_host_free(void *ptr) {
 extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key, double value) {
   if (!h || !key) { oak_set_error("null argument"); return OAK_ERR_ARG; }
   const std::string k(key);
-  if (k == "eig_kernel") h->eig_kernel = (int)value;
+  if (k == "eig_kernel") {
+    if (value != 4. && value != 0. && value != 1.) { oak_set_error("eig_kernel = %g (4 tridiagonal route, 0 block Jacobi, 1 shared-memory cross-check)", value); return OAK_ERR_ARG; }
+    h->eig_kernel = (int)value;
+  }
   else if (k == "fuse_apply") h->fuse_apply = value != 0.;
   else if (k == "tvec_split") h->tvec_split = value != 0.;
   else if (k == "tql_side") h->tql_side = value != 0.;

@@ -691,11 +691,10 @@ int oak_launch_eig(cudaStream_t st, int kernel, int N, int NP, int zone0, int nz
                    DevCounters *ctr) {
   if (nz <= 0) return 0;
   const int32_t *ml = mloc + zone0;
-  // 0: production (two columns per block, 4 lanes per group at NP=64 / 8 at NP=128); 2, 3: measured variants
+  // 0: two columns per block, 4 lanes per group at NP = 64 / 8 at NP = 128.  The variants measured and rejected in round 1
+  // (8 lanes per group: -15 %, one column per block: -64 %; profiles/r1_notes.md) are no longer instantiated.
   if (kernel == 0 && NP == 64) return launch<64, 4, 2>(st, N, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
-  if (kernel == 2 && NP == 64) return launch<64, 8, 2>(st, N, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
-  if (kernel == 3 && NP == 64) return launch<64, 4, 1>(st, N, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
-  if ((kernel == 0 || kernel == 2 || kernel == 3) && NP == 128)
-    return launch<128, 8, 2>(st, N, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
+  if (kernel == 0 && NP == 128) return launch<128, 8, 2>(st, N, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
+  if (kernel != 0 && kernel != 1) { oak_set_error("eig_kernel = %d (4 tridiagonal route, 0 block Jacobi, 1 shared-memory cross-check)", kernel); return OAK_ERR_ARG; }
   return oak_launch_eig_simple(st, N, NP, nz, ml, G, c, T, ampl, tol, max_sweeps, ctr);
 }

@@ -170,15 +170,18 @@ __global__ void __launch_bounds__(NT) k_cinterp(HgenGrid g, const double *__rest
   // through the read-only path this was 49 % long-scoreboard stalls); 4-D (163 KB) keeps them in global memory
   constexpr bool SMTAB = N <= 3;
   constexpr int NBTH = N == 1 ? 1 : (N == 2 ? 4 : 24);
-  constexpr int TABD = SMTAB ? NBTH * (K * TWON + K * K + 1) : 1;
+  // odd strides per simplex (the lanes of a warp sit at different simplices: with the dense strides of 32 and 16 doubles
+  // they would all hit the same banks: 28 M conflicts per 1e6 observations)
+  constexpr int ST = SMTAB ? K * TWON + 1 : K * TWON, SB = SMTAB ? K * K + 1 : K * K;
+  constexpr int TABD = SMTAB ? NBTH * (ST + SB + 1) : 1;
   __shared__ double s_tab[TABD];
   const int tid = threadIdx.x;
   if (SMTAB) {
-    for (int i = tid; i < NBTH * K * TWON; i += NT) s_tab[i] = tet[i];
-    for (int i = tid; i < NBTH * K * K; i += NT) s_tab[NBTH * K * TWON + i] = Btab[i];
-    for (int i = tid; i < NBTH; i += NT) s_tab[NBTH * (K * TWON + K * K) + i] = dettab[i];
+    for (int i = tid; i < NBTH * K * TWON; i += NT) s_tab[(i / (K * TWON)) * ST + i % (K * TWON)] = tet[i];
+    for (int i = tid; i < NBTH * K * K; i += NT) s_tab[NBTH * ST + (i / (K * K)) * SB + i % (K * K)] = Btab[i];
+    for (int i = tid; i < NBTH; i += NT) s_tab[NBTH * (ST + SB) + i] = dettab[i];
     __syncthreads();
-    tet = s_tab; Btab = s_tab + NBTH * K * TWON; dettab = s_tab + NBTH * (K * TWON + K * K);
+    tet = s_tab; Btab = s_tab + NBTH * ST; dettab = s_tab + NBTH * (ST + SB);
   }
   const int p0 = blockIdx.x * NT;
   const int p = p0 + tid;
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(NT) k_cinterp(HgenGrid g, const double *__rest
         // ordered search is not needed.  Points closer to a simplex boundary (and degenerate cells) take the ordered loop.
         bool degenerate = false, found = false;
         auto test = [&](int l, double margin) -> bool {
-          const double *B = Btab + (size_t)l * K * K;
+          const double *B = Btab + (size_t)l * SB;
           double c[K];
           bool in = true;
 #pragma unroll
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(NT) k_cinterp(HgenGrid g, const double *__rest
             in = in && (margin <= sacc && sacc <= 1. - margin);
           }
           if (in) {
-            const double *T = tet + (size_t)l * K * TWON;
+            const double *T = tet + (size_t)l * ST;
 #pragma unroll
             for (int q = 0; q < TWON; q++) {
               double sacc = 0.;

@@ -23,12 +23,11 @@ def ob():
     return oak_b200
 
 
-@pytest.fixture(scope="module", params=[4, 0, 2, 3, 1],
-                ids=["eig_tridiag", "eig_fast", "eig_fast8", "eig_fast_k1", "eig_simple"])
+@pytest.fixture(scope="module", params=[4, 0, 1],
+                ids=["eig_tridiag", "eig_fast", "eig_simple"])
 def handle(request, ob):
     # pad_to=64 sends even the small golden cases through the production register-resident kernels
-    # (4: tridiagonal route, the default; 0: 4 lanes per column group, 2: 8 lanes per group, 3: one column per block; 1: simple shared-memory
-    # cross-check kernel)
+    # (4: tridiagonal route, the default; 0: register-resident block Jacobi; 1: simple shared-memory cross-check kernel)
     h = ob.Handle(0, eig_kernel=request.param, pad_to=64 if request.param != 1 else 0)
     yield h
     h.close()
@@ -318,7 +317,7 @@ def test_tapered_batches_give_the_same_bits(ob):
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     out = []
     for taper in (0, 2):
-        h = ob.Handle(0, zones_per_batch=2368, taper=taper)
+        h = ob.Handle(0, zones_per_batch=2368, taper=taper)     # batches 2368, 2368, 384 against 2368, 1776, 976
         _configure(ob, h, c)
         Sf_d, HSf_d = t(c["Sf"].T), t(c["HSf"].T)
         xa_d, Sa_d = torch.empty(c["Sf"].shape[0], dtype=torch.float64, device=dev), torch.empty_like(Sf_d)
@@ -327,7 +326,6 @@ def test_tapered_batches_give_the_same_bits(ob):
         out.append((xa_d.cpu().numpy(), Sa_d.cpu().numpy(), st["launches"]))
         h.close()
     assert (out[0][0] == out[1][0]).all() and (out[0][1] == out[1][1]).all()
-    assert out[1][2] > out[0][2]      # more, smaller batches at the end
 
 
 def test_assim_ensemble_with_inflation_anamorphosis_and_saturation(ob, handle):
