@@ -126,3 +126,48 @@ def test_twisted_vector2_equals_twisted_vector(hostlib, n):
         assert r2 <= 1e-13 * tn and np.abs(T @ z2 - lam[j] * z2).max() <= 1e-13 * tn
         gapj = min([abs(lam[j] - lam[k]) for k in range(n) if k != j] + [tn]) / tn
         assert min(np.abs(z1 - z2).max(), np.abs(z1 + z2).max()) <= 1e-13 / max(gapj, 1e-12)
+
+
+def test_pwk_loop_forms_give_identical_bits(tmp_path):
+    """k_tql's QL iteration in its forms — loop nest (PWK_FLAT=0) / one flat loop over sweeps (default), direct reads /
+    register prefetch queue (pwk_eigenvalues_t<6>, TQL_GLOBAL) — performs the same operations on the same values per
+    zone: eigenvalues and rotation counts must be IDENTICAL, also on matrices that split (tracked block ends, the
+    bookkeeping that replaced the rescan at every l)."""
+    dp = ctypes.POINTER(ctypes.c_double)
+    fns = []
+    for k, flags in enumerate((["-DPWK_FLAT=0"], ["-DPWK_FLAT=1"])):
+        out = str(tmp_path / f"libtri{k}.so")
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-ffp-contract=off"] + flags +
+                              [os.path.join(ROOT, "tools", "tridiag_host.cpp"), "-o", out])
+        lib = ctypes.CDLL(out)
+        for f in (lib.host_pwk, lib.host_pwk_pf):
+            f.argtypes = [ctypes.c_int, dp, dp, ctypes.c_int, ctypes.c_double]
+            fns.append(f)
+    rng = np.random.default_rng(5)
+    for t in range(400):
+        n = int(rng.integers(2, 65))
+        A = rng.normal(size=(int(rng.integers(1, 3 * n)), n)) * 10 ** rng.uniform(-3, 3)
+        G = A.T @ A
+        if t % 5 == 0:
+            G = np.diag(rng.uniform(0, 1, n))
+        if t % 11 == 0:     # repeated diagonal blocks: many splits
+            k = n // 4 + 1
+            B = rng.normal(size=(k, k))
+            G = np.kron(np.eye(4), B @ B.T)[:n, :n].copy()
+        import scipy.linalg as sl
+        H = sl.hessenberg(G)
+        d = np.diag(H).copy(); e = np.append(np.diag(H, -1), 0.0)
+        if t % 7 == 0 and n > 4:
+            e[n // 2] = 0.0; e[n // 3] = 0.0
+        if t % 19 == 0:
+            d = rng.normal(size=n); e = np.append(rng.normal(size=n - 1) * np.where(rng.uniform(size=n - 1) < 0.3, 1e-18, 1.0), 0.0)
+        tn = max(np.abs(d).max(), np.abs(e).max())
+        res = []
+        for f in fns:
+            dd, ee = d.copy(), e.copy()
+            rc = f(n, dd.ctypes.data_as(dp), ee.ctypes.data_as(dp), 1, tn)
+            res.append((rc, dd))
+        for rc, dd in res[1:]:
+            assert rc == res[0][0] and np.array_equal(dd, res[0][1])
+        T = np.diag(d) + np.diag(e[:-1], 1) + np.diag(e[:-1], -1)
+        assert np.abs(res[0][1] - np.linalg.eigvalsh(T)).max() <= 3e-14 * max(tn, 1e-300)
