@@ -615,22 +615,39 @@ def main():
                    "d2h_bytes_per_step": ste["d2h_bytes"], "steps": a.e2e_steps,
                    "note": "oakb200_set_observations + oakb200_local_analysis on pinned host buffers; state streamed in zone chunks; "
                            "bytes are per rank; no all-gather of host buffers" + ("" if ok else "; MISMATCH vs resident run")}
-            # the same call on PAGEABLE host arrays (what a Fortran caller's allocatables are): once with the library
-            # page-locking them for the call (option host_register, the default) and once leaving them pageable
+            # the same call on PAGEABLE host arrays (what a Fortran caller's allocatables are): through the library's pinned
+            # staging ring filled by host threads (option host_stage, the default for large calls), with direct asynchronous
+            # copies from the pageable arrays (the driver stages them), and with the arrays page-locked for the call
             if world == 1 and not a.no_pageable:
                 pg = {}
                 q = hb[0]
                 pb = {k: torch.empty_like(v, pin_memory=False).copy_(v) for k, v in q.items()}
-                for mode in (1, 0):
-                    h.set_option("host_register", mode)
+
+                def timed_pageable():
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
                     h.set_observations(obs_x=phases[0]["ox"], obs_y=phases[0]["oy"])
                     h.local_analysis_pinned(pb["xf"], pb["Hxf"], pb["yo"], pb["Sf"], pb["HSf"], pb["var"], pb["xa"], pb["Sa"])
                     torch.cuda.synchronize()
-                    pg["host_register=%d" % mode] = nzones / (time.perf_counter() - t0)
-                h.set_option("host_register", 0)
-                pg["identical_to_pinned_run"] = bool(torch.equal(pb["Sa"], q["Sa"]))
+                    return nzones / (time.perf_counter() - t0)
+                same = True
+                for thr in [int(x) for x in os.environ.get("OAK_B200_STAGE_THREADS", "0").split(",")]:
+                    h.set_option("host_stage", 1); h.set_option("stage_threads", thr)
+                    timed_pageable()                       # first call allocates the pinned staging buffers
+                    pb["Sa"].zero_()
+                    pg["host_stage=1,threads=%s" % (thr or "default")] = timed_pageable()
+                    same = same and bool(torch.equal(pb["Sa"], q["Sa"]))
+                h.set_option("stage_threads", 0)
+                h.set_option("host_stage", 0)
+                pb["Sa"].zero_()
+                pg["host_stage=0"] = timed_pageable()
+                same = same and bool(torch.equal(pb["Sa"], q["Sa"]))
+                if os.environ.get("OAK_B200_BENCH_HOST_REGISTER"):   # measured in round 2: 0.09 - 0.20 M columns/s, kept out of the default run
+                    h.set_option("host_register", 1)
+                    pg["host_register=1"] = timed_pageable()
+                    h.set_option("host_register", 0)
+                h.set_option("host_stage", -1)
+                pg["identical_to_pinned_run"] = same
                 e2e["pageable_columns_per_s"] = pg
                 del pb
             del hb

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -89,7 +90,20 @@ struct DevBuf {
   template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// Pinned staging of a chunk of the caller's PAGEABLE state arrays (option host_stage): copies from pageable memory are
+// staged by the driver through one thread (measured 0.37 M columns/s end to end on C3 against 2.6 M from pinned arrays,
+// and cudaHostRegister per call costs more than it saves); here the library owns two pinned buffers per stream slot and
+// moves the chunk in and out with several host threads, overlapped with the kernels of the other slots.
+struct HostStage {
+  double *in = nullptr, *out = nullptr;
+  size_t cap = 0;
+  cudaEvent_t ev_out = nullptr;
+  bool pending = false;          // a finished chunk sits in `out` and has not been copied to the caller's arrays yet
+  int64_t r0 = 0, rows = 0;
+};
+
 struct Slot {
+  HostStage hs;
   cudaStream_t st = nullptr;
   cudaStream_t cst = nullptr;  // copy-engine pushes of finished batches to the peers (peer_mode 1)
   bool cst_used = false;
@@ -120,6 +134,10 @@ struct oakb200_handle {
                               // (27.9 ms per step) than under the HBM-bound streaming kernels (27.1 ms)
   EnsFuse ens{};              // set for the duration of such a call
   int apply_tma = 1;          // k_apply_tma (zone rows staged by 2-D tensor copies) where its conditions hold, else k_apply
+  int host_stage = -1;        // host-buffer entry points, pageable caller arrays: 1 = chunks go through pinned staging buffers filled by
+                              // `stage_threads` host threads, 0 = asynchronous copies straight from the caller's arrays, -1 (default) = 1 for
+                              // calls of 32 MB and more
+  int stage_threads = 0;      // 0: min(16, hardware threads)
   int host_register = 0;      // host-buffer entry points: 1 = page-lock the caller's pageable arrays for the duration of the call
                               // (measured on C3: registering 31 GB per call costs more than the driver's staged copies:
                               // 0.09 vs 0.40 M columns/s; pinned buffers from oakb200_host_alloc: 2.68 M)
@@ -214,6 +232,51 @@ struct HostPins {
   }
   ~HostPins() { for (void *q : regs) cudaHostUnregister(q); }
 };
+
+// dst(rows x ncols, leading dimension dld) = src(rows x ncols, leading dimension sld) with `nt` host threads, each a
+// contiguous share of the flattened (column, row) range
+void par_copy_cols(double *dst, size_t dld, const double *src, size_t sld, size_t rows, int ncols, int nt) {
+  const size_t total = rows * (size_t)ncols;
+  if (total == 0) return;
+  auto work = [=](size_t a, size_t b) {
+    while (a < b) {
+      const size_t col = a / rows, r = a - col * rows, len = std::min(rows - r, b - a);
+      memcpy(dst + col * dld + r, src + col * sld + r, len * sizeof(double));
+      a += len;
+    }
+  };
+  nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)nt, total / (1u << 16) + 1));   // >= 512 KB per thread
+  if (nt == 1) { work(0, total); return; }
+  std::vector<std::thread> th;
+  th.reserve(nt - 1);
+  for (int t = 1; t < nt; t++) th.emplace_back(work, total * t / nt, total * (t + 1) / nt);
+  work(0, total / nt);
+  for (auto &x : th) x.join();
+}
+
+int ensure_stage(Slot &s, size_t doubles) {
+  if (!s.hs.ev_out) CUDA_TRY(cudaEventCreateWithFlags(&s.hs.ev_out, cudaEventDisableTiming));
+  if (doubles <= s.hs.cap) return 0;
+  if (s.hs.in) cudaFreeHost(s.hs.in);
+  if (s.hs.out) cudaFreeHost(s.hs.out);
+  s.hs.in = s.hs.out = nullptr; s.hs.cap = 0;
+  void *a = nullptr, *b = nullptr;
+  if (cudaHostAlloc(&a, doubles * sizeof(double), cudaHostAllocPortable) != cudaSuccess ||
+      cudaHostAlloc(&b, doubles * sizeof(double), cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    if (a) cudaFreeHost(a);
+    oak_set_error("host_stage: cannot allocate %zu bytes of page-locked staging memory", 2 * doubles * sizeof(double));
+    return OAK_ERR_NOMEM;
+  }
+  s.hs.in = (double *)a; s.hs.out = (double *)b; s.hs.cap = doubles;
+  return 0;
+}
+
+bool is_pageable(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeUnregistered;
+}
 
 struct DeviceGuard {
   int prev = -1;
@@ -586,6 +649,9 @@ extern "C" OAKB200_API int oakb200_destroy(oakb200_handle *h) {
   for (int i = 0; i < NSLOT; i++) {
     Slot &s = h->slot[i];
     s.Wv.release(); s.G.release(); s.T.release(); s.c.release(); s.ampl.release(); s.tri.release(); s.S.release(); s.xf.release(); s.xa.release();
+    if (s.hs.in) cudaFreeHost(s.hs.in);
+    if (s.hs.out) cudaFreeHost(s.hs.out);
+    if (s.hs.ev_out) cudaEventDestroy(s.hs.ev_out);
     for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
     if (s.st) cudaStreamDestroy(s.st);
     if (s.cst) cudaStreamDestroy(s.cst);
@@ -763,6 +829,8 @@ extern "C" OAKB200_API int oakb200_set_option(oakb200_handle *h, const char *key
   else if (k == "tql_side") h->tql_side = value != 0.;
   else if (k == "localise_obs") h->localise_obs = value != 0.;
   else if (k == "host_register") h->host_register = value != 0.;
+  else if (k == "host_stage") h->host_stage = value < 0. ? -1 : (value != 0.);
+  else if (k == "stage_threads") h->stage_threads = std::max(0, (int)value);
   else if (k == "apply_tma") h->apply_tma = value != 0.;
   else if (k == "ens_fuse") h->ens_fuse = value < 0. ? -1 : (value != 0.);
   else if (k == "push_kernel") h->push_kernel = value != 0.;
@@ -1140,6 +1208,20 @@ extern "C" OAKB200_API int oakb200_local_analysis(oakb200_handle *h, int64_t n, 
   const int64_t rows_target = std::max<int64_t>(1, (int64_t)(h->chunk_mb * 1024. * 1024. / (8. * N)));
   int64_t launches = 1;
   ProfAcc prof;
+  // pageable caller arrays: through the slot's pinned staging buffers, filled / drained by several host threads
+  const bool stage = !h->host_register && n > 0 &&
+                     (h->host_stage == 1 || (h->host_stage < 0 && 8. * (double)n * N >= 32. * 1024 * 1024)) &&
+                     (is_pageable(Sf) || is_pageable(Sa));
+  const int nthreads = h->stage_threads > 0 ? h->stage_threads : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  for (int i = 0; i < NSLOT; i++) h->slot[i].hs.pending = false;   // nothing of an earlier (failed) call is drained into these arrays
+  auto drain = [&](Slot &s) -> int {   // the slot's finished chunk: pinned buffer -> the caller's Sa, xa
+    if (!s.hs.pending) return 0;
+    CUDA_TRY(cudaEventSynchronize(s.hs.ev_out));
+    par_copy_cols(Sa + s.hs.r0, (size_t)ldSa, s.hs.out, (size_t)s.hs.rows, (size_t)s.hs.rows, N, nthreads);
+    memcpy(xa + s.hs.r0, s.hs.out + (size_t)s.hs.rows * N, sizeof(double) * (size_t)s.hs.rows);
+    s.hs.pending = false;
+    return 0;
+  };
   int ci = 0;
   for (int z0 = 0; z0 < h->nzones; ci++) {
     int z1 = z0;
@@ -1149,20 +1231,40 @@ extern "C" OAKB200_API int oakb200_local_analysis(oakb200_handle *h, int64_t n, 
     Slot &s = h->slot[h->profile ? 0 : ci % NSLOT];
     if (rows > 0) {
       if ((rc = s.S.ensure(8 * (size_t)rows * N)) || (rc = s.xf.ensure(8 * (size_t)rows)) || (rc = s.xa.ensure(8 * (size_t)rows))) return rc;
-      CUDA_TRY(cudaMemcpy2DAsync(s.S.p, 8 * (size_t)rows, Sf + r0, 8 * (size_t)ldSf, 8 * (size_t)rows, N, cudaMemcpyHostToDevice, s.st));
-      CUDA_TRY(cudaMemcpyAsync(s.xf.p, xf + r0, 8 * (size_t)rows, cudaMemcpyHostToDevice, s.st));
+      if (stage) {
+        // the slot's previous chunk leaves its output buffer first (its device-to-host copy is behind its host-to-device
+        // copy in the slot's stream, so the input buffer is free as well)
+        if ((rc = drain(s)) || (rc = ensure_stage(s, (size_t)rows * (N + 1)))) return rc;
+        par_copy_cols(s.hs.in, (size_t)rows, Sf + r0, (size_t)ldSf, (size_t)rows, N, nthreads);
+        memcpy(s.hs.in + (size_t)rows * N, xf + r0, sizeof(double) * (size_t)rows);
+        CUDA_TRY(cudaMemcpyAsync(s.S.p, s.hs.in, 8 * (size_t)rows * N, cudaMemcpyHostToDevice, s.st));
+        CUDA_TRY(cudaMemcpyAsync(s.xf.p, s.hs.in + (size_t)rows * N, 8 * (size_t)rows, cudaMemcpyHostToDevice, s.st));
+      } else {
+        CUDA_TRY(cudaMemcpy2DAsync(s.S.p, 8 * (size_t)rows, Sf + r0, 8 * (size_t)ldSf, 8 * (size_t)rows, N, cudaMemcpyHostToDevice, s.st));
+        CUDA_TRY(cudaMemcpyAsync(s.xf.p, xf + r0, 8 * (size_t)rows, cudaMemcpyHostToDevice, s.st));
+      }
       h2d += 8ll * rows * (N + 1);
     }
     if ((rc = run_zones(h, s, N, NP, z0, z1, r0, s.xf.as<double>(), s.S.as<double>(), rows, s.xa.as<double>(),
                         s.S.as<double>(), rows, &launches, h->profile ? &prof : nullptr, false, d_ampl_out, rows)))
       return rc;
     if (rows > 0) {
-      CUDA_TRY(cudaMemcpy2DAsync(Sa + r0, 8 * (size_t)ldSa, s.S.p, 8 * (size_t)rows, 8 * (size_t)rows, N, cudaMemcpyDeviceToHost, s.st));
-      CUDA_TRY(cudaMemcpyAsync(xa + r0, s.xa.p, 8 * (size_t)rows, cudaMemcpyDeviceToHost, s.st));
+      if (stage) {
+        CUDA_TRY(cudaMemcpyAsync(s.hs.out, s.S.p, 8 * (size_t)rows * N, cudaMemcpyDeviceToHost, s.st));
+        CUDA_TRY(cudaMemcpyAsync(s.hs.out + (size_t)rows * N, s.xa.p, 8 * (size_t)rows, cudaMemcpyDeviceToHost, s.st));
+        CUDA_TRY(cudaEventRecord(s.hs.ev_out, s.st));
+        s.hs.pending = true; s.hs.r0 = r0; s.hs.rows = rows;
+      } else {
+        CUDA_TRY(cudaMemcpy2DAsync(Sa + r0, 8 * (size_t)ldSa, s.S.p, 8 * (size_t)rows, 8 * (size_t)rows, N, cudaMemcpyDeviceToHost, s.st));
+        CUDA_TRY(cudaMemcpyAsync(xa + r0, s.xa.p, 8 * (size_t)rows, cudaMemcpyDeviceToHost, s.st));
+      }
       d2h += 8ll * rows * (N + 1);
     }
     z0 = z1;
   }
+  if (stage)
+    for (int i = 0; i < NSLOT; i++)
+      if ((rc = drain(h->slot[i]))) return rc;
   for (int i = 1; i < NSLOT; i++) {
     CUDA_TRY(cudaEventRecord(h->slot[i].ev[5], h->slot[i].st));
     CUDA_TRY(cudaStreamWaitEvent(s0, h->slot[i].ev[5], 0));

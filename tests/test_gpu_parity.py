@@ -306,6 +306,28 @@ def test_in_place_chunked_and_device_resident_paths_agree(ob):
     h.close()
 
 
+@pytest.mark.parametrize("in_place", [False, True])
+def test_pageable_arrays_through_the_pinned_staging_ring(ob, in_place):
+    # option host_stage (default for calls of 32 MB and more on pageable arrays, forced here): the chunks of the state
+    # travel through the stream slots' pinned buffers, filled and drained by several host threads; same bits as the
+    # direct asynchronous copies, with many chunks per slot, ragged zones, in place or not
+    from oak_b200 import synthetic
+    c = synthetic.small_case(nx=40, ny=30, nz=6, N=64, m=2500, corr=2500.0, maxlen=5000.0, seed=11)
+    out = {}
+    for stage in (0, 1):
+        h = ob.Handle(0, host_stage=stage, stage_threads=3, chunk_mb=0.3, zones_per_batch=64)
+        _configure(ob, h, c)
+        S = c["Sf"].copy(order="F")
+        xa, Sa, _, st = h.local_analysis(c["xf"], c["Hxf"], c["yo"], S, c["HSf"], ob.DiagCovar(c["var"]),
+                                         **({"out_Sa": S} if in_place else {}))
+        assert (Sa is S) == in_place
+        out[stage] = (xa.copy(), Sa.copy(), st["h2d_bytes"], st["d2h_bytes"])
+        h.close()
+    assert (out[0][0] == out[1][0]).all() and (out[0][1] == out[1][1]).all() and out[0][2:] == out[1][2:]
+    xo, So, _, _ = _oracle_loc(c)
+    assert rel(out[1][0], xo) < RTOL and rel(out[1][1], So) < RTOL
+
+
 @pytest.mark.needs_torch_cuda
 def test_tapered_batches_give_the_same_bits(ob):
     # option taper (device-resident entry point): the last batches of a call halve so that the chain of kernels that
