@@ -278,11 +278,56 @@ bool is_pageable(const void *p) {
   return a.type == cudaMemoryTypeUnregistered;
 }
 
+// A pageable host array (rows x ncols, leading dimension ld) to / from a dense device array (leading dimension dld)
+// through the pinned staging buffers of slots 0 and 1: pieces of <= 64 MB, filled / drained by host threads while the
+// previous piece is on the bus.  Synchronous: complete on return.  Not to be used while chunks of an analysis are in
+// flight on those slots (the callers run it before / after the analysis).
+int staged_copy(oakb200_handle *h, bool to_device, double *dev, size_t dld, double *host, size_t ld, size_t rows, int ncols,
+                int nthreads);
+
 struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
+
+int staged_copy(oakb200_handle *h, bool to_device, double *dev, size_t dld, double *host, size_t ld, size_t rows, int ncols,
+                int nthreads) {
+  if (rows == 0 || ncols == 0) return 0;
+  const size_t piece = (size_t)8 << 20;   // doubles per piece (64 MB)
+  const size_t rb = std::min(rows, piece);
+  const int cb = (int)std::max<size_t>(1, std::min<size_t>((size_t)ncols, piece / rb));
+  int rc, k = 0;
+  struct Pending { size_t r0, nr; int c0, nc; bool on = false; } pend[2];
+  auto finish = [&](int i) -> int {   // device-to-host: the piece that has landed in the slot's buffer goes to the caller
+    Slot &s = h->slot[i];
+    CUDA_TRY(cudaEventSynchronize(s.hs.ev_out));
+    if (!to_device && pend[i].on)
+      par_copy_cols(host + (size_t)pend[i].c0 * ld + pend[i].r0, ld, s.hs.out, pend[i].nr, pend[i].nr, pend[i].nc, nthreads);
+    pend[i].on = false;
+    return 0;
+  };
+  for (size_t r0 = 0; r0 < rows; r0 += rb)
+    for (int c0 = 0; c0 < ncols; c0 += cb, k++) {
+      const size_t nr = std::min(rb, rows - r0);
+      const int nc = std::min(cb, ncols - c0);
+      const int i = k & 1;
+      Slot &s = h->slot[i];
+      if (k >= 2 && (rc = finish(i))) return rc;
+      if ((rc = ensure_stage(s, std::max(s.hs.cap, nr * (size_t)nc)))) return rc;
+      if (to_device) {
+        par_copy_cols(s.hs.in, nr, host + (size_t)c0 * ld + r0, ld, nr, nc, nthreads);
+        CUDA_TRY(cudaMemcpy2DAsync(dev + (size_t)c0 * dld + r0, 8 * dld, s.hs.in, 8 * nr, 8 * nr, nc, cudaMemcpyHostToDevice, s.st));
+      } else {
+        CUDA_TRY(cudaMemcpy2DAsync(s.hs.out, 8 * nr, dev + (size_t)c0 * dld + r0, 8 * dld, 8 * nr, nc, cudaMemcpyDeviceToHost, s.st));
+      }
+      CUDA_TRY(cudaEventRecord(s.hs.ev_out, s.st));
+      pend[i] = Pending{r0, nr, c0, nc, true};
+    }
+  for (int i = 0; i < 2; i++)
+    if (pend[i].on && (rc = finish(i))) return rc;
+  return 0;
+}
 
 int ensure_ws(oakb200_handle *h, Slot &s, int NP, int zb) {
   int rc;
@@ -1185,8 +1230,16 @@ extern "C" OAKB200_API int oakb200_local_analysis(oakb200_handle *h, int64_t n, 
   if ((rc = h->d_HSf.ensure(8 * mb * N)) || (rc = h->d_yo.ensure(8 * mb)) || (rc = h->d_Hxf.ensure(8 * mb)) ||
       (rc = h->d_R.ensure(8 * mb)) || (rc = h->d_d01.ensure(8 * mb)))
     return rc;
+  // pageable caller arrays: through the slot's pinned staging buffers, filled / drained by several host threads
+  const bool stage = !h->host_register && n > 0 &&
+                     (h->host_stage == 1 || (h->host_stage < 0 && 8. * (double)n * N >= 32. * 1024 * 1024)) &&
+                     (is_pageable(Sf) || is_pageable(Sa));
+  const int nthreads = h->stage_threads > 0 ? h->stage_threads : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   if (m > 0) {
-    CUDA_TRY(cudaMemcpy2DAsync(h->d_HSf.p, 8 * (size_t)m, HSf, 8 * (size_t)ldHSf, 8 * (size_t)m, N, cudaMemcpyHostToDevice, s0));
+    if (stage && is_pageable(HSf)) {
+      if ((rc = staged_copy(h, true, h->d_HSf.as<double>(), (size_t)m, const_cast<double *>(HSf), (size_t)ldHSf, (size_t)m, N, nthreads))) return rc;
+    } else
+      CUDA_TRY(cudaMemcpy2DAsync(h->d_HSf.p, 8 * (size_t)m, HSf, 8 * (size_t)ldHSf, 8 * (size_t)m, N, cudaMemcpyHostToDevice, s0));
     CUDA_TRY(cudaMemcpyAsync(h->d_yo.p, yo, 8 * (size_t)m, cudaMemcpyHostToDevice, s0));
     CUDA_TRY(cudaMemcpyAsync(h->d_Hxf.p, Hxf, 8 * (size_t)m, cudaMemcpyHostToDevice, s0));
     CUDA_TRY(cudaMemcpyAsync(h->d_R.p, Rdiag, 8 * (size_t)m, cudaMemcpyHostToDevice, s0));
@@ -1208,11 +1261,6 @@ extern "C" OAKB200_API int oakb200_local_analysis(oakb200_handle *h, int64_t n, 
   const int64_t rows_target = std::max<int64_t>(1, (int64_t)(h->chunk_mb * 1024. * 1024. / (8. * N)));
   int64_t launches = 1;
   ProfAcc prof;
-  // pageable caller arrays: through the slot's pinned staging buffers, filled / drained by several host threads
-  const bool stage = !h->host_register && n > 0 &&
-                     (h->host_stage == 1 || (h->host_stage < 0 && 8. * (double)n * N >= 32. * 1024 * 1024)) &&
-                     (is_pageable(Sf) || is_pageable(Sa));
-  const int nthreads = h->stage_threads > 0 ? h->stage_threads : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   for (int i = 0; i < NSLOT; i++) h->slot[i].hs.pending = false;   // nothing of an earlier (failed) call is drained into these arrays
   auto drain = [&](Slot &s) -> int {   // the slot's finished chunk: pinned buffer -> the caller's Sa, xa
     if (!s.hs.pending) return 0;
@@ -1556,7 +1604,12 @@ extern "C" OAKB200_API int oakb200_assim_ensemble(oakb200_handle *h, int64_t n, 
       (rc = dmaxc.ensure(8 * nb)) || (rc = dxf.ensure(8 * nb)) || (rc = dxa.ensure(8 * nb))) { cleanup(); return rc; }
   cudaError_t e = cudaSuccess;
   auto up = [&](void *d, const void *s, size_t bytes) { if (e == cudaSuccess && bytes && s) e = cudaMemcpy(d, s, bytes, cudaMemcpyHostToDevice); };
-  if (n > 0) e = cudaMemcpy2D(h->d_E.p, 8 * (size_t)n, E, 8 * (size_t)ldE, 8 * (size_t)n, N, cudaMemcpyHostToDevice);
+  // pageable E / Ea of 32 MB and more: through the pinned staging buffers with host threads (option host_stage)
+  const bool stage = !h->host_register && n > 0 && (h->host_stage == 1 || (h->host_stage < 0 && 8. * (double)n * N >= 32. * 1024 * 1024));
+  const int nthreads = h->stage_threads > 0 ? h->stage_threads : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  if (n > 0 && stage && is_pageable(E)) {
+    if ((rc = staged_copy(h, true, h->d_E.as<double>(), (size_t)n, const_cast<double *>(E), (size_t)ldE, (size_t)n, N, nthreads))) { cleanup(); return rc; }
+  } else if (n > 0) e = cudaMemcpy2D(h->d_E.p, 8 * (size_t)n, E, 8 * (size_t)ldE, 8 * (size_t)n, N, cudaMemcpyHostToDevice);
   up(dHi.p, Hi, 4 * (size_t)nnz); up(dHj.p, Hj, 4 * (size_t)nnz); up(dHs.p, Hs, 8 * (size_t)nnz);
   up(dHshift.p, Hshift, 8 * (size_t)m); up(dyo.p, yo, 8 * (size_t)m); up(dR.p, Rdiag, 8 * (size_t)m);
   up(dd01.p, d01, 8 * (size_t)m); up(dmaxc.p, maxCorrection, 8 * (size_t)n);
@@ -1567,7 +1620,9 @@ extern "C" OAKB200_API int oakb200_assim_ensemble(oakb200_handle *h, int64_t n, 
                                   maxCorrection ? dmaxc.as<double>() : nullptr, h->d_E.as<double>(), n,
                                   dxf.as<double>(), dxa.as<double>(), nullptr, stats);
   if (rc == 0) {
-    if (n > 0) e = cudaMemcpy2D(Ea, 8 * (size_t)ldEa, h->d_E.p, 8 * (size_t)n, 8 * (size_t)n, N, cudaMemcpyDeviceToHost);
+    if (n > 0 && stage && is_pageable(Ea)) {
+      if ((rc = staged_copy(h, false, h->d_E.as<double>(), (size_t)n, Ea, (size_t)ldEa, (size_t)n, N, nthreads))) { cleanup(); return rc; }
+    } else if (n > 0) e = cudaMemcpy2D(Ea, 8 * (size_t)ldEa, h->d_E.p, 8 * (size_t)n, 8 * (size_t)n, N, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && xf_out) e = cudaMemcpy(xf_out, dxf.p, 8 * (size_t)n, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && xa_out) e = cudaMemcpy(xa_out, dxa.p, 8 * (size_t)n, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { oak_set_error("assim_ensemble: D2H copy failed: %s", cudaGetErrorString(e)); rc = OAK_ERR_CUDA; }

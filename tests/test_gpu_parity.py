@@ -328,6 +328,32 @@ def test_pageable_arrays_through_the_pinned_staging_ring(ob, in_place):
     assert rel(out[1][0], xo) < RTOL and rel(out[1][1], So) < RTOL
 
 
+def test_ensemble_entry_point_through_the_staging_buffers(ob):
+    # oakb200_assim_ensemble on pageable arrays with host_stage = 1: E up and Ea down in pieces through the pinned
+    # buffers (staged_copy), HSf of the local analysis likewise; identical to the plain copies
+    from oak_b200 import synthetic
+    g = synthetic.Grid(14, 11, 4)
+    N, m = 24, 90
+    rows = np.arange(g.n, dtype=np.int64)
+    E = np.exp(0.3 * synthetic.ensemble_rows(np, g, rows, N, 5)).T.copy(order="F")
+    obs = synthetic.observations(np, g, m, 5)
+    Hi, Hj, Hs = synthetic.coo_operator(g, obs)
+    yo = 1.0 + 0.1 * synthetic.normal(np, np.arange(m, dtype=np.int64), 8, 5)
+    zx, zy = g.zone_xy(np, np.arange(g.nzones, dtype=np.int64))
+    zs = np.full(g.nzones, 4, np.int32)
+    sel = ob.Selector(zone_x=zx, zone_y=zy, corrLen=3000.0, maxLen=6000.0, obs_x=obs["ox"], obs_y=obs["oy"], metrictype=0)
+    out = []
+    for stage in (0, 1):
+        h = ob.Handle(0, host_stage=stage, stage_threads=3)
+        h.set_option("scheme", 1)
+        h.configure(zs, sel)
+        Ea, xf, xa, _ = h.assim_ensemble(E, Hi, Hj, Hs, None, yo, ob.DiagCovar(obs["var"]), anamtype=2, inflation=1.02)
+        out.append((Ea, xf, xa))
+        h.close()
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.needs_torch_cuda
 def test_tapered_batches_give_the_same_bits(ob):
     # option taper (device-resident entry point): the last batches of a call halve so that the chain of kernels that
