@@ -39,6 +39,10 @@
 #ifndef EIG_HALVES
 #define EIG_HALVES 1   // 2: a batch goes through tridiag / QL / eigenvectors in two software-pipelined halves
 #endif
+#ifndef TVEC_DOT8
+#define TVEC_DOT8 0     // 1: 8 instead of 4 accumulation chains in the dot products of the back-transformation and 4 partial sums in the
+                        // N-long sums behind it: measured equal (k_tvec 75.9 -> 76.4 ms per C3 step), the chains are not what bounds it
+#endif
 #ifndef TQL_GLOBAL
 #define TQL_GLOBAL 0   // k_tql: 1 = d, e of the warp's 32 zones transposed into a GLOBAL scratch array (L1 / L2 resident) and read
                        // through a register prefetch queue, no shared memory; 0 = transposed into 33 KB of shared memory per warp
@@ -604,6 +608,26 @@ struct BackTile {
       double2 vv[M1];
 #pragma unroll
       for (int m = M0; m < M1; m++) vv[m] = *reinterpret_cast<const double2 *>(v + 4 * m);
+#if TVEC_DOT8
+      // eight accumulation chains instead of four: a dependent DFMA costs ~25 cycles on this part, so four chains of up
+      // to 16 links (400 cycles per reflector) were longer than the 128 issue cycles of the 64 FMAs of the dot products
+      double a0 = 0., a1 = 0., b0 = 0., b1 = 0., a2 = 0., a3 = 0., b2 = 0., b3 = 0.;
+#pragma unroll
+      for (int m = M0; m < M1; m++) {
+        if ((m - M0) & 1) {
+          a2 = fma(u[0][2 * m], vv[m].x, a2);
+          a3 = fma(u[0][2 * m + 1], vv[m].y, a3);
+          b2 = fma(u[1][2 * m], vv[m].x, b2);
+          b3 = fma(u[1][2 * m + 1], vv[m].y, b3);
+        } else {
+          a0 = fma(u[0][2 * m], vv[m].x, a0);
+          a1 = fma(u[0][2 * m + 1], vv[m].y, a1);
+          b0 = fma(u[1][2 * m], vv[m].x, b0);
+          b1 = fma(u[1][2 * m + 1], vv[m].y, b1);
+        }
+      }
+      double d0 = (a0 + a1) + (a2 + a3), d1 = (b0 + b1) + (b2 + b3);
+#else
       double a0 = 0., a1 = 0., b0 = 0., b1 = 0.;
 #pragma unroll
       for (int m = M0; m < M1; m++) {
@@ -613,6 +637,7 @@ struct BackTile {
         b1 = fma(u[1][2 * m + 1], vv[m].y, b1);
       }
       double d0 = a0 + a1, d1 = b0 + b1;
+#endif
       d0 += __shfl_xor_sync(FULL, d0, 1);
       d1 += __shfl_xor_sync(FULL, d1, 1);
       const double s0 = -tau * d0, s1 = -tau * d1;
@@ -963,11 +988,29 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
     double am = 0.;
     if (j < N) {
       am = sc[j]; vi = 1.;
+#if TVEC_DOT8
+      // four partial sums per result (see BackTile): chains of N/4 instead of N dependent FMAs
+      double am1 = 0., am2 = 0., am3 = 0., vi1 = 0., vi2 = 0., vi3 = 0.;
+      int k = 0;
+      for (; k + 3 < N; k += 4) {
+        const double y0 = Yt[k * LDY + j], y1 = Yt[(k + 1) * LDY + j], y2 = Yt[(k + 2) * LDY + j], y3 = Yt[(k + 3) * LDY + j];
+        am = fma(y0, sa[k], am); am1 = fma(y1, sa[k + 1], am1); am2 = fma(y2, sa[k + 2], am2); am3 = fma(y3, sa[k + 3], am3);
+        vi = fma(y0, sb[k], vi); vi1 = fma(y1, sb[k + 1], vi1); vi2 = fma(y2, sb[k + 2], vi2); vi3 = fma(y3, sb[k + 3], vi3);
+      }
+      for (; k < N; k++) {
+        const double yv = Yt[k * LDY + j];
+        am = fma(yv, sa[k], am);
+        vi = fma(yv, sb[k], vi);
+      }
+      am = (am + am1) + (am2 + am3);
+      vi = (vi + vi1) + (vi2 + vi3);
+#else
       for (int k = 0; k < N; k++) {
         const double yv = Yt[k * LDY + j];
         am = fma(yv, sa[k], am);
         vi = fma(yv, sb[k], vi);
       }
+#endif
     }
     if (am != am) atomicExch(&ctr->nan_flag, 1);
     ampl_out[(int64_t)zl * NP + j] = am;
@@ -1014,11 +1057,28 @@ __global__ void __launch_bounds__(NP, TVEC_MINB) k_tvec(int N, const int32_t *__
   __syncthreads();
   {
     double g1 = suv[j], gm2 = sdw[j];
+#if TVEC_DOT8
+    double g11 = 0., g12 = 0., g13 = 0., g21 = 0., g22 = 0., g23 = 0.;
+    int k = 0;
+    for (; k + 3 < N; k += 4) {
+      const double y0 = Yt[k * LDY + j], y1 = Yt[(k + 1) * LDY + j], y2 = Yt[(k + 2) * LDY + j], y3 = Yt[(k + 3) * LDY + j];
+      g1 = fma(-y0, sa[k], g1); g11 = fma(-y1, sa[k + 1], g11); g12 = fma(-y2, sa[k + 2], g12); g13 = fma(-y3, sa[k + 3], g13);
+      gm2 = fma(-y0, sb[k], gm2); g21 = fma(-y1, sb[k + 1], g21); g22 = fma(-y2, sb[k + 2], g22); g23 = fma(-y3, sb[k + 3], g23);
+    }
+    for (; k < N; k++) {
+      const double yv = Yt[k * LDY + j];
+      g1 = fma(-yv, sa[k], g1);
+      gm2 = fma(-yv, sb[k], gm2);
+    }
+    g1 = (g1 + g11) + (g12 + g13);
+    gm2 = (gm2 + g21) + (g22 + g23);
+#else
     for (int k = 0; k < N; k++) {
       const double yv = Yt[k * LDY + j];
       g1 = fma(-yv, sa[k], g1);
       gm2 = fma(-yv, sb[k], gm2);
     }
+#endif
     sg1[j] = g1;
     sg2[j] = gm2 - kappa * g1;
   }

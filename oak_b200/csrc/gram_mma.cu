@@ -53,6 +53,9 @@ struct TileMap {
   }
 };
 
+#ifndef GRAM_C4
+#define GRAM_C4 0   // 1: c = sum coef delta a in four partial sums: measured SLOWER (k_gram_mma 59.0 -> 63.0 ms per C3 step)
+#endif
 #ifndef GRAM_EVAL_PREFETCH
 #define GRAM_EVAL_PREFETCH 1
 #endif
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
   double acc[NACC][2];
 #pragma unroll
   for (int a = 0; a < NACC; a++) acc[a][0] = acc[a][1] = 0.;
-  double cacc = 0.;
+  double cacc = 0., cacc1 = 0., cacc2 = 0., cacc3 = 0.;
   int nrel_total = 0;
   long long ncand_total = 0;
   if (threadIdx.x == 0) s_true = 0;   // ordered before its first use by the barrier at the head of the cell loop
@@ -227,11 +230,27 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
       const double *cd = s_cd[lb];
       // the two evaluating warps' finds one after the other (same order as the merged list, no index select per row)
       const double *rp = rows + ci;
+      const int cnt1 = total - cnt0;
+#if GRAM_C4
+      // four partial sums instead of one chain of up to 64 dependent FMAs per chunk (experiment, off: see GRAM_C4)
+      int r = 0;
+      for (; r + 3 < cnt0; r += 4, rp += 4 * LDR) {
+        cacc = fma(cd[r], rp[0], cacc); cacc1 = fma(cd[r + 1], rp[LDR], cacc1);
+        cacc2 = fma(cd[r + 2], rp[2 * LDR], cacc2); cacc3 = fma(cd[r + 3], rp[3 * LDR], cacc3);
+      }
+      for (; r < cnt0; r++, rp += LDR) cacc = fma(cd[r], *rp, cacc);
+      r = 0;
+      for (; r + 3 < cnt1; r += 4, rp += 4 * LDR) {
+        cacc = fma(cd[32 + r], rp[0], cacc); cacc1 = fma(cd[33 + r], rp[LDR], cacc1);
+        cacc2 = fma(cd[34 + r], rp[2 * LDR], cacc2); cacc3 = fma(cd[35 + r], rp[3 * LDR], cacc3);
+      }
+      for (; r < cnt1; r++, rp += LDR) cacc = fma(cd[32 + r], *rp, cacc);
+#else
 #pragma unroll 4
       for (int r = 0; r < cnt0; r++, rp += LDR) cacc = fma(cd[r], *rp, cacc);
-      const int cnt1 = total - cnt0;
 #pragma unroll 4
       for (int r = 0; r < cnt1; r++, rp += LDR) cacc = fma(cd[32 + r], *rp, cacc);
+#endif
     }
   };
 
@@ -302,7 +321,7 @@ __global__ void __launch_bounds__(32 * NW) k_gram_mma(ZoneGeom zg, ObsGrid og, O
     if (warp == 0) GramMma<NP, NW, 0>::store(acc, Gz, g, t);
     else GramMma<NP, NW, 1>::store(acc, Gz, g, t);
   }
-  if (ci >= 0) cvec[(int64_t)zl * NP + ci] = cacc;
+  if (ci >= 0) cvec[(int64_t)zl * NP + ci] = (cacc + cacc1) + (cacc2 + cacc3);
   if (tid == 0) {
     // localise_obs = .false.: a zone without any relevant observation is still skipped (rrsqrt.F90:371-372)
     const int used = (q.noloc && s_true == 0) ? 0 : nrel_total;
