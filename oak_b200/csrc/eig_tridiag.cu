@@ -435,14 +435,13 @@ __global__ void __launch_bounds__(64, TRI_MINB) k_tridiag_tile(int N, const int3
 // k_tql : one thread per zone; d, e transposed into shared memory with an odd stride
 // ---------------------------------------------------------------------------------------------------
 #if TQL_GLOBAL
-// k_tql, no shared memory.  Why: the kernel is a latency-bound scalar chain per zone (~0.7 ms per launch whatever the
-// batch), overlapped with the throughput kernels of the other stream slots.  With d, e in shared memory every resident
-// warp held 33.8 KB of it for that time, 3.5 - 5 warps per SM, i.e. half of the SM's shared memory: the kernel running
-// beside it (k_gram_mma 70 KB, k_tvec 43 KB, k_apply 50 KB per CTA) lost about half of its CTAs, which is where the
-// ~20 ms per C3 step came from that the overlap never hid (the same 20 ms at 63 x 0.65 ms and at 41 x 0.70 ms of k_tql).
-// Here the transposed copy [i][lane] of the warp's 32 problems lives in a global scratch array (32 KB per warp, L2 /
-// L1 resident; lanes at the same i read one 256-byte run), and pwk_eigenvalues_t<PF> loads (d_i, e_i) PF rotations
-// ahead so the load latency is off the dependent chain.  What the warp still takes from its neighbours is registers.
+// k_tql without shared memory (TQL_GLOBAL = 1; measured, OFF).  Hypothesis: the ~20 ms per C3 step of k_tql that the overlap
+// with the other stream slots never hides come from the 33.8 KB of shared memory every resident warp holds for ~0.7 ms
+// (3.5 - 5 warps per SM: half of the SM's shared memory, taken from k_gram_mma / k_tvec / k_apply beside it).  Here the
+// transposed copy [i][lane] of the warp's 32 problems lives in a global scratch array (32 KB per warp, L2 / L1 resident;
+// lanes at the same i read one 256-byte run), and pwk_eigenvalues_t<PF> loads (d_i, e_i) PF rotations ahead so the load
+// latency is off the dependent chain.  Result on a B200: bit-identical, but the kernel is slower (56.5 against 40.1 ms
+// serial per C3 step) and the exposed share is unchanged (step 243.8 against 233.9 ms): refuted, see DESIGN.md 3.3c.
 template <int NP>
 __global__ void __launch_bounds__(32) k_tql(int N, int nz, const int32_t *__restrict__ mloc,
                                              double *__restrict__ ws, int32_t *__restrict__ flags, double *__restrict__ scr) {
