@@ -93,7 +93,8 @@ OAKB200_API int oakb200_destroy(oakb200_handle *h);
  *                     "stage_threads" host threads (default min(16, hardware threads)) while the other slots compute;
  *                     0 = asynchronous copies straight from / to the caller's arrays (staged by the driver, one thread);
  *                     -1 (default) = 1 for calls of 32 MB and more.  Measured on C3 end to end: 1.18 M columns/s against
- *                     0.40 M (pinned caller arrays: 2.6 M).  Results are identical
+ *                     0.40 M (pinned caller arrays: 2.6 M).  Results are identical.  Host memory: two page-locked buffers of one
+ *                     chunk ("chunk_mb", 256 MB) per stream slot, 2 GB in total, allocated on first use and kept by the handle
  *   "host_register"   host-buffer entry points: 1 = pageable caller arrays are page-locked (cudaHostRegister) for the
  *                     duration of the call; 0 (default) = left as they are (the driver stages the copies).  Measured on
  *                     C3: pinned arrays (oakb200_host_alloc) 2.68 M columns/s, pageable 0.40 M, registered per call 0.09 M
