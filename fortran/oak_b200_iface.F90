@@ -133,6 +133,13 @@ module oak_b200_iface
      type(oakb200_stats) :: stats
      integer(c_int) :: rc
    end function
+   ! relevant observations per zone as counted by the production kernel of the last analysis (diagnostics)
+   function oakb200_zone_counts(h, mloc) bind(C, name='oakb200_zone_counts') result(rc)
+     import
+     type(c_ptr), value :: h
+     integer(c_int32_t) :: mloc(*)              ! one entry per zone
+     integer(c_int) :: rc
+   end function
    ! observation operator: batched cinterp (ndgrid.F90:1183-1257) for one model grid with separable axes; called from
    ! genObservationOper (assimilation.F90:2569-2585) once per model variable instead of once per observation
    function oakb200_cinterp(h, ndim, gshape, axes, masked, nobs, xi, indexes, coeff, nbp, ndegenerate) &

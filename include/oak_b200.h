@@ -257,6 +257,11 @@ OAKB200_API int oakb200_assim_ensemble_dev(oakb200_handle *h, int64_t n, int32_t
  * speeds: rank p of P owns zones [first[p], first[p+1]) ; first has P+1 entries (0-based). */
 OAKB200_API int oakb200_partition_zones(int32_t nzones, int32_t nranks, int32_t *first);
 
+/* mloc[nzones]: the number of relevant observations per zone as counted by the production kernel of the LAST analysis
+ * (the selection fused into the Gram kernel); cross-check of oakb200_select_observations, which evaluates the same
+ * predicate in a kernel of its own. */
+OAKB200_API int oakb200_zone_counts(oakb200_handle *h, int32_t *mloc);
+
 /* Observation-operator generation: the batched form of `cinterp`
  * (ndgrid.F90:1183-1257), the arithmetic inside genObservationOper (assimilation.F90:2471-2656, the calls at
  * :2569-2585): for each of the m observation positions xi[m][ndim] (row-major, one row per observation) locate the cell

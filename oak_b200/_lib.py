@@ -74,6 +74,7 @@ SIGNATURES = {
                                              C.c_void_p, C.POINTER(Stats)]),
     "oakb200_synchronize": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "oakb200_partition_zones": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p]),
+    "oakb200_zone_counts": (C.c_int, [C.c_void_p, C.c_void_p]),
     "oakb200_cinterp": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "oakb200_cinterp_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,

@@ -371,6 +371,12 @@ class Handle:
                                               _ptr(xf), _ptr(xa), C.byref(st)))
         return Ea, xf, xa, st.asdict()
 
+    def zone_counts(self):
+        """Relevant observations per zone as the Gram kernel of the last analysis counted them."""
+        out = np.zeros(self.nzones, dtype=np.int32)
+        _check(self._L.oakb200_zone_counts(self._h, _ptr(out)))
+        return out
+
     def cinterp(self, gshape, axes, xi, masked=None):
         """Batched cinterp (ndgrid.F90:1183-1257) on the device for one model grid with separable axes: returns
         (indexes[m][2^n][n] 1-based, coeff[m][2^n], nbp[m]).  Raises when observations fall into degenerate cells."""

@@ -1185,6 +1185,18 @@ extern "C" OAKB200_API int oakb200_local_analysis_dev(oakb200_handle *h, int64_t
   return end_call(h, stats, launches, prof, ms, msp);
 }
 
+// Number of relevant observations of every zone as the PRODUCTION kernel of the last analysis counted them (the
+// selection fused into the Gram kernel: k_gram / k_gram_mma), for diagnostics and for the parity tests: the index sets
+// themselves come from oakb200_select_observations (k_select), this is the cross-check that both evaluate the same sets.
+extern "C" OAKB200_API int oakb200_zone_counts(oakb200_handle *h, int32_t *mloc) {
+  if (!h || !mloc) { oak_set_error("zone_counts: null argument"); return OAK_ERR_ARG; }
+  if (h->nzones <= 0 || !h->d_mloc.p) { oak_set_error("zone_counts: no zones configured"); return OAK_ERR_STATE; }
+  DeviceGuard guard(h->device);
+  for (int i = 0; i < NSLOT; i++) CUDA_TRY(cudaStreamSynchronize(h->slot[i].st));
+  CUDA_TRY(cudaMemcpy(mloc, h->d_mloc.p, sizeof(int32_t) * (size_t)h->nzones, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 extern "C" OAKB200_API int oakb200_synchronize(oakb200_handle *h, oakb200_stats *stats) {
   if (!h) { oak_set_error("null handle"); return OAK_ERR_ARG; }
   DeviceGuard guard(h->device);

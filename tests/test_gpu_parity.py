@@ -454,6 +454,31 @@ def test_assim_ensemble_fused_in_the_apply_kernel_equals_the_three_pass_form(ob,
     assert rel(xf, xfo) < 1e-14 and rel(xa, xao) < RTOL and rel(Ea, Eo) < RTOL
 
 
+@pytest.mark.parametrize("metric,weightfun", [(0, 0), (1, 0), (2, 1)])
+def test_production_selection_counts_per_zone_equal_the_index_sets(ob, metric, weightfun):
+    # the selection that matters runs inside the Gram kernel; its per-zone counts (oakb200_zone_counts) must equal the
+    # sizes of the index sets of k_select (oakb200_select_observations, compared bit for bit with the oracle in
+    # test_selection_index_sets_bit_exact) and the oracle's own counts: Cartesian, both spherical metrics, Gaussian and
+    # Gaspari-Cohn weights
+    from oak_b200 import synthetic
+    c = synthetic.small_case(nx=30, ny=24, nz=3, N=32, m=1800, corr=2500.0, maxlen=5000.0, seed=17)
+    zx, zy, ox, oy, corr, maxlen = c["zx"], c["zy"], c["obs"]["ox"], c["obs"]["oy"], c["corr"], c["maxlen"]
+    if metric != 0:      # metres -> degrees around 45 N, lengths stay in metres
+        zx, zy, ox, oy = zx / 80e3, 45.0 + zy / 111e3, ox / 80e3, 45.0 + oy / 111e3
+    sel = ob.Selector(zone_x=zx, zone_y=zy, corrLen=corr, maxLen=maxlen, obs_x=ox, obs_y=oy, metrictype=metric, weightfun=weightfun)
+    with ob.Handle(0) as h:
+        h.configure(c["zoneSize"], sel)
+        xa, Sa, _, st = h.local_analysis(c["xf"], c["Hxf"], c["yo"], c["Sf"], c["HSf"], ob.DiagCovar(c["var"]))
+        counts = h.zone_counts()
+        off, idx, _ = h.select_observations(0, len(c["zoneSize"]))
+    assert (counts == np.diff(off)).all() and counts.sum() == st["obs_relevant_sum"]
+    obs = oracle.make_obs(c["m"], obsx=ox, obsy=oy, metrictype=metric, weightfun=weightfun, trig=1)
+    xo, So, _, mloc = oracle.loc_analysis(c["zoneSize"], dict(x=zx, y=zy), corr, maxlen, obs, c["xf"], c["Hxf"], c["yo"],
+                                          c["Sf"], c["HSf"], c["var"])
+    assert (counts == mloc).all() and mloc.max() > 20
+    assert rel(xa, xo) < RTOL and rel(Sa, So) < RTOL
+
+
 def test_error_behaviour(ob):
     h = ob.Handle(0)
     with pytest.raises(ob.OakB200Error):      # analysis before configuration
